@@ -1,0 +1,127 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libgfsref.so).
+
+Run in a container that has /root/reference:   python -m oracle.make_golden
+Every array stored here came out of reference code (see oracle/ref_harness.cpp for the entry points);
+inputs are stored alongside so the fixtures are self-contained.  The reference has no golden vectors of
+its own, so these files are what pins the oracle -- and through it the CUDA path --
+on machines where the reference cannot be built.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gridfluidsim3d_b200 import synth          # noqa: E402
+from oracle.pyoracle import Reference           # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rough_fields(dims, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return tuple((scale * rng.standard_normal(a * b * c)).astype(np.float32) for a, b, c in synth.face_dims(dims))
+
+
+def probes(dims, dx, n, seed):
+    rng = np.random.default_rng(seed)
+    ext = np.array(dims) * dx
+    pos = rng.uniform(-0.6 * dx, ext + 0.6 * dx, size=(n, 3))
+    pos[: n // 10] = np.round(pos[: n // 10] / dx) * dx
+    pos[n // 10: n // 5] = np.round(pos[n // 10: n // 5] / (0.5 * dx)) * 0.5 * dx
+    return pos.astype(np.float32)
+
+
+def main():
+    ref = Reference()
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- primitives: index, sampling, RK1-4, splat ---------------------------------------------
+    dims, dx = (10, 8, 12), 0.25
+    u, v, w = rough_fields(dims, 101)
+    pos = probes(dims, dx, 1500, 102)
+    g = dict(dims=np.array(dims, np.int32), dx=np.float64(dx), u=u, v=v, w=w, pos=pos)
+    for d in (0.125, 0.1, 1.0 / 3.0):
+        g["cell_dx_%g" % d] = ref.cell_index(pos, d)
+    g["sample_trilinear"] = ref.sample(pos, u, v, w, dims, dx, 0)
+    g["sample_tricubic"] = ref.sample(pos, u, v, w, dims, dx, 1)
+    g["dt"] = np.float64(0.11)
+    for order in (1, 2, 3, 4):
+        g["rk%d" % order] = ref.advect(pos, u, v, w, dims, dx, 0.11, order)
+    inside = pos[np.all((pos > 0) & (pos < np.array(dims) * dx), 1)]
+    vals = np.random.default_rng(103).standard_normal(len(inside)).astype(np.float32)
+    g["splat_pos"], g["splat_values"] = inside, vals
+    for comp, nd in enumerate(synth.face_dims(dims)):
+        off = np.array([0.0 if comp == 0 else 0.5 * dx, 0.0 if comp == 1 else 0.5 * dx,
+                        0.0 if comp == 2 else 0.5 * dx], np.float32)
+        f, wt = ref.add_point_values(inside, vals, dx, off, dx, nd)
+        g["splat_field_%d" % comp], g["splat_weight_%d" % comp] = f, wt
+    np.savez_compressed(os.path.join(OUT, "primitives.npz"), **g)
+
+    # ---- stage level: classification + P2G, PIC/FLIP + RK4, on a scene with interior solids and sources
+    dims, dx = (12, 10, 14), 0.25
+    I, J, K = dims
+    material = synth.border_material(dims)
+    m3 = material.reshape(K, J, I)
+    m3[2:5, 1:4, 3:6] = synth.SOLID
+    mask = synth.fluid_cells("dam", dims, material)
+    p = synth.make_particles(mask, dx, seed=777)
+    vel = synth.particle_velocities(p, dims, dx) + \
+        0.05 * np.random.default_rng(104).standard_normal(p.shape).astype(np.float32)
+    vel = vel.astype(np.float32)
+    kk, jj, ii = np.nonzero(m3 == synth.SOLID)
+    solid_ijk = np.stack([ii, jj, kk], 1).astype(np.int32)
+    sources = [dict(kind=0, p=(1.2, 1.0, 1.5), a=0.7, velocity=(0.5, -1.0, 0.25)),
+               dict(kind=1, p=(0.5, 0.5, 2.0), a=1.0, b=0.8, c=0.9, velocity=(-0.3, 0.2, 0.7))]
+
+    sim = ref.sim(dims, dx)
+    sim.add_solid_cells(solid_ijk)
+    sim.initialize()
+    sim.set_particles(p, vel)
+    sim.update_fluid_cells()
+    assert sim.n == len(p)
+    for s in sources:
+        sim.add_inflow_source(s["kind"], s["p"], s.get("a", 0), s.get("b", 0), s.get("c", 0), s["velocity"])
+    sim.advect_velocity_field()
+    mat_out = sim.get_material()
+    pu, pv, pw = sim.get_fields()
+
+    new, saved = rough_fields(dims, 105, 0.3), rough_fields(dims, 106, 0.3)
+    dt = 0.25 * dx
+    sim.set_fields(new, saved)
+    sim.update_particle_velocities()
+    sim.advance_particles(dt)
+    pos1, vel1 = sim.get_particles()
+    sim.close()
+
+    src_arr = np.array([[s["kind"], *s["p"], s.get("a", 0), s.get("b", 0), s.get("c", 0), *s["velocity"]]
+                        for s in sources], np.float64)
+    np.savez_compressed(os.path.join(OUT, "stages.npz"),
+                        dims=np.array(dims, np.int32), dx=np.float64(dx), material_in=material,
+                        pos=p, vel=vel, sources=src_arr, material_out=mat_out, p2g_u=pu, p2g_v=pv, p2g_w=pw,
+                        new_u=new[0], new_v=new[1], new_w=new[2], saved_u=saved[0], saved_v=saved[1],
+                        saved_w=saved[2], dt=np.float64(dt), pos_out=pos1, vel_out=vel1)
+
+    # ---- whole-simulator: Hello-World-like drop at 16^3, two frames of FluidSimulation::update, with the
+    # particle set before/after each hot-path stage of the second frame captured through the stage calls.
+    dims, dx = (16, 16, 16), 0.5
+    sim = ref.sim(dims, dx)
+    sim.add_fluid_sphere((4.0, 4.0, 4.0), 5.0)
+    sim.add_body_force((0.0, -25.0, 0.0))
+    sim.initialize()
+    p0, v0 = sim.get_particles()
+    sim.update(1.0 / 30.0)
+    p1, v1 = sim.get_particles()
+    mat1 = sim.get_material()
+    u1, vv1, w1 = sim.get_fields()
+    sim.close()
+    np.savez_compressed(os.path.join(OUT, "helloworld16.npz"), dims=np.array(dims, np.int32), dx=np.float64(dx),
+                        pos0=p0, vel0=v0, pos1=p1, vel1=v1, material1=mat1, u1=u1, v1=vv1, w1=w1)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,314 @@
+"""ctypes front-ends for the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``Oracle``    -> oracle/liboracle.so   (plain-C restatement, oracle.c; exists everywhere)
+* ``Reference`` -> oracle/_ref/libgfsref.so (the unmodified reference sources + ref_harness.cpp;
+  built only where /root/reference exists, but the built .so travels to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (gridfluidsim3d_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libgfsref.so")
+
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+class Source(C.Structure):
+    _fields_ = [("kind", C.c_int), ("p", C.c_float * 3), ("a", C.c_double), ("b", C.c_double),
+                ("c", C.c_double), ("velocity", C.c_float * 3)]
+
+
+def make_sources(sources):
+    """sources: list of dicts {kind, p, a, b, c, velocity} -> (ctypes array, count)."""
+    arr = (Source * max(1, len(sources)))()
+    for s, d in zip(arr, sources):
+        s.kind = d["kind"]
+        s.p[:] = d["p"]
+        s.a, s.b, s.c = d.get("a", 0.0), d.get("b", 0.0), d.get("c", 0.0)
+        s.velocity[:] = d["velocity"]
+    return arr, len(sources)
+
+
+def build_oracle(force=False):
+    if force or not os.path.exists(ORACLE_SO) or \
+            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    return ORACLE_SO
+
+
+def build_reference(force=False):
+    """Build oracle/_ref/libgfsref.so if the reference tree is present; return path or None."""
+    if os.path.isdir("/root/reference/src"):
+        if force or not os.path.exists(REF_SO) or \
+                os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_harness.cpp")):
+            subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+def face_dims(I, J, K):
+    return (I + 1, J, K), (I, J + 1, K), (I, J, K + 1)
+
+
+def face_counts(I, J, K):
+    return tuple(a * b * c for a, b, c in face_dims(I, J, K))
+
+
+def _c(a, dt=np.float32):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = L = C.CDLL(build_oracle())
+        L.orc_max_threads.restype = C.c_int
+        L.orc_cell_index.argtypes = [_f32, C.c_long, C.c_double, _i32]
+        L.orc_sample.argtypes = [_f32, C.c_long, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_int, C.c_int, _f32]
+        L.orc_advect.argtypes = [_f32, C.c_long, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_int, C.c_int, _f32]
+        L.orc_picflip.argtypes = [_f32, _f32, C.c_long, _f32, _f32, _f32, _f32, _f32, _f32,
+                                  C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _f32]
+        L.orc_splat.argtypes = [_f32, _f32, C.c_long, C.c_long, C.c_double, _f32, C.c_double,
+                                C.c_int, C.c_int, C.c_int, _f32, _f32]
+        L.orc_apply_weight.argtypes = [_f32, _f32, C.c_long]
+        L.orc_border_solid.argtypes = [C.c_int, C.c_int, C.c_int, _u8]
+        L.orc_classify.argtypes = [_f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, _u8]
+        L.orc_classify.restype = C.c_long
+        L.orc_p2g_component.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        _u8, C.c_void_p, C.c_int, _f32]
+        L.orc_p2g.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double,
+                              _u8, C.c_void_p, C.c_int, _f32, _f32, _f32]
+        L.orc_solid_test.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, _u8, _u8]
+        L.orc_solid_test.restype = C.c_long
+        L.orc_g2p_advect.argtypes = [_f32, _f32, C.c_long, _f32, _f32, _f32, _f32, _f32, _f32,
+                                     C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                     C.c_int, C.c_int, C.c_void_p, _f32, _f32, C.c_void_p]
+
+    def cell_index(self, pos, dx):
+        pos = _c(pos)
+        out = np.empty((len(pos), 3), np.int32)
+        self.lib.orc_cell_index(pos, len(pos), dx, out)
+        return out
+
+    def sample(self, pos, u, v, w, dims, dx, mode, validate=True):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self.lib.orc_sample(pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, mode, int(validate), out)
+        return out
+
+    def advect(self, pos, u, v, w, dims, dx, dt, order=4, mode=1):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self.lib.orc_advect(pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, dt, order, mode, out)
+        return out
+
+    def picflip(self, pos, vel, new, saved, dims, dx, ratio=float(np.float32(0.05)), mode=1):
+        pos, vel = _c(pos), _c(vel)
+        out = np.empty_like(vel)
+        self.lib.orc_picflip(pos, vel, len(pos), *[_c(a) for a in new], *[_c(a) for a in saved],
+                             *dims, dx, ratio, mode, out)
+        return out
+
+    def splat(self, pos, values, radius, offset, dx, ndims, field=None, weight=None):
+        pos, values = _c(pos), _c(values)
+        cnt = ndims[0] * ndims[1] * ndims[2]
+        field = np.zeros(cnt, np.float32) if field is None else field
+        weight = np.zeros(cnt, np.float32) if weight is None else weight
+        self.lib.orc_splat(pos, values, 1, len(pos), radius, _c(offset), dx, *ndims, field, weight)
+        return field, weight
+
+    def apply_weight(self, field, weight):
+        self.lib.orc_apply_weight(field, weight, field.size)
+        return field
+
+    def border_material(self, dims):
+        m = np.zeros(dims[0] * dims[1] * dims[2], np.uint8)
+        self.lib.orc_border_solid(*dims, m)
+        return m
+
+    def classify(self, pos, dims, dx, material):
+        pos = _c(pos)
+        bad = self.lib.orc_classify(pos, len(pos), *dims, dx, material)
+        return material, bad
+
+    def p2g(self, pos, vel, dims, dx, material, sources=()):
+        pos, vel = _c(pos), _c(vel)
+        src, ns = make_sources(list(sources))
+        nu, nv, nw = face_counts(*dims)
+        u, v, w = np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32)
+        self.lib.orc_p2g(pos, vel, len(pos), *dims, dx, material, C.cast(src, C.c_void_p), ns, u, v, w)
+        return u, v, w
+
+    def g2p_advect(self, pos, vel, new, saved, dims, dx, dt, ratio=float(np.float32(0.05)), order=4, mode=1,
+                   material=None):
+        pos, vel = _c(pos), _c(vel)
+        pos_out, vel_out = np.empty_like(pos), np.empty_like(vel)
+        flags = np.zeros(len(pos), np.uint8)
+        mptr = material.ctypes.data_as(C.c_void_p) if material is not None else None
+        self.lib.orc_g2p_advect(pos, vel, len(pos), *[_c(a) for a in new], *[_c(a) for a in saved],
+                                *dims, dx, ratio, dt, order, mode, mptr, pos_out, vel_out,
+                                flags.ctypes.data_as(C.c_void_p))
+        return pos_out, vel_out, flags
+
+
+class Reference:
+    """The unmodified reference, driven through oracle/ref_harness.cpp."""
+
+    def __init__(self, build=True):
+        path = build_reference() if build else (REF_SO if os.path.exists(REF_SO) else None)
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libgfsref.so is not built and /root/reference is absent")
+        self.lib = L = C.CDLL(path)
+        V = C.c_void_p
+        L.ref_max_threads.restype = C.c_int
+        L.ref_cell_index.argtypes = [_f32, C.c_long, C.c_double, _i32]
+        L.ref_sample.argtypes = [_f32, C.c_long, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _f32]
+        L.ref_advect.argtypes = [_f32, C.c_long, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_int, _f32]
+        L.ref_add_point_values.argtypes = [_f32, _f32, C.c_long, C.c_double, _f32, C.c_double,
+                                           C.c_int, C.c_int, C.c_int, _f32, _f32]
+        L.ref_sim_create.restype = V
+        L.ref_sim_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+        for name in ("ref_sim_initialize", "ref_sim_destroy", "ref_sim_update_fluid_cells",
+                     "ref_sim_advect_velocity_field", "ref_sim_update_particle_velocities"):
+            getattr(L, name).argtypes = [V]
+        L.ref_sim_add_fluid_sphere.argtypes = [V, C.c_float, C.c_float, C.c_float, C.c_double]
+        L.ref_sim_add_fluid_cuboid.argtypes = [V, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double]
+        L.ref_sim_add_body_force.argtypes = [V, C.c_float, C.c_float, C.c_float]
+        L.ref_sim_add_solid_cells.argtypes = [V, _i32, C.c_long]
+        L.ref_sim_add_inflow_source.argtypes = [V, C.c_int, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double,
+                                                C.c_double, C.c_float, C.c_float, C.c_float]
+        L.ref_sim_num_particles.argtypes = [V]
+        L.ref_sim_num_particles.restype = C.c_long
+        L.ref_sim_set_particles.argtypes = [V, _f32, _f32, C.c_long]
+        L.ref_sim_get_particles.argtypes = [V, _f32, _f32]
+        L.ref_sim_get_material.argtypes = [V, _u8]
+        L.ref_sim_set_fields.argtypes = [V, _f32, _f32, _f32, _f32, _f32, _f32]
+        L.ref_sim_get_fields.argtypes = [V, _f32, _f32, _f32]
+        L.ref_sim_advance_particles.argtypes = [V, C.c_double]
+        L.ref_sim_update.argtypes = [V, C.c_double]
+        L.ref_time_hotpath.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       _f32, _f32, _f32, _f32, _f32, _f32, C.c_double, C.c_int, _f64]
+        L.ref_time_hotpath.restype = C.c_double
+
+    # -- primitives
+    def cell_index(self, pos, dx):
+        pos = _c(pos)
+        out = np.empty((len(pos), 3), np.int32)
+        self.lib.ref_cell_index(pos, len(pos), dx, out)
+        return out
+
+    def sample(self, pos, u, v, w, dims, dx, mode):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self.lib.ref_sample(pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, mode, out)
+        return out
+
+    def advect(self, pos, u, v, w, dims, dx, dt, order=4):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self.lib.ref_advect(pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, dt, order, out)
+        return out
+
+    def add_point_values(self, pos, values, radius, offset, dx, ndims):
+        pos, values = _c(pos), _c(values)
+        cnt = ndims[0] * ndims[1] * ndims[2]
+        field, weight = np.zeros(cnt, np.float32), np.zeros(cnt, np.float32)
+        self.lib.ref_add_point_values(pos, values, len(pos), radius, _c(offset), dx, *ndims, field, weight)
+        return field, weight
+
+    # -- simulation-level
+    def sim(self, dims, dx):
+        return RefSim(self.lib, dims, dx)
+
+    def time_hotpath(self, pos, vel, dims, dx, new, saved, dt, nthreads):
+        stages = np.zeros(3)
+        pos, vel = _c(pos), _c(vel)
+        t = self.lib.ref_time_hotpath(pos, vel, len(pos), *dims, dx, *[_c(a) for a in new],
+                                      *[_c(a) for a in saved], dt, nthreads, stages)
+        return t, stages
+
+
+class RefSim:
+    def __init__(self, lib, dims, dx):
+        self.lib, self.dims, self.dx = lib, tuple(dims), dx
+        self.h = lib.ref_sim_create(*dims, dx)
+        self._init = False
+
+    def add_fluid_sphere(self, c, r):
+        self.lib.ref_sim_add_fluid_sphere(self.h, *c, r)
+
+    def add_fluid_cuboid(self, p, w, h, d):
+        self.lib.ref_sim_add_fluid_cuboid(self.h, *p, w, h, d)
+
+    def add_body_force(self, f):
+        self.lib.ref_sim_add_body_force(self.h, *f)
+
+    def add_solid_cells(self, ijk):
+        ijk = _c(ijk, np.int32)
+        self.lib.ref_sim_add_solid_cells(self.h, ijk, len(ijk))
+
+    def add_inflow_source(self, kind, p, a, b, c, velocity):
+        self.lib.ref_sim_add_inflow_source(self.h, kind, *p, a, b, c, *velocity)
+
+    def initialize(self):
+        self.lib.ref_sim_initialize(self.h)
+        self._init = True
+
+    @property
+    def n(self):
+        return self.lib.ref_sim_num_particles(self.h)
+
+    def set_particles(self, pos, vel):
+        pos, vel = _c(pos), _c(vel)
+        self.lib.ref_sim_set_particles(self.h, pos, vel, len(pos))
+
+    def get_particles(self):
+        n = self.n
+        pos, vel = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        self.lib.ref_sim_get_particles(self.h, pos, vel)
+        return pos, vel
+
+    def get_material(self):
+        m = np.empty(self.dims[0] * self.dims[1] * self.dims[2], np.uint8)
+        self.lib.ref_sim_get_material(self.h, m)
+        return m
+
+    def set_fields(self, new, saved):
+        self.lib.ref_sim_set_fields(self.h, *[_c(a) for a in new], *[_c(a) for a in saved])
+
+    def get_fields(self):
+        nu, nv, nw = face_counts(*self.dims)
+        u, v, w = np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32)
+        self.lib.ref_sim_get_fields(self.h, u, v, w)
+        return u, v, w
+
+    def update_fluid_cells(self):
+        self.lib.ref_sim_update_fluid_cells(self.h)
+
+    def advect_velocity_field(self):
+        self.lib.ref_sim_advect_velocity_field(self.h)
+
+    def update_particle_velocities(self):
+        self.lib.ref_sim_update_particle_velocities(self.h)
+
+    def advance_particles(self, dt):
+        self.lib.ref_sim_advance_particles(self.h, dt)
+
+    def update(self, dt):
+        self.lib.ref_sim_update(self.h, dt)
+
+    def close(self):
+        if self.h:
+            self.lib.ref_sim_destroy(self.h)
+            self.h = None
