@@ -1,0 +1,281 @@
+"""ctypes binding of include/gfs_b200.h (gridfluidsim3d_b200/libgfs_b200.so).
+
+This is the reference-side binding a maintainer would write (cf. the reference's own
+src/pyfluid/pybindings.py:11-36 over its C bindings).  There is no fallback of any kind: if the shared
+library is missing or no CUDA device is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgfs_b200.so")
+
+TRILINEAR, TRICUBIC = 0, 1
+FAST, EXACT = 0, 1
+FIELD_NEW, FIELD_SAVED, FIELD_P2G = 0, 1, 2
+AIR, FLUID, SOLID = 0, 1, 2
+
+#: every symbol include/gfs_b200.h declares (tests check the .so exports each one)
+SYMBOLS = [
+    "gfs_get_error_message", "gfs_create", "gfs_destroy", "gfs_device_info", "gfs_sync", "gfs_get_stats",
+    "gfs_sample", "gfs_advect", "gfs_add_point_values",
+    "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
+    "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
+    "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
+    "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
+]
+
+
+class GfsError(RuntimeError):
+    pass
+
+
+class Source(C.Structure):
+    _fields_ = [("kind", C.c_int), ("p", C.c_float * 3), ("a", C.c_double), ("b", C.c_double),
+                ("c", C.c_double), ("velocity", C.c_float * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("num_particles", "out_of_grid", "in_solid", "solid_hits",
+                                         "fluid_cells", "kernel_launches")]
+
+
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_err = C.POINTER(C.c_int)
+_lib = None
+
+
+def load_library():
+    """Load libgfs_b200.so and declare prototypes.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GfsError("%s is missing: build it with `make -C gridfluidsim3d_b200/csrc` (or "
+                       "__graft_entry__.build()).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    V, I, D, L64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+    L.gfs_get_error_message.restype = C.c_char_p
+    L.gfs_create.restype = V
+    L.gfs_create.argtypes = [I, V, _err]
+    L.gfs_destroy.argtypes = [V, _err]
+    L.gfs_device_info.argtypes = [V, C.c_char_p, I, _err]
+    L.gfs_sync.argtypes = [V, _err]
+    L.gfs_get_stats.argtypes = [V, C.POINTER(Stats), _err]
+    L.gfs_sample.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, I, I, I, _f32, _err]
+    L.gfs_advect.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, D, I, I, I, _f32, _err]
+    L.gfs_add_point_values.argtypes = [V, _f32, _f32, L64, D, _f32, D, I, I, I, _f32, V, I, I, _err]
+    L.gfs_domain_init.argtypes = [V, I, I, I, D, _err]
+    L.gfs_set_material.argtypes = [V, _u8, _err]
+    L.gfs_get_material.argtypes = [V, _u8, _err]
+    L.gfs_set_sources.argtypes = [V, V, I, _err]
+    L.gfs_set_particles.argtypes = [V, _f32, L64, _err]
+    L.gfs_num_particles.argtypes = [V, _err]
+    L.gfs_num_particles.restype = L64
+    L.gfs_get_particles.argtypes = [V, _f32, _err]
+    L.gfs_get_particle_order.argtypes = [V, _i32, _err]
+    L.gfs_set_field.argtypes = [V, I, _f32, _f32, _f32, _err]
+    L.gfs_get_field.argtypes = [V, I, _f32, _f32, _f32, _err]
+    L.gfs_sort.argtypes = [V, _err]
+    L.gfs_p2g.argtypes = [V, I, _err]
+    L.gfs_g2p_advect.argtypes = [V, D, D, I, I, I, _err]
+    L.gfs_substep.argtypes = [V, D, D, I, I, I, _err]
+    L.gfs_device_ptr.argtypes = [V, I, _err]
+    L.gfs_device_ptr.restype = V
+    L.gfs_resize_particles.argtypes = [V, L64, _err]
+    L.gfs_slab_range.argtypes = [I, I, I, C.POINTER(I), C.POINTER(I), _err]
+    L.gfs_slab_owner.argtypes = [I, I, I, _err]
+    L.gfs_slab_owner.restype = I
+    L.gfs_slab_halo_cells.argtypes = [I, D, D, _err]
+    L.gfs_slab_halo_cells.restype = I
+    _lib = L
+    return L
+
+
+def _check(err):
+    if err.value != 1:
+        raise GfsError(load_library().gfs_get_error_message().decode("utf-8", "replace"))
+
+
+def _c(a, dt=np.float32):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def face_counts(dims):
+    I, J, K = dims
+    return (I + 1) * J * K, I * (J + 1) * K, I * J * (K + 1)
+
+
+PICFLIP_RATIO = float(np.float32(0.05))      # double _ratioPICFLIP = 0.05f  (src/fluidsimulation.h:1161)
+
+
+# ---- z-slab arithmetic (host only; usable without a GPU) ----------------------------------------
+def slab_range(ksize, nranks, rank):
+    L = load_library()
+    k0, k1, err = C.c_int(), C.c_int(), C.c_int()
+    L.gfs_slab_range(ksize, nranks, rank, C.byref(k0), C.byref(k1), C.byref(err))
+    _check(err)
+    return k0.value, k1.value
+
+
+def slab_owner(ksize, nranks, k):
+    L = load_library()
+    err = C.c_int()
+    r = L.gfs_slab_owner(ksize, nranks, int(k), C.byref(err))
+    _check(err)
+    return r
+
+
+def slab_halo_cells(interp, max_displacement, dx):
+    L = load_library()
+    err = C.c_int()
+    r = L.gfs_slab_halo_cells(interp, max_displacement, dx, C.byref(err))
+    _check(err)
+    return r
+
+
+class Context:
+    """One CUDA device + stream.  Mirrors the accelerator objects FluidSimulation owns
+    (ParticleAdvector / CLScalarField, src/fluidsimulation.h:1170-1171)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        err = C.c_int()
+        self.h = self.lib.gfs_create(device, stream, C.byref(err))
+        _check(err)
+        self.dims = None
+        self.dx = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            err = C.c_int()
+            self.lib.gfs_destroy(self.h, C.byref(err))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, fn, *args):
+        err = C.c_int()
+        r = fn(self.h, *args, C.byref(err))
+        _check(err)
+        return r
+
+    def device_info(self):
+        buf = C.create_string_buffer(512)
+        self._call(self.lib.gfs_device_info, buf, 512)
+        return buf.value.decode()
+
+    def sync(self):
+        self._call(self.lib.gfs_sync)
+
+    def stats(self):
+        s = Stats()
+        self._call(self.lib.gfs_get_stats, C.byref(s))
+        return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    # ---- host-pointer operators (ParticleAdvector / CLScalarField) --------------------------------
+    def sample(self, pos, u, v, w, dims, dx, interp=TRICUBIC, arith=FAST, validate=True):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self._call(self.lib.gfs_sample, pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, interp, arith, int(validate), out)
+        return out
+
+    def advect(self, pos, u, v, w, dims, dx, dt, order=4, interp=TRICUBIC, arith=FAST):
+        pos = _c(pos)
+        out = np.empty_like(pos)
+        self._call(self.lib.gfs_advect, pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, dt, order, interp, arith, out)
+        return out
+
+    def add_point_values(self, pos, values, radius, offset, dx, ndims, field=None, weight=None,
+                         accumulate=False, arith=FAST, with_weight=True):
+        pos, values = _c(pos), _c(values)
+        cnt = ndims[0] * ndims[1] * ndims[2]
+        field = np.zeros(cnt, np.float32) if field is None else field
+        if with_weight and weight is None:
+            weight = np.zeros(cnt, np.float32)
+        wptr = weight.ctypes.data_as(C.c_void_p) if weight is not None else None
+        self._call(self.lib.gfs_add_point_values, pos, values, len(pos), radius, _c(offset), dx, *ndims,
+                   field, wptr, int(accumulate), arith)
+        return field, weight
+
+    # ---- device-resident domain ---------------------------------------------------------------------
+    def domain_init(self, dims, dx):
+        self.dims, self.dx = tuple(int(d) for d in dims), float(dx)
+        self._call(self.lib.gfs_domain_init, *self.dims, self.dx)
+
+    def set_material(self, material):
+        self._call(self.lib.gfs_set_material, _c(material, np.uint8))
+
+    def get_material(self):
+        m = np.empty(self.dims[0] * self.dims[1] * self.dims[2], np.uint8)
+        self._call(self.lib.gfs_get_material, m)
+        return m
+
+    def set_sources(self, sources):
+        arr = (Source * max(1, len(sources)))()
+        for s, d in zip(arr, sources):
+            s.kind = d["kind"]
+            s.p[:] = d["p"]
+            s.a, s.b, s.c = d.get("a", 0.0), d.get("b", 0.0), d.get("c", 0.0)
+            s.velocity[:] = d["velocity"]
+        self._call(self.lib.gfs_set_sources, C.cast(arr, C.c_void_p), len(sources))
+
+    def set_particles(self, pos, vel):
+        """pos, vel: (N,3) float32 -> MarkerParticle_t AoS (24 B) -> device SoA."""
+        aos = np.ascontiguousarray(np.concatenate([_c(pos), _c(vel)], axis=1))
+        self.set_particles_aos(aos)
+
+    def set_particles_aos(self, aos):
+        aos = _c(aos).reshape(-1)
+        self._call(self.lib.gfs_set_particles, aos, aos.size // 6)
+
+    @property
+    def num_particles(self):
+        return self._call(self.lib.gfs_num_particles)
+
+    def get_particles_aos(self, out=None):
+        n = self.num_particles
+        out = np.empty(n * 6, np.float32) if out is None else out
+        self._call(self.lib.gfs_get_particles, out)
+        return out
+
+    def get_particles(self):
+        aos = self.get_particles_aos().reshape(-1, 6)
+        return np.ascontiguousarray(aos[:, :3]), np.ascontiguousarray(aos[:, 3:])
+
+    def get_particle_order(self):
+        o = np.empty(self.num_particles, np.int32)
+        self._call(self.lib.gfs_get_particle_order, o)
+        return o
+
+    def set_field(self, slot, u, v, w):
+        self._call(self.lib.gfs_set_field, slot, _c(u), _c(v), _c(w))
+
+    def get_field(self, slot):
+        nu, nv, nw = face_counts(self.dims)
+        u, v, w = np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32)
+        self._call(self.lib.gfs_get_field, slot, u, v, w)
+        return u, v, w
+
+    def sort(self):
+        self._call(self.lib.gfs_sort)
+
+    def p2g(self, arith=FAST):
+        self._call(self.lib.gfs_p2g, arith)
+
+    def g2p_advect(self, dt, ratio=PICFLIP_RATIO, order=4, interp=TRICUBIC, arith=FAST):
+        self._call(self.lib.gfs_g2p_advect, dt, ratio, order, interp, arith)
+
+    def substep(self, dt, ratio=PICFLIP_RATIO, order=4, interp=TRICUBIC, arith=FAST):
+        self._call(self.lib.gfs_substep, dt, ratio, order, interp, arith)
+
+    def device_ptr(self, which):
+        return self._call(self.lib.gfs_device_ptr, which)

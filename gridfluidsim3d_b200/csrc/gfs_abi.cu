@@ -1,0 +1,689 @@
+// gfs_abi.cu -- the C-ABI of include/gfs_b200.h: context, device-resident domain, operator launches.
+//
+// Host code is C++11; all device memory is owned by the context; every entry point reports through the
+// reference's error convention (trailing int *err, 1 = success, 0 = fail, message buffer), see
+// /root/reference/src/c_bindings/cbindings.cpp:11-19.  No CPU fallback exists: without a usable CUDA
+// device gfs_create fails and nothing else can be called.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gfs_kernels.cuh"
+
+namespace {
+
+thread_local char g_error[4096] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+struct GfsError : std::runtime_error {
+    explicit GfsError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define GFS_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw GfsError(b_);                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define GFS_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) throw GfsError(std::string(msg) + " (" #cond ")");                            \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        GFS_CUDA(cudaMalloc((void **)&p, n * sizeof(T)));
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct gfs_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+
+    // ---- domain
+    bool has_domain = false;
+    gfs::Grid grid;
+    size_t face_count[3] = {0, 0, 0};
+    size_t cell_count = 0;
+    uint32_t nkeys = 0;
+    DevBuf<float> field[3][3];            // [slot][comp]
+    DevBuf<uint8_t> material;
+    DevBuf<float> val[3];                 // node grids after normalisation ("ugrid")
+    DevBuf<uint8_t> setmask[3];
+    DevBuf<unsigned long long> acc[3];    // fixed-point accumulators, 2 per node
+    DevBuf<int2> cells;
+    gfs::Sources sources;
+
+    // ---- particles (double-buffered SoA: x,y,z,vx,vy,vz) + original-index tags
+    int64_t n = 0;
+    int cur = 0;
+    bool sorted = false;
+    DevBuf<float> soa[2][6];
+    DevBuf<int32_t> tag[2];
+    DevBuf<uint32_t> keys[2];
+    DevBuf<int32_t> perm[2];
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<int32_t> n_valid;              // 1 word
+    DevBuf<unsigned int> vmax_bits;       // 1 word
+    DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
+    int64_t out_of_grid = 0;
+
+    // ---- scratch for host-pointer operators
+    DevBuf<float> h_pos, h_out, h_val, h_fld, h_wgt, h_field[3];
+    DevBuf<unsigned long long> h_acc;
+
+    void reserve_particles(int64_t m) {
+        for (int b = 0; b < 2; b++) {
+            for (int a = 0; a < 6; a++) soa[b][a].reserve((size_t)m);
+            tag[b].reserve((size_t)m);
+            keys[b].reserve((size_t)m);
+            perm[b].reserve((size_t)m);
+        }
+    }
+};
+
+namespace {
+
+using gfs::Grid;
+
+Grid make_grid(int I, int J, int K, double dx, int k0, int k1) {
+    Grid g;
+    g.I = I; g.J = J; g.K = K; g.k0 = k0; g.k1 = k1;
+    g.dx = dx; g.invdx = 1.0 / dx;
+    g.xmax = dx * I; g.ymax = dx * J; g.zmax = dx * K;
+    g.halfdx = 0.5 * dx;
+    g.nbi = (I + 1 + gfs::kBrick - 1) / gfs::kBrick;
+    g.nbj = (J + 1 + gfs::kBrick - 1) / gfs::kBrick;
+    g.nbk = (k1 - k0 + 1 + gfs::kBrick - 1) / gfs::kBrick;
+    return g;
+}
+
+gfs::SplatParams make_splat(double r, const unsigned int *vmax_bits) {
+    gfs::SplatParams sp;
+    sp.radius = r; sp.rsq = r * r;
+    sp.c1 = (4.0 / 9.0) * (1.0 / (r * r * r * r * r * r));
+    sp.c2 = (17.0 / 9.0) * (1.0 / (r * r * r * r));
+    sp.c3 = (22.0 / 9.0) * (1.0 / (r * r));
+    sp.c1f = (float)sp.c1; sp.c2f = (float)sp.c2; sp.c3f = (float)sp.c3;
+    sp.vmax_bits = vmax_bits;
+    return sp;
+}
+
+gfs::RkCoef make_rk(double dt) {       // casts exactly where the reference casts (particleadvector.cpp:1045-1078)
+    gfs::RkCoef c;
+    c.dt = (float)dt;
+    c.half_dt = (float)(0.5 * dt);
+    c.three_quarter_dt = (float)(0.75 * dt);
+    c.dt_over_6 = (float)(dt / 6.0f);
+    c.dt_over_9 = (float)(dt / 9.0f);
+    return c;
+}
+
+dim3 grid3(int ni, int nj, int nk, int bx = 128) { return dim3((unsigned)ceil_div(ni, bx), (unsigned)nj, (unsigned)nk); }
+
+#define LAUNCH(ctx, kernel, gridDim, blockDim, ...)                                                \
+    do {                                                                                           \
+        kernel<<<(gridDim), (blockDim), 0, (ctx)->stream>>>(__VA_ARGS__);                          \
+        (ctx)->launches++;                                                                         \
+        GFS_CUDA(cudaGetLastError());                                                              \
+    } while (0)
+
+void require_domain(gfs_context *c) { GFS_REQUIRE(c && c->has_domain, "gfs_domain_init has not been called"); }
+
+gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
+    gfs::FieldPtrs f;
+    for (int a = 0; a < 3; a++) f.c[a] = c->field[slot][a].p;
+    return f;
+}
+
+void do_sort(gfs_context *c) {
+    require_domain(c);
+    const int64_t n = c->n;
+    const int src = c->cur, dst = 1 - c->cur;
+    GFS_CUDA(cudaMemsetAsync(c->cells.p, 0, sizeof(int2) * (size_t)c->nkeys, c->stream));
+    GFS_CUDA(cudaMemsetAsync(c->n_valid.p, 0, sizeof(int32_t), c->stream));
+    GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
+    if (n > 0) {
+        const int B = 256;
+        LAUNCH(c, gfs::k_keys, ceil_div(n, B), B, c->grid, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
+               c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->perm[0].p, c->vmax_bits.p);
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (unsigned long long)c->nkeys) bits++;
+        bits = bits < 32 ? bits + 1 : 32;                      // one more so the all-ones sentinel sorts last
+        // the sentinel is 0xFFFFFFFF: with end_bit = bits it compares as (2^bits - 1) >= nkeys, i.e. last
+        size_t tmp_bytes = 0;
+        GFS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p, c->perm[1].p,
+                                                  (int)n, 0, bits, c->stream));
+        c->cub_tmp.reserve(tmp_bytes);
+        GFS_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p,
+                                                  c->perm[1].p, (int)n, 0, bits, c->stream));
+        c->launches += 4;      // cub: histogram + onesweep passes (counted conservatively)
+        LAUNCH(c, gfs::k_reorder, ceil_div(n, B), B, n, c->perm[1].p,
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+               c->tag[src].p,
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+               c->tag[dst].p);
+        LAUNCH(c, gfs::k_cell_ranges, ceil_div(n, B), B, n, c->keys[1].p, c->cells.p, c->n_valid.p);
+        c->cur = dst;
+    }
+    c->sorted = true;
+}
+
+void do_p2g(gfs_context *c, int arith) {
+    require_domain(c);
+    GFS_REQUIRE(c->sorted, "gfs_p2g needs gfs_sort first");
+    const Grid &g = c->grid;
+    const int kl = g.k1 - g.k0;
+    const int b = c->cur;
+    gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
+    GFS_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    LAUNCH(c, gfs::k_classify, grid3(g.I, g.J, kl), 128, g, c->cells.p, c->material.p, c->counters.p);
+    const int dims[3][3] = {{g.I + 1, g.J, kl}, {g.I, g.J + 1, kl}, {g.I, g.J, kl + 1}};
+    if (arith == GFS_EXACT) {
+        for (int comp = 0; comp < 3; comp++)
+            LAUNCH(c, gfs::k_p2g_gather<1>, grid3(dims[comp][0], dims[comp][1], dims[comp][2], 64), 64, g, comp, sp, c->sources,
+                   c->cells.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3 + comp].p,
+                   c->val[comp].p, c->setmask[comp].p);
+    } else {
+        if (c->n > 0)
+            LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->n_valid.p,
+                   c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                   c->acc[0].p, c->acc[1].p, c->acc[2].p);
+        for (int comp = 0; comp < 3; comp++)
+            LAUNCH(c, gfs::k_p2g_finalize, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, sp, c->sources,
+                   c->acc[comp].p, c->val[comp].p, c->setmask[comp].p);
+    }
+    for (int comp = 0; comp < 3; comp++)
+        LAUNCH(c, gfs::k_assemble, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, c->material.p,
+               c->val[comp].p, c->setmask[comp].p, c->field[GFS_FIELD_P2G][comp].p);
+}
+
+void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith) {
+    require_domain(c);
+    GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
+    GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    if (c->n == 0) return;
+    const int src = c->cur, dst = 1 - c->cur;
+    gfs::RkCoef rk = make_rk(dt);
+    float rp = (float)ratio, rf = (float)(1 - ratio);      // fluidsimulation.cpp:3126
+    GFS_CUDA(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), c->stream));
+    if (arith == GFS_EXACT)
+        LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED),
+               c->material.p, interp, order, rk, rp, rf, c->n,
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+               c->counters.p);
+    else
+        LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED),
+               c->material.p, interp, order, rk, rp, rf, c->n,
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+               c->counters.p);
+    // tags travel with the slot: the G2P kernel keeps slot order, so copy the tag array across buffers
+    GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    c->cur = dst;
+    c->sorted = false;          // positions moved: the cell table no longer describes them
+}
+
+// upload three host face arrays of a full (non-slab) field into scratch and return device pointers
+gfs::FieldPtrs upload_field(gfs_context *c, const float *u, const float *v, const float *w, int I, int J, int K) {
+    const size_t cnt[3] = {(size_t)(I + 1) * J * K, (size_t)I * (J + 1) * K, (size_t)I * J * (K + 1)};
+    const float *h[3] = {u, v, w};
+    gfs::FieldPtrs f;
+    for (int a = 0; a < 3; a++) {
+        GFS_REQUIRE(h[a] != nullptr, "null field pointer");
+        c->h_field[a].reserve(cnt[a]);
+        GFS_CUDA(cudaMemcpyAsync(c->h_field[a].p, h[a], cnt[a] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        f.c[a] = c->h_field[a].p;
+    }
+    return f;
+}
+
+}  // namespace
+
+#define GFS_BEGIN                                                                                  \
+    if (err) *err = GFS_SUCCESS;                                                                   \
+    try {
+#define GFS_END(retval)                                                                            \
+    } catch (const std::exception &ex) {                                                           \
+        set_error("%s", ex.what());                                                                \
+        if (err) *err = GFS_FAIL;                                                                  \
+        return retval;                                                                             \
+    }
+
+extern "C" {
+
+const char *gfs_get_error_message(void) { return g_error; }
+
+gfs_context *gfs_create(int device, void *stream, int *err) {
+    GFS_BEGIN
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw GfsError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                       "); this library has no CPU fallback");
+    GFS_REQUIRE(device >= 0 && device < count, "device index out of range");
+    GFS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GFS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        char b[256];
+        snprintf(b, sizeof(b), "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; kernels are built for sm_100a only",
+                 device, prop.name, prop.major, prop.minor);
+        throw GfsError(b);
+    }
+    gfs_context *c = new gfs_context();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { GFS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->n_valid.reserve(1);
+    c->vmax_bits.reserve(1);
+    c->counters.reserve(4);
+    GFS_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    c->sources.n = 0;
+    return c;
+    GFS_END(nullptr)
+}
+
+void gfs_destroy(gfs_context *c, int *err) {
+    GFS_BEGIN
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < 3; s++) for (int a = 0; a < 3; a++) c->field[s][a].release();
+    for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
+    c->material.release(); c->cells.release();
+    for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
+    c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
+    c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    GFS_END()
+}
+
+void gfs_device_info(gfs_context *c, char *buf, int buflen, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && buf && buflen > 0, "bad arguments");
+    cudaDeviceProp prop;
+    GFS_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    snprintf(buf, (size_t)buflen, "CUDA device %d: %s, sm_%d%d, %d SMs, %.1f GB, L2 %.0f MB, %d KB smem/SM",
+             c->device, prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+             (double)prop.totalGlobalMem / 1e9, (double)prop.l2CacheSize / 1048576.0,
+             (int)(prop.sharedMemPerMultiprocessor / 1024));
+    GFS_END()
+}
+
+void gfs_sync(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && out, "bad arguments");
+    unsigned long long h[4] = {0, 0, 0, 0};
+    int32_t nv = 0;
+    GFS_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaMemcpyAsync(&nv, c->n_valid.p, sizeof(nv), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    out->num_particles = c->n;
+    out->out_of_grid = c->sorted ? c->n - nv : 0;
+    out->in_solid = (int64_t)h[0];
+    out->fluid_cells = (int64_t)h[1];
+    out->solid_hits = (int64_t)h[2];
+    out->kernel_launches = c->launches;
+    GFS_END()
+}
+
+/* ---- host-pointer operators ------------------------------------------------------------------ */
+
+void gfs_sample(gfs_context *c, const float *pos, int64_t n, const float *u, const float *v, const float *w,
+                int I, int J, int K, double dx, int interp, int arith, int validate, float *out, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (n == 0 || (pos && out)), "bad arguments");
+    GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
+    GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    if (n == 0) return;
+    GFS_CUDA(cudaSetDevice(c->device));
+    Grid g = make_grid(I, J, K, dx, 0, K);
+    gfs::FieldPtrs f = upload_field(c, u, v, w, I, J, K);
+    c->h_pos.reserve((size_t)n * 3); c->h_out.reserve((size_t)n * 3);
+    GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    if (arith == GFS_EXACT) LAUNCH(c, gfs::k_sample<1>, ceil_div(n, 128), 128, g, f, interp, validate, n, c->h_pos.p, c->h_out.p);
+    else LAUNCH(c, gfs::k_sample<0>, ceil_div(n, 128), 128, g, f, interp, validate, n, c->h_pos.p, c->h_out.p);
+    GFS_CUDA(cudaMemcpyAsync(out, c->h_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_advect(gfs_context *c, const float *pos, int64_t n, const float *u, const float *v, const float *w,
+                int I, int J, int K, double dx, double dt, int order, int interp, int arith, float *out, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (n == 0 || (pos && out)), "bad arguments");
+    GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
+    GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
+    GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    if (n == 0) return;
+    GFS_CUDA(cudaSetDevice(c->device));
+    Grid g = make_grid(I, J, K, dx, 0, K);
+    gfs::FieldPtrs f = upload_field(c, u, v, w, I, J, K);
+    c->h_pos.reserve((size_t)n * 3); c->h_out.reserve((size_t)n * 3);
+    GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    gfs::RkCoef rk = make_rk(dt);
+    if (arith == GFS_EXACT) LAUNCH(c, gfs::k_advect<1>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
+    else LAUNCH(c, gfs::k_advect<0>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
+    GFS_CUDA(cudaMemcpyAsync(out, c->h_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_add_point_values(gfs_context *c, const float *pos, const float *values, int64_t n, double radius,
+                          const float *offset3, double dx, int ni, int nj, int nk, float *field, float *weight,
+                          int accumulate, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && field && offset3 && (n == 0 || (pos && values)), "bad arguments");
+    GFS_REQUIRE(ni > 0 && nj > 0 && nk > 0 && dx > 0 && radius > 0, "bad grid");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const size_t count = (size_t)ni * nj * nk;
+    c->h_acc.reserve(2 * count);
+    c->h_fld.reserve(count); c->h_wgt.reserve(count);
+    GFS_CUDA(cudaMemsetAsync(c->h_acc.p, 0, 2 * count * sizeof(unsigned long long), c->stream));
+    // numerator scale from the largest |value| (order-independent, so the result stays order-independent)
+    float vmax = 0.0f;
+    for (int64_t i = 0; i < n; i++) { float a = std::fabs(values[i]); if (a < 3.0e38f && a > vmax) vmax = a; }
+    int vexp = 0;
+    if (vmax > 0.0f) { int e; std::frexp(vmax, &e); vexp = e; }      // vmax < 2^e
+    vexp = vexp < -24 ? -24 : (vexp > 40 ? 40 : vexp);
+    gfs::SplatParams sp = make_splat(radius, nullptr);
+    if (n > 0) {
+        c->h_pos.reserve((size_t)n * 3); c->h_val.reserve((size_t)n);
+        GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        GFS_CUDA(cudaMemcpyAsync(c->h_val.p, values, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (arith == GFS_EXACT)
+            LAUNCH(c, gfs::k_splat_points<1>, ceil_div(n, 128), 128, sp, vexp, dx, offset3[0], offset3[1], offset3[2], ni, nj, nk, n,
+                   c->h_pos.p, c->h_val.p, c->h_acc.p);
+        else
+            LAUNCH(c, gfs::k_splat_points<0>, ceil_div(n, 128), 128, sp, vexp, dx, offset3[0], offset3[1], offset3[2], ni, nj, nk, n,
+                   c->h_pos.p, c->h_val.p, c->h_acc.p);
+    }
+    if (accumulate) {
+        GFS_CUDA(cudaMemcpyAsync(c->h_fld.p, field, count * 4, cudaMemcpyHostToDevice, c->stream));
+        if (weight) GFS_CUDA(cudaMemcpyAsync(c->h_wgt.p, weight, count * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    LAUNCH(c, gfs::k_splat_points_store, ceil_div((int64_t)count, 256), 256, (int64_t)count, vexp, c->h_acc.p, c->h_fld.p,
+           weight ? c->h_wgt.p : nullptr, accumulate);
+    GFS_CUDA(cudaMemcpyAsync(field, c->h_fld.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (weight) GFS_CUDA(cudaMemcpyAsync(weight, c->h_wgt.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+/* ---- device-resident domain ------------------------------------------------------------------- */
+
+void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
+    GFS_CUDA(cudaSetDevice(c->device));
+    c->grid = make_grid(I, J, K, dx, 0, K);
+    const Grid &g = c->grid;
+    const int kl = g.k1 - g.k0;
+    GFS_REQUIRE((uint64_t)g.nbi * g.nbj * g.nbk * gfs::kBrickCells < 0x7FFFFFFFull, "grid too large for 31-bit cell keys");
+    c->nkeys = (uint32_t)((uint64_t)g.nbi * g.nbj * g.nbk * gfs::kBrickCells);
+    c->face_count[0] = (size_t)(I + 1) * J * kl;
+    c->face_count[1] = (size_t)I * (J + 1) * kl;
+    c->face_count[2] = (size_t)I * J * (kl + 1);
+    c->cell_count = (size_t)I * J * kl;
+    for (int s = 0; s < 3; s++)
+        for (int a = 0; a < 3; a++) {
+            c->field[s][a].reserve(c->face_count[a]);
+            GFS_CUDA(cudaMemsetAsync(c->field[s][a].p, 0, c->face_count[a] * sizeof(float), c->stream));
+        }
+    for (int a = 0; a < 3; a++) {
+        c->val[a].reserve(c->face_count[a]);
+        c->setmask[a].reserve(c->face_count[a]);
+        c->acc[a].reserve(2 * c->face_count[a]);
+        GFS_CUDA(cudaMemsetAsync(c->acc[a].p, 0, 2 * c->face_count[a] * sizeof(unsigned long long), c->stream));
+    }
+    c->material.reserve(c->cell_count);
+    c->cells.reserve(c->nkeys);
+    c->has_domain = true;
+    c->sorted = false;
+    LAUNCH(c, gfs::k_border_solid, grid3(I, J, kl), 128, g, c->material.p);
+    GFS_END()
+}
+
+void gfs_set_material(gfs_context *c, const uint8_t *material, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(material, "null pointer");
+    GFS_CUDA(cudaMemcpyAsync(c->material.p, material, c->cell_count, cudaMemcpyHostToDevice, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_material(gfs_context *c, uint8_t *material, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(material, "null pointer");
+    GFS_CUDA(cudaMemcpyAsync(material, c->material.p, c->cell_count, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_set_sources(gfs_context *c, const gfs_source_t *sources, int nsources, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_REQUIRE(nsources >= 0 && nsources <= 8, "at most 8 inflow sources");
+    GFS_REQUIRE(nsources == 0 || sources, "null pointer");
+    c->sources.n = nsources;
+    for (int i = 0; i < nsources; i++) c->sources.s[i] = sources[i];
+    GFS_END()
+}
+
+void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, int64_t n, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && n >= 0 && (n == 0 || particles), "bad arguments");
+    GFS_REQUIRE(n < 0x7FFFFFFFll, "particle count must fit int32");
+    GFS_CUDA(cudaSetDevice(c->device));
+    c->reserve_particles(n > 0 ? n : 1);
+    c->n = n; c->cur = 0; c->sorted = false;
+    if (n > 0) {
+        // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
+        c->h_pos.reserve((size_t)n * 6);
+        GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, particles, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, gfs::k_aos_to_soa, ceil_div(n, 256), 256, n, c->h_pos.p, c->soa[0][0].p, c->soa[0][1].p, c->soa[0][2].p,
+               c->soa[0][3].p, c->soa[0][4].p, c->soa[0][5].p, c->tag[0].p);
+    }
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+int64_t gfs_num_particles(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    return c->n;
+    GFS_END(-1)
+}
+
+void gfs_get_particles(gfs_context *c, gfs_marker_particle_t *particles, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (c->n == 0 || particles), "bad arguments");
+    if (c->n == 0) return;
+    const int b = c->cur;
+    c->h_pos.reserve((size_t)c->n * 6);
+    LAUNCH(c, gfs::k_soa_to_aos, ceil_div(c->n, 256), 256, c->n, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p,
+           c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p, c->h_pos.p);
+    GFS_CUDA(cudaMemcpyAsync(particles, c->h_pos.p, (size_t)c->n * 24, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_particle_order(gfs_context *c, int32_t *order, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (c->n == 0 || order), "bad arguments");
+    if (c->n == 0) return;
+    GFS_CUDA(cudaMemcpyAsync(order, c->tag[c->cur].p, (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_set_field(gfs_context *c, int slot, const float *u, const float *v, const float *w, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
+    const float *h[3] = {u, v, w};
+    for (int a = 0; a < 3; a++)
+        GFS_CUDA(cudaMemcpyAsync(c->field[slot][a].p, h[a], c->face_count[a] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_field(gfs_context *c, int slot, float *u, float *v, float *w, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
+    float *h[3] = {u, v, w};
+    for (int a = 0; a < 3; a++)
+        GFS_CUDA(cudaMemcpyAsync(h[a], c->field[slot][a].p, c->face_count[a] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_sort(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_sort(c);
+    GFS_END()
+}
+
+void gfs_p2g(gfs_context *c, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_p2g(c, arith);
+    GFS_END()
+}
+
+void gfs_g2p_advect(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_g2p(c, dt, ratio, order, interp, arith);
+    GFS_END()
+}
+
+void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_sort(c);
+    do_p2g(c, arith);
+    do_g2p(c, dt, ratio, order, interp, arith);
+    GFS_END()
+}
+
+void *gfs_device_ptr(gfs_context *c, int which, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    if (which >= 0 && which < 9) return c->field[which / 3][which % 3].p;
+    if (which == 9) return c->material.p;
+    if (which >= 10 && which < 16) return c->soa[c->cur][which - 10].p;
+    throw GfsError("gfs_device_ptr: unknown buffer id");
+    GFS_END(nullptr)
+}
+
+void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && n >= 0 && n < 0x7FFFFFFFll, "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if ((size_t)n > c->soa[0][0].cap) {
+        // grow both buffer sets, keeping the current contents
+        const int b = c->cur;
+        int64_t keep = c->n < n ? c->n : n;
+        size_t newcap = (size_t)n + (size_t)n / 8 + 1024;
+        for (int a = 0; a < 6; a++) {
+            DevBuf<float> nb; nb.reserve(newcap);
+            if (keep > 0) GFS_CUDA(cudaMemcpyAsync(nb.p, c->soa[b][a].p, (size_t)keep * 4, cudaMemcpyDeviceToDevice, c->stream));
+            GFS_CUDA(cudaStreamSynchronize(c->stream));
+            c->soa[b][a].release(); c->soa[b][a] = nb;
+            c->soa[1 - b][a].release(); c->soa[1 - b][a].reserve(newcap);
+        }
+        DevBuf<int32_t> nt; nt.reserve(newcap);
+        if (keep > 0) GFS_CUDA(cudaMemcpyAsync(nt.p, c->tag[b].p, (size_t)keep * 4, cudaMemcpyDeviceToDevice, c->stream));
+        GFS_CUDA(cudaStreamSynchronize(c->stream));
+        c->tag[b].release(); c->tag[b] = nt;
+        c->tag[1 - b].release(); c->tag[1 - b].reserve(newcap);
+        for (int q = 0; q < 2; q++) { c->keys[q].release(); c->keys[q].reserve(newcap); c->perm[q].release(); c->perm[q].reserve(newcap); }
+    }
+    c->n = n;
+    c->sorted = false;
+    GFS_END()
+}
+
+/* ---- z-slab helpers (host arithmetic only) ------------------------------------------------------ */
+
+void gfs_slab_range(int ksize, int nranks, int rank, int *k0, int *k1, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(ksize > 0 && nranks > 0 && rank >= 0 && rank < nranks && k0 && k1, "bad arguments");
+    *k0 = (int)((int64_t)ksize * rank / nranks);
+    *k1 = (int)((int64_t)ksize * (rank + 1) / nranks);
+    GFS_END()
+}
+
+int gfs_slab_owner(int ksize, int nranks, int k, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(ksize > 0 && nranks > 0, "bad arguments");
+    if (k < 0) k = 0;
+    if (k >= ksize) k = ksize - 1;
+    // inverse of gfs_slab_range: the largest r with floor(ksize*r/nranks) <= k
+    int r = (int)(((int64_t)(k + 1) * nranks - 1) / ksize);
+    while (r > 0 && (int64_t)ksize * r / nranks > k) r--;
+    while (r + 1 < nranks && (int64_t)ksize * (r + 1) / nranks <= k) r++;
+    return r;
+    GFS_END(-1)
+}
+
+int gfs_slab_halo_cells(int interp, double max_displacement, double dx, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(dx > 0 && max_displacement >= 0, "bad arguments");
+    int stencil = interp == GFS_TRICUBIC ? 2 : 1;
+    return stencil + (int)std::ceil(max_displacement / dx);
+    GFS_END(-1)
+}
+
+}  // extern "C"

@@ -1,0 +1,526 @@
+// gfs_kernels.cuh -- the sm_100a kernels of the particle<->grid transfer path (round-1 set).
+//
+//   K0  k_keys / cub radix sort / k_reorder / k_cell_start     cell binning (brick-major keys)
+//   K1  k_classify, k_p2g_scatter (fast, order-independent fixed point) or k_p2g_gather (exact,
+//       reference summation order), k_p2g_finalize, k_assemble   P2G + classification
+//   K2  k_g2p_advect                                            PIC/FLIP + RK1..4 + solid test
+//   plus the host-pointer operators k_sample / k_advect / k_splat_points
+#pragma once
+#include "gfs_device.cuh"
+#include "../../include/gfs_b200.h"
+
+namespace gfs {
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-point accumulation (fast P2G).  Weights and weight*value products are converted to 64-bit
+// fixed point and added with integer atomics: integer addition is associative, so every node sum is
+// independent of particle order, brick decomposition and GPU count -- bit-reproducible without
+// ordering constraints and without float atomics.
+//   weight:  S_w = 2^48            (sum of weights < 2^14)
+//   num:     S_n = 2^(48 - vexp)   where 2^vexp >= max |velocity component|  (|sum| < 2^(14+vexp))
+// ------------------------------------------------------------------------------------------------
+constexpr int kWeightFracBits = 48;
+
+struct SplatParams {
+    double radius, rsq;           // ScalarField::setPointRadius (scalarfield.cpp:40-46)
+    double c1, c2, c3;            // (4/9)/r^6, (17/9)/r^4, (22/9)/r^2
+    float  c1f, c2f, c3f;
+    const unsigned int *vmax_bits;   // device word: float bits of max |velocity component| (k_keys / caller)
+};
+
+// 2^vexp >= max|v|, clamped to [2^-24, 2^40]; the numerator scale is 2^(48 - vexp)
+__device__ __forceinline__ int num_exponent(const SplatParams &sp) {
+    int e = (int)((__ldg(sp.vmax_bits) >> 23) & 0xffu) - 127 + 1;
+    return max(-24, min(40, e));
+}
+__device__ __forceinline__ float num_scale_f(int vexp) { return __uint_as_float((unsigned)(127 + kWeightFracBits - vexp) << 23); }
+__device__ __forceinline__ double inv_num_scale_d(int vexp) {
+    return __longlong_as_double((long long)(1023 - kWeightFracBits + vexp) << 52);
+}
+
+struct Sources {
+    int n;
+    gfs_source_t s[8];
+};
+
+// d^2 in float exactly as the reference forms it (vmath::dot, vmath.h:71-73; no contraction)
+__device__ __forceinline__ float dist2(float vx, float vy, float vz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+}
+
+// ScalarField::_evaluateTricubicFieldFunctionForRadiusSquared (scalarfield.cpp:569-571)
+__device__ __forceinline__ double kernel_weight_exact(const SplatParams &sp, double d) {
+    double a = __dmul_rn(__dmul_rn(__dmul_rn(sp.c1, d), d), d);
+    double b = __dmul_rn(__dmul_rn(sp.c2, d), d);
+    double c = __dmul_rn(sp.c3, d);
+    return __dsub_rn(__dadd_rn(__dsub_rn(1.0, a), b), c);
+}
+__device__ __forceinline__ float kernel_weight_fast(const SplatParams &sp, float d) {
+    return fmaf(d, fmaf(d, fmaf(d, -sp.c1f, sp.c2f), -sp.c3f), 1.0f);
+}
+
+// node coordinate (float)((float)i*dx)  (Grid3d::GridIndexToPosition(int,int,int,dx), grid3d.h:73-75)
+__device__ __forceinline__ float node_pos(int i, double dx) { return (float)__dmul_rn((double)(float)i, dx); }
+
+// ------------------------------------------------------------------------------------------------
+// K0: keys
+// ------------------------------------------------------------------------------------------------
+// One thread per particle.  key = brick-major id of the particle's cell, or the sentinel when the cell is
+// outside the grid / outside this slab's stored layers.  Also tracks max |velocity| (as float bits).
+__global__ void k_keys(Grid g, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                       const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                       int64_t n, uint32_t *__restrict__ keys, int32_t *__restrict__ perm,
+                       unsigned int *__restrict__ vmax_bits) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (r < n) {
+        int i = cell_floor((double)x[r], g.invdx), j = cell_floor((double)y[r], g.invdx), k = cell_floor((double)z[r], g.invdx);
+        uint32_t key = kKeySentinel;
+        if (i >= 0 && j >= 0 && i < g.I && j < g.J && k >= g.k0 && k < g.k1 && k >= 0 && k < g.K) key = brick_key(g, i, j, k - g.k0);
+        keys[r] = key;
+        perm[r] = (int32_t)r;
+        m = fmaxf(fabsf(vx[r]), fmaxf(fabsf(vy[r]), fabsf(vz[r])));
+        if (!(m < 3.0e38f)) m = 0.0f;          // NaN/Inf velocities do not steer the scale
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(vmax_bits, __float_as_uint(m));
+}
+
+// sorted SoA <- unsorted SoA through the sorted permutation; also carries the original-index tag
+__global__ void k_reorder(int64_t n, const int32_t *__restrict__ perm,
+                          const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
+                          const float *__restrict__ svx, const float *__restrict__ svy, const float *__restrict__ svz,
+                          const int32_t *__restrict__ stag,
+                          float *__restrict__ dx_, float *__restrict__ dy, float *__restrict__ dz,
+                          float *__restrict__ dvx, float *__restrict__ dvy, float *__restrict__ dvz,
+                          int32_t *__restrict__ dtag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int32_t s = perm[r];
+    dx_[r] = sx[s]; dy[r] = sy[s]; dz[r] = sz[s];
+    dvx[r] = svx[s]; dvy[r] = svy[s]; dvz[r] = svz[s];
+    dtag[r] = stag[s];
+}
+
+// cells[key] = {first sorted slot, one past the last} for every occupied key (the table is zeroed first, so
+// empty cells read {0,0}); *n_valid = number of in-grid particles (first sentinel slot).  One thread per slot.
+__global__ void k_cell_ranges(int64_t n, const uint32_t *__restrict__ keys, int2 *__restrict__ cells, int32_t *__restrict__ n_valid) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t k = keys[r];
+    uint32_t kp = r > 0 ? keys[r - 1] : kKeySentinel - 1;     // anything != k for r == 0 (k is never sentinel-1)
+    if (r == 0 || k != kp) {
+        if (k != kKeySentinel) cells[k].x = (int32_t)r; else *n_valid = (int32_t)r;
+        if (r > 0) cells[kp].y = (int32_t)r;
+    }
+    if (r == n - 1 && k != kKeySentinel) { cells[k].y = (int32_t)n; *n_valid = (int32_t)n; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: classification  (FluidSimulation::_updateFluidCells marking loop, fluidsimulation.cpp:1998-2017)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_classify(Grid g, const int2 *__restrict__ cells, uint8_t *__restrict__ material,
+                           unsigned long long *__restrict__ counters /* [0]=in_solid particles, [1]=fluid cells */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y, kl = blockIdx.z;
+    if (i >= g.I) return;
+    int k = kl + g.k0;
+    uint32_t key = brick_key(g, i, j, kl);
+    int2 cr = cells[key];
+    int cnt = cr.y - cr.x;
+    size_t idx = (size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl);
+    uint8_t m = material[idx];
+    bool interior = i >= 1 && i < g.I - 1 && j >= 1 && j < g.J - 1 && k >= 1 && k < g.K - 1;
+    if (interior && m == GFS_FLUID) m = GFS_AIR;
+    if (cnt > 0) {
+        if (m == GFS_SOLID) atomicAdd(&counters[0], (unsigned long long)cnt);
+        else m = GFS_FLUID;
+    }
+    material[idx] = m;
+    if (m == GFS_FLUID) atomicAdd(&counters[1], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b (fast): particle-centric splat of u,v,w into 64-bit fixed-point accumulators.
+// acc layout: for comp c, node n: acc[c][2*n] = sum w*v, acc[c][2*n+1] = sum w  (int64, global).
+// Candidate nodes per axis are the contiguous run of {c-1,c,c+1} whose 1-D distance already passes
+// d^2 < R^2 (a necessary condition: the float sum of non-negative squares is monotone); the full float
+// distance test of scalarfield.cpp:186-189 then decides, as in the reference.  (The reference also clips
+// to Grid3d::getGridIndexBounds; that only ever removes pairs at distance R +- 1 ulp whose weight is
+// ~1e-14 -- the exact-mode gather below applies the clip literally.)
+// ------------------------------------------------------------------------------------------------
+template <int ARITH>
+__device__ __forceinline__ void splat_component(const Grid &g, const SplatParams &sp, int comp, float px, float py, float pz,
+                                                float value, int ni, int nj, int nkl, int koff,
+                                                float off, float num_scale, unsigned long long *__restrict__ acc) {
+    // p -= offset (scalarfield.cpp:168); offset is (0,.5,.5)dx / (.5,0,.5)dx / (.5,.5,0)dx narrowed to float
+    float q[3] = {comp == 0 ? px : __fsub_rn(px, off), comp == 1 ? py : __fsub_rn(py, off), comp == 2 ? pz : __fsub_rn(pz, off)};
+    int   lo[3], hi[3], base[3];
+    float d1[3][3];
+    const int nmax[3] = {ni - 1, nj - 1, nkl - 1 + koff};
+    const int nmin[3] = {0, 0, koff};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int c = cell_floor((double)q[a], g.invdx);
+        int l = 2, h = -1;
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            float d = __fsub_rn(node_pos(c - 1 + s, g.dx), q[a]);
+            d1[a][s] = d;
+            if ((double)__fmul_rn(d, d) < sp.rsq) { l = min(l, s); h = max(h, s); }
+        }
+        base[a] = c - 1;
+        lo[a] = max(c - 1 + l, nmin[a]) - base[a];      // slot range in {0,1,2}, clamped to the node grid
+        hi[a] = min(c - 1 + h, nmax[a]) - base[a];
+    }
+    const int bi = base[0], bj = base[1], bk = base[2];
+    for (int sk = lo[2]; sk <= hi[2]; sk++)
+        for (int sj = lo[1]; sj <= hi[1]; sj++)
+            for (int si = lo[0]; si <= hi[0]; si++) {
+                float vx = si == 0 ? d1[0][0] : (si == 1 ? d1[0][1] : d1[0][2]);
+                float vy = sj == 0 ? d1[1][0] : (sj == 1 ? d1[1][1] : d1[1][2]);
+                float vz = sk == 0 ? d1[2][0] : (sk == 1 ? d1[2][1] : d1[2][2]);
+                float d2 = dist2(vx, vy, vz);
+                if ((double)d2 < sp.rsq) {
+                    size_t node = (size_t)(bi + si) + (size_t)ni * ((size_t)(bj + sj) + (size_t)nj * (size_t)(bk + sk - koff));
+                    long long wn, ww;
+                    if (ARITH == 1) {
+                        double w = kernel_weight_exact(sp, (double)d2);
+                        ww = __double2ll_rn(w * 281474976710656.0);                               // 2^48
+                        wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
+                    } else {
+                        float w = kernel_weight_fast(sp, d2);
+                        ww = __float2ll_rn(w * 281474976710656.0f);
+                        wn = __float2ll_rn((w * value) * num_scale);
+                    }
+                    atomicAdd(acc + 2 * node, (unsigned long long)wn);
+                    atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+                }
+            }
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_p2g_scatter(Grid g, SplatParams sp, const int32_t *__restrict__ n_valid,
+                              const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                              const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                              unsigned long long *__restrict__ accu, unsigned long long *__restrict__ accv,
+                              unsigned long long *__restrict__ accw) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)__ldg(n_valid)) return;
+    float px = x[r], py = y[r], pz = z[r];
+    float off = (float)g.halfdx;
+    int kl = g.k1 - g.k0;
+    float ns = num_scale_f(num_exponent(sp));
+    splat_component<ARITH>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu);
+    splat_component<ARITH>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv);
+    splat_component<ARITH>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw);
+}
+
+// source->containsPoint(face position)  (fluidsimulation.cpp:2489-2524)
+__device__ __forceinline__ bool source_contains(const gfs_source_t &s, float fx, float fy, float fz) {
+    if (s.kind == 0) {
+        float vx = __fsub_rn(fx, s.p[0]), vy = __fsub_rn(fy, s.p[1]), vz = __fsub_rn(fz, s.p[2]);
+        return (double)dist2(vx, vy, vz) < __dmul_rn(s.a, s.a);
+    }
+    return fx >= s.p[0] && fy >= s.p[1] && fz >= s.p[2] &&
+           (double)fx < __dadd_rn((double)s.p[0], s.a) && (double)fy < __dadd_rn((double)s.p[1], s.b) &&
+           (double)fz < __dadd_rn((double)s.p[2], s.c);
+}
+
+// normalise (ScalarField::applyWeightField, scalarfield.cpp:90-106), isValueSet = weight > 1e-9 and the
+// inflow override on set faces (fluidsimulation.cpp:2571-2594).  val holds the node grid "ugrid",
+// setmask its isValueSet.  Also clears the accumulators for the next substep.
+__global__ void k_p2g_finalize(Grid g, int comp, SplatParams sp, Sources src, unsigned long long *__restrict__ acc,
+                               float *__restrict__ val, uint8_t *__restrict__ setmask) {
+    int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
+    if (i >= ni || j >= nj || kl >= nkl) return;
+    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+    long long n = (long long)acc[2 * node], w = (long long)acc[2 * node + 1];
+    acc[2 * node] = 0ull; acc[2 * node + 1] = 0ull;
+    float wf = (float)((double)w * (1.0 / 281474976710656.0));
+    float nf = (float)((double)n * inv_num_scale_d(num_exponent(sp)));
+    float value = nf;
+    if (wf > 0.0f) value = nf / wf;
+    bool isset = (double)wf > 1e-9;
+    if (isset) {
+        for (int s = 0; s < src.n; s++) {
+            int k = kl + g.k0;
+            float fx = (float)(comp == 0 ? __dmul_rn((double)(float)i, g.dx) : __dmul_rn(__dadd_rn((double)(float)i, 0.5), g.dx));
+            float fy = (float)(comp == 1 ? __dmul_rn((double)(float)j, g.dx) : __dmul_rn(__dadd_rn((double)(float)j, 0.5), g.dx));
+            float fz = (float)(comp == 2 ? __dmul_rn((double)(float)k, g.dx) : __dmul_rn(__dadd_rn((double)(float)k, 0.5), g.dx));
+            if (source_contains(src.s[s], fx, fy, fz)) value = src.s[s].velocity[comp];
+        }
+    }
+    val[node] = value;
+    setmask[node] = isset ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b (exact): node-centric gather in the reference's summation order.  One thread per node of one
+// component; it visits the 27 surrounding cells in ascending (k,j,i) and each cell's particles in
+// stored (stable-sorted) order, i.e. exactly the order ScalarField::addPointValue would have been called
+// in had the particle array been sorted by linear cell index -- float accumulation included
+// (array3d.h:263-271).  Parity tool, not the fast path.
+// ------------------------------------------------------------------------------------------------
+// is node index `node` inside [gmin, gmax] of Grid3d::getGridIndexBounds for offset-space coordinate q?
+__device__ __forceinline__ bool in_index_bounds(float q, int node, double radius, const Grid &g) {
+    int c = cell_floor((double)q, g.invdx);
+    float trans = __fsub_rn(q, node_pos(c, g.dx));
+    int gmin = c - (int)fmax(0.0, ceil(__dmul_rn(__dsub_rn(radius, (double)trans), g.invdx)));
+    int gmax = c + (int)fmax(0.0, ceil(__dmul_rn(__dadd_rn(__dsub_rn(radius, g.dx), (double)trans), g.invdx)));
+    return node >= gmin && node <= gmax;
+}
+
+template <int ARITH>
+__global__ void k_p2g_gather(Grid g, int comp, SplatParams sp, Sources src, const int2 *__restrict__ cells,
+                             const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                             const float *__restrict__ vel, float *__restrict__ val, uint8_t *__restrict__ setmask) {
+    int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
+    if (i >= ni || j >= nj || kl >= nkl) return;
+    int k = kl + g.k0;
+    float off = (float)g.halfdx;
+    float gx = node_pos(i, g.dx), gy = node_pos(j, g.dx), gz = node_pos(k, g.dx);
+    float field = 0.0f, weight = 0.0f;
+    // A contributing particle lies within one cell (plus rounding slop) of the node in offset space, i.e.
+    // within two real-space cells: scan the 5x5x5 real-space cell block, ascending (k,j,i).
+    for (int ck = k - 2; ck <= k + 2; ck++) {
+        if (ck < g.k0 || ck >= g.k1 || ck < 0 || ck >= g.K) continue;
+        for (int cj = j - 2; cj <= j + 2; cj++) {
+            if (cj < 0 || cj >= g.J) continue;
+            for (int ci = i - 2; ci <= i + 2; ci++) {
+                if (ci < 0 || ci >= g.I) continue;
+                int2 cr = cells[brick_key(g, ci, cj, ck - g.k0)];
+                for (int r = cr.x; r < cr.y; r++) {
+                    float qx = comp == 0 ? x[r] : __fsub_rn(x[r], off);
+                    float qy = comp == 1 ? y[r] : __fsub_rn(y[r], off);
+                    float qz = comp == 2 ? z[r] : __fsub_rn(z[r], off);
+                    // the reference only visits nodes inside Grid3d::getGridIndexBounds (grid3d.h:350-371)
+                    if (!in_index_bounds(qx, i, sp.radius, g) || !in_index_bounds(qy, j, sp.radius, g) ||
+                        !in_index_bounds(qz, k, sp.radius, g)) continue;
+                    float d2 = dist2(__fsub_rn(gx, qx), __fsub_rn(gy, qy), __fsub_rn(gz, qz));
+                    if ((double)d2 < sp.rsq) {
+                        double w = (ARITH == 1) ? kernel_weight_exact(sp, (double)d2) : (double)kernel_weight_fast(sp, d2);
+                        field = __fadd_rn(field, (float)__dmul_rn(w, (double)vel[r]));
+                        weight = __fadd_rn(weight, (float)w);
+                    }
+                }
+            }
+        }
+    }
+    float value = field;
+    if (weight > 0.0f) value = __fdiv_rn(field, weight);
+    bool isset = (double)weight > 1e-9;
+    if (isset) {
+        for (int s = 0; s < src.n; s++) {
+            float fx = (float)(comp == 0 ? __dmul_rn((double)(float)i, g.dx) : __dmul_rn(__dadd_rn((double)(float)i, 0.5), g.dx));
+            float fy = (float)(comp == 1 ? __dmul_rn((double)(float)j, g.dx) : __dmul_rn(__dadd_rn((double)(float)j, 0.5), g.dx));
+            float fz = (float)(comp == 2 ? __dmul_rn((double)(float)k, g.dx) : __dmul_rn(__dadd_rn((double)(float)k, 0.5), g.dx));
+            if (source_contains(src.s[s], fx, fy, fz)) value = src.s[s].velocity[comp];
+        }
+    }
+    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+    val[node] = value;
+    setmask[node] = isset ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: face assembly  (FluidSimulation::_advectVelocityField{U,V,W}, fluidsimulation.cpp:2597-2730)
+// faces bordering a fluid cell take the node value if set, else the mean of the in-range 26 neighbours
+// that qualify (U: |value| > 0, :2630;  V,W: isValueSet, :2675/:2720); every other face is 0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cell_is_fluid(const Grid &g, const uint8_t *__restrict__ m, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i >= g.I || j >= g.J || k >= g.K) return false;   // out of range reads as solid
+    int kl = k - g.k0;
+    if (kl < 0 || kl >= g.k1 - g.k0) return false;
+    return m[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_FLUID;
+}
+
+__global__ void k_assemble(Grid g, int comp, const uint8_t *__restrict__ material, const float *__restrict__ val,
+                           const uint8_t *__restrict__ setmask, float *__restrict__ out) {
+    int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
+    if (i >= ni || j >= nj || kl >= nkl) return;
+    int k = kl + g.k0;
+    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+    int di = comp == 0, dj = comp == 1, dk = comp == 2;
+    // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W} (fluidmaterialgrid.cpp:119-143)
+    bool borders = cell_is_fluid(g, material, i, j, k) || cell_is_fluid(g, material, i - di, j - dj, k - dk);
+    float r = 0.0f;
+    if (borders) {
+        if (setmask[node]) {
+            r = val[node];
+        } else {
+            double avg = 0.0, cnt = 0.0;
+            for (int nk = kl - 1; nk <= kl + 1; nk++)
+                for (int nj_ = j - 1; nj_ <= j + 1; nj_++)
+                    for (int ni_ = i - 1; ni_ <= i + 1; ni_++) {
+                        if (ni_ == i && nj_ == j && nk == kl) continue;
+                        if (ni_ < 0 || nj_ < 0 || nk < 0 || ni_ >= ni || nj_ >= nj || nk >= nkl) continue;
+                        size_t nn = (size_t)ni_ + (size_t)ni * ((size_t)nj_ + (size_t)nj * (size_t)nk);
+                        float v = val[nn];
+                        bool ok = comp == 0 ? (fabs((double)v) > 0.0) : (setmask[nn] != 0);
+                        if (ok) { avg = __dadd_rn(avg, (double)v); cnt += 1.0; }
+                    }
+            if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
+        }
+    }
+    out[node] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: fused G2P.  One thread per (sorted) particle:
+//   vnew = sample(NEW, p0), vold = sample(SAVED, p0), both validated        (fluidsimulation.cpp:3115-3116)
+//   v   <- (float)ratio*vnew + (float)(1-ratio)*((v + vnew) - vold)         (:3118-3128)
+//   p1  = RK{order}(p0) through NEW; its k1 is the unvalidated sample at p0  (particleadvector.cpp:1045-1078)
+//   solid test on cell(p1) (out of range reads as solid); a hit keeps p0 and is counted  (:3198-3208)
+// ------------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, FieldPtrs fsaved, const uint8_t *__restrict__ material,
+                             int interp, int order, RkCoef rk, float ratio_pic, float ratio_flip, int64_t n,
+                             const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                             const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
+                             float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
+                             unsigned long long *__restrict__ counters /* [2] = solid hits */) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float px = x[r], py = y[r], pz = z[r];
+    float k1x, k1y, k1z, sx, sy, sz;
+    evaluate<ARITH>(g, fnew, interp, px, py, pz, k1x, k1y, k1z);
+    evaluate<ARITH>(g, fsaved, interp, px, py, pz, sx, sy, sz);
+    float nx = k1x, ny = k1y, nz = k1z;
+    validate3(nx, ny, nz);
+    validate3(sx, sy, sz);
+    float ux = vx[r], uy = vy[r], uz = vz[r];
+    ovx[r] = __fadd_rn(__fmul_rn(nx, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(ux, nx), sx), ratio_flip));
+    ovy[r] = __fadd_rn(__fmul_rn(ny, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uy, ny), sy), ratio_flip));
+    ovz[r] = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
+
+    float qx, qy, qz;
+    rk_advance<ARITH>(g, fnew, interp, order, rk, px, py, pz, k1x, k1y, k1z, qx, qy, qz);
+    if (material) {
+        int i = cell_floor((double)qx, g.invdx), j = cell_floor((double)qy, g.invdx), k = cell_floor((double)qz, g.invdx);
+        bool solid = true;                                   // NaN -> huge negative index -> out of range -> solid
+        if (i >= 0 && j >= 0 && k >= 0 && i < g.I && j < g.J && k < g.K) {
+            int kl = k - g.k0;
+            // a particle that leaves this slab's stored layers is not judged here: it migrates first
+            solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
+        }
+        if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
+    }
+    ox[r] = qx; oy[r] = qy; oz[r] = qz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-pointer operators (packed float triples in, packed float triples out)
+// ------------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void k_sample(Grid g, FieldPtrs f, int interp, int validate, int64_t n, const float *__restrict__ pos, float *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float ox, oy, oz;
+    evaluate<ARITH>(g, f, interp, pos[3 * r], pos[3 * r + 1], pos[3 * r + 2], ox, oy, oz);
+    if (validate) validate3(ox, oy, oz);
+    out[3 * r] = ox; out[3 * r + 1] = oy; out[3 * r + 2] = oz;
+}
+
+template <int ARITH>
+__global__ void k_advect(Grid g, FieldPtrs f, int interp, int order, RkCoef rk, int64_t n, const float *__restrict__ pos, float *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float px = pos[3 * r], py = pos[3 * r + 1], pz = pos[3 * r + 2];
+    float k1x, k1y, k1z, ox, oy, oz;
+    evaluate<ARITH>(g, f, interp, px, py, pz, k1x, k1y, k1z);
+    rk_advance<ARITH>(g, f, interp, order, rk, px, py, pz, k1x, k1y, k1z, ox, oy, oz);
+    out[3 * r] = ox; out[3 * r + 1] = oy; out[3 * r + 2] = oz;
+}
+
+// General ScalarField::addPointValue for arbitrary radius / offset / grid (CLScalarField::addPointValues):
+// particle-centric, index bounds exactly as Grid3d::getGridIndexBounds (grid3d.h:350-371), fixed-point
+// accumulation as above.  acc[2*node], acc[2*node+1].
+template <int ARITH>
+__global__ void k_splat_points(SplatParams sp, int vexp, double dx, float offx, float offy, float offz, int ni, int nj, int nk,
+                               int64_t n, const float *__restrict__ pos, const float *__restrict__ values,
+                               unsigned long long *__restrict__ acc) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float q[3] = {__fsub_rn(pos[3 * r], offx), __fsub_rn(pos[3 * r + 1], offy), __fsub_rn(pos[3 * r + 2], offz)};
+    float value = values[r];
+    double inv = 1.0 / dx;
+    float num_scale = num_scale_f(vexp);
+    int lo[3], hi[3];
+    const int size[3] = {ni, nj, nk};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int c = cell_floor((double)q[a], inv);
+        float cpos = node_pos(c, dx);
+        float trans = __fsub_rn(q[a], cpos);
+        int gmin = c - (int)fmax(0.0, ceil(__dmul_rn(__dsub_rn(sp.radius, (double)trans), inv)));
+        int gmax = c + (int)fmax(0.0, ceil(__dmul_rn(__dadd_rn(__dsub_rn(sp.radius, dx), (double)trans), inv)));
+        lo[a] = max(gmin, 0);
+        hi[a] = min(gmax, size[a] - 1);
+    }
+    for (int k = lo[2]; k <= hi[2]; k++) {
+        float vz = __fsub_rn(node_pos(k, dx), q[2]);
+        for (int j = lo[1]; j <= hi[1]; j++) {
+            float vy = __fsub_rn(node_pos(j, dx), q[1]);
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                float vx = __fsub_rn(node_pos(i, dx), q[0]);
+                float d2 = dist2(vx, vy, vz);
+                if ((double)d2 < sp.rsq) {
+                    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)k);
+                    long long wn, ww;
+                    if (ARITH == 1) {
+                        double w = kernel_weight_exact(sp, (double)d2);
+                        ww = __double2ll_rn(w * 281474976710656.0);
+                        wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
+                    } else {
+                        float w = kernel_weight_fast(sp, d2);
+                        ww = __float2ll_rn(w * 281474976710656.0f);
+                        wn = __float2ll_rn((w * value) * num_scale);
+                    }
+                    atomicAdd(acc + 2 * node, (unsigned long long)wn);
+                    atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+                }
+            }
+        }
+    }
+}
+
+// field[n] (+)= fixed-point num, weight[n] (+)= fixed-point weight  -- epilogue of gfs_add_point_values
+__global__ void k_splat_points_store(int64_t count, int vexp, const unsigned long long *__restrict__ acc,
+                                     float *__restrict__ field, float *__restrict__ weight, int accumulate) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= count) return;
+    float nf = (float)((double)(long long)acc[2 * n] * inv_num_scale_d(vexp));
+    float wf = (float)((double)(long long)acc[2 * n + 1] * (1.0 / 281474976710656.0));
+    field[n] = accumulate ? __fadd_rn(field[n], nf) : nf;
+    if (weight) weight[n] = accumulate ? __fadd_rn(weight[n], wf) : wf;
+}
+
+// AoS MarkerParticle_t <-> SoA
+__global__ void k_aos_to_soa(int64_t n, const float *__restrict__ aos, float *x, float *y, float *z, float *vx, float *vy, float *vz, int32_t *tag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float *p = aos + 6 * r;
+    x[r] = p[0]; y[r] = p[1]; z[r] = p[2]; vx[r] = p[3]; vy[r] = p[4]; vz[r] = p[5];
+    tag[r] = (int32_t)r;
+}
+__global__ void k_soa_to_aos(int64_t n, const float *x, const float *y, const float *z, const float *vx, const float *vy, const float *vz, float *__restrict__ aos) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float *p = aos + 6 * r;
+    p[0] = x[r]; p[1] = y[r]; p[2] = z[r]; p[3] = vx[r]; p[4] = vy[r]; p[5] = vz[r];
+}
+
+__global__ void k_border_solid(Grid g, uint8_t *__restrict__ material) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
+    if (i >= g.I) return;
+    int k = kl + g.k0;
+    bool border = i == 0 || j == 0 || k == 0 || i == g.I - 1 || j == g.J - 1 || k == g.K - 1;
+    material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] = border ? GFS_SOLID : GFS_AIR;
+}
+
+}  // namespace gfs

@@ -1,0 +1,181 @@
+/*
+ * gfs_b200.h -- C-ABI of the B200-native PIC/FLIP particle<->grid transfer path.
+ *
+ * Drop-in boundary for rlguy/GridFluidSim3D's two accelerator classes (the only two that touch
+ * OpenCL in the reference) and for the FluidSimulation stages that call them.  Citations are
+ * file:line under /root/reference.
+ *
+ * Conventions follow the reference's own C bindings (src/c_bindings/cbindings.cpp:11-19,
+ * src/c_bindings/fluidsimulation_c.cpp:15-77):
+ *   - extern "C", opaque handle, plain pointers and sizes, no C++ or torch types;
+ *   - every call takes a trailing `int *err`, set to GFS_SUCCESS (1) or GFS_FAIL (0);
+ *   - on failure gfs_get_error_message() returns a NUL-terminated description (CUDA error string +
+ *     call site) from a per-thread 4096-byte buffer;
+ *   - POD structs are layout-identical to Vector3_t / MarkerParticle_t / GridIndex_t
+ *     (src/c_bindings/vector3_c.h, markerparticle_c.h, gridindex_c.h).
+ *
+ * Data layout contracts (what crosses the boundary without conversion):
+ *   - positions / velocities: packed float triples, 12 B (vmath::vec3, src/vmath.h:33-57)
+ *   - particles: AoS {position, velocity}, 24 B (MarkerParticle, src/markerparticle.h:25-37)
+ *   - grids: dense float, flat = i + width*(j + height*k) (Array3d, src/array3d.h:394-397);
+ *     U is (I+1,J,K), V is (I,J+1,K), W is (I,J,K+1) floats, i.e. exactly
+ *     MACVelocityField::getRawArrayU/V/W() (src/macvelocityfield.cpp:37-45, :87-97)
+ *   - material: one byte per cell, 0 air / 1 fluid / 2 solid (src/fluidmaterialgrid.h:29-33)
+ *
+ * There is no CPU fallback: every entry point runs CUDA kernels on the context's device and fails
+ * (err = 0) if that is impossible.
+ */
+#ifndef GFS_B200_H
+#define GFS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)      /* the library is built with -fvisibility=hidden */
+#endif
+
+#define GFS_SUCCESS 1
+#define GFS_FAIL    0
+
+#define GFS_AIR   0
+#define GFS_FLUID 1
+#define GFS_SOLID 2
+
+/* interpolation of the staggered MAC field */
+#define GFS_TRILINEAR 0   /* MACVelocityField::evaluateVelocityAtPositionLinear, src/macvelocityfield.cpp:561-575 */
+#define GFS_TRICUBIC  1   /* MACVelocityField::evaluateVelocityAtPosition,       src/macvelocityfield.cpp:549-559 */
+
+/* arithmetic mode */
+#define GFS_FAST  0       /* fp32 tap contraction / fp32 kernel weights (index + fraction still exact) */
+#define GFS_EXACT 1       /* the reference's own operation sequence in fp64, no contraction: bit-for-bit */
+
+/* field slots of a device-resident domain */
+#define GFS_FIELD_NEW    0   /* FluidSimulation::_MACVelocity at G2P time (post pressure solve) */
+#define GFS_FIELD_SAVED  1   /* FluidSimulation::_savedVelocityField                           */
+#define GFS_FIELD_P2G    2   /* what stage 5 (_advectVelocityField) produces                    */
+
+typedef struct gfs_context gfs_context;
+
+typedef struct gfs_vec3_t { float x, y, z; } gfs_vec3_t;                                   /* Vector3_t */
+typedef struct gfs_marker_particle_t { gfs_vec3_t position, velocity; } gfs_marker_particle_t;  /* MarkerParticle_t */
+typedef struct gfs_grid_index_t { int i, j, k; } gfs_grid_index_t;                           /* GridIndex_t */
+
+/* An active inflow source, as FluidSimulation::_applyFluidSourceToVelocityField sees it
+ * (src/fluidsimulation.cpp:2489-2524).  kind 0: sphere, centre p, radius a
+ * (SphericalFluidSource::containsPoint, src/sphericalfluidsource.cpp:54-58); kind 1: cuboid, min corner
+ * p, extents a,b,c (AABB::isPointInside, src/aabb.cpp:123-126). */
+typedef struct gfs_source_t {
+    int    kind;
+    float  p[3];
+    double a, b, c;
+    float  velocity[3];
+} gfs_source_t;
+
+/* per-substep counters (device-resident path) */
+typedef struct gfs_stats_t {
+    int64_t num_particles;        /* particles currently resident                                   */
+    int64_t out_of_grid;          /* particles whose cell lies outside the grid (ignored by P2G)     */
+    int64_t in_solid;             /* particles whose cell is solid at classification (src/fluidsimulation.cpp:2015 asserts 0) */
+    int64_t solid_hits;           /* particles whose advected position fell in a solid cell (kept at p0) */
+    int64_t fluid_cells;          /* cells classified fluid by the last P2G                         */
+    int64_t kernel_launches;      /* CUDA kernels launched by this context since creation           */
+} gfs_stats_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Error text of the last failed call on this thread (CBindings_get_error_message,
+ * src/c_bindings/cbindings.cpp:76-80). */
+const char *gfs_get_error_message(void);
+
+/* One context = one CUDA device + one stream.  `stream` is a cudaStream_t to enqueue on (so a caller
+ * can time with its own events), or NULL to let the context create one.  Replaces the OpenCL
+ * context/queue set-up of ParticleAdvector::initialize (src/particleadvector.cpp:30-58) and
+ * CLScalarField::initialize (src/clscalarfield.cpp:27-58). */
+gfs_context *gfs_create(int device, void *stream, int *err);
+void gfs_destroy(gfs_context *ctx, int *err);
+/* ParticleAdvector::getDeviceInfo (src/particleadvector.cpp:87-118) */
+void gfs_device_info(gfs_context *ctx, char *buf, int buflen, int *err);
+void gfs_sync(gfs_context *ctx, int *err);
+void gfs_get_stats(gfs_context *ctx, gfs_stats_t *out, int *err);
+
+/* ---- host-pointer, synchronous operators (mirror the accelerator classes one call each) ------- */
+
+/* ParticleAdvector::tricubicInterpolate (src/particleadvector.cpp:401-455; NoCL body :1124-1137) and
+ * its trilinear sibling.  out[n*3] = velocity at pos[n*3]; validate != 0 applies _validateOutput
+ * (:1139-1149: any NaN/Inf component zeroes the vector). */
+void gfs_sample(gfs_context *ctx, const float *pos, int64_t n,
+                const float *u, const float *v, const float *w, int isize, int jsize, int ksize, double dx,
+                int interp, int arith, int validate, float *out, int *err);
+
+/* ParticleAdvector::advectParticlesRK1..4 (src/particleadvector.cpp:209-399; NoCL bodies :1045-1122).
+ * order in 1..4. */
+void gfs_advect(gfs_context *ctx, const float *pos, int64_t n,
+                const float *u, const float *v, const float *w, int isize, int jsize, int ksize, double dx,
+                double dt, int order, int interp, int arith, float *out, int *err);
+
+/* CLScalarField::addPointValues(points, values, radius, offset, dx, scalarfield, weightfield)
+ * (src/clscalarfield.cpp:200-267) == ScalarField::addPointValue per point (src/scalarfield.cpp:167-201).
+ * field/weight are (ni,nj,nk) float grids; weight may be NULL (the no-weight overload, :147-198).
+ * accumulate != 0 adds into the caller's arrays (the OpenCL path's semantics, :1427-1455);
+ * accumulate == 0 overwrites them (the NoCL path's semantics, :1521-1551). */
+void gfs_add_point_values(gfs_context *ctx, const float *pos, const float *values, int64_t n,
+                          double radius, const float *offset3, double dx, int ni, int nj, int nk,
+                          float *field, float *weight, int accumulate, int arith, int *err);
+
+/* ---- device-resident domain (particles, fields and material stay in HBM between calls) -------- */
+
+/* Allocate grids for an isize x jsize x ksize domain of cell size dx (FluidSimulation(isize,jsize,ksize,dx),
+ * src/fluidsimulation.cpp:25-32) and mark the border cells solid (_initializeSolidCells, :1191-1213). */
+void gfs_domain_init(gfs_context *ctx, int isize, int jsize, int ksize, double dx, int *err);
+void gfs_set_material(gfs_context *ctx, const uint8_t *material, int *err);
+void gfs_get_material(gfs_context *ctx, uint8_t *material, int *err);
+/* inflow sources used by P2G (copied) */
+void gfs_set_sources(gfs_context *ctx, const gfs_source_t *sources, int nsources, int *err);
+/* AoS MarkerParticle_t[n] <-> device SoA */
+void gfs_set_particles(gfs_context *ctx, const gfs_marker_particle_t *particles, int64_t n, int *err);
+int64_t gfs_num_particles(gfs_context *ctx, int *err);
+void gfs_get_particles(gfs_context *ctx, gfs_marker_particle_t *particles, int *err);
+/* order[r] = index, in the array last passed to gfs_set_particles, of the particle now stored at r */
+void gfs_get_particle_order(gfs_context *ctx, int32_t *order, int *err);
+/* raw u,v,w arrays in the reference's layout; slot is GFS_FIELD_* */
+void gfs_set_field(gfs_context *ctx, int slot, const float *u, const float *v, const float *w, int *err);
+void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int *err);
+
+/* K0: bin particles by cell (brick-major key, stable radix sort) and build the cell table. */
+void gfs_sort(gfs_context *ctx, int *err);
+/* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
+ * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
+ * assembly (:2526-2730).  Result in slot GFS_FIELD_P2G; material updated.  Requires gfs_sort. */
+void gfs_p2g(gfs_context *ctx, int arith, int *err);
+/* K2: stage 11 + stage 12 (src/fluidsimulation.cpp:3104-3129, :3181-3209; no shuffle/cap): PIC/FLIP
+ * velocity update from slots NEW and SAVED, RK advance through NEW, solid test. */
+void gfs_g2p_advect(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
+/* gfs_sort + gfs_p2g + gfs_g2p_advect, stream-ordered, no host synchronisation. */
+void gfs_substep(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
+
+/* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).
+ * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz. */
+void *gfs_device_ptr(gfs_context *ctx, int which, int *err);
+/* Resize the resident particle set to n (contents of [0,min(old,n)) kept) -- used by slab migration. */
+void gfs_resize_particles(gfs_context *ctx, int64_t n, int *err);
+
+/* ---- z-slab helpers for the multi-GPU driver (host-only arithmetic, usable without a GPU) ----- */
+
+/* Cell range [k0,k1) owned by `rank` of `nranks` z-slabs over ksize cells. */
+void gfs_slab_range(int ksize, int nranks, int rank, int *k0, int *k1, int *err);
+/* Rank owning cell layer k. */
+int gfs_slab_owner(int ksize, int nranks, int k, int *err);
+/* Ghost-layer width (cells) a slab needs for G2P: stencil radius of `interp` + ceil(max_displacement/dx). */
+int gfs_slab_halo_cells(int interp, double max_displacement, double dx, int *err);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

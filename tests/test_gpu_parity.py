@@ -1,0 +1,418 @@
+"""Parity of the CUDA path (through the C-ABI, include/gfs_b200.h) against the oracle.  GPU only.
+
+Bars (BASELINE.json north_star):
+  * bit-exact: particle->cell indexing (sort order / cell table), material classification;
+  * GFS_EXACT arithmetic: bit-exact everywhere (sampled velocities, RK positions, PIC/FLIP velocities,
+    splatted u/v/w when the oracle is fed the particles in cell order);
+  * GFS_FAST arithmetic: |a-b| <= 1e-5*max(|a|,|b|) + 1e-5*max|reference array|  (the mixed fp32 tolerance
+    of SURVEY.md §7: element-wise relative error is meaningless where contributions cancel).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from gridfluidsim3d_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def assert_close(a, b, what, rtol=RTOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = np.abs(b).max() if b.size else 0.0
+    tol = rtol * np.maximum(np.abs(a), np.abs(b)) + rtol * scale
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), "%s: %d of %d outside tolerance, worst |a-b|=%g at scale %g" % (
+        what, bad.sum(), bad.size, np.abs(a - b).max(), scale)
+
+
+def rough_fields(dims, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return tuple((scale * rng.standard_normal(a * b * c)).astype(np.float32) for a, b, c in synth.face_dims(dims))
+
+
+def probes(dims, dx, n, seed):
+    rng = np.random.default_rng(seed)
+    ext = np.array(dims) * dx
+    pos = rng.uniform(-0.6 * dx, ext + 0.6 * dx, size=(n, 3))
+    pos[: n // 10] = np.round(pos[: n // 10] / dx) * dx
+    pos[n // 10: n // 5] = np.round(pos[n // 10: n // 5] / (0.5 * dx)) * 0.5 * dx
+    return pos.astype(np.float32)
+
+
+def linear_cell_order(oracle, pos, dims, dx):
+    """Stable order of particles by linear cell index i + I*(j + J*k) (out-of-grid last)."""
+    ijk = oracle.cell_index(pos, dx).astype(np.int64)
+    I, J, K = dims
+    inside = np.all((ijk >= 0) & (ijk < np.array(dims)), 1)
+    lin = np.where(inside, ijk[:, 0] + I * (ijk[:, 1] + J * ijk[:, 2]), I * J * K)
+    return np.argsort(lin, kind="stable")
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-pointer operators
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dx", [0.25, 0.1, 1.0 / 3.0])
+@pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
+def test_sample(ctx, oracle, interp, dx):
+    dims = (12, 10, 14)
+    u, v, w = rough_fields(dims, 2)
+    pos = probes(dims, dx, 30000, 3)
+    ref = oracle.sample(pos, u, v, w, dims, dx, interp, validate=True)
+    exact = ctx.sample(pos, u, v, w, dims, dx, interp, capi.EXACT)
+    assert np.array_equal(bits(exact), bits(ref))
+    fast = ctx.sample(pos, u, v, w, dims, dx, interp, capi.FAST)
+    assert_close(fast, ref, "fast sample")
+    # outside the grid the sample is exactly zero in both modes
+    outside = ~np.all((pos >= 0) & (pos < np.array(dims) * np.float64(dx)), 1)
+    assert outside.any() and not fast[outside].any()
+
+
+def test_sample_validate(ctx, oracle):
+    dims, dx = (12, 10, 14), 0.25
+    u, v, w = rough_fields(dims, 4)
+    u = u.copy(); u[::7] = np.inf
+    v = v.copy(); v[::11] = np.nan
+    pos = probes(dims, dx, 5000, 5)
+    for interp in (capi.TRILINEAR, capi.TRICUBIC):
+        ref = oracle.sample(pos, u, v, w, dims, dx, interp, validate=True)
+        out = ctx.sample(pos, u, v, w, dims, dx, interp, capi.EXACT, validate=True)
+        assert np.isfinite(out).all()
+        assert np.array_equal(bits(out), bits(ref))
+        raw = ctx.sample(pos, u, v, w, dims, dx, interp, capi.EXACT, validate=False)
+        assert not np.isfinite(raw).all()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
+def test_advect(ctx, oracle, interp, order):
+    dims, dx = (12, 10, 14), 0.25
+    u, v, w = rough_fields(dims, 6)
+    pos = probes(dims, dx, 10000, 7)
+    for dt in (1.0 / 30.0, 0.37):
+        ref = oracle.advect(pos, u, v, w, dims, dx, dt, order, interp)
+        exact = ctx.advect(pos, u, v, w, dims, dx, dt, order, interp, capi.EXACT)
+        assert np.array_equal(bits(exact), bits(ref))
+    # fast mode on a smooth field (a rough field makes RK4 chaotic: errors are amplified by the field, not
+    # by the arithmetic)
+    s = synth.make_scene("tiny16")
+    ref = oracle.advect(s["pos"], *s["new"], s["dims"], s["dx"], s["dt"], order, interp)
+    fast = ctx.advect(s["pos"], *s["new"], s["dims"], s["dx"], s["dt"], order, interp, capi.FAST)
+    assert_close(fast, ref, "fast advect")
+    assert_close(fast - s["pos"], ref - s["pos"], "fast displacement", rtol=2e-5)
+
+
+def test_empty_inputs(ctx):
+    dims, dx = (8, 8, 8), 0.5
+    u, v, w = rough_fields(dims, 1)
+    e = np.zeros((0, 3), np.float32)
+    assert ctx.sample(e, u, v, w, dims, dx).shape == (0, 3)
+    assert ctx.advect(e, u, v, w, dims, dx, 0.1).shape == (0, 3)
+    f, wt = ctx.add_point_values(e, np.zeros(0, np.float32), dx, np.zeros(3, np.float32), dx, dims)
+    assert not f.any() and not wt.any()
+
+
+def test_bad_arguments_report_errors(ctx):
+    u, v, w = rough_fields((4, 4, 4), 1)
+    p = np.zeros((1, 3), np.float32)
+    with pytest.raises(capi.GfsError):
+        ctx.advect(p, u, v, w, (4, 4, 4), 0.5, 0.1, order=7)
+    with pytest.raises(capi.GfsError):
+        ctx.sample(p, u, v, w, (4, 4, 4), -1.0)
+    c2 = capi.Context(0)
+    with pytest.raises(capi.GfsError):
+        c2.sort()                       # no domain yet
+    c2.close()
+
+
+@pytest.mark.parametrize("comp", [0, 1, 2])
+def test_add_point_values(ctx, oracle, comp):
+    dims, dx = (12, 10, 14), 0.25
+    nd = synth.face_dims(dims)[comp]
+    off = np.array([0.0 if comp == 0 else 0.5 * dx, 0.0 if comp == 1 else 0.5 * dx,
+                    0.0 if comp == 2 else 0.5 * dx], np.float32)
+    pos = probes(dims, dx, 20000, 8 + comp)
+    pos = pos[np.all((pos > 0) & (pos < np.array(dims) * dx), 1)]
+    vals = np.random.default_rng(9).standard_normal(len(pos)).astype(np.float32)
+    for radius in (dx, 1.7 * dx):
+        fr, wr = oracle.splat(pos, vals, radius, off, dx, nd)
+        for arith in (capi.FAST, capi.EXACT):
+            f, wt = ctx.add_point_values(pos, vals, radius, off, dx, nd, arith=arith)
+            assert_close(wt, wr, "weight")
+            assert_close(f, fr, "field")
+            assert np.array_equal(wt > 0, wr > 0)          # same support, node for node
+    # accumulate semantics (the OpenCL path adds, src/clscalarfield.cpp:1427-1455)
+    f0, w0 = ctx.add_point_values(pos[:100], vals[:100], dx, off, dx, nd)
+    f1, w1 = ctx.add_point_values(pos[100:], vals[100:], dx, off, dx, nd, field=f0.copy(), weight=w0.copy(), accumulate=True)
+    fr, wr = oracle.splat(pos, vals, dx, off, dx, nd)
+    assert_close(f1, fr, "accumulated field")
+    # no weight grid (src/clscalarfield.cpp:147-198)
+    f2, none = ctx.add_point_values(pos, vals, dx, off, dx, nd, with_weight=False)
+    assert none is None
+    assert_close(f2, fr, "field without weight grid")
+    # order independence: bitwise identical for any particle order
+    perm = np.random.default_rng(10).permutation(len(pos))
+    f3, w3 = ctx.add_point_values(pos[perm], vals[perm], dx, off, dx, nd)
+    f4, w4 = ctx.add_point_values(pos, vals, dx, off, dx, nd)
+    assert np.array_equal(bits(f3), bits(f4)) and np.array_equal(bits(w3), bits(w4))
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident domain
+# ---------------------------------------------------------------------------------------------------
+def scene(name, interior_solids=False, seed=12345):
+    s = synth.make_scene(name, seed=seed)
+    if interior_solids:
+        I, J, K = s["dims"]
+        m = s["material"].reshape(K, J, I)
+        m[2:5, 1:4, 3:6] = synth.SOLID
+        mask = synth.fluid_cells(synth.CONFIGS[name][2], s["dims"], s["material"])
+        s["pos"] = synth.make_particles(mask, s["dx"], seed)
+        s["vel"] = synth.particle_velocities(s["pos"], s["dims"], s["dx"])
+    return s
+
+
+SOURCES = [dict(kind=0, p=(1.5, 1.5, 1.5), a=0.9, velocity=(0.5, -1.0, 0.25)),
+           dict(kind=1, p=(2.0, 0.5, 2.0), a=1.0, b=0.8, c=1.3, velocity=(-0.3, 0.2, 0.7))]
+
+
+def load_domain(ctx, s, sources=()):
+    ctx.domain_init(s["dims"], s["dx"])
+    ctx.set_material(s["material"])
+    ctx.set_sources(list(sources))
+    ctx.set_particles(s["pos"], s["vel"])
+
+
+@pytest.mark.parametrize("name", ["tiny16", "slab24", "small32"])
+def test_sort_is_exact_and_stable(ctx, oracle, name):
+    s = scene(name)
+    # add some particles outside the grid and exactly on cell faces
+    extra = probes(s["dims"], s["dx"], 500, 77)
+    pos = np.concatenate([s["pos"], extra])
+    vel = np.concatenate([s["vel"], np.zeros_like(extra)])
+    s = dict(s, pos=pos, vel=vel)
+    load_domain(ctx, s)
+    ctx.sort()
+    order = ctx.get_particle_order()
+    p, v = ctx.get_particles()
+    assert sorted(order.tolist()) == list(range(len(pos)))          # a permutation
+    assert np.array_equal(bits(p), bits(pos[order])) and np.array_equal(bits(v), bits(vel[order]))
+    # recompute the brick-major key on the host from the oracle's (bit-exact) cell index
+    ijk = oracle.cell_index(pos, s["dx"]).astype(np.int64)
+    I, J, K = s["dims"]
+    inside = np.all((ijk >= 0) & (ijk < np.array(s["dims"])), 1)
+    nbi, nbj = (I + 1 + 7) // 8, (J + 1 + 7) // 8
+    b = ((ijk[:, 2] >> 3) * nbj + (ijk[:, 1] >> 3)) * nbi + (ijk[:, 0] >> 3)
+    key = (b << 9) | ((ijk[:, 2] & 7) << 6) | ((ijk[:, 1] & 7) << 3) | (ijk[:, 0] & 7)
+    key = np.where(inside, key, 1 << 40)
+    expect = np.argsort(key, kind="stable")
+    assert np.array_equal(order, expect.astype(np.int32))
+    assert ctx.stats()["out_of_grid"] == int((~inside).sum())
+
+
+@pytest.mark.parametrize("name,solids", [("tiny16", False), ("slab24", True), ("small32", False)])
+def test_p2g(ctx, oracle, name, solids):
+    s = scene(name, solids)
+    mat_ref = s["material"].copy()
+    order = linear_cell_order(oracle, s["pos"], s["dims"], s["dx"])
+    u_ref, v_ref, w_ref = oracle.p2g(s["pos"][order], s["vel"][order], s["dims"], s["dx"], mat_ref, SOURCES)
+
+    load_domain(ctx, s, SOURCES)
+    ctx.sort()
+    ctx.p2g(capi.EXACT)
+    st = ctx.stats()
+    assert st["in_solid"] == 0 and st["fluid_cells"] == int((mat_ref == synth.FLUID).sum())
+    assert np.array_equal(ctx.get_material(), mat_ref)                      # classification: bit-exact
+    for a, b in zip(ctx.get_field(capi.FIELD_P2G), (u_ref, v_ref, w_ref)):
+        assert np.array_equal(bits(a), bits(b))                             # exact mode: bit-exact
+
+    # fast mode: tolerance vs the oracle in the ORIGINAL (shuffled) particle order too
+    mat2 = s["material"].copy()
+    ref2 = oracle.p2g(s["pos"], s["vel"], s["dims"], s["dx"], mat2, SOURCES)
+    load_domain(ctx, s, SOURCES)
+    ctx.sort()
+    ctx.p2g(capi.FAST)
+    assert np.array_equal(ctx.get_material(), mat_ref)
+    fast = ctx.get_field(capi.FIELD_P2G)
+    for a, b, c, nm in zip(fast, (u_ref, v_ref, w_ref), ref2, "uvw"):
+        assert_close(a, b, "fast p2g " + nm)
+        assert_close(a, c, "fast p2g (shuffled oracle order) " + nm)
+        assert np.array_equal(a != 0, b != 0)                               # same faces written
+
+    # determinism: any input order, bitwise the same grid
+    perm = np.random.default_rng(3).permutation(len(s["pos"]))
+    load_domain(ctx, dict(s, pos=s["pos"][perm], vel=s["vel"][perm]), SOURCES)
+    ctx.sort()
+    ctx.p2g(capi.FAST)
+    for a, b in zip(ctx.get_field(capi.FIELD_P2G), fast):
+        assert np.array_equal(bits(a), bits(b))
+
+
+def test_p2g_reclassifies_and_keeps_solids(ctx, oracle):
+    """fluid cells left empty become air (interior only), solids are never overwritten, and particles
+    that sit in a solid cell are counted instead of marking it (src/fluidsimulation.cpp:1998-2017)."""
+    s = scene("tiny16")
+    mat = s["material"].copy()
+    I, J, K = s["dims"]
+    m3 = mat.reshape(K, J, I)
+    m3[3, 3, 3] = synth.FLUID          # stale fluid cell with no particle in it -> air
+    m3[0, 5, 5] = synth.FLUID          # stale fluid in the border layer -> untouched by the interior reset
+    pos = np.array([[6.2, 6.2, 6.2], [0.1, 3.0, 3.0]], np.float32)       # second one sits in the solid border
+    vel = np.ones_like(pos)
+    ref = mat.copy()
+    _, bad = oracle.classify(pos, s["dims"], s["dx"], ref)
+    assert bad == 1
+    ctx.domain_init(s["dims"], s["dx"]); ctx.set_material(mat); ctx.set_sources([]); ctx.set_particles(pos, vel)
+    ctx.sort(); ctx.p2g(capi.FAST)
+    assert np.array_equal(ctx.get_material(), ref)
+    assert ctx.stats()["in_solid"] == 1
+
+
+@pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
+@pytest.mark.parametrize("name", ["tiny16", "slab24"])
+def test_g2p_advect(ctx, oracle, name, interp):
+    s = scene(name, interior_solids=(name == "slab24"))
+    new, saved = rough_fields(s["dims"], 21, 0.3), rough_fields(s["dims"], 22, 0.3)
+    dt = 0.6 * s["dx"]
+    mat = s["material"].copy()
+    oracle.classify(s["pos"], s["dims"], s["dx"], mat)
+    p_ref, v_ref, flags = oracle.g2p_advect(s["pos"], s["vel"], new, saved, s["dims"], s["dx"], dt, order=4,
+                                            mode=interp, material=mat)
+    for order_rk in (4,):
+        load_domain(ctx, s)
+        ctx.set_material(mat)
+        ctx.set_field(capi.FIELD_NEW, *new); ctx.set_field(capi.FIELD_SAVED, *saved)
+        ctx.sort()
+        ctx.g2p_advect(dt, order=order_rk, interp=interp, arith=capi.EXACT)
+        o = ctx.get_particle_order()
+        p, v = ctx.get_particles()
+        assert np.array_equal(bits(v), bits(v_ref[o]))
+        assert np.array_equal(bits(p), bits(p_ref[o]))
+        assert ctx.stats()["solid_hits"] == int(flags.sum())
+    if name == "slab24":
+        assert flags.sum() > 0          # the solid test is actually exercised
+
+    # fast mode on the smooth vortex fields
+    p_ref, v_ref, flags = oracle.g2p_advect(s["pos"], s["vel"], s["new"], s["saved"], s["dims"], s["dx"], s["dt"],
+                                            order=4, mode=interp, material=mat)
+    load_domain(ctx, s)
+    ctx.set_material(mat)
+    ctx.set_field(capi.FIELD_NEW, *s["new"]); ctx.set_field(capi.FIELD_SAVED, *s["saved"])
+    ctx.sort()
+    ctx.g2p_advect(s["dt"], interp=interp, arith=capi.FAST)
+    o = ctx.get_particle_order()
+    p, v = ctx.get_particles()
+    assert_close(v, v_ref[o], "fast picflip velocity")
+    assert_close(p, p_ref[o], "fast advected position")
+    assert_close(p - s["pos"][o], p_ref[o] - s["pos"][o], "fast displacement", rtol=2e-5)
+
+
+@pytest.mark.parametrize("order_rk", [1, 2, 3])
+def test_g2p_lower_rk_orders(ctx, oracle, order_rk):
+    s = scene("tiny16")
+    p_ref, v_ref, _ = oracle.g2p_advect(s["pos"], s["vel"], s["new"], s["saved"], s["dims"], s["dx"], s["dt"],
+                                        order=order_rk, mode=1, material=None)
+    load_domain(ctx, s)
+    ctx.set_field(capi.FIELD_NEW, *s["new"]); ctx.set_field(capi.FIELD_SAVED, *s["saved"])
+    ctx.sort()
+    ctx.g2p_advect(s["dt"], order=order_rk, interp=capi.TRICUBIC, arith=capi.EXACT)
+    o = ctx.get_particle_order()
+    p, v = ctx.get_particles()
+    assert np.array_equal(bits(p), bits(p_ref[o])) and np.array_equal(bits(v), bits(v_ref[o]))
+
+
+def test_substep_sequence_matches_oracle(ctx, oracle):
+    """Three chained substeps (sort, P2G, G2P/RK4) in exact mode track the oracle bit for bit, including the
+    material grid of every step.  The exact P2G sums each node's contributions in ascending cell order and,
+    inside a cell, in the order the particles are stored after the (stable) sort -- so the oracle is fed the
+    particles in exactly that order."""
+    s = scene("tiny16")
+    load_domain(ctx, s)
+    ctx.set_field(capi.FIELD_NEW, *s["new"]); ctx.set_field(capi.FIELD_SAVED, *s["saved"])
+    pos, vel, mat = s["pos"].copy(), s["vel"].copy(), s["material"].copy()     # indexed by original particle id
+    for step in range(3):
+        ctx.sort()
+        o = ctx.get_particle_order()
+        stored_p, stored_v = pos[o], vel[o]
+        lin = linear_cell_order(oracle, stored_p, s["dims"], s["dx"])
+        u, v, w = oracle.p2g(stored_p[lin], stored_v[lin], s["dims"], s["dx"], mat)
+        pos, vel, _ = oracle.g2p_advect(pos, vel, s["new"], s["saved"], s["dims"], s["dx"], s["dt"], mode=0, material=mat)
+        ctx.p2g(capi.EXACT)
+        ctx.g2p_advect(s["dt"], interp=capi.TRILINEAR, arith=capi.EXACT)
+        assert np.array_equal(ctx.get_material(), mat)
+        for a, b in zip(ctx.get_field(capi.FIELD_P2G), (u, v, w)):
+            assert np.array_equal(bits(a), bits(b))
+        o = ctx.get_particle_order()
+        p, vv = ctx.get_particles()
+        assert np.array_equal(bits(p), bits(pos[o])) and np.array_equal(bits(vv), bits(vel[o]))
+
+
+def test_golden_fixtures_through_cuda(ctx):
+    """The committed reference outputs (tests/golden, produced by the unmodified reference) straight
+    against the CUDA path -- no oracle in between."""
+    g = np.load(os.path.join(GOLD, "primitives.npz"))
+    dims, dx = tuple(int(x) for x in g["dims"]), float(g["dx"])
+    u, v, w, pos = g["u"], g["v"], g["w"], g["pos"]
+    assert np.array_equal(bits(ctx.sample(pos, u, v, w, dims, dx, capi.TRILINEAR, capi.EXACT, validate=False)),
+                          bits(g["sample_trilinear"]))
+    assert np.array_equal(bits(ctx.sample(pos, u, v, w, dims, dx, capi.TRICUBIC, capi.EXACT)), bits(g["sample_tricubic"]))
+    for order in (1, 2, 3, 4):
+        out = ctx.advect(pos, u, v, w, dims, dx, float(g["dt"]), order, capi.TRICUBIC, capi.EXACT)
+        assert np.array_equal(bits(out), bits(g["rk%d" % order]))
+
+    g = np.load(os.path.join(GOLD, "stages.npz"))
+    dims, dx = tuple(int(x) for x in g["dims"]), float(g["dx"])
+    src = [dict(kind=int(r[0]), p=tuple(r[1:4]), a=r[4], b=r[5], c=r[6], velocity=tuple(r[7:10])) for r in g["sources"]]
+    ctx.domain_init(dims, dx); ctx.set_material(g["material_in"]); ctx.set_sources(src)
+    ctx.set_particles(g["pos"], g["vel"])
+    ctx.sort(); ctx.p2g(capi.FAST)
+    assert np.array_equal(ctx.get_material(), g["material_out"])
+    for a, nm in zip(ctx.get_field(capi.FIELD_P2G), ("p2g_u", "p2g_v", "p2g_w")):
+        assert_close(a, g[nm], nm)
+    ctx.set_field(capi.FIELD_NEW, g["new_u"], g["new_v"], g["new_w"])
+    ctx.set_field(capi.FIELD_SAVED, g["saved_u"], g["saved_v"], g["saved_w"])
+    ctx.g2p_advect(float(g["dt"]), interp=capi.TRICUBIC, arith=capi.EXACT)
+    o = ctx.get_particle_order()
+    p, vv = ctx.get_particles()
+    assert np.array_equal(bits(vv), bits(g["vel_out"][o]))
+    hit = ~np.all(bits(p) == bits(g["pos_out"][o]), 1)
+    assert hit.sum() == 1 and ctx.stats()["solid_hits"] == 1       # the one collision case of the fixture
+    assert np.array_equal(bits(p[hit]), bits(g["pos"][o][hit]))
+
+
+def test_hello_world_64_full_parity(ctx, oracle):
+    """BASELINE.json configs[0]: 64^3, dx = 0.125, sphere drop, 8 particles per cell (~0.46 M particles):
+    one full substep, fast arithmetic, every array compared in full."""
+    s = synth.make_scene("hello64")
+    mat = s["material"].copy()
+    u, v, w = oracle.p2g(s["pos"], s["vel"], s["dims"], s["dx"], mat)
+    p_ref, v_ref, flags = oracle.g2p_advect(s["pos"], s["vel"], s["new"], s["saved"], s["dims"], s["dx"], s["dt"],
+                                            mode=1, material=mat)
+    load_domain(ctx, s)
+    ctx.set_field(capi.FIELD_NEW, *s["new"]); ctx.set_field(capi.FIELD_SAVED, *s["saved"])
+    ctx.substep(s["dt"], interp=capi.TRICUBIC, arith=capi.FAST)
+    assert np.array_equal(ctx.get_material(), mat)
+    for a, b, nm in zip(ctx.get_field(capi.FIELD_P2G), (u, v, w), "uvw"):
+        assert_close(a, b, "p2g " + nm)
+    o = ctx.get_particle_order()
+    p, vv = ctx.get_particles()
+    assert_close(vv, v_ref[o], "velocity")
+    assert_close(p, p_ref[o], "position")
+    # next-step cell indices computed from GPU positions equal those from oracle positions almost
+    # everywhere (a 1e-7 position difference can only flip a cell for a particle sitting on a face)
+    ca, cb = oracle.cell_index(p, s["dx"]), oracle.cell_index(p_ref[o], s["dx"])
+    assert (ca != cb).any(1).mean() < 1e-4
