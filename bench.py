@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- particle-substeps/sec of the PIC/FLIP transfer hot path (P2G + PIC/FLIP G2P + RK4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gfs|reference] [--workload NAME]
+
+One "step" = one substep of the hot path over the whole particle set of the workload: cell sort,
+classification + u/v/w splat + normalisation + face assembly (P2G), then PIC/FLIP velocity update + RK4
+advection + solid test (G2P).  Metric and roofline definitions: SURVEY.md §8(d), DESIGN.md §5.
+
+  value     device-resident throughput (inputs already in HBM), CUDA events on the launch stream
+  e2e       the same substep through the host-pointer C-ABI calls, with the host->device copy of particles and
+            of the new/saved fields and the device->host read of particles, P2G fields and material inside the
+            timed region
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the unmodified reference's CPU stages (oracle/_ref/libgfsref.so; the oracle port if that library is
+            absent) on a bounded sample of the same workload, all host threads
+
+Multi-GPU (N > 1, launched by torch.distributed.run): z-slab sharding, see gridfluidsim3d_b200/slabs.py.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec (P2G+RK4 G2P)"
+UNIT = "particle-substeps/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback ("of fallback")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload on the device (same construction as gridfluidsim3d_b200/synth.py, generated with torch so
+# that the 100 M-particle scene takes seconds, not minutes)
+# ---------------------------------------------------------------------------------------------------------
+def vortex_t(x, y, z, ext):
+    import torch
+    pi = float(np.pi)
+    xh, yh, zh = x / ext[0], y / ext[1], z / ext[2]
+    u = -torch.sin(pi * xh) ** 2 * torch.sin(2 * pi * yh) * torch.cos(pi * zh)
+    v = torch.sin(2 * pi * xh) * torch.sin(pi * yh) ** 2 * torch.cos(pi * zh)
+    w = 0.5 * torch.sin(2 * pi * xh) * torch.sin(2 * pi * zh) * torch.sin(pi * yh)
+    return u, v, w
+
+
+def make_scene_device(name, device, seed=12345, k_range=None):
+    """Particles (AoS float32 [N,6]), new/saved fields and material of workload `name` as torch tensors on
+    `device`.  k_range=(k0,k1) keeps only particles whose cell layer is in [k0,k1) (slab ownership)."""
+    import torch
+    from gridfluidsim3d_b200 import synth
+    dims, dx, shape = synth.CONFIGS[name]
+    I, J, K = dims
+    material = synth.border_material(dims)
+    mask = torch.from_numpy(synth.fluid_cells(shape, dims, material)).to(device)
+    if k_range is not None:
+        keep = torch.zeros(K, dtype=torch.bool, device=device)
+        keep[k_range[0]:k_range[1]] = True
+        mask &= keep[:, None, None]
+    kk, jj, ii = torch.nonzero(mask, as_tuple=True)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    centre = (torch.stack([ii, jj, kk], 1).to(torch.float32) + 0.5) * dx
+    q = 0.25 * dx
+    sub = torch.tensor([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1],
+                        [-1, 1, -1], [1, 1, -1], [1, 1, 1], [-1, 1, 1]], dtype=torch.float32, device=device) * q
+    pos = (centre[:, None, :] + sub[None, :, :]).reshape(-1, 3)
+    del centre
+    jit = 0.25 * 0.1 * dx
+    pos += (torch.rand(pos.shape, generator=gen, device=device, dtype=torch.float32) * 2 - 1) * jit
+    perm = torch.randperm(pos.shape[0], generator=gen, device=device)      # the reference shuffles every step
+    pos = pos[perm].contiguous()
+    del perm
+    ext = (I * dx, J * dx, K * dx)
+    u, v, w = vortex_t(pos[:, 0], pos[:, 1], pos[:, 2], ext)
+    aos = torch.cat([pos, torch.stack([u, v, w], 1)], 1).contiguous()
+    del pos, u, v, w
+    new = []
+    for comp, (ni, nj, nk) in enumerate(synth.face_dims(dims)):
+        i = torch.arange(ni, device=device, dtype=torch.float32)[None, None, :]
+        j = torch.arange(nj, device=device, dtype=torch.float32)[None, :, None]
+        k = torch.arange(nk, device=device, dtype=torch.float32)[:, None, None]
+        x = (i + (0.0 if comp == 0 else 0.5)) * dx
+        y = (j + (0.0 if comp == 1 else 0.5)) * dx
+        z = (k + (0.0 if comp == 2 else 0.5)) * dx
+        new.append(vortex_t(x, y, z, ext)[comp].expand(nk, nj, ni).contiguous().reshape(-1))
+    saved = [a * 0.9 for a in new]
+    return dict(name=name, dims=dims, dx=dx, dt=synth.cfl_dt(dx), material=material, aos=aos, new=new, saved=saved)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU reference timing (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+def host_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = [int(l.split()[1]) for l in f if l.startswith("MemAvailable")][0]
+    except (OSError, IndexError):
+        avail_kb = 64 << 20
+    return n, avail_kb
+
+
+class CpuHotpath:
+    """The reference's CPU stages on a bounded particle sample against the full-size grid.  Grid-proportional
+    cost (measured once with zero particles) is charged pro rata n_sample/N, so the figure estimates the
+    throughput of the full workload spread over `cores` threads."""
+
+    def __init__(self, scene_host, interp, per_thread):
+        from oracle import pyoracle
+        self.s, self.interp = scene_host, interp
+        dims = scene_host["dims"]
+        cells = dims[0] * dims[1] * dims[2]
+        ncpu, avail_kb = host_threads()
+        per_sim_kb = max(1, cells * 90 // 1024)          # ~90 B/cell per private simulator (measured at 128^3)
+        self.cores = int(max(1, min(ncpu, 32, avail_kb // 2 // per_sim_kb)))
+        self.kind, self.ref = "port", None
+        try:
+            self.ref = pyoracle.Reference(build=os.path.isdir("/root/reference/src"))
+            self.kind = "reference"
+        except (FileNotFoundError, OSError) as e:
+            log("reference library unavailable (%s): timing the oracle port instead" % e)
+            self.orc = pyoracle.Oracle()
+            self.cores = int(min(ncpu, self.orc.lib.orc_max_threads()))
+        N = len(scene_host["pos"])
+        self.n = int(min(N, per_thread * self.cores))
+        self.N = N
+        if self.kind == "reference":
+            self.hp = self.ref.hotpath(self.cores, dims, scene_host["dx"], scene_host["new"], scene_host["saved"])
+            _, st = self.hp.step(scene_host["pos"][:0], scene_host["vel"][:0], scene_host["dt"], interp)
+            self.t_grid = float(st.sum())
+        else:
+            self.t_grid = 0.0
+
+    def sample_desc(self):
+        return ("%d of %d particles (first %d of the shuffled array, %d per thread) against the full %dx%dx%d grid; "
+                "grid-proportional cost %.2fs (zero-particle run) charged pro rata" %
+                (self.n, self.N, self.n, self.n // self.cores, *self.s["dims"], self.t_grid))
+
+    def step(self):
+        """-> (particle-substeps/s estimate for the full workload, seconds spent)"""
+        s = self.s
+        pos, vel = s["pos"][:self.n], s["vel"][:self.n]
+        t0 = time.time()
+        if self.kind == "reference":
+            t, st = self.hp.step(pos, vel, s["dt"], self.interp)
+            t_eff = max(t - self.t_grid, 1e-9) + self.t_grid * self.n / self.N
+        else:
+            mat = s["material"].copy()
+            self.orc.p2g(pos, vel, s["dims"], s["dx"], mat)
+            self.orc.g2p_advect(pos, vel, s["new"], s["saved"], s["dims"], s["dx"], s["dt"], mode=self.interp, material=mat)
+            t_eff = time.time() - t0
+        return self.n / t_eff, time.time() - t0
+
+    def close(self):
+        if self.kind == "reference":
+            self.hp.close()
+
+
+def scene_to_host(sc, max_particles=None):
+    aos = sc["aos"] if max_particles is None else sc["aos"][:max_particles]
+    a = aos.cpu().numpy()
+    return dict(dims=sc["dims"], dx=sc["dx"], dt=sc["dt"], material=sc["material"],
+                pos=np.ascontiguousarray(a[:, :3]), vel=np.ascontiguousarray(a[:, 3:]),
+                new=[t.cpu().numpy() for t in sc["new"]], saved=[t.cpu().numpy() for t in sc["saved"]])
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this arm's config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from gridfluidsim3d_b200 import synth
+    interp = 0 if args.interp == "trilinear" else 1
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    per_thread = args.cpu_sample
+    dims, dx, _ = synth.CONFIGS[args.workload]
+    sc = make_scene_device(args.workload, dev)
+    N = sc["aos"].shape[0]
+    ncpu, _ = host_threads()
+    host = scene_to_host(sc, max_particles=per_thread * min(ncpu, 32))
+    host_full_n = N
+    del sc
+    cpu = CpuHotpath(host, interp, per_thread)
+    cpu.N = host_full_n
+    for _ in range(args.warmup):
+        cpu.step()
+    vals, t0 = [], time.time()
+    for _ in range(args.steps):
+        v, _ = cpu.step()
+        vals.append(v)
+    wall = time.time() - t0
+    value = float(len(vals) / sum(1.0 / v for v in vals))        # harmonic mean = total particles / total time
+    G = dims[0] * dims[1] * dims[2]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * host_full_n / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 (fp64 index/interpolation arithmetic)", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": list(dims), "dx": dx, "particles": host_full_n, "cells": G,
+                   "interp": args.interp, "rk_order": 4, "note": "CPU, OpenCL disabled; ms_per_step is the full-workload estimate"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_desc()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    cpu.close()
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+ALG_BYTES = {   # algorithmic bytes per launch of each hot kernel: (per particle, per cell)
+    "gfs::k_p2g_scatter<0>": (24, 13), "gfs::k_p2g_tile<0>": (24, 13),
+    "gfs::k_g2p_advect<0>": (48, 24), "gfs::k_g2p_advect<1>": (48, 24), "gfs::k_g2p_brick<0>": (48, 24),
+}
+
+
+def run_gfs(args):
+    import torch
+    import torch.distributed as dist
+    from gridfluidsim3d_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus:
+        log("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))
+    interp = capi.TRILINEAR if args.interp == "trilinear" else capi.TRICUBIC
+    dims, dx, _ = synth.CONFIGS[args.workload]
+    G = dims[0] * dims[1] * dims[2]
+    hbm_gbs, peak_src = measured_peaks()
+
+    if world > 1:
+        from gridfluidsim3d_b200 import slabs
+        return slabs.bench_main(args, METRIC, UNIT, hbm_gbs, peak_src, make_scene_device, ClockSampler, log)
+
+    t_gen = time.time()
+    sc = make_scene_device(args.workload, dev)
+    torch.cuda.synchronize()
+    N = sc["aos"].shape[0]
+    log("scene %s: %d particles, %d cells, generated in %.1fs" % (args.workload, N, G, time.time() - t_gen))
+
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(local, stream=stream.cuda_stream)
+    log(ctx.device_info())
+    ctx.domain_init(dims, dx)
+    ctx.set_material(sc["material"])
+    # pinned host copies: the e2e leg's inputs, and the source of the resident upload
+    aos_host = torch.empty(sc["aos"].shape, dtype=torch.float32, pin_memory=True)
+    aos_host.copy_(sc["aos"])
+    new_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["new"]]
+    saved_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["saved"]]
+    torch.cuda.synchronize()
+    ctx.set_particles_aos(aos_host.numpy())
+    ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])
+    ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])
+    dt = sc["dt"]
+    host_small = scene_to_host(sc, max_particles=args.cpu_sample * 32)
+    del sc["aos"]
+    torch.cuda.empty_cache()
+
+    def substep():
+        ctx.substep(dt, order=4, interp=interp, arith=capi.FAST)
+
+    # ---- value: device-resident substeps --------------------------------------------------------------
+    for _ in range(args.warmup):
+        substep()
+    torch.cuda.synchronize()
+    launches0 = ctx.stats()["kernel_launches"]
+    ctx.profile_enable(True)
+    ctx.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            substep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    st = ctx.stats()
+    launches = st["kernel_launches"] - launches0
+    ms_per_step = ms / args.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # dominant kernel and its roofline
+    ranked = sorted(prof.items(), key=lambda kv: -kv[1][0])
+    kernels = {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches_per_step": v[1] / args.steps,
+                   "share_of_step": v[0] / ms} for k, v in ranked}
+    top = next((k for k, _ in ranked if k in ALG_BYTES), ranked[0][0])
+    pb, cb = ALG_BYTES.get(top, (0, 0))
+    top_ms = prof[top][0] / max(1, prof[top][1])
+    alg_bytes = pb * N + cb * G
+    achieved = alg_bytes / (top_ms * 1e-3) / 1e9
+    step_alg_bytes = 72 * N + 37 * G
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_ms,
+                "substep_algorithmic_bytes": step_alg_bytes,
+                "substep_frac": step_alg_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the ncu capture
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            roofline["traffic"] = json.load(f).get(args.workload, {}).get(top)
+
+    # ---- e2e: the same substep through host buffers ------------------------------------------------------
+    aos_out = torch.empty_like(aos_host)
+    p2g_out = [np.empty(t.numel(), np.float32) for t in new_host]
+    nu, nv, nw = [t.numel() for t in new_host]
+    h2d = N * 24 + 2 * 4 * (nu + nv + nw)
+    d2h = N * 24 + 4 * (nu + nv + nw) + G
+
+    def e2e_step():
+        ctx.set_particles_aos(aos_host.numpy())                                  # H2D 24 B/particle
+        ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])           # H2D post-pressure field
+        ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])       # H2D saved field
+        substep()
+        ctx.get_particles_aos(aos_out.numpy().reshape(-1))                       # D2H particles
+        ctx.get_field(capi.FIELD_P2G, out=p2g_out)                               # D2H P2G u,v,w
+        ctx.get_material()                                                        # D2H material
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "gfs_set_particles + gfs_set_field x2 + gfs_substep + gfs_get_particles + gfs_get_field + gfs_get_material"}
+
+    # ---- tricubic / trilinear variant (the other interpolation), short ------------------------------------
+    other = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR
+    other_name = "tricubic" if interp == capi.TRILINEAR else "trilinear"
+    for _ in range(2):
+        ctx.substep(dt, order=4, interp=other, arith=capi.FAST)
+    torch.cuda.synchronize()
+    vs = max(3, min(args.steps, 5))
+    e0.record(stream)
+    for _ in range(vs):
+        ctx.substep(dt, order=4, interp=other, arith=capi.FAST)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    oms = e0.elapsed_time(e1) / vs
+    variants = {other_name: {"value": N / (oms * 1e-3), "ms_per_step": oms,
+                             "substep_frac": step_alg_bytes / (oms * 1e-3) / 1e9 / hbm_gbs}}
+
+    # ---- cpu baseline (bounded sample, rank 0, N = 1 only) ---------------------------------------------
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = CpuHotpath(host_small, interp, args.cpu_sample)
+            cpu.N = N
+            v, spent = cpu.step()
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_desc(),
+                            "seconds": spent}
+            cpu.close()
+        except Exception as e:          # the baseline leg must never take the GPU numbers down with it
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (fp64 index arithmetic, 64-bit fixed-point P2G accumulation)", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": list(dims), "dx": dx, "particles": N, "cells": G,
+                   "interp": args.interp, "rk_order": 4, "arith": "fast", "cfl": 0.5,
+                   "l2": "inputs (%.2f GB particles + %.2f GB fields) exceed the 126 MB L2; no flush needed"
+                         % (N * 24 / 1e9, 8 * (nu + nv + nw) / 1e9)},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks.summary(), "kernels": kernels, "variants": variants,
+        "stats": {k: int(v) for k, v in st.items()},
+    }
+    ctx.close()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gfs", choices=["gfs", "reference"])
+    ap.add_argument("--workload", default="splash256")
+    ap.add_argument("--interp", default="trilinear", choices=["trilinear", "tricubic"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gfs" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gfs(args)
+
+
+if __name__ == "__main__":
+    main()

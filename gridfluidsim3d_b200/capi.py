@@ -20,6 +20,7 @@ AIR, FLUID, SOLID = 0, 1, 2
 #: every symbol include/gfs_b200.h declares (tests check the .so exports each one)
 SYMBOLS = [
     "gfs_get_error_message", "gfs_create", "gfs_destroy", "gfs_device_info", "gfs_sync", "gfs_get_stats",
+    "gfs_profile_enable", "gfs_profile_read",
     "gfs_sample", "gfs_advect", "gfs_add_point_values",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
@@ -66,6 +67,9 @@ def load_library():
     L.gfs_device_info.argtypes = [V, C.c_char_p, I, _err]
     L.gfs_sync.argtypes = [V, _err]
     L.gfs_get_stats.argtypes = [V, C.POINTER(Stats), _err]
+    L.gfs_profile_enable.argtypes = [V, I, _err]
+    L.gfs_profile_read.argtypes = [V, C.c_char_p, C.POINTER(D), C.POINTER(L64), I, I, _err]
+    L.gfs_profile_read.restype = I
     L.gfs_sample.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, I, I, I, _f32, _err]
     L.gfs_advect.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, D, I, I, I, _f32, _err]
     L.gfs_add_point_values.argtypes = [V, _f32, _f32, L64, D, _f32, D, I, I, I, _f32, V, I, I, _err]
@@ -181,6 +185,17 @@ class Context:
         self._call(self.lib.gfs_get_stats, C.byref(s))
         return {n: getattr(s, n) for n, _ in Stats._fields_}
 
+    def profile_enable(self, on=True):
+        self._call(self.lib.gfs_profile_enable, int(on))
+
+    def profile_read(self, reset=True):
+        """{kernel name: (total milliseconds, launches)} since the last reset (CUDA events, device time)."""
+        cap = 64
+        names = C.create_string_buffer(64 * cap)
+        ms, cnt = (C.c_double * cap)(), (C.c_int64 * cap)()
+        n = self._call(self.lib.gfs_profile_read, names, ms, cnt, cap, int(reset))
+        return {names.raw[64 * i:64 * (i + 1)].split(b"\0")[0].decode(): (ms[i], cnt[i]) for i in range(n)}
+
     # ---- host-pointer operators (ParticleAdvector / CLScalarField) --------------------------------
     def sample(self, pos, u, v, w, dims, dx, interp=TRICUBIC, arith=FAST, validate=True):
         pos = _c(pos)
@@ -259,11 +274,12 @@ class Context:
     def set_field(self, slot, u, v, w):
         self._call(self.lib.gfs_set_field, slot, _c(u), _c(v), _c(w))
 
-    def get_field(self, slot):
-        nu, nv, nw = face_counts(self.dims)
-        u, v, w = np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32)
-        self._call(self.lib.gfs_get_field, slot, u, v, w)
-        return u, v, w
+    def get_field(self, slot, out=None):
+        if out is None:
+            nu, nv, nw = face_counts(self.dims)
+            out = (np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32))
+        self._call(self.lib.gfs_get_field, slot, *out)
+        return out
 
     def sort(self):
         self._call(self.lib.gfs_sort)

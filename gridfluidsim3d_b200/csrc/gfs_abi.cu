@@ -65,11 +65,37 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
 
+struct ProfSpan { int name; cudaEvent_t a, b; };
+
 struct gfs_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
+
+    // ---- optional per-kernel CUDA-event timing (gfs_profile_*): one event pair per launch
+    bool profiling = false;
+    std::vector<std::string> prof_names;
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+
+    int prof_name_id(const char *nm) {
+        for (size_t i = 0; i < prof_names.size(); i++) if (prof_names[i] == nm) return (int)i;
+        prof_names.push_back(nm);
+        return (int)prof_names.size() - 1;
+    }
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    int prof_begin(const char *nm) {
+        if (!profiling) return -1;
+        ProfSpan sp; sp.name = prof_name_id(nm); sp.a = prof_event(); sp.b = prof_event();
+        cudaEventRecord(sp.a, stream);
+        prof_spans.push_back(sp);
+        return (int)prof_spans.size() - 1;
+    }
+    void prof_end(int id) { if (id >= 0) cudaEventRecord(prof_spans[id].b, stream); }
 
     // ---- domain
     bool has_domain = false;
@@ -154,7 +180,9 @@ dim3 grid3(int ni, int nj, int nk, int bx = 128) { return dim3((unsigned)ceil_di
 
 #define LAUNCH(ctx, kernel, gridDim, blockDim, ...)                                                \
     do {                                                                                           \
+        int prof_id_ = (ctx)->prof_begin(#kernel);                                                 \
         kernel<<<(gridDim), (blockDim), 0, (ctx)->stream>>>(__VA_ARGS__);                          \
+        (ctx)->prof_end(prof_id_);                                                                 \
         (ctx)->launches++;                                                                         \
         GFS_CUDA(cudaGetLastError());                                                              \
     } while (0)
@@ -186,8 +214,10 @@ void do_sort(gfs_context *c) {
         GFS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p, c->perm[1].p,
                                                   (int)n, 0, bits, c->stream));
         c->cub_tmp.reserve(tmp_bytes);
+        int prof_id = c->prof_begin("cub::DeviceRadixSort::SortPairs");
         GFS_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p,
                                                   c->perm[1].p, (int)n, 0, bits, c->stream));
+        c->prof_end(prof_id);
         c->launches += 4;      // cub: histogram + onesweep passes (counted conservatively)
         LAUNCH(c, gfs::k_reorder, ceil_div(n, B), B, n, c->perm[1].p,
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
@@ -366,6 +396,35 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     out->solid_hits = (int64_t)h[2];
     out->kernel_launches = c->launches;
     GFS_END()
+}
+
+void gfs_profile_enable(gfs_context *c, int on, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    c->profiling = on != 0;
+    GFS_END()
+}
+
+int gfs_profile_read(gfs_context *c, char *names, double *total_ms, int64_t *counts, int cap, int reset, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && names && total_ms && counts && cap > 0, "bad arguments");
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    int nn = (int)c->prof_names.size() < cap ? (int)c->prof_names.size() : cap;
+    for (int i = 0; i < nn; i++) {
+        snprintf(names + 64 * i, 64, "%s", c->prof_names[i].c_str());
+        total_ms[i] = 0.0; counts[i] = 0;
+    }
+    for (size_t i = 0; i < c->prof_spans.size(); i++) {
+        const ProfSpan &sp = c->prof_spans[i];
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.name < nn) { total_ms[sp.name] += ms; counts[sp.name]++; }
+    }
+    if (reset) {
+        for (size_t i = 0; i < c->prof_spans.size(); i++) { c->prof_pool.push_back(c->prof_spans[i].a); c->prof_pool.push_back(c->prof_spans[i].b); }
+        c->prof_spans.clear();
+    }
+    return nn;
+    GFS_END(-1)
 }
 
 /* ---- host-pointer operators ------------------------------------------------------------------ */

@@ -49,10 +49,10 @@ def fluid_cells(shape, dims, material=None):
         mask = (cx - 0.5) ** 2 + (cy - 0.5) ** 2 + (cz - 0.5) ** 2 < 0.375 ** 2
     elif shape == "dam":             # cuboid x < 0.5 W, y < 0.95 H, all interior z
         mask = (cx < 0.5) & (cy < 0.95) & (cz > -1)
-    elif shape == "splash":          # pool y < 0.36 H plus two balls of radius 0.15 W above it
-        ball1 = (cx - 0.3) ** 2 + (cy - 0.7) ** 2 + (cz - 0.3) ** 2 < 0.15 ** 2
-        ball2 = (cx - 0.7) ** 2 + (cy - 0.65) ** 2 + (cz - 0.7) ** 2 < 0.15 ** 2
-        mask = (cy < 0.36) | ball1 | ball2
+    elif shape == "splash":          # deep pool y < 0.72 H plus two inflow balls of radius 0.12 W above it
+        ball1 = (cx - 0.3) ** 2 + (cy - 0.86) ** 2 + (cz - 0.3) ** 2 < 0.12 ** 2
+        ball2 = (cx - 0.7) ** 2 + (cy - 0.85) ** 2 + (cz - 0.7) ** 2 < 0.12 ** 2
+        mask = (cy < 0.72) | ball1 | ball2
         mask = mask & (cx > -1) & (cz > -1)
     elif shape == "river":           # channel y < 0.47 H
         mask = (cy < 0.47) & (cx > -1) & (cz > -1)

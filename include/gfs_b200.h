@@ -102,6 +102,12 @@ void gfs_device_info(gfs_context *ctx, char *buf, int buflen, int *err);
 void gfs_sync(gfs_context *ctx, int *err);
 void gfs_get_stats(gfs_context *ctx, gfs_stats_t *out, int *err);
 
+/* Per-kernel timing with CUDA events on the context's stream (one event pair per launch while enabled).
+ * gfs_profile_read synchronises, writes up to `cap` kernel names (64 bytes each, NUL-terminated) with their
+ * summed milliseconds and launch counts, optionally resets, and returns the number of names. */
+void gfs_profile_enable(gfs_context *ctx, int on, int *err);
+int gfs_profile_read(gfs_context *ctx, char *names, double *total_ms, int64_t *counts, int cap, int reset, int *err);
+
 /* ---- host-pointer, synchronous operators (mirror the accelerator classes one call each) ------- */
 
 /* ParticleAdvector::tricubicInterpolate (src/particleadvector.cpp:401-455; NoCL body :1124-1137) and

@@ -197,9 +197,12 @@ class Reference:
         L.ref_sim_get_fields.argtypes = [V, _f32, _f32, _f32]
         L.ref_sim_advance_particles.argtypes = [V, C.c_double]
         L.ref_sim_update.argtypes = [V, C.c_double]
-        L.ref_time_hotpath.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double,
-                                       _f32, _f32, _f32, _f32, _f32, _f32, C.c_double, C.c_int, _f64]
-        L.ref_time_hotpath.restype = C.c_double
+        L.ref_hotpath_create.restype = V
+        L.ref_hotpath_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.ref_hotpath_destroy.argtypes = [V]
+        L.ref_hotpath_set_fields.argtypes = [V, _f32, _f32, _f32, _f32, _f32, _f32]
+        L.ref_hotpath_step.argtypes = [V, _f32, _f32, C.c_long, C.c_double, C.c_int, _f64]
+        L.ref_hotpath_step.restype = C.c_double
 
     # -- primitives
     def cell_index(self, pos, dx):
@@ -231,12 +234,29 @@ class Reference:
     def sim(self, dims, dx):
         return RefSim(self.lib, dims, dx)
 
-    def time_hotpath(self, pos, vel, dims, dx, new, saved, dt, nthreads):
+    def hotpath(self, nthreads, dims, dx, new, saved):
+        return RefHotpath(self.lib, nthreads, dims, dx, new, saved)
+
+
+class RefHotpath:
+    """nthreads private reference simulators timing the three hot-path stages (see ref_harness.cpp)."""
+
+    def __init__(self, lib, nthreads, dims, dx, new, saved):
+        self.lib, self.nthreads = lib, nthreads
+        self.h = lib.ref_hotpath_create(nthreads, *dims, dx)
+        lib.ref_hotpath_set_fields(self.h, *[_c(a) for a in new], *[_c(a) for a in saved])
+
+    def step(self, pos, vel, dt, mode):
+        """-> (seconds, [P2G, PIC/FLIP, RK4] seconds)"""
         stages = np.zeros(3)
         pos, vel = _c(pos), _c(vel)
-        t = self.lib.ref_time_hotpath(pos, vel, len(pos), *dims, dx, *[_c(a) for a in new],
-                                      *[_c(a) for a in saved], dt, nthreads, stages)
+        t = self.lib.ref_hotpath_step(self.h, pos, vel, len(pos), dt, mode, stages)
         return t, stages
+
+    def close(self):
+        if self.h:
+            self.lib.ref_hotpath_destroy(self.h)
+            self.h = None
 
 
 class RefSim:
