@@ -315,7 +315,8 @@ def run_gfs(args):
     N = sc["aos"].shape[0]
     log("scene %s: %d particles, %d cells, generated in %.1fs" % (args.workload, N, G, time.time() - t_gen))
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
     ctx = capi.Context(local, stream=stream.cuda_stream)
     log(ctx.device_info())
     ctx.domain_init(dims, dx)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "gfs_sample", "gfs_advect", "gfs_add_point_values",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
-    "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
+    "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -85,6 +85,8 @@ def load_library():
     L.gfs_set_field.argtypes = [V, I, _f32, _f32, _f32, _err]
     L.gfs_get_field.argtypes = [V, I, _f32, _f32, _f32, _err]
     L.gfs_sort.argtypes = [V, _err]
+    L.gfs_sort_unstable.argtypes = [V, _err]
+    L.gfs_set_option.argtypes = [V, I, I, _err]
     L.gfs_p2g.argtypes = [V, I, _err]
     L.gfs_g2p_advect.argtypes = [V, D, D, I, I, I, _err]
     L.gfs_substep.argtypes = [V, D, D, I, I, I, _err]
@@ -283,6 +285,12 @@ class Context:
 
     def sort(self):
         self._call(self.lib.gfs_sort)
+
+    def sort_unstable(self):
+        self._call(self.lib.gfs_sort_unstable)
+
+    def set_option(self, option, value):
+        self._call(self.lib.gfs_set_option, option, value)
 
     def p2g(self, arith=FAST):
         self._call(self.lib.gfs_p2g, arith)

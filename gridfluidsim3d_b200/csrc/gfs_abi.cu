@@ -5,6 +5,7 @@
 // /root/reference/src/c_bindings/cbindings.cpp:11-19.  No CPU fallback exists: without a usable CUDA
 // device gfs_create fails and nothing else can be called.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cmath>
 #include <cstdarg>
@@ -108,7 +109,8 @@ struct gfs_context {
     DevBuf<float> val[3];                 // node grids after normalisation ("ugrid")
     DevBuf<uint8_t> setmask[3];
     DevBuf<unsigned long long> acc[3];    // fixed-point accumulators, 2 per node
-    DevBuf<int2> cells;
+    DevBuf<int32_t> cell_start;           // nkeys + 2: exclusive scan of the per-cell counts (+ overflow bin)
+    DevBuf<uint32_t> counts;              // nkeys + 2
     gfs::Sources sources;
 
     // ---- particles (double-buffered SoA: x,y,z,vx,vy,vz) + original-index tags
@@ -118,12 +120,15 @@ struct gfs_context {
     DevBuf<float> soa[2][6];
     DevBuf<int32_t> tag[2];
     DevBuf<uint32_t> keys[2];
+    DevBuf<uint32_t> rank;
     DevBuf<int32_t> perm[2];
+    bool keys_ready = false;              // keys/rank/counts/vmax of the current buffer were produced by the G2P epilogue
     DevBuf<unsigned char> cub_tmp;
     DevBuf<int32_t> n_valid;              // 1 word
     DevBuf<unsigned int> vmax_bits;       // 1 word
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
+    int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
 
     // ---- scratch for host-pointer operators
     DevBuf<float> h_pos, h_out, h_val, h_fld, h_wgt, h_field[3];
@@ -136,6 +141,7 @@ struct gfs_context {
             keys[b].reserve((size_t)m);
             perm[b].reserve((size_t)m);
         }
+        rank.reserve((size_t)m);
     }
 };
 
@@ -149,6 +155,10 @@ Grid make_grid(int I, int J, int K, double dx, int k0, int k1) {
     g.dx = dx; g.invdx = 1.0 / dx;
     g.xmax = dx * I; g.ymax = dx * J; g.zmax = dx * K;
     g.halfdx = 0.5 * dx;
+    g.dxf = (float)dx; g.invdxf = (float)g.invdx; g.halfdxf = (float)g.halfdx;
+    g.xmaxf = (float)g.xmax; g.ymaxf = (float)g.ymax; g.zmaxf = (float)g.zmax;
+    int e = 0;
+    g.pow2 = (std::frexp(dx, &e) == 0.5 && I < (1 << 20) && J < (1 << 20) && K < (1 << 20) && e > -100 && e < 100) ? 1 : 0;
     g.nbi = (I + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbj = (J + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbk = (k1 - k0 + 1 + gfs::kBrick - 1) / gfs::kBrick;
@@ -195,38 +205,62 @@ gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
     return f;
 }
 
-void do_sort(gfs_context *c) {
+// K0.  stable = true: LSD radix sort of (key, index) pairs (cub), particles keep their relative order inside a
+// cell -- what the exact-arithmetic P2G needs to reproduce the reference's summation order.  stable = false:
+// counting sort (cell histogram with atomic tickets, exclusive scan, scatter); when the previous G2P already
+// binned the advected positions in its epilogue only the scan and the scatter remain.
+void do_sort(gfs_context *c, bool stable) {
     require_domain(c);
     const int64_t n = c->n;
     const int src = c->cur, dst = 1 - c->cur;
-    GFS_CUDA(cudaMemsetAsync(c->cells.p, 0, sizeof(int2) * (size_t)c->nkeys, c->stream));
-    GFS_CUDA(cudaMemsetAsync(c->n_valid.p, 0, sizeof(int32_t), c->stream));
-    GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
-    if (n > 0) {
-        const int B = 256;
-        LAUNCH(c, gfs::k_keys, ceil_div(n, B), B, c->grid, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
-               c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->perm[0].p, c->vmax_bits.p);
-        int bits = 1;
-        while (bits < 32 && (1ull << bits) < (unsigned long long)c->nkeys) bits++;
-        bits = bits < 32 ? bits + 1 : 32;                      // one more so the all-ones sentinel sorts last
-        // the sentinel is 0xFFFFFFFF: with end_bit = bits it compares as (2^bits - 1) >= nkeys, i.e. last
+    const int B = 256;
+    const size_t nbins = (size_t)c->nkeys + 2;
+    if (!c->keys_ready) {
+        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * nbins, c->stream));
+        GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
+        if (n > 0)
+            LAUNCH(c, gfs::k_hist, ceil_div(n, B), B, c->grid, c->nkeys, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
+                   c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->rank.p, c->perm[0].p,
+                   c->counts.p, c->vmax_bits.p);
+    }
+    {
         size_t tmp_bytes = 0;
-        GFS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p, c->perm[1].p,
-                                                  (int)n, 0, bits, c->stream));
+        GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
         c->cub_tmp.reserve(tmp_bytes);
-        int prof_id = c->prof_begin("cub::DeviceRadixSort::SortPairs");
-        GFS_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p,
-                                                  c->perm[1].p, (int)n, 0, bits, c->stream));
+        int prof_id = c->prof_begin("cub::DeviceScan::ExclusiveSum");
+        GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
         c->prof_end(prof_id);
-        c->launches += 4;      // cub: histogram + onesweep passes (counted conservatively)
-        LAUNCH(c, gfs::k_reorder, ceil_div(n, B), B, n, c->perm[1].p,
-               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
-               c->tag[src].p,
-               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
-               c->tag[dst].p);
-        LAUNCH(c, gfs::k_cell_ranges, ceil_div(n, B), B, n, c->keys[1].p, c->cells.p, c->n_valid.p);
+        c->launches += 2;
+    }
+    if (n > 0) {
+        if (stable) {
+            GFS_REQUIRE(!c->keys_ready, "internal: stable sort after a binning G2P");
+            int bits = 1;
+            while (bits < 32 && (1ull << bits) <= (unsigned long long)c->nkeys) bits++;      // keys are in [0, nkeys]
+            size_t tmp_bytes = 0;
+            GFS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p, c->perm[1].p,
+                                                      (int)n, 0, bits, c->stream));
+            c->cub_tmp.reserve(tmp_bytes);
+            int prof_id = c->prof_begin("cub::DeviceRadixSort::SortPairs");
+            GFS_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys[0].p, c->keys[1].p, c->perm[0].p,
+                                                      c->perm[1].p, (int)n, 0, bits, c->stream));
+            c->prof_end(prof_id);
+            c->launches += 4;      // cub: histogram + onesweep passes (counted conservatively)
+            LAUNCH(c, gfs::k_reorder, ceil_div(n, B), B, n, c->perm[1].p,
+                   c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+                   c->tag[src].p,
+                   c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+                   c->tag[dst].p);
+        } else {
+            LAUNCH(c, gfs::k_scatter_sorted, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p,
+                   c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+                   c->tag[src].p,
+                   c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+                   c->tag[dst].p);
+        }
         c->cur = dst;
     }
+    c->keys_ready = false;
     c->sorted = true;
 }
 
@@ -238,18 +272,30 @@ void do_p2g(gfs_context *c, int arith) {
     const int b = c->cur;
     gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
     GFS_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, gfs::k_classify, grid3(g.I, g.J, kl), 128, g, c->cells.p, c->material.p, c->counters.p);
+    LAUNCH(c, gfs::k_classify, grid3(g.I, g.J, kl), 128, g, c->cell_start.p, c->material.p, c->counters.p);
     const int dims[3][3] = {{g.I + 1, g.J, kl}, {g.I, g.J + 1, kl}, {g.I, g.J, kl + 1}};
     if (arith == GFS_EXACT) {
         for (int comp = 0; comp < 3; comp++)
             LAUNCH(c, gfs::k_p2g_gather<1>, grid3(dims[comp][0], dims[comp][1], dims[comp][2], 64), 64, g, comp, sp, c->sources,
-                   c->cells.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3 + comp].p,
+                   c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3 + comp].p,
                    c->val[comp].p, c->setmask[comp].p);
     } else {
-        if (c->n > 0)
-            LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->n_valid.p,
-                   c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
-                   c->acc[0].p, c->acc[1].p, c->acc[2].p);
+        if (c->n > 0) {
+            if (c->p2g_variant == 0) {
+                LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                       c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                       c->acc[0].p, c->acc[1].p, c->acc[2].p);
+            } else {
+                const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
+                int prof_id_ = c->prof_begin("gfs::k_p2g_tile<0>");
+                gfs::k_p2g_tile<0><<<nbricks, 256, 12 * gfs::kTileNodes * sizeof(uint32_t), c->stream>>>(
+                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
+                c->prof_end(prof_id_);
+                c->launches++;
+                GFS_CUDA(cudaGetLastError());
+            }
+        }
         for (int comp = 0; comp < 3; comp++)
             LAUNCH(c, gfs::k_p2g_finalize, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, sp, c->sources,
                    c->acc[comp].p, c->val[comp].p, c->setmask[comp].p);
@@ -259,7 +305,7 @@ void do_p2g(gfs_context *c, int arith) {
                c->val[comp].p, c->setmask[comp].p, c->field[GFS_FIELD_P2G][comp].p);
 }
 
-void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith) {
+void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next) {
     require_domain(c);
     GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
     GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
@@ -268,22 +314,26 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     gfs::RkCoef rk = make_rk(dt);
     float rp = (float)ratio, rf = (float)(1 - ratio);      // fluidsimulation.cpp:3126
     GFS_CUDA(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), c->stream));
-    if (arith == GFS_EXACT)
-        LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED),
-               c->material.p, interp, order, rk, rp, rf, c->n,
-               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
-               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
-               c->counters.p);
-    else
-        LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED),
-               c->material.p, interp, order, rk, rp, rf, c->n,
-               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
-               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
-               c->counters.p);
+    // fast arithmetic: bin the advected positions for the next counting sort in the kernel's epilogue
+    uint32_t *keys_out = nullptr, *rank_out = nullptr, *counts = nullptr;
+    if (bin_next) {
+        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * ((size_t)c->nkeys + 2), c->stream));
+        GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
+        keys_out = c->keys[0].p; rank_out = c->rank.p; counts = c->counts.p;
+    }
+#define GFS_G2P_ARGS c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, interp, order, rk, rp, rf, c->n, \
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
+    if (arith == GFS_EXACT) LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
+    else if (c->grid.pow2) LAUNCH(c, gfs::k_g2p_advect<2>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
+    else LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
+#undef GFS_G2P_ARGS
     // tags travel with the slot: the G2P kernel keeps slot order, so copy the tag array across buffers
     GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     c->cur = dst;
     c->sorted = false;          // positions moved: the cell table no longer describes them
+    c->keys_ready = bin_next;
 }
 
 // upload three host face arrays of a full (non-slab) field into scratch and return device pointers
@@ -353,7 +403,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 3; s++) for (int a = 0; a < 3; a++) c->field[s][a].release();
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
-    c->material.release(); c->cells.release();
+    c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
     c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
@@ -387,7 +437,8 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     unsigned long long h[4] = {0, 0, 0, 0};
     int32_t nv = 0;
     GFS_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    GFS_CUDA(cudaMemcpyAsync(&nv, c->n_valid.p, sizeof(nv), cudaMemcpyDeviceToHost, c->stream));
+    if (c->has_domain && c->sorted)
+        GFS_CUDA(cudaMemcpyAsync(&nv, c->cell_start.p + c->nkeys, sizeof(nv), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     out->num_particles = c->n;
     out->out_of_grid = c->sorted ? c->n - nv : 0;
@@ -538,7 +589,9 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
         GFS_CUDA(cudaMemsetAsync(c->acc[a].p, 0, 2 * c->face_count[a] * sizeof(unsigned long long), c->stream));
     }
     c->material.reserve(c->cell_count);
-    c->cells.reserve(c->nkeys);
+    c->cell_start.reserve((size_t)c->nkeys + 2);
+    c->counts.reserve((size_t)c->nkeys + 2);
+    c->keys_ready = false;
     c->has_domain = true;
     c->sorted = false;
     LAUNCH(c, gfs::k_border_solid, grid3(I, J, kl), 128, g, c->material.p);
@@ -579,7 +632,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_REQUIRE(n < 0x7FFFFFFFll, "particle count must fit int32");
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
-    c->n = n; c->cur = 0; c->sorted = false;
+    c->n = n; c->cur = 0; c->sorted = false; c->keys_ready = false;
     if (n > 0) {
         // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
         c->h_pos.reserve((size_t)n * 6);
@@ -646,7 +699,23 @@ void gfs_sort(gfs_context *c, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
     GFS_CUDA(cudaSetDevice(c->device));
-    do_sort(c);
+    do_sort(c, true);
+    GFS_END()
+}
+
+void gfs_sort_unstable(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_sort(c, false);
+    GFS_END()
+}
+
+void gfs_set_option(gfs_context *c, int option, int value, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    if (option == 0) { GFS_REQUIRE(value == 0 || value == 1, "p2g variant must be 0 or 1"); c->p2g_variant = value; }
+    else throw GfsError("gfs_set_option: unknown option");
     GFS_END()
 }
 
@@ -662,7 +731,7 @@ void gfs_g2p_advect(gfs_context *c, double dt, double ratio, int order, int inte
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
     GFS_CUDA(cudaSetDevice(c->device));
-    do_g2p(c, dt, ratio, order, interp, arith);
+    do_g2p(c, dt, ratio, order, interp, arith, false);
     GFS_END()
 }
 
@@ -670,9 +739,12 @@ void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp,
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
     GFS_CUDA(cudaSetDevice(c->device));
-    do_sort(c);
+    // exact arithmetic needs the stable order; fast arithmetic is order-independent and uses the counting sort,
+    // binned for the following substep by the G2P kernel's epilogue
+    if (c->keys_ready && arith == GFS_EXACT) c->keys_ready = false;
+    do_sort(c, arith == GFS_EXACT);
     do_p2g(c, arith);
-    do_g2p(c, dt, ratio, order, interp, arith);
+    do_g2p(c, dt, ratio, order, interp, arith, arith != GFS_EXACT);
     GFS_END()
 }
 
@@ -708,9 +780,11 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
         c->tag[b].release(); c->tag[b] = nt;
         c->tag[1 - b].release(); c->tag[1 - b].reserve(newcap);
         for (int q = 0; q < 2; q++) { c->keys[q].release(); c->keys[q].reserve(newcap); c->perm[q].release(); c->perm[q].reserve(newcap); }
+        c->rank.release(); c->rank.reserve(newcap);
     }
     c->n = n;
     c->sorted = false;
+    c->keys_ready = false;
     GFS_END()
 }
 

@@ -23,6 +23,10 @@ struct Grid {
     double dx, invdx;     // invdx = 1.0/dx as the reference computes it
     double xmax, ymax, zmax;   // dx*I, dx*J, dx*K (Grid3d::isPositionInGrid, grid3d.h:137-139)
     double halfdx;        // 0.5*dx
+    // fp32 mirrors, used by the fast path when dx is a power of two: then x*invdx, i*dx, x-i*dx, x-0.5dx and
+    // dx*I are all exact in fp32 for in-grid positions, so the fp32 index/fraction equal the reference's fp64 ones
+    float dxf, invdxf, halfdxf, xmaxf, ymaxf, zmaxf;
+    int pow2;             // dx is a power of two (and the extents are exactly representable in fp32)
 };
 
 struct FieldPtrs {        // one MAC field: u (I+1,J,kl), v (I,J+1,kl), w (I,J,kl+1), kl = k1-k0
@@ -121,13 +125,27 @@ __device__ __forceinline__ void cr_weights(float t, float w[4]) {
     w[3] = 0.5f * (t3 - t2);
 }
 
+struct AxisIdxF { int i; float t; };
+
+__device__ __forceinline__ AxisIdxF to_f(const AxisIdx &a) { AxisIdxF r; r.i = a.i; r.t = (float)a.t; return r; }
+
+// fp32 index + fraction; exact (== axis_index) when dx is a power of two, see Grid::pow2
+__device__ __forceinline__ AxisIdxF axis_index_f(float x, const Grid &g) {
+    AxisIdxF r;
+    float s = __fmul_rn(x, g.invdxf);
+    float fl = floorf(s);
+    r.i = (int)fl;
+    r.t = __fmul_rn(__fsub_rn(x, __fmul_rn(fl, g.dxf)), g.invdxf);
+    return r;
+}
+
 template <int COMP>
 __device__ __forceinline__ float sample_component_fast(const Grid &g, const float *__restrict__ a, int interp,
-                                                       const AxisIdx &ax, const AxisIdx &ay, const AxisIdx &az) {
+                                                       const AxisIdxF &ax, const AxisIdxF &ay, const AxisIdxF &az) {
     const int ni = g.I + (COMP == 0), nj = g.J + (COMP == 1);
     const int nkl = g.k1 - g.k0 + (COMP == 2);
     const int i = ax.i, j = ay.i, kl = az.i - g.k0;
-    const float tx = (float)ax.t, ty = (float)ay.t, tz = (float)az.t;
+    const float tx = ax.t, ty = ay.t, tz = az.t;
     if (interp == 1) {
         float wx[4], wy[4], wz[4];
         cr_weights(tx, wx); cr_weights(ty, wy); cr_weights(tz, wz);
@@ -200,10 +218,31 @@ __device__ __forceinline__ void evaluate(const Grid &g, const FieldPtrs &f, int 
         oy = sample_component_exact<1>(g, f.c[1], interp, sx, uy, sz);
         oz = sample_component_exact<2>(g, f.c[2], interp, sx, sy, uz);
     } else {
-        ox = sample_component_fast<0>(g, f.c[0], interp, ux, sy, sz);
-        oy = sample_component_fast<1>(g, f.c[1], interp, sx, uy, sz);
-        oz = sample_component_fast<2>(g, f.c[2], interp, sx, sy, uz);
+        AxisIdxF fux = to_f(ux), fuy = to_f(uy), fuz = to_f(uz), fsx = to_f(sx), fsy = to_f(sy), fsz = to_f(sz);
+        ox = sample_component_fast<0>(g, f.c[0], interp, fux, fsy, fsz);
+        oy = sample_component_fast<1>(g, f.c[1], interp, fsx, fuy, fsz);
+        oz = sample_component_fast<2>(g, f.c[2], interp, fsx, fsy, fuz);
     }
+}
+
+// Fast path with all index arithmetic in fp32 (valid when g.pow2): same results as evaluate<0>.
+__device__ __forceinline__ void evaluate_pow2(const Grid &g, const FieldPtrs &f, int interp, float px, float py, float pz,
+                                              float &ox, float &oy, float &oz) {
+    if (!(px >= 0.0f && py >= 0.0f && pz >= 0.0f && px < g.xmaxf && py < g.ymaxf && pz < g.zmaxf)) { ox = oy = oz = 0.0f; return; }
+    AxisIdxF ux = axis_index_f(px, g), uy = axis_index_f(py, g), uz = axis_index_f(pz, g);
+    AxisIdxF sx = axis_index_f(__fsub_rn(px, g.halfdxf), g), sy = axis_index_f(__fsub_rn(py, g.halfdxf), g),
+             sz = axis_index_f(__fsub_rn(pz, g.halfdxf), g);
+    ox = sample_component_fast<0>(g, f.c[0], interp, ux, sy, sz);
+    oy = sample_component_fast<1>(g, f.c[1], interp, sx, uy, sz);
+    oz = sample_component_fast<2>(g, f.c[2], interp, sx, sy, uz);
+}
+
+// mode dispatch: ARITH 1 = exact fp64, 0 = fast (fp64 index), 2 = fast with fp32 index (power-of-two dx)
+template <int ARITH>
+__device__ __forceinline__ void evaluate_any(const Grid &g, const FieldPtrs &f, int interp, float px, float py, float pz,
+                                             float &ox, float &oy, float &oz) {
+    if (ARITH == 2) evaluate_pow2(g, f, interp, px, py, pz, ox, oy, oz);
+    else evaluate<ARITH>(g, f, interp, px, py, pz, ox, oy, oz);
 }
 
 // ParticleAdvector::_validateOutput (particleadvector.cpp:1139-1149)
@@ -225,21 +264,21 @@ __device__ __forceinline__ void rk_advance(const Grid &g, const FieldPtrs &f, in
                                            float &ox, float &oy, float &oz) {
     if (order == 1) { ox = axpy(px, c.dt, k1x); oy = axpy(py, c.dt, k1y); oz = axpy(pz, c.dt, k1z); return; }
     float k2x, k2y, k2z;
-    evaluate<ARITH>(g, f, interp, axpy(px, c.half_dt, k1x), axpy(py, c.half_dt, k1y), axpy(pz, c.half_dt, k1z), k2x, k2y, k2z);
+    evaluate_any<ARITH>(g, f, interp, axpy(px, c.half_dt, k1x), axpy(py, c.half_dt, k1y), axpy(pz, c.half_dt, k1z), k2x, k2y, k2z);
     if (order == 2) { ox = axpy(px, c.dt, k2x); oy = axpy(py, c.dt, k2y); oz = axpy(pz, c.dt, k2z); return; }
     float k3x, k3y, k3z;
     if (order == 3) {
-        evaluate<ARITH>(g, f, interp, axpy(px, c.three_quarter_dt, k2x), axpy(py, c.three_quarter_dt, k2y),
-                        axpy(pz, c.three_quarter_dt, k2z), k3x, k3y, k3z);
+        evaluate_any<ARITH>(g, f, interp, axpy(px, c.three_quarter_dt, k2x), axpy(py, c.three_quarter_dt, k2y),
+                            axpy(pz, c.three_quarter_dt, k2z), k3x, k3y, k3z);
         float sx = __fadd_rn(__fadd_rn(__fmul_rn(k1x, 2.0f), __fmul_rn(k2x, 3.0f)), __fmul_rn(k3x, 4.0f));
         float sy = __fadd_rn(__fadd_rn(__fmul_rn(k1y, 2.0f), __fmul_rn(k2y, 3.0f)), __fmul_rn(k3y, 4.0f));
         float sz = __fadd_rn(__fadd_rn(__fmul_rn(k1z, 2.0f), __fmul_rn(k2z, 3.0f)), __fmul_rn(k3z, 4.0f));
         ox = axpy(px, c.dt_over_9, sx); oy = axpy(py, c.dt_over_9, sy); oz = axpy(pz, c.dt_over_9, sz);
         return;
     }
-    evaluate<ARITH>(g, f, interp, axpy(px, c.half_dt, k2x), axpy(py, c.half_dt, k2y), axpy(pz, c.half_dt, k2z), k3x, k3y, k3z);
+    evaluate_any<ARITH>(g, f, interp, axpy(px, c.half_dt, k2x), axpy(py, c.half_dt, k2y), axpy(pz, c.half_dt, k2z), k3x, k3y, k3z);
     float k4x, k4y, k4z;
-    evaluate<ARITH>(g, f, interp, axpy(px, c.dt, k3x), axpy(py, c.dt, k3y), axpy(pz, c.dt, k3z), k4x, k4y, k4z);
+    evaluate_any<ARITH>(g, f, interp, axpy(px, c.dt, k3x), axpy(py, c.dt, k3y), axpy(pz, c.dt, k3z), k4x, k4y, k4z);
     float sx = __fadd_rn(__fadd_rn(__fadd_rn(k1x, __fmul_rn(k2x, 2.0f)), __fmul_rn(k3x, 2.0f)), k4x);
     float sy = __fadd_rn(__fadd_rn(__fadd_rn(k1y, __fmul_rn(k2y, 2.0f)), __fmul_rn(k3y, 2.0f)), k4y);
     float sz = __fadd_rn(__fadd_rn(__fadd_rn(k1z, __fmul_rn(k2z, 2.0f)), __fmul_rn(k3z, 2.0f)), k4z);

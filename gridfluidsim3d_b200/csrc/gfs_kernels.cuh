@@ -1,6 +1,6 @@
 // gfs_kernels.cuh -- the sm_100a kernels of the particle<->grid transfer path (round-1 set).
 //
-//   K0  k_keys / cub radix sort / k_reorder / k_cell_start     cell binning (brick-major keys)
+//   K0  k_hist + exclusive scan + k_scatter_sorted (counting sort; stable variant: cub radix sort + k_reorder)
 //   K1  k_classify, k_p2g_scatter (fast, order-independent fixed point) or k_p2g_gather (exact,
 //       reference summation order), k_p2g_finalize, k_assemble   P2G + classification
 //   K2  k_g2p_advect                                            PIC/FLIP + RK1..4 + solid test
@@ -16,10 +16,16 @@ namespace gfs {
 // fixed point and added with integer atomics: integer addition is associative, so every node sum is
 // independent of particle order, brick decomposition and GPU count -- bit-reproducible without
 // ordering constraints and without float atomics.
-//   weight:  S_w = 2^48            (sum of weights < 2^14)
-//   num:     S_n = 2^(48 - vexp)   where 2^vexp >= max |velocity component|  (|sum| < 2^(14+vexp))
+//   weight:  S_w = 2^40            (sum of weights < 2^22)
+//   num:     S_n = 2^(40 - vexp)   where 2^vexp >= max |velocity component|  (|sum| < 2^(22+vexp))
+// One contribution is < 2^40 in magnitude, so it splits exactly into a signed high word (>> 20) and an
+// unsigned 20-bit low word; the brick-tile kernel accumulates the two words separately with native
+// 32-bit shared-memory atomics (exact for up to 2047 contributions per node per CTA) and the 64-bit
+// value is rebuilt as (sum_hi << 20) + sum_lo.  Global accumulators are plain 64-bit integer atomics.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWeightFracBits = 48;
+constexpr int kWeightFracBits = 40;
+constexpr float kWeightScaleF = 1099511627776.0f;       // 2^40
+constexpr double kWeightScaleD = 1099511627776.0;
 
 struct SplatParams {
     double radius, rsq;           // ScalarField::setPointRadius (scalarfield.cpp:40-46)
@@ -65,28 +71,65 @@ __device__ __forceinline__ float node_pos(int i, double dx) { return (float)__dm
 // ------------------------------------------------------------------------------------------------
 // K0: keys
 // ------------------------------------------------------------------------------------------------
-// One thread per particle.  key = brick-major id of the particle's cell, or the sentinel when the cell is
-// outside the grid / outside this slab's stored layers.  Also tracks max |velocity| (as float bits).
-__global__ void k_keys(Grid g, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
-                       const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
-                       int64_t n, uint32_t *__restrict__ keys, int32_t *__restrict__ perm,
-                       unsigned int *__restrict__ vmax_bits) {
+// block-wide max of a non-negative float into *vmax_bits (float bits order like unsigned ints)
+__device__ __forceinline__ void block_vmax(float m, unsigned int *__restrict__ vmax_bits) {
+    __shared__ float s_m[32];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x + 31) / 32 ? s_m[threadIdx.x] : 0.0f;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0 && m > __uint_as_float(*(volatile unsigned int *)vmax_bits)) atomicMax(vmax_bits, __float_as_uint(m));
+    }
+}
+
+// key of a position: brick-major id of its cell, or nkeys (the overflow bin, sorts last) when the cell is
+// outside the grid / outside this slab's stored layers.  fp64 index arithmetic: bit-exact.
+__device__ __forceinline__ uint32_t position_key(const Grid &g, uint32_t nkeys, float px, float py, float pz) {
+    int i = cell_floor((double)px, g.invdx), j = cell_floor((double)py, g.invdx), k = cell_floor((double)pz, g.invdx);
+    if (i >= 0 && j >= 0 && i < g.I && j < g.J && k >= g.k0 && k < g.k1 && k >= 0 && k < g.K) return brick_key(g, i, j, k - g.k0);
+    return nkeys;
+}
+
+// K0a.  One thread per particle: key, rank inside its cell (atomic ticket on the cell counter -- the count
+// is deterministic, the ticket order is not and does not need to be: the fast P2G is order-independent),
+// identity permutation for the stable path, and max |velocity|.
+__global__ void __launch_bounds__(256) k_hist(Grid g, uint32_t nkeys, const float *__restrict__ x, const float *__restrict__ y,
+                       const float *__restrict__ z, const float *__restrict__ vx, const float *__restrict__ vy,
+                       const float *__restrict__ vz, int64_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ rank,
+                       int32_t *__restrict__ perm, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (r < n) {
-        int i = cell_floor((double)x[r], g.invdx), j = cell_floor((double)y[r], g.invdx), k = cell_floor((double)z[r], g.invdx);
-        uint32_t key = kKeySentinel;
-        if (i >= 0 && j >= 0 && i < g.I && j < g.J && k >= g.k0 && k < g.k1 && k >= 0 && k < g.K) key = brick_key(g, i, j, k - g.k0);
+        uint32_t key = position_key(g, nkeys, x[r], y[r], z[r]);
         keys[r] = key;
+        rank[r] = atomicAdd(counts + key, 1u);
         perm[r] = (int32_t)r;
         m = fmaxf(fabsf(vx[r]), fmaxf(fabsf(vy[r]), fabsf(vz[r])));
         if (!(m < 3.0e38f)) m = 0.0f;          // NaN/Inf velocities do not steer the scale
     }
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(vmax_bits, __float_as_uint(m));
+    block_vmax(m, vmax_bits);
 }
 
-// sorted SoA <- unsorted SoA through the sorted permutation; also carries the original-index tag
+// K0c (counting sort).  sorted slot = cell_start[key] + rank.
+__global__ void __launch_bounds__(256) k_scatter_sorted(int64_t n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                 const int32_t *__restrict__ cell_start,
+                                 const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
+                                 const float *__restrict__ svx, const float *__restrict__ svy, const float *__restrict__ svz,
+                                 const int32_t *__restrict__ stag,
+                                 float *__restrict__ dx_, float *__restrict__ dy, float *__restrict__ dz,
+                                 float *__restrict__ dvx, float *__restrict__ dvy, float *__restrict__ dvz,
+                                 int32_t *__restrict__ dtag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t d = (int64_t)cell_start[keys[r]] + rank[r];
+    dx_[d] = sx[r]; dy[d] = sy[r]; dz[d] = sz[r];
+    dvx[d] = svx[r]; dvy[d] = svy[r]; dvz[d] = svz[r];
+    dtag[d] = stag[r];
+}
+
+// K0c (stable path).  sorted SoA <- unsorted SoA through the radix-sorted permutation
 __global__ void k_reorder(int64_t n, const int32_t *__restrict__ perm,
                           const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
                           const float *__restrict__ svx, const float *__restrict__ svy, const float *__restrict__ svz,
@@ -102,32 +145,17 @@ __global__ void k_reorder(int64_t n, const int32_t *__restrict__ perm,
     dtag[r] = stag[s];
 }
 
-// cells[key] = {first sorted slot, one past the last} for every occupied key (the table is zeroed first, so
-// empty cells read {0,0}); *n_valid = number of in-grid particles (first sentinel slot).  One thread per slot.
-__global__ void k_cell_ranges(int64_t n, const uint32_t *__restrict__ keys, int2 *__restrict__ cells, int32_t *__restrict__ n_valid) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    uint32_t k = keys[r];
-    uint32_t kp = r > 0 ? keys[r - 1] : kKeySentinel - 1;     // anything != k for r == 0 (k is never sentinel-1)
-    if (r == 0 || k != kp) {
-        if (k != kKeySentinel) cells[k].x = (int32_t)r; else *n_valid = (int32_t)r;
-        if (r > 0) cells[kp].y = (int32_t)r;
-    }
-    if (r == n - 1 && k != kKeySentinel) { cells[k].y = (int32_t)n; *n_valid = (int32_t)n; }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1a: classification  (FluidSimulation::_updateFluidCells marking loop, fluidsimulation.cpp:1998-2017)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_classify(Grid g, const int2 *__restrict__ cells, uint8_t *__restrict__ material,
+__global__ void k_classify(Grid g, const int32_t *__restrict__ cell_start, uint8_t *__restrict__ material,
                            unsigned long long *__restrict__ counters /* [0]=in_solid particles, [1]=fluid cells */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y, kl = blockIdx.z;
     if (i >= g.I) return;
     int k = kl + g.k0;
     uint32_t key = brick_key(g, i, j, kl);
-    int2 cr = cells[key];
-    int cnt = cr.y - cr.x;
+    int cnt = cell_start[key + 1] - cell_start[key];
     size_t idx = (size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl);
     uint8_t m = material[idx];
     bool interior = i >= 1 && i < g.I - 1 && j >= 1 && j < g.J - 1 && k >= 1 && k < g.K - 1;
@@ -149,10 +177,17 @@ __global__ void k_classify(Grid g, const int2 *__restrict__ cells, uint8_t *__re
 // to Grid3d::getGridIndexBounds; that only ever removes pairs at distance R +- 1 ulp whose weight is
 // ~1e-14 -- the exact-mode gather below applies the clip literally.)
 // ------------------------------------------------------------------------------------------------
+// tile: shared-memory accumulators of one brick (nullptr = accumulate straight into global memory).
+// Layout tile[word][node], word = 0 num_hi, 1 num_lo, 2 wt_hi, 3 wt_lo, node = li + 10*(lj + 10*lk) with
+// l = global node index - (tile origin ti,tj,tk).
+constexpr int kTileEdge = 10;
+constexpr int kTileNodes = kTileEdge * kTileEdge * kTileEdge;
+
 template <int ARITH>
 __device__ __forceinline__ void splat_component(const Grid &g, const SplatParams &sp, int comp, float px, float py, float pz,
                                                 float value, int ni, int nj, int nkl, int koff,
-                                                float off, float num_scale, unsigned long long *__restrict__ acc) {
+                                                float off, float num_scale, unsigned long long *__restrict__ acc,
+                                                uint32_t *tile = nullptr, int ti = 0, int tj = 0, int tk = 0) {
     // p -= offset (scalarfield.cpp:168); offset is (0,.5,.5)dx / (.5,0,.5)dx / (.5,.5,0)dx narrowed to float
     float q[3] = {comp == 0 ? px : __fsub_rn(px, off), comp == 1 ? py : __fsub_rn(py, off), comp == 2 ? pz : __fsub_rn(pz, off)};
     int   lo[3], hi[3], base[3];
@@ -186,17 +221,77 @@ __device__ __forceinline__ void splat_component(const Grid &g, const SplatParams
                     long long wn, ww;
                     if (ARITH == 1) {
                         double w = kernel_weight_exact(sp, (double)d2);
-                        ww = __double2ll_rn(w * 281474976710656.0);                               // 2^48
+                        ww = __double2ll_rn(w * kWeightScaleD);                               // 2^48
                         wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
                     } else {
                         float w = kernel_weight_fast(sp, d2);
-                        ww = __float2ll_rn(w * 281474976710656.0f);
+                        ww = __float2ll_rn(w * kWeightScaleF);
                         wn = __float2ll_rn((w * value) * num_scale);
                     }
-                    atomicAdd(acc + 2 * node, (unsigned long long)wn);
-                    atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+                    int li = bi + si - ti, lj = bj + sj - tj, lk = bk + sk - tk;
+                    if (tile && (unsigned)li < (unsigned)kTileEdge && (unsigned)lj < (unsigned)kTileEdge && (unsigned)lk < (unsigned)kTileEdge) {
+                        int t = li + kTileEdge * (lj + kTileEdge * lk);
+                        atomicAdd(tile + t, (uint32_t)(wn >> 20));
+                        atomicAdd(tile + kTileNodes + t, (uint32_t)wn & 0xFFFFFu);
+                        atomicAdd(tile + 2 * kTileNodes + t, (uint32_t)(ww >> 20));
+                        atomicAdd(tile + 3 * kTileNodes + t, (uint32_t)ww & 0xFFFFFu);
+                    } else {
+                        atomicAdd(acc + 2 * node, (unsigned long long)wn);
+                        atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+                    }
                 }
             }
+}
+
+// K1b (fast, brick tiles).  One CTA per brick of 8^3 cells: the brick's particles are one contiguous run of
+// the sorted arrays (coalesced loads, each particle read once); their contributions land in a 10^3-node
+// shared-memory tile per component through native 32-bit integer atomics (hi/lo words, see above); the tile is
+// then flushed to the global 64-bit accumulators with one integer atomic per touched value.  Because every
+// add is an integer add, the result is bit-identical to k_p2g_scatter's for any particle order.
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start,
+                              const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                              const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                              unsigned long long *__restrict__ accu, unsigned long long *__restrict__ accv,
+                              unsigned long long *__restrict__ accw) {
+    extern __shared__ uint32_t tile[];                    // [3 comps][4 words][1000 nodes] = 48 000 B
+    const uint32_t b = blockIdx.x;
+    const int start = cell_start[(size_t)b * kBrickCells], end = cell_start[(size_t)(b + 1) * kBrickCells];
+    if (start == end) return;
+    // a cell with more than 255 particles could overflow the 32-bit words (2047 contributions per node): such
+    // a brick accumulates straight into the 64-bit global accumulators instead
+    int dense = 0;
+    for (int c = threadIdx.x; c < kBrickCells; c += blockDim.x)
+        dense |= (cell_start[(size_t)b * kBrickCells + c + 1] - cell_start[(size_t)b * kBrickCells + c]) > 255;
+    for (int t = threadIdx.x; t < 12 * kTileNodes; t += blockDim.x) tile[t] = 0u;
+    dense = __syncthreads_or(dense);
+    const int bi = (int)(b % (uint32_t)g.nbi), bj = (int)((b / (uint32_t)g.nbi) % (uint32_t)g.nbj), bk = (int)(b / ((uint32_t)g.nbi * (uint32_t)g.nbj));
+    const int ti = bi * kBrick - 1, tj = bj * kBrick - 1, tk = bk * kBrick - 1 + g.k0;
+    const float off = (float)g.halfdx;
+    const int kl = g.k1 - g.k0;
+    const float ns = num_scale_f(num_exponent(sp));
+    uint32_t *t0 = dense ? nullptr : tile, *t1 = dense ? nullptr : tile + 4 * kTileNodes, *t2 = dense ? nullptr : tile + 8 * kTileNodes;
+    for (int r = start + threadIdx.x; r < end; r += blockDim.x) {
+        float px = x[r], py = y[r], pz = z[r];
+        splat_component<ARITH>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu, t0, ti, tj, tk);
+        splat_component<ARITH>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv, t1, ti, tj, tk);
+        splat_component<ARITH>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw, t2, ti, tj, tk);
+    }
+    if (dense) return;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * kTileNodes; t += blockDim.x) {
+        const int comp = t / kTileNodes, nloc = t - comp * kTileNodes;
+        const uint32_t *tw = tile + comp * 4 * kTileNodes + nloc;
+        long long wn = ((long long)(int32_t)tw[0] << 20) + (long long)tw[kTileNodes];
+        long long ww = ((long long)(int32_t)tw[2 * kTileNodes] << 20) + (long long)tw[3 * kTileNodes];
+        if (wn == 0 && ww == 0) continue;
+        const int li = nloc % kTileEdge, lj = (nloc / kTileEdge) % kTileEdge, lk = nloc / (kTileEdge * kTileEdge);
+        const int ni = g.I + (comp == 0), nj = g.J + (comp == 1);
+        const size_t node = (size_t)(ti + li) + (size_t)ni * ((size_t)(tj + lj) + (size_t)nj * (size_t)(tk + lk - g.k0));
+        unsigned long long *acc = comp == 0 ? accu : (comp == 1 ? accv : accw);
+        if (wn) atomicAdd(acc + 2 * node, (unsigned long long)wn);
+        if (ww) atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+    }
 }
 
 template <int ARITH>
@@ -238,7 +333,7 @@ __global__ void k_p2g_finalize(Grid g, int comp, SplatParams sp, Sources src, un
     size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
     long long n = (long long)acc[2 * node], w = (long long)acc[2 * node + 1];
     acc[2 * node] = 0ull; acc[2 * node + 1] = 0ull;
-    float wf = (float)((double)w * (1.0 / 281474976710656.0));
+    float wf = (float)((double)w * (1.0 / kWeightScaleD));
     float nf = (float)((double)n * inv_num_scale_d(num_exponent(sp)));
     float value = nf;
     if (wf > 0.0f) value = nf / wf;
@@ -273,7 +368,7 @@ __device__ __forceinline__ bool in_index_bounds(float q, int node, double radius
 }
 
 template <int ARITH>
-__global__ void k_p2g_gather(Grid g, int comp, SplatParams sp, Sources src, const int2 *__restrict__ cells,
+__global__ void k_p2g_gather(Grid g, int comp, SplatParams sp, Sources src, const int32_t *__restrict__ cell_start,
                              const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
                              const float *__restrict__ vel, float *__restrict__ val, uint8_t *__restrict__ setmask) {
     int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
@@ -291,8 +386,8 @@ __global__ void k_p2g_gather(Grid g, int comp, SplatParams sp, Sources src, cons
             if (cj < 0 || cj >= g.J) continue;
             for (int ci = i - 2; ci <= i + 2; ci++) {
                 if (ci < 0 || ci >= g.I) continue;
-                int2 cr = cells[brick_key(g, ci, cj, ck - g.k0)];
-                for (int r = cr.x; r < cr.y; r++) {
+                uint32_t key = brick_key(g, ci, cj, ck - g.k0);
+                for (int r = cell_start[key], e = cell_start[key + 1]; r < e; r++) {
                     float qx = comp == 0 ? x[r] : __fsub_rn(x[r], off);
                     float qy = comp == 1 ? y[r] : __fsub_rn(y[r], off);
                     float qz = comp == 2 ? z[r] : __fsub_rn(z[r], off);
@@ -383,34 +478,47 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
                              const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
                              float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
                              float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
-                             unsigned long long *__restrict__ counters /* [2] = solid hits */) {
+                             unsigned long long *__restrict__ counters /* [2] = solid hits */,
+                             uint32_t nkeys, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out,
+                             uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    float px = x[r], py = y[r], pz = z[r];
-    float k1x, k1y, k1z, sx, sy, sz;
-    evaluate<ARITH>(g, fnew, interp, px, py, pz, k1x, k1y, k1z);
-    evaluate<ARITH>(g, fsaved, interp, px, py, pz, sx, sy, sz);
-    float nx = k1x, ny = k1y, nz = k1z;
-    validate3(nx, ny, nz);
-    validate3(sx, sy, sz);
-    float ux = vx[r], uy = vy[r], uz = vz[r];
-    ovx[r] = __fadd_rn(__fmul_rn(nx, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(ux, nx), sx), ratio_flip));
-    ovy[r] = __fadd_rn(__fmul_rn(ny, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uy, ny), sy), ratio_flip));
-    ovz[r] = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
+    float m = 0.0f;
+    if (r < n) {
+        float px = x[r], py = y[r], pz = z[r];
+        float k1x, k1y, k1z, sx, sy, sz;
+        evaluate_any<ARITH>(g, fnew, interp, px, py, pz, k1x, k1y, k1z);
+        evaluate_any<ARITH>(g, fsaved, interp, px, py, pz, sx, sy, sz);
+        float nx = k1x, ny = k1y, nz = k1z;
+        validate3(nx, ny, nz);
+        validate3(sx, sy, sz);
+        float ux = vx[r], uy = vy[r], uz = vz[r];
+        float wx = __fadd_rn(__fmul_rn(nx, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(ux, nx), sx), ratio_flip));
+        float wy = __fadd_rn(__fmul_rn(ny, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uy, ny), sy), ratio_flip));
+        float wz = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
+        ovx[r] = wx; ovy[r] = wy; ovz[r] = wz;
 
-    float qx, qy, qz;
-    rk_advance<ARITH>(g, fnew, interp, order, rk, px, py, pz, k1x, k1y, k1z, qx, qy, qz);
-    if (material) {
-        int i = cell_floor((double)qx, g.invdx), j = cell_floor((double)qy, g.invdx), k = cell_floor((double)qz, g.invdx);
-        bool solid = true;                                   // NaN -> huge negative index -> out of range -> solid
-        if (i >= 0 && j >= 0 && k >= 0 && i < g.I && j < g.J && k < g.K) {
-            int kl = k - g.k0;
-            // a particle that leaves this slab's stored layers is not judged here: it migrates first
-            solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
+        float qx, qy, qz;
+        rk_advance<ARITH>(g, fnew, interp, order, rk, px, py, pz, k1x, k1y, k1z, qx, qy, qz);
+        if (material) {
+            int i = cell_floor((double)qx, g.invdx), j = cell_floor((double)qy, g.invdx), k = cell_floor((double)qz, g.invdx);
+            bool solid = true;                                   // NaN -> huge negative index -> out of range -> solid
+            if (i >= 0 && j >= 0 && k >= 0 && i < g.I && j < g.J && k < g.K) {
+                int kl = k - g.k0;
+                // a particle that leaves this slab's stored layers is not judged here: it migrates first
+                solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
+            }
+            if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
         }
-        if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
+        ox[r] = qx; oy[r] = qy; oz[r] = qz;
+        if (keys_out) {          // bin for the next substep's counting sort while the position is in registers
+            uint32_t key = position_key(g, nkeys, qx, qy, qz);
+            keys_out[r] = key;
+            rank_out[r] = atomicAdd(counts + key, 1u);
+            m = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
+            if (!(m < 3.0e38f)) m = 0.0f;
+        }
     }
-    ox[r] = qx; oy[r] = qy; oz[r] = qz;
+    if (keys_out) block_vmax(m, vmax_bits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,11 +582,11 @@ __global__ void k_splat_points(SplatParams sp, int vexp, double dx, float offx, 
                     long long wn, ww;
                     if (ARITH == 1) {
                         double w = kernel_weight_exact(sp, (double)d2);
-                        ww = __double2ll_rn(w * 281474976710656.0);
+                        ww = __double2ll_rn(w * kWeightScaleD);
                         wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
                     } else {
                         float w = kernel_weight_fast(sp, d2);
-                        ww = __float2ll_rn(w * 281474976710656.0f);
+                        ww = __float2ll_rn(w * kWeightScaleF);
                         wn = __float2ll_rn((w * value) * num_scale);
                     }
                     atomicAdd(acc + 2 * node, (unsigned long long)wn);
@@ -495,7 +603,7 @@ __global__ void k_splat_points_store(int64_t count, int vexp, const unsigned lon
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= count) return;
     float nf = (float)((double)(long long)acc[2 * n] * inv_num_scale_d(vexp));
-    float wf = (float)((double)(long long)acc[2 * n + 1] * (1.0 / 281474976710656.0));
+    float wf = (float)((double)(long long)acc[2 * n + 1] * (1.0 / kWeightScaleD));
     field[n] = accumulate ? __fadd_rn(field[n], nf) : nf;
     if (weight) weight[n] = accumulate ? __fadd_rn(weight[n], wf) : wf;
 }

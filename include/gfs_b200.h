@@ -151,8 +151,14 @@ void gfs_get_particle_order(gfs_context *ctx, int32_t *order, int *err);
 void gfs_set_field(gfs_context *ctx, int slot, const float *u, const float *v, const float *w, int *err);
 void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int *err);
 
-/* K0: bin particles by cell (brick-major key, stable radix sort) and build the cell table. */
+/* K0: bin particles by cell (brick-major key) and build the cell table.  gfs_sort is stable (radix sort: particles
+ * of one cell keep their relative order, which the exact-arithmetic P2G relies on); gfs_sort_unstable is the
+ * counting sort the fast substep uses (the order inside a cell is unspecified; nothing in fast mode depends on it). */
 void gfs_sort(gfs_context *ctx, int *err);
+void gfs_sort_unstable(gfs_context *ctx, int *err);
+/* Tuning switches.  option 0: fast-P2G variant, 1 = brick tiles in shared memory (default), 0 = global atomics
+ * only; both produce bit-identical grids. */
+void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
  * assembly (:2526-2730).  Result in slot GFS_FIELD_P2G; material updated.  Requires gfs_sort. */

@@ -224,6 +224,85 @@ def test_sort_is_exact_and_stable(ctx, oracle, name):
     assert ctx.stats()["out_of_grid"] == int((~inside).sum())
 
 
+@pytest.mark.parametrize("name", ["tiny16", "slab24"])
+def test_counting_sort(ctx, oracle, name):
+    """The fast substep's counting sort: a permutation, keys non-decreasing, same cell table as the stable sort."""
+    s = scene(name)
+    extra = probes(s["dims"], s["dx"], 300, 78)
+    pos = np.concatenate([s["pos"], extra]); vel = np.concatenate([s["vel"], np.ones_like(extra)])
+    load_domain(ctx, dict(s, pos=pos, vel=vel))
+    ctx.sort_unstable()
+    order = ctx.get_particle_order()
+    p, v = ctx.get_particles()
+    assert sorted(order.tolist()) == list(range(len(pos)))
+    assert np.array_equal(bits(p), bits(pos[order])) and np.array_equal(bits(v), bits(vel[order]))
+    ijk = oracle.cell_index(p, s["dx"]).astype(np.int64)
+    I, J, K = s["dims"]
+    inside = np.all((ijk >= 0) & (ijk < np.array(s["dims"])), 1)
+    nbi, nbj = (I + 1 + 7) // 8, (J + 1 + 7) // 8
+    b = ((ijk[:, 2] >> 3) * nbj + (ijk[:, 1] >> 3)) * nbi + (ijk[:, 0] >> 3)
+    key = np.where(inside, (b << 9) | ((ijk[:, 2] & 7) << 6) | ((ijk[:, 1] & 7) << 3) | (ijk[:, 0] & 7), 1 << 40)
+    assert (np.diff(key) >= 0).all()
+    assert ctx.stats()["out_of_grid"] == int((~inside).sum())
+
+
+def test_p2g_variants_bit_identical(ctx):
+    """Brick-tile P2G (shared-memory hi/lo integer words) == global-atomic P2G, bit for bit, after either sort."""
+    s = scene("small32")
+    out = []
+    for variant, stable in ((1, True), (0, True), (1, False), (0, False)):
+        load_domain(ctx, s, SOURCES)
+        ctx.set_option(0, variant)
+        ctx.sort() if stable else ctx.sort_unstable()
+        ctx.p2g(capi.FAST)
+        out.append(ctx.get_field(capi.FIELD_P2G))
+    ctx.set_option(0, 1)
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert np.array_equal(bits(a), bits(b))
+    assert np.count_nonzero(out[0][0]) > 1000
+
+
+def test_p2g_dense_cells(ctx, oracle):
+    """More than 255 particles in one cell: the tile kernel must take its 64-bit path for that brick and still
+    agree with the oracle (the reference caps at 100 per cell, src/fluidsimulation.cpp:3221-3243, so this is
+    beyond anything the simulator produces)."""
+    s = scene("tiny16")
+    rng = np.random.default_rng(11)
+    blob = (np.array([5.25, 5.25, 5.25]) + rng.uniform(-0.2, 0.2, size=(700, 3))).astype(np.float32)
+    pos = np.concatenate([s["pos"], blob]); vel = np.concatenate([s["vel"], rng.standard_normal((700, 3)).astype(np.float32)])
+    mat = s["material"].copy()
+    ref = oracle.p2g(pos, vel, s["dims"], s["dx"], mat)
+    load_domain(ctx, dict(s, pos=pos, vel=vel))
+    ctx.sort_unstable(); ctx.p2g(capi.FAST)
+    for a, b, nm in zip(ctx.get_field(capi.FIELD_P2G), ref, "uvw"):
+        assert_close(a, b, "dense p2g " + nm)
+
+
+def test_fast_substeps_track_oracle(ctx, oracle):
+    """Four chained fast substeps (counting sort binned by the previous G2P's epilogue, tile P2G, fp32-index
+    G2P): material bit-exact every step, fields / velocities / positions within tolerance of the oracle run
+    on the GPU's own previous state (so arithmetic differences do not accumulate into the comparison)."""
+    s = scene("small32")
+    load_domain(ctx, s)
+    ctx.set_field(capi.FIELD_NEW, *s["new"]); ctx.set_field(capi.FIELD_SAVED, *s["saved"])
+    mat = s["material"].copy()
+    pos, vel = s["pos"].copy(), s["vel"].copy()            # indexed by original particle id
+    for step in range(4):
+        u, v, w = oracle.p2g(pos, vel, s["dims"], s["dx"], mat)
+        p_ref, v_ref, _ = oracle.g2p_advect(pos, vel, s["new"], s["saved"], s["dims"], s["dx"], s["dt"], mode=0, material=mat)
+        ctx.substep(s["dt"], interp=capi.TRILINEAR, arith=capi.FAST)
+        assert np.array_equal(ctx.get_material(), mat)
+        for a, b, nm in zip(ctx.get_field(capi.FIELD_P2G), (u, v, w), "uvw"):
+            assert_close(a, b, "step %d p2g %s" % (step, nm))
+        o = ctx.get_particle_order()
+        p, vv = ctx.get_particles()
+        assert sorted(o.tolist()) == list(range(len(pos)))
+        assert_close(vv, v_ref[o], "step %d velocity" % step)
+        assert_close(p, p_ref[o], "step %d position" % step)
+        pos[o], vel[o] = p, vv                # continue the oracle from the GPU state
+
+
 @pytest.mark.parametrize("name,solids", [("tiny16", False), ("slab24", True), ("small32", False)])
 def test_p2g(ctx, oracle, name, solids):
     s = scene(name, solids)
