@@ -279,8 +279,8 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------------
 ALG_BYTES = {   # algorithmic bytes per launch of each hot kernel: (per particle, per cell)
-    "gfs::k_p2g_scatter<0>": (24, 13), "gfs::k_p2g_tile<0>": (24, 13),
-    "gfs::k_g2p_advect<0>": (48, 24), "gfs::k_g2p_advect<1>": (48, 24), "gfs::k_g2p_brick<0>": (48, 24),
+    "gfs::k_p2g_scatter<0>": (24, 13), "gfs::k_p2g_tile<0>": (24, 13), "gfs::k_p2g_scatter<2>": (24, 13), "gfs::k_p2g_tile<2>": (24, 13),
+    "gfs::k_g2p_advect<0>": (48, 24), "gfs::k_g2p_advect<1>": (48, 24), "gfs::k_g2p_advect<2>": (48, 24), "gfs::k_g2p_brick<0>": (48, 24), "gfs::k_g2p_brick<1>": (48, 24),
 }
 
 

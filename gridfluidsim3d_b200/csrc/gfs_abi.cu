@@ -129,6 +129,10 @@ struct gfs_context {
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
     int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
+    int g2p_variant = 1;                  // 1 = TMA-staged brick tiles (default where applicable), 0 = global loads only
+    gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
+    bool have_maps = false;
+    size_t field_floats[3] = {0, 0, 0};   // padded element counts of the resident u,v,w arrays
 
     // ---- scratch for host-pointer operators
     DevBuf<float> h_pos, h_out, h_val, h_fld, h_wgt, h_field[3];
@@ -149,7 +153,7 @@ namespace {
 
 using gfs::Grid;
 
-Grid make_grid(int I, int J, int K, double dx, int k0, int k1) {
+Grid make_grid(int I, int J, int K, double dx, int k0, int k1, bool padded = false) {
     Grid g;
     g.I = I; g.J = J; g.K = K; g.k0 = k0; g.k1 = k1;
     g.dx = dx; g.invdx = 1.0 / dx;
@@ -159,6 +163,8 @@ Grid make_grid(int I, int J, int K, double dx, int k0, int k1) {
     g.xmaxf = (float)g.xmax; g.ymaxf = (float)g.ymax; g.zmaxf = (float)g.zmax;
     int e = 0;
     g.pow2 = (std::frexp(dx, &e) == 0.5 && I < (1 << 20) && J < (1 << 20) && K < (1 << 20) && e > -100 && e < 100) ? 1 : 0;
+    const int ni[3] = {I + 1, I, I};
+    for (int a = 0; a < 3; a++) g.pitch[a] = padded ? (ni[a] + 3) / 4 * 4 : ni[a];
     g.nbi = (I + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbj = (J + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbk = (k1 - k0 + 1 + gfs::kBrick - 1) / gfs::kBrick;
@@ -172,6 +178,10 @@ gfs::SplatParams make_splat(double r, const unsigned int *vmax_bits) {
     sp.c2 = (17.0 / 9.0) * (1.0 / (r * r * r * r));
     sp.c3 = (22.0 / 9.0) * (1.0 / (r * r));
     sp.c1f = (float)sp.c1; sp.c2f = (float)sp.c2; sp.c3f = (float)sp.c3;
+    sp.inv_rsq = 1.0 / sp.rsq;
+    sp.inv_rsqf = (float)sp.inv_rsq;
+    sp.rsqf = (float)sp.rsq;                     // smallest float >= rsq: d2 < rsqf  <=>  (double)d2 < rsq
+    if ((double)sp.rsqf < sp.rsq) sp.rsqf = std::nextafterf(sp.rsqf, INFINITY);
     sp.vmax_bits = vmax_bits;
     return sp;
 }
@@ -281,24 +291,41 @@ void do_p2g(gfs_context *c, int arith) {
                    c->val[comp].p, c->setmask[comp].p);
     } else {
         if (c->n > 0) {
+            const bool pow2 = g.pow2 != 0;
             if (c->p2g_variant == 0) {
-                LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
-                       c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
-                       c->acc[0].p, c->acc[1].p, c->acc[2].p);
+                if (pow2)
+                    LAUNCH(c, gfs::k_p2g_scatter<2>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                           c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                           c->acc[0].p, c->acc[1].p, c->acc[2].p);
+                else
+                    LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                           c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                           c->acc[0].p, c->acc[1].p, c->acc[2].p);
             } else {
                 const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
-                int prof_id_ = c->prof_begin("gfs::k_p2g_tile<0>");
-                gfs::k_p2g_tile<0><<<nbricks, 256, 12 * gfs::kTileNodes * sizeof(uint32_t), c->stream>>>(
-                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
-                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
+                const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
+                int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
+                if (pow2)
+                    gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(
+                        g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                        c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
+                else
+                    gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(
+                        g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                        c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
                 c->prof_end(prof_id_);
                 c->launches++;
                 GFS_CUDA(cudaGetLastError());
             }
         }
-        for (int comp = 0; comp < 3; comp++)
-            LAUNCH(c, gfs::k_p2g_finalize, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, sp, c->sources,
-                   c->acc[comp].p, c->val[comp].p, c->setmask[comp].p);
+        gfs::FinalizeArgs fa;
+        long long total = 0;
+        for (int comp = 0; comp < 3; comp++) {
+            fa.acc[comp] = c->acc[comp].p; fa.val[comp] = c->val[comp].p; fa.setmask[comp] = c->setmask[comp].p;
+            fa.count[comp] = (long long)c->face_count[comp];
+            total += fa.count[comp];
+        }
+        LAUNCH(c, gfs::k_p2g_finalize, ceil_div(total, 256), 256, g, sp, c->sources, fa);
     }
     for (int comp = 0; comp < 3; comp++)
         LAUNCH(c, gfs::k_assemble, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, c->material.p,
@@ -325,7 +352,25 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
                c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
-    if (arith == GFS_EXACT) LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
+    const bool brick = arith != GFS_EXACT && c->grid.pow2 && c->sorted && c->have_maps && c->g2p_variant == 1;
+    if (brick) {
+        const int nb = (int)(c->nkeys / gfs::kBrickCells) + 1;          // + the overflow-bin CTA
+#define GFS_BRICK_ARGS c->grid, c->maps[interp], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, c->cell_start.p, \
+               order, rk, rp, rf, c->n,                                                                                                  \
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
+        int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
+        if (interp == GFS_TRICUBIC)
+            gfs::k_g2p_brick<1><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        else
+            gfs::k_g2p_brick<0><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        c->prof_end(prof_id_);
+        c->launches++;
+        GFS_CUDA(cudaGetLastError());
+#undef GFS_BRICK_ARGS
+    }
+    else if (arith == GFS_EXACT) LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
     else if (c->grid.pow2) LAUNCH(c, gfs::k_g2p_advect<2>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
     else LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
 #undef GFS_G2P_ARGS
@@ -351,6 +396,56 @@ gfs::FieldPtrs upload_field(gfs_context *c, const float *u, const float *v, cons
 }
 
 }  // namespace
+
+// ---- TMA tensor maps over the resident (row-padded) field arrays ----------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    GFS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    GFS_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+void make_field_map(CUtensorMap *map, float *base, int ni, int pitch, int nj, int nkl, int bx, int by, int bz) {
+    cuuint64_t dims[3] = {(cuuint64_t)ni, (cuuint64_t)nj, (cuuint64_t)nkl};        // x beyond ni is out of bounds -> 0
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * (cuuint64_t)nj * 4};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d, pitch %d)", (int)r, ni, nj, nkl, pitch);
+        throw GfsError(b);
+    }
+}
+
+void make_brick_maps(gfs_context *c) {
+    const Grid &g = c->grid;
+    const int kl = g.k1 - g.k0;
+    const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
+    for (int a = 0; a < 3; a++) {
+        make_field_map(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
+                       gfs::BrickTile<0>::nX, gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nY);
+        make_field_map(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
+                       gfs::BrickTile<0>::sX, gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sY);
+        make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
+                       gfs::BrickTile<1>::nX, gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nY);
+        make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
+                       gfs::BrickTile<1>::sX, gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sY);
+    }
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
+    c->have_maps = true;
+}
 
 #define GFS_BEGIN                                                                                  \
     if (err) *err = GFS_SUCCESS;                                                                   \
@@ -568,9 +663,12 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     GFS_REQUIRE(c, "null context");
     GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
     GFS_CUDA(cudaSetDevice(c->device));
-    c->grid = make_grid(I, J, K, dx, 0, K);
+    c->grid = make_grid(I, J, K, dx, 0, K, true);
     const Grid &g = c->grid;
     const int kl = g.k1 - g.k0;
+    c->field_floats[0] = (size_t)g.pitch[0] * J * kl;
+    c->field_floats[1] = (size_t)g.pitch[1] * (J + 1) * kl;
+    c->field_floats[2] = (size_t)g.pitch[2] * J * (kl + 1);
     GFS_REQUIRE((uint64_t)g.nbi * g.nbj * g.nbk * gfs::kBrickCells < 0x7FFFFFFFull, "grid too large for 31-bit cell keys");
     c->nkeys = (uint32_t)((uint64_t)g.nbi * g.nbj * g.nbk * gfs::kBrickCells);
     c->face_count[0] = (size_t)(I + 1) * J * kl;
@@ -579,8 +677,8 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->cell_count = (size_t)I * J * kl;
     for (int s = 0; s < 3; s++)
         for (int a = 0; a < 3; a++) {
-            c->field[s][a].reserve(c->face_count[a]);
-            GFS_CUDA(cudaMemsetAsync(c->field[s][a].p, 0, c->face_count[a] * sizeof(float), c->stream));
+            c->field[s][a].reserve(c->field_floats[a]);
+            GFS_CUDA(cudaMemsetAsync(c->field[s][a].p, 0, c->field_floats[a] * sizeof(float), c->stream));
         }
     for (int a = 0; a < 3; a++) {
         c->val[a].reserve(c->face_count[a]);
@@ -594,6 +692,8 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->keys_ready = false;
     c->has_domain = true;
     c->sorted = false;
+    c->have_maps = false;
+    if (g.pow2) make_brick_maps(c);
     LAUNCH(c, gfs::k_border_solid, grid3(I, J, kl), 128, g, c->material.p);
     GFS_END()
 }
@@ -678,8 +778,10 @@ void gfs_set_field(gfs_context *c, int slot, const float *u, const float *v, con
     require_domain(c);
     GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
     const float *h[3] = {u, v, w};
-    for (int a = 0; a < 3; a++)
-        GFS_CUDA(cudaMemcpyAsync(c->field[slot][a].p, h[a], c->face_count[a] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const int ni[3] = {c->grid.I + 1, c->grid.I, c->grid.I};
+    for (int a = 0; a < 3; a++)        // reference rows (ni floats) -> resident rows (pitch floats)
+        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p, (size_t)c->grid.pitch[a] * 4, h[a], (size_t)ni[a] * 4, (size_t)ni[a] * 4,
+                                   c->face_count[a] / (size_t)ni[a], cudaMemcpyHostToDevice, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
@@ -689,8 +791,10 @@ void gfs_get_field(gfs_context *c, int slot, float *u, float *v, float *w, int *
     require_domain(c);
     GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
     float *h[3] = {u, v, w};
+    const int ni[3] = {c->grid.I + 1, c->grid.I, c->grid.I};
     for (int a = 0; a < 3; a++)
-        GFS_CUDA(cudaMemcpyAsync(h[a], c->field[slot][a].p, c->face_count[a] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        GFS_CUDA(cudaMemcpy2DAsync(h[a], (size_t)ni[a] * 4, c->field[slot][a].p, (size_t)c->grid.pitch[a] * 4, (size_t)ni[a] * 4,
+                                   c->face_count[a] / (size_t)ni[a], cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
@@ -715,6 +819,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
     if (option == 0) { GFS_REQUIRE(value == 0 || value == 1, "p2g variant must be 0 or 1"); c->p2g_variant = value; }
+    else if (option == 1) { GFS_REQUIRE(value == 0 || value == 1, "g2p variant must be 0 or 1"); c->g2p_variant = value; }
     else throw GfsError("gfs_set_option: unknown option");
     GFS_END()
 }

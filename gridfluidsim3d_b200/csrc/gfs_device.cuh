@@ -27,6 +27,8 @@ struct Grid {
     // dx*I are all exact in fp32 for in-grid positions, so the fp32 index/fraction equal the reference's fp64 ones
     float dxf, invdxf, halfdxf, xmaxf, ymaxf, zmaxf;
     int pow2;             // dx is a power of two (and the extents are exactly representable in fp32)
+    int pitch[3];         // row pitch (floats) of the u, v, w arrays: >= I+1, I, I; resident fields pad it to a
+                          // multiple of 4 so that TMA global strides are multiples of 16 bytes
 };
 
 struct FieldPtrs {        // one MAC field: u (I+1,J,kl), v (I,J+1,kl), w (I,J,kl+1), kl = k1-k0
@@ -49,7 +51,7 @@ __device__ __forceinline__ float tap(const Grid &g, const float *__restrict__ a,
     int ni = g.I + (comp == 0), nj = g.J + (comp == 1);
     int kl = k - g.k0, nkl = g.k1 - g.k0 + (comp == 2);
     if ((unsigned)i >= (unsigned)ni || (unsigned)j >= (unsigned)nj || (unsigned)kl >= (unsigned)nkl) return 0.0f;
-    return __ldg(a + ((size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl)));
+    return __ldg(a + ((size_t)i + (size_t)g.pitch[comp] * ((size_t)j + (size_t)nj * (size_t)kl)));
 }
 
 struct AxisIdx { int i; double t; };
@@ -146,18 +148,19 @@ __device__ __forceinline__ float sample_component_fast(const Grid &g, const floa
     const int nkl = g.k1 - g.k0 + (COMP == 2);
     const int i = ax.i, j = ay.i, kl = az.i - g.k0;
     const float tx = ax.t, ty = ay.t, tz = az.t;
+    const size_t pitch = (size_t)g.pitch[COMP];
     if (interp == 1) {
         float wx[4], wy[4], wz[4];
         cr_weights(tx, wx); cr_weights(ty, wy); cr_weights(tz, wz);
         float acc = 0.0f;
         if (i >= 1 && i + 2 < ni && j >= 1 && j + 2 < nj && kl >= 1 && kl + 2 < nkl) {   // interior: no range checks
-            const float *base = a + ((size_t)(i - 1) + (size_t)ni * ((size_t)(j - 1) + (size_t)nj * (size_t)(kl - 1)));
+            const float *base = a + ((size_t)(i - 1) + pitch * ((size_t)(j - 1) + (size_t)nj * (size_t)(kl - 1)));
 #pragma unroll
             for (int pk = 0; pk < 4; pk++) {
                 float sk = 0.0f;
 #pragma unroll
                 for (int pj = 0; pj < 4; pj++) {
-                    const float *r = base + (size_t)ni * ((size_t)pj + (size_t)nj * (size_t)pk);
+                    const float *r = base + pitch * ((size_t)pj + (size_t)nj * (size_t)pk);
                     float sj = wx[0] * __ldg(r);
                     sj = fmaf(wx[1], __ldg(r + 1), sj);
                     sj = fmaf(wx[2], __ldg(r + 2), sj);
@@ -185,8 +188,8 @@ __device__ __forceinline__ float sample_component_fast(const Grid &g, const floa
     }
     float p000, p100, p010, p001, p101, p011, p110, p111;
     if (i >= 0 && i + 1 < ni && j >= 0 && j + 1 < nj && kl >= 0 && kl + 1 < nkl) {
-        const float *r = a + ((size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl));
-        const size_t sj = (size_t)ni, sk = (size_t)ni * (size_t)nj;
+        const float *r = a + ((size_t)i + pitch * ((size_t)j + (size_t)nj * (size_t)kl));
+        const size_t sj = pitch, sk = pitch * (size_t)nj;
         p000 = __ldg(r);           p100 = __ldg(r + 1);
         p010 = __ldg(r + sj);      p110 = __ldg(r + sj + 1);
         p001 = __ldg(r + sk);      p101 = __ldg(r + sk + 1);

@@ -6,6 +6,7 @@
 //   K2  k_g2p_advect                                            PIC/FLIP + RK1..4 + solid test
 //   plus the host-pointer operators k_sample / k_advect / k_splat_points
 #pragma once
+#include <cuda.h>
 #include "gfs_device.cuh"
 #include "../../include/gfs_b200.h"
 
@@ -16,21 +17,28 @@ namespace gfs {
 // fixed point and added with integer atomics: integer addition is associative, so every node sum is
 // independent of particle order, brick decomposition and GPU count -- bit-reproducible without
 // ordering constraints and without float atomics.
-//   weight:  S_w = 2^40            (sum of weights < 2^22)
-//   num:     S_n = 2^(40 - vexp)   where 2^vexp >= max |velocity component|  (|sum| < 2^(22+vexp))
-// One contribution is < 2^40 in magnitude, so it splits exactly into a signed high word (>> 20) and an
-// unsigned 20-bit low word; the brick-tile kernel accumulates the two words separately with native
-// 32-bit shared-memory atomics (exact for up to 2047 contributions per node per CTA) and the 64-bit
-// value is rebuilt as (sum_hi << 20) + sum_lo.  Global accumulators are plain 64-bit integer atomics.
+//   weight:  S_w = 2^44            (sum of weights < 2^18)
+//   num:     S_n = 2^(44 - vexp)   where 2^vexp >= max |velocity component|  (|sum| < 2^(18+vexp))
+// One contribution is < 2^44 in magnitude, so it splits exactly into a signed high word (>> 22) and an
+// unsigned 22-bit low word; the brick-tile kernel accumulates the two words separately with native
+// 32-bit shared-memory atomics (exact for up to 511 contributions per node per CTA, guaranteed by sending
+// bricks that hold a cell with more than 63 particles down the 64-bit path) and the 64-bit value is
+// rebuilt as (sum_hi << 22) + sum_lo.  Global accumulators are plain 64-bit integer atomics.
+// Resolution 2^-44 = 5.7e-14: a node whose total weight is 1e-8 still carries 5.7e-6 relative precision
+// (fp32 accumulation, which the reference uses, carries 6e-8 relative but depends on particle order).
 // ------------------------------------------------------------------------------------------------
-constexpr int kWeightFracBits = 40;
-constexpr float kWeightScaleF = 1099511627776.0f;       // 2^40
-constexpr double kWeightScaleD = 1099511627776.0;
+constexpr int kWeightFracBits = 44;
+constexpr int kLoBits = 22;
+constexpr float kWeightScaleF = 17592186044416.0f;       // 2^44
+constexpr double kWeightScaleD = 17592186044416.0;
 
 struct SplatParams {
     double radius, rsq;           // ScalarField::setPointRadius (scalarfield.cpp:40-46)
     double c1, c2, c3;            // (4/9)/r^6, (17/9)/r^4, (22/9)/r^2
     float  c1f, c2f, c3f;
+    float  rsqf;                  // float r such that (d2 < rsqf) == ((double)d2 < rsq) for every float d2
+    float  inv_rsqf;              // 1/R^2 (exact when R is a power of two)
+    double inv_rsq;
     const unsigned int *vmax_bits;   // device word: float bits of max |velocity component| (k_keys / caller)
 };
 
@@ -61,8 +69,15 @@ __device__ __forceinline__ double kernel_weight_exact(const SplatParams &sp, dou
     double c = __dmul_rn(sp.c3, d);
     return __dsub_rn(__dadd_rn(__dsub_rn(1.0, a), b), c);
 }
+// Same polynomial with u = 1 - d^2/R^2:  1 - (4/9)s^3 + (17/9)s^2 - (22/9)s  ==  u^2 (5/9 + (4/9) u).  The
+// reference's form cancels three O(1) terms down to ~0 near the rim of the support (harmless in its fp64, a
+// 3e-7 ABSOLUTE error in fp32, i.e. tens of percent of a rim weight); this form has no cancellation, so the
+// fp32 weight is relatively accurate everywhere.  R^2 - d^2 is formed in fp64 unless R^2 is exact in fp32.
+template <bool POW2>
 __device__ __forceinline__ float kernel_weight_fast(const SplatParams &sp, float d) {
-    return fmaf(d, fmaf(d, fmaf(d, -sp.c1f, sp.c2f), -sp.c3f), 1.0f);
+    float u = POW2 ? __fmul_rn(__fsub_rn(sp.rsqf, d), sp.inv_rsqf)
+                   : (float)__dmul_rn(__dsub_rn(sp.rsq, (double)d), sp.inv_rsq);
+    return __fmul_rn(__fmul_rn(u, u), fmaf(u, 0.44444444444444444f, 0.55555555555555556f));
 }
 
 // node coordinate (float)((float)i*dx)  (Grid3d::GridIndexToPosition(int,int,int,dx), grid3d.h:73-75)
@@ -224,23 +239,87 @@ __device__ __forceinline__ void splat_component(const Grid &g, const SplatParams
                         ww = __double2ll_rn(w * kWeightScaleD);                               // 2^48
                         wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
                     } else {
-                        float w = kernel_weight_fast(sp, d2);
+                        float w = kernel_weight_fast<false>(sp, d2);
                         ww = __float2ll_rn(w * kWeightScaleF);
                         wn = __float2ll_rn((w * value) * num_scale);
                     }
                     int li = bi + si - ti, lj = bj + sj - tj, lk = bk + sk - tk;
                     if (tile && (unsigned)li < (unsigned)kTileEdge && (unsigned)lj < (unsigned)kTileEdge && (unsigned)lk < (unsigned)kTileEdge) {
                         int t = li + kTileEdge * (lj + kTileEdge * lk);
-                        atomicAdd(tile + t, (uint32_t)(wn >> 20));
-                        atomicAdd(tile + kTileNodes + t, (uint32_t)wn & 0xFFFFFu);
-                        atomicAdd(tile + 2 * kTileNodes + t, (uint32_t)(ww >> 20));
-                        atomicAdd(tile + 3 * kTileNodes + t, (uint32_t)ww & 0xFFFFFu);
+                        atomicAdd(tile + t, (uint32_t)(wn >> kLoBits));
+                        atomicAdd(tile + kTileNodes + t, (uint32_t)wn & ((1u << kLoBits) - 1u));
+                        atomicAdd(tile + 2 * kTileNodes + t, (uint32_t)(ww >> kLoBits));
+                        atomicAdd(tile + 3 * kTileNodes + t, (uint32_t)ww & ((1u << kLoBits) - 1u));
                     } else {
                         atomicAdd(acc + 2 * node, (unsigned long long)wn);
                         atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
                     }
                 }
             }
+}
+
+// ---- power-of-two dx: all index arithmetic in fp32, exactly --------------------------------------------
+// For dx = 2^-k the offset-space coordinate q, its cell c = floor(q/dx), t = q - c*dx and dx - t are all exact
+// in fp32, node positions (float)(i*dx) are exact, and the only nodes that can pass d^2 < R^2 = dx^2 are c and
+// c+1 on every axis: 8 candidates per component instead of the reference's 27, same hits.
+struct AxisCand { int c; float e0, e1; };      // base node, squared 1-D distances to nodes c and c+1 (+inf: no such node)
+
+__device__ __forceinline__ AxisCand axis_cand(float q, const Grid &g, int nmin, int nmax) {
+    AxisCand r;
+    float fl = floorf(__fmul_rn(q, g.invdxf));
+    r.c = (int)fl;
+    float t = __fmaf_rn(-fl, g.dxf, q);          // q - c*dx, exact
+    float u = __fsub_rn(g.dxf, t);               // (c+1)*dx - q, exact
+    r.e0 = (r.c >= nmin && r.c <= nmax) ? __fmul_rn(t, t) : __int_as_float(0x7f800000);
+    r.e1 = (r.c + 1 >= nmin && r.c + 1 <= nmax) ? __fmul_rn(u, u) : __int_as_float(0x7f800000);
+    return r;
+}
+
+template <bool TILE>
+__device__ __forceinline__ void splat_comp_pow2(const SplatParams &sp, const AxisCand &X, const AxisCand &Y, const AxisCand &Z,
+                                                float value, float num_scale, int ni, int nj, int koff,
+                                                unsigned long long *__restrict__ acc, uint32_t *tile, int ti, int tj, int tk) {
+    const int tbase = (X.c - ti) + kTileEdge * ((Y.c - tj) + kTileEdge * (Z.c - tk));
+    const long long nbase = (long long)X.c + (long long)ni * ((long long)Y.c + (long long)nj * (long long)(Z.c - koff));   // only used for valid nodes
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                float d2 = __fadd_rn(__fadd_rn(a ? X.e1 : X.e0, b ? Y.e1 : Y.e0), c ? Z.e1 : Z.e0);
+                if (d2 < sp.rsqf) {
+                    float w = kernel_weight_fast<true>(sp, d2);
+                    long long ww = __float2ll_rn(w * kWeightScaleF);
+                    long long wn = __float2ll_rn((w * value) * num_scale);
+                    if (TILE) {
+                        int t = tbase + a + kTileEdge * (b + kTileEdge * c);
+                        atomicAdd(tile + t, (uint32_t)(wn >> kLoBits));
+                        atomicAdd(tile + kTileNodes + t, (uint32_t)wn & ((1u << kLoBits) - 1u));
+                        atomicAdd(tile + 2 * kTileNodes + t, (uint32_t)(ww >> kLoBits));
+                        atomicAdd(tile + 3 * kTileNodes + t, (uint32_t)ww & ((1u << kLoBits) - 1u));
+                    } else {
+                        long long node = nbase + a + (long long)ni * (b + (long long)nj * c);
+                        atomicAdd(acc + 2 * node, (unsigned long long)wn);
+                        atomicAdd(acc + 2 * node + 1, (unsigned long long)ww);
+                    }
+                }
+            }
+}
+
+template <bool TILE>
+__device__ __forceinline__ void splat_pow2(const Grid &g, const SplatParams &sp, float ns, float px, float py, float pz,
+                                           float vx, float vy, float vz, uint32_t *tile, int ti, int tj, int tk,
+                                           unsigned long long *__restrict__ accu, unsigned long long *__restrict__ accv,
+                                           unsigned long long *__restrict__ accw) {
+    const int kl = g.k1 - g.k0;
+    // the staggered axis of each component is unshifted (offset 0), the other two are shifted by 0.5dx
+    const AxisCand ux = axis_cand(px, g, 0, g.I), uy = axis_cand(py, g, 0, g.J), uz = axis_cand(pz, g, g.k0, g.k0 + kl);
+    const AxisCand sx = axis_cand(__fsub_rn(px, g.halfdxf), g, 0, g.I - 1), sy = axis_cand(__fsub_rn(py, g.halfdxf), g, 0, g.J - 1),
+                   sz = axis_cand(__fsub_rn(pz, g.halfdxf), g, g.k0, g.k0 + kl - 1);
+    splat_comp_pow2<TILE>(sp, ux, sy, sz, vx, ns, g.I + 1, g.J, g.k0, accu, tile, ti, tj, tk);
+    splat_comp_pow2<TILE>(sp, sx, uy, sz, vy, ns, g.I, g.J + 1, g.k0, accv, tile + 4 * kTileNodes, ti, tj, tk);
+    splat_comp_pow2<TILE>(sp, sx, sy, uz, vz, ns, g.I, g.J, g.k0, accw, tile + 8 * kTileNodes, ti, tj, tk);
 }
 
 // K1b (fast, brick tiles).  One CTA per brick of 8^3 cells: the brick's particles are one contiguous run of
@@ -258,11 +337,11 @@ __global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const 
     const uint32_t b = blockIdx.x;
     const int start = cell_start[(size_t)b * kBrickCells], end = cell_start[(size_t)(b + 1) * kBrickCells];
     if (start == end) return;
-    // a cell with more than 255 particles could overflow the 32-bit words (2047 contributions per node): such
+    // a cell with more than 63 particles could overflow the 32-bit words (511 contributions per node): such
     // a brick accumulates straight into the 64-bit global accumulators instead
     int dense = 0;
     for (int c = threadIdx.x; c < kBrickCells; c += blockDim.x)
-        dense |= (cell_start[(size_t)b * kBrickCells + c + 1] - cell_start[(size_t)b * kBrickCells + c]) > 255;
+        dense |= (cell_start[(size_t)b * kBrickCells + c + 1] - cell_start[(size_t)b * kBrickCells + c]) > 63;
     for (int t = threadIdx.x; t < 12 * kTileNodes; t += blockDim.x) tile[t] = 0u;
     dense = __syncthreads_or(dense);
     const int bi = (int)(b % (uint32_t)g.nbi), bj = (int)((b / (uint32_t)g.nbi) % (uint32_t)g.nbj), bk = (int)(b / ((uint32_t)g.nbi * (uint32_t)g.nbj));
@@ -271,19 +350,26 @@ __global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const 
     const int kl = g.k1 - g.k0;
     const float ns = num_scale_f(num_exponent(sp));
     uint32_t *t0 = dense ? nullptr : tile, *t1 = dense ? nullptr : tile + 4 * kTileNodes, *t2 = dense ? nullptr : tile + 8 * kTileNodes;
-    for (int r = start + threadIdx.x; r < end; r += blockDim.x) {
-        float px = x[r], py = y[r], pz = z[r];
-        splat_component<ARITH>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu, t0, ti, tj, tk);
-        splat_component<ARITH>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv, t1, ti, tj, tk);
-        splat_component<ARITH>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw, t2, ti, tj, tk);
+    if (ARITH == 2) {
+        if (dense) for (int r = start + threadIdx.x; r < end; r += blockDim.x)
+            splat_pow2<false>(g, sp, ns, x[r], y[r], z[r], vx[r], vy[r], vz[r], tile, ti, tj, tk, accu, accv, accw);
+        else for (int r = start + threadIdx.x; r < end; r += blockDim.x)
+            splat_pow2<true>(g, sp, ns, x[r], y[r], z[r], vx[r], vy[r], vz[r], tile, ti, tj, tk, accu, accv, accw);
+    } else {
+        for (int r = start + threadIdx.x; r < end; r += blockDim.x) {
+            float px = x[r], py = y[r], pz = z[r];
+            splat_component<0>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu, t0, ti, tj, tk);
+            splat_component<0>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv, t1, ti, tj, tk);
+            splat_component<0>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw, t2, ti, tj, tk);
+        }
     }
     if (dense) return;
     __syncthreads();
     for (int t = threadIdx.x; t < 3 * kTileNodes; t += blockDim.x) {
         const int comp = t / kTileNodes, nloc = t - comp * kTileNodes;
         const uint32_t *tw = tile + comp * 4 * kTileNodes + nloc;
-        long long wn = ((long long)(int32_t)tw[0] << 20) + (long long)tw[kTileNodes];
-        long long ww = ((long long)(int32_t)tw[2 * kTileNodes] << 20) + (long long)tw[3 * kTileNodes];
+        long long wn = ((long long)(int32_t)tw[0] << kLoBits) + (long long)tw[kTileNodes];
+        long long ww = ((long long)(int32_t)tw[2 * kTileNodes] << kLoBits) + (long long)tw[3 * kTileNodes];
         if (wn == 0 && ww == 0) continue;
         const int li = nloc % kTileEdge, lj = (nloc / kTileEdge) % kTileEdge, lk = nloc / (kTileEdge * kTileEdge);
         const int ni = g.I + (comp == 0), nj = g.J + (comp == 1);
@@ -306,9 +392,10 @@ __global__ void __launch_bounds__(256) k_p2g_scatter(Grid g, SplatParams sp, con
     float off = (float)g.halfdx;
     int kl = g.k1 - g.k0;
     float ns = num_scale_f(num_exponent(sp));
-    splat_component<ARITH>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu);
-    splat_component<ARITH>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv);
-    splat_component<ARITH>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw);
+    if (ARITH == 2) { splat_pow2<false>(g, sp, ns, px, py, pz, vx[r], vy[r], vz[r], nullptr, 0, 0, 0, accu, accv, accw); return; }
+    splat_component<0>(g, sp, 0, px, py, pz, vx[r], g.I + 1, g.J, kl, g.k0, off, ns, accu);
+    splat_component<0>(g, sp, 1, px, py, pz, vy[r], g.I, g.J + 1, kl, g.k0, off, ns, accv);
+    splat_component<0>(g, sp, 2, px, py, pz, vz[r], g.I, g.J, kl + 1, g.k0, off, ns, accw);
 }
 
 // source->containsPoint(face position)  (fluidsimulation.cpp:2489-2524)
@@ -324,31 +411,40 @@ __device__ __forceinline__ bool source_contains(const gfs_source_t &s, float fx,
 
 // normalise (ScalarField::applyWeightField, scalarfield.cpp:90-106), isValueSet = weight > 1e-9 and the
 // inflow override on set faces (fluidsimulation.cpp:2571-2594).  val holds the node grid "ugrid",
-// setmask its isValueSet.  Also clears the accumulators for the next substep.
-__global__ void k_p2g_finalize(Grid g, int comp, SplatParams sp, Sources src, unsigned long long *__restrict__ acc,
-                               float *__restrict__ val, uint8_t *__restrict__ setmask) {
-    int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
-    if (i >= ni || j >= nj || kl >= nkl) return;
-    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
-    long long n = (long long)acc[2 * node], w = (long long)acc[2 * node + 1];
-    acc[2 * node] = 0ull; acc[2 * node + 1] = 0ull;
+// setmask its isValueSet.  Also clears the accumulators for the next substep.  Flat over the nodes of all
+// three components (one 16-byte load per node); node coordinates are only recovered when sources exist.
+struct FinalizeArgs {
+    unsigned long long *acc[3];
+    float *val[3];
+    uint8_t *setmask[3];
+    long long count[3];
+};
+
+__global__ void __launch_bounds__(256) k_p2g_finalize(Grid g, SplatParams sp, Sources src, FinalizeArgs fa) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int comp = 0;
+    if (t >= fa.count[0]) { t -= fa.count[0]; comp = 1; if (t >= fa.count[1]) { t -= fa.count[1]; comp = 2; if (t >= fa.count[2]) return; } }
+    const size_t node = (size_t)t;
+    ulonglong2 *a = reinterpret_cast<ulonglong2 *>(fa.acc[comp]) + node;
+    ulonglong2 v = *a;
+    if (v.x | v.y) *a = make_ulonglong2(0ull, 0ull);
+    const long long n = (long long)v.x, w = (long long)v.y;
     float wf = (float)((double)w * (1.0 / kWeightScaleD));
     float nf = (float)((double)n * inv_num_scale_d(num_exponent(sp)));
     float value = nf;
     if (wf > 0.0f) value = nf / wf;
     bool isset = (double)wf > 1e-9;
-    if (isset) {
-        for (int s = 0; s < src.n; s++) {
-            int k = kl + g.k0;
-            float fx = (float)(comp == 0 ? __dmul_rn((double)(float)i, g.dx) : __dmul_rn(__dadd_rn((double)(float)i, 0.5), g.dx));
-            float fy = (float)(comp == 1 ? __dmul_rn((double)(float)j, g.dx) : __dmul_rn(__dadd_rn((double)(float)j, 0.5), g.dx));
-            float fz = (float)(comp == 2 ? __dmul_rn((double)(float)k, g.dx) : __dmul_rn(__dadd_rn((double)(float)k, 0.5), g.dx));
-            if (source_contains(src.s[s], fx, fy, fz)) value = src.s[s].velocity[comp];
-        }
+    if (isset && src.n > 0) {
+        const int ni = g.I + (comp == 0), nj = g.J + (comp == 1);
+        const int i = (int)(node % (size_t)ni), j = (int)((node / (size_t)ni) % (size_t)nj), k = (int)(node / ((size_t)ni * (size_t)nj)) + g.k0;
+        float fx = (float)(comp == 0 ? __dmul_rn((double)(float)i, g.dx) : __dmul_rn(__dadd_rn((double)(float)i, 0.5), g.dx));
+        float fy = (float)(comp == 1 ? __dmul_rn((double)(float)j, g.dx) : __dmul_rn(__dadd_rn((double)(float)j, 0.5), g.dx));
+        float fz = (float)(comp == 2 ? __dmul_rn((double)(float)k, g.dx) : __dmul_rn(__dadd_rn((double)(float)k, 0.5), g.dx));
+        for (int q = 0; q < src.n; q++)
+            if (source_contains(src.s[q], fx, fy, fz)) value = src.s[q].velocity[comp];
     }
-    val[node] = value;
-    setmask[node] = isset ? 1 : 0;
+    fa.val[comp][node] = value;
+    fa.setmask[comp][node] = isset ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,7 +492,7 @@ __global__ void k_p2g_gather(Grid g, int comp, SplatParams sp, Sources src, cons
                         !in_index_bounds(qz, k, sp.radius, g)) continue;
                     float d2 = dist2(__fsub_rn(gx, qx), __fsub_rn(gy, qy), __fsub_rn(gz, qz));
                     if ((double)d2 < sp.rsq) {
-                        double w = (ARITH == 1) ? kernel_weight_exact(sp, (double)d2) : (double)kernel_weight_fast(sp, d2);
+                        double w = (ARITH == 1) ? kernel_weight_exact(sp, (double)d2) : (double)kernel_weight_fast<false>(sp, d2);
                         field = __fadd_rn(field, (float)__dmul_rn(w, (double)vel[r]));
                         weight = __fadd_rn(weight, (float)w);
                     }
@@ -461,7 +557,7 @@ __global__ void k_assemble(Grid g, int comp, const uint8_t *__restrict__ materia
             if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
         }
     }
-    out[node] = r;
+    out[(size_t)i + (size_t)g.pitch[comp] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +612,226 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
             rank_out[r] = atomicAdd(counts + key, 1u);
             m = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (!(m < 3.0e38f)) m = 0.0f;
+        }
+    }
+    if (keys_out) block_vmax(m, vmax_bits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (brick tiles, TMA).  One CTA per brick of 8^3 cells, whose particles are one contiguous run of the
+// sorted arrays.  The u/v/w sub-blocks of the NEW and SAVED fields that the brick's particles can touch are
+// staged into shared memory by six TMA tiled loads (cp.async.bulk.tensor.3d, completion on one mbarrier);
+// TMA's zero fill of out-of-bounds box elements IS the reference's "taps outside the array read 0"
+// (macvelocityfield.cpp:99-145).  NEW is staged with a margin of kMargin cells for the RK stage positions;
+// a stage position that leaves the staged block falls back to global loads (same arithmetic).
+// Power-of-two dx only (fp32-exact index arithmetic); other grids use k_g2p_advect.
+// ------------------------------------------------------------------------------------------------
+struct BrickMaps { CUtensorMap m[6]; };     // NEW u,v,w then SAVED u,v,w
+
+template <int INTERP> struct BrickTile {
+    // trilinear: taps c, c+1;  tricubic: taps c-1 .. c+2.  c ranges over [8b-1-M, 8b+7+M] (M = motion margin).
+    static constexpr int kMargin = 1;
+    static constexpr int kLo = (INTERP == 1) ? 1 : 0, kHi = (INTERP == 1) ? 2 : 1;
+    // NEW box: nodes [8b - 1 - M - kLo, 8b + 7 + M + kHi], x extent rounded up to a multiple of 4 floats (TMA: 16 B)
+    static constexpr int nOrg = 1 + kMargin + kLo;                          // origin = 8b - nOrg
+    static constexpr int nY = 9 + 2 * kMargin + kLo + kHi, nX = (nY + 3) / 4 * 4;
+    // SAVED box (sampled at p0 only, no margin)
+    static constexpr int sOrg = 1 + kLo;
+    static constexpr int sY = 9 + kLo + kHi, sX = (sY + 3) / 4 * 4;
+    static constexpr int nBox = nX * nY * nY, sBox = sX * sY * sY;           // floats per staged box
+    static constexpr int nCount = (nBox + 31) / 32 * 32, sCount = (sBox + 31) / 32 * 32;   // 128-byte aligned slots
+    static constexpr uint32_t kTxBytes = 3 * (nBox + sBox) * sizeof(float);
+    static constexpr size_t kSmemBytes = 3 * (nCount + sCount) * sizeof(float);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// one component from a staged tile: ax/ay/az are global node indices + fractions, (ox,oy,oz) the tile origin
+template <int INTERP, int BX, int BY>
+__device__ __forceinline__ float tile_sample(const float *__restrict__ t, const AxisIdxF &ax, const AxisIdxF &ay, const AxisIdxF &az,
+                                             int ox, int oy, int oz) {
+    const float *r = t + (ax.i - ox) + BX * ((ay.i - oy) + BY * (az.i - oz));
+    if (INTERP == 1) {
+        float wx[4], wy[4], wz[4];
+        cr_weights(ax.t, wx); cr_weights(ay.t, wy); cr_weights(az.t, wz);
+        float acc = 0.0f;
+#pragma unroll
+        for (int pk = 0; pk < 4; pk++) {
+            float sk = 0.0f;
+#pragma unroll
+            for (int pj = 0; pj < 4; pj++) {
+                const float *q = r + BX * ((pj - 1) + BY * (pk - 1)) - 1;
+                float sj = wx[0] * q[0];
+                sj = fmaf(wx[1], q[1], sj); sj = fmaf(wx[2], q[2], sj); sj = fmaf(wx[3], q[3], sj);
+                sk = fmaf(wy[pj], sj, sk);
+            }
+            acc = fmaf(wz[pk], sk, acc);
+        }
+        return acc;
+    }
+    const float p000 = r[0], p100 = r[1], p010 = r[BX], p110 = r[BX + 1];
+    const float p001 = r[BX * BY], p101 = r[BX * BY + 1], p011 = r[BX * BY + BX], p111 = r[BX * BY + BX + 1];
+    float c00 = fmaf(ax.t, p100 - p000, p000), c10 = fmaf(ax.t, p110 - p010, p010);
+    float c01 = fmaf(ax.t, p101 - p001, p001), c11 = fmaf(ax.t, p111 - p011, p011);
+    float c0 = fmaf(ay.t, c10 - c00, c00), c1 = fmaf(ay.t, c11 - c01, c01);
+    return fmaf(az.t, c1 - c0, c0);
+}
+
+// all six index/fraction pairs of a position (fp32-exact for power-of-two dx)
+struct SampleIdx { AxisIdxF ux, uy, uz, sx, sy, sz; };
+__device__ __forceinline__ SampleIdx sample_idx(const Grid &g, float px, float py, float pz) {
+    SampleIdx s;
+    s.ux = axis_index_f(px, g); s.uy = axis_index_f(py, g); s.uz = axis_index_f(pz, g);
+    s.sx = axis_index_f(__fsub_rn(px, g.halfdxf), g); s.sy = axis_index_f(__fsub_rn(py, g.halfdxf), g);
+    s.sz = axis_index_f(__fsub_rn(pz, g.halfdxf), g);
+    return s;
+}
+
+// sample through the NEW tile if every tap of every component lies inside it, else through global memory
+template <int INTERP>
+__device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f, const float *__restrict__ tile, int bx, int by, int bz,
+                                              float px, float py, float pz, float &ox, float &oy, float &oz) {
+    typedef BrickTile<INTERP> T;
+    if (!(px >= 0.0f && py >= 0.0f && pz >= 0.0f && px < g.xmaxf && py < g.ymaxf && pz < g.zmaxf)) { ox = oy = oz = 0.0f; return; }
+    const SampleIdx s = sample_idx(g, px, py, pz);
+    const int x0 = bx - T::nOrg, y0 = by - T::nOrg, z0 = bz - T::nOrg;
+    // c - kLo >= origin and c + kHi <= origin + extent - 1, for the six index variants (y/z extent nY; x uses nY too:
+    // the x padding columns are real data but not guaranteed beyond nY)
+    const int lo = T::kLo, hi = T::nY - 1 - T::kHi;
+    const unsigned span = (unsigned)(hi - lo);
+    bool in = (unsigned)(s.ux.i - x0 - lo) <= span && (unsigned)(s.sx.i - x0 - lo) <= span &&
+              (unsigned)(s.uy.i - y0 - lo) <= span && (unsigned)(s.sy.i - y0 - lo) <= span &&
+              (unsigned)(s.uz.i - z0 - lo) <= span && (unsigned)(s.sz.i - z0 - lo) <= span;
+    if (in) {
+        ox = tile_sample<INTERP, T::nX, T::nY>(tile, s.ux, s.sy, s.sz, x0, y0, z0);
+        oy = tile_sample<INTERP, T::nX, T::nY>(tile + T::nCount, s.sx, s.uy, s.sz, x0, y0, z0);
+        oz = tile_sample<INTERP, T::nX, T::nY>(tile + 2 * T::nCount, s.sx, s.sy, s.uz, x0, y0, z0);
+    } else {
+        ox = sample_component_fast<0>(g, f.c[0], INTERP, s.ux, s.sy, s.sz);
+        oy = sample_component_fast<1>(g, f.c[1], INTERP, s.sx, s.uy, s.sz);
+        oz = sample_component_fast<2>(g, f.c[2], INTERP, s.sx, s.sy, s.uz);
+    }
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
+                            const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start, int order, RkCoef rk,
+                            float ratio_pic, float ratio_flip, int64_t n,
+                            const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                            const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                            float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
+                            float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
+                            unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
+                            uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
+    typedef BrickTile<INTERP> T;
+    extern __shared__ __align__(128) float tiles[];          // NEW u,v,w [nCount each] then SAVED u,v,w [sCount each]
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t b = blockIdx.x, nbricks = nkeys / kBrickCells;
+    // the last CTA takes the overflow bin (particles outside the grid): no tile, global path only
+    const bool overflow = b == nbricks;
+    const int start = cell_start[(size_t)b * kBrickCells];
+    const int end = overflow ? (int)n : cell_start[(size_t)(b + 1) * kBrickCells];
+    if (start >= end) return;
+    const int bi = (int)(b % (uint32_t)g.nbi), bj = (int)((b / (uint32_t)g.nbi) % (uint32_t)g.nbj), bk = (int)(b / ((uint32_t)g.nbi * (uint32_t)g.nbj));
+    const int bx = bi * kBrick, by = bj * kBrick, bz = bk * kBrick + g.k0;       // global node index of the brick origin
+    float *tnew = tiles, *tsav = tiles + 3 * T::nCount;
+    if (!overflow) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(T::kTxBytes) : "memory");
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                // z coordinate is local to the stored layers
+                tma_load_3d(tnew + c * T::nCount, &maps.m[c], bx - T::nOrg, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
+                tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], bx - T::sOrg, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
+            }
+        }
+        __syncthreads();                                     // barrier init visible to the waiters
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    }
+    float m = 0.0f;
+    for (int r = start + threadIdx.x; r < end; r += blockDim.x) {
+        const float px = x[r], py = y[r], pz = z[r];
+        float k1x, k1y, k1z, sx, sy, sz;
+        if (!overflow) {
+            // p0 lies in this brick: NEW and SAVED taps are all staged, and share the index/fraction set
+            const SampleIdx s = sample_idx(g, px, py, pz);
+            const int n0x = bx - T::nOrg, n0y = by - T::nOrg, n0z = bz - T::nOrg;
+            k1x = tile_sample<INTERP, T::nX, T::nY>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
+            k1y = tile_sample<INTERP, T::nX, T::nY>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
+            k1z = tile_sample<INTERP, T::nX, T::nY>(tnew + 2 * T::nCount, s.sx, s.sy, s.uz, n0x, n0y, n0z);
+            const int s0x = bx - T::sOrg, s0y = by - T::sOrg, s0z = bz - T::sOrg;
+            sx = tile_sample<INTERP, T::sX, T::sY>(tsav, s.ux, s.sy, s.sz, s0x, s0y, s0z);
+            sy = tile_sample<INTERP, T::sX, T::sY>(tsav + T::sCount, s.sx, s.uy, s.sz, s0x, s0y, s0z);
+            sz = tile_sample<INTERP, T::sX, T::sY>(tsav + 2 * T::sCount, s.sx, s.sy, s.uz, s0x, s0y, s0z);
+        } else {
+            evaluate_pow2(g, fnew, INTERP, px, py, pz, k1x, k1y, k1z);
+            evaluate_pow2(g, fsaved, INTERP, px, py, pz, sx, sy, sz);
+        }
+        float nx = k1x, ny = k1y, nz = k1z;
+        validate3(nx, ny, nz);
+        validate3(sx, sy, sz);
+        const float ux = vx[r], uy = vy[r], uz = vz[r];
+        const float wx = __fadd_rn(__fmul_rn(nx, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(ux, nx), sx), ratio_flip));
+        const float wy = __fadd_rn(__fmul_rn(ny, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uy, ny), sy), ratio_flip));
+        const float wz = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
+        ovx[r] = wx; ovy[r] = wy; ovz[r] = wz;
+
+        // RK (particleadvector.cpp:1045-1078); stage positions sample the NEW tile (or global memory beyond it)
+        float qx, qy, qz;
+        if (order == 1) { qx = axpy(px, rk.dt, k1x); qy = axpy(py, rk.dt, k1y); qz = axpy(pz, rk.dt, k1z); }
+        else {
+            float k2x, k2y, k2z;
+            if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, rk.half_dt, k1x), axpy(py, rk.half_dt, k1y), axpy(pz, rk.half_dt, k1z), k2x, k2y, k2z);
+            else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, rk.half_dt, k1x), axpy(py, rk.half_dt, k1y), axpy(pz, rk.half_dt, k1z), k2x, k2y, k2z);
+            if (order == 2) { qx = axpy(px, rk.dt, k2x); qy = axpy(py, rk.dt, k2y); qz = axpy(pz, rk.dt, k2z); }
+            else {
+                const float c3 = order == 3 ? rk.three_quarter_dt : rk.half_dt;
+                float k3x, k3y, k3z;
+                if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, c3, k2x), axpy(py, c3, k2y), axpy(pz, c3, k2z), k3x, k3y, k3z);
+                else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, c3, k2x), axpy(py, c3, k2y), axpy(pz, c3, k2z), k3x, k3y, k3z);
+                if (order == 3) {
+                    float ax_ = __fadd_rn(__fadd_rn(__fmul_rn(k1x, 2.0f), __fmul_rn(k2x, 3.0f)), __fmul_rn(k3x, 4.0f));
+                    float ay_ = __fadd_rn(__fadd_rn(__fmul_rn(k1y, 2.0f), __fmul_rn(k2y, 3.0f)), __fmul_rn(k3y, 4.0f));
+                    float az_ = __fadd_rn(__fadd_rn(__fmul_rn(k1z, 2.0f), __fmul_rn(k2z, 3.0f)), __fmul_rn(k3z, 4.0f));
+                    qx = axpy(px, rk.dt_over_9, ax_); qy = axpy(py, rk.dt_over_9, ay_); qz = axpy(pz, rk.dt_over_9, az_);
+                } else {
+                    float k4x, k4y, k4z;
+                    if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, rk.dt, k3x), axpy(py, rk.dt, k3y), axpy(pz, rk.dt, k3z), k4x, k4y, k4z);
+                    else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, rk.dt, k3x), axpy(py, rk.dt, k3y), axpy(pz, rk.dt, k3z), k4x, k4y, k4z);
+                    float ax_ = __fadd_rn(__fadd_rn(__fadd_rn(k1x, __fmul_rn(k2x, 2.0f)), __fmul_rn(k3x, 2.0f)), k4x);
+                    float ay_ = __fadd_rn(__fadd_rn(__fadd_rn(k1y, __fmul_rn(k2y, 2.0f)), __fmul_rn(k3y, 2.0f)), k4y);
+                    float az_ = __fadd_rn(__fadd_rn(__fadd_rn(k1z, __fmul_rn(k2z, 2.0f)), __fmul_rn(k3z, 2.0f)), k4z);
+                    qx = axpy(px, rk.dt_over_6, ax_); qy = axpy(py, rk.dt_over_6, ay_); qz = axpy(pz, rk.dt_over_6, az_);
+                }
+            }
+        }
+        if (material) {
+            // cell of the advected position (fp32-exact here); out of range reads as solid, NaN compares false -> solid
+            bool solid = true;
+            if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {
+                const int i = (int)floorf(__fmul_rn(qx, g.invdxf)), j = (int)floorf(__fmul_rn(qy, g.invdxf)), k = (int)floorf(__fmul_rn(qz, g.invdxf));
+                const int kl = k - g.k0;
+                solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
+            }
+            if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
+        }
+        ox[r] = qx; oy[r] = qy; oz[r] = qz;
+        if (keys_out) {
+            uint32_t key = position_key(g, nkeys, qx, qy, qz);
+            keys_out[r] = key;
+            rank_out[r] = atomicAdd(counts + key, 1u);
+            float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
+            if (mm < 3.0e38f) m = fmaxf(m, mm);
         }
     }
     if (keys_out) block_vmax(m, vmax_bits);
@@ -585,7 +901,7 @@ __global__ void k_splat_points(SplatParams sp, int vexp, double dx, float offx, 
                         ww = __double2ll_rn(w * kWeightScaleD);
                         wn = __double2ll_rn(__dmul_rn(w, (double)value) * (double)num_scale);
                     } else {
-                        float w = kernel_weight_fast(sp, d2);
+                        float w = kernel_weight_fast<false>(sp, d2);
                         ww = __float2ll_rn(w * kWeightScaleF);
                         wn = __float2ll_rn((w * value) * num_scale);
                     }

@@ -22,6 +22,7 @@ CONFIGS = {
     "tiny16": ((16, 16, 16), 0.5, "sphere"),             # test-only
     "small32": ((32, 32, 32), 0.25, "sphere"),           # test-only
     "slab24": ((24, 20, 28), 0.25, "dam"),               # test-only, non-cubic
+    "odd20": ((20, 18, 22), 0.3, "sphere"),              # test-only, dx not a power of two (fp64 index path)
 }
 
 

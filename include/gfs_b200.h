@@ -157,7 +157,8 @@ void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int
 void gfs_sort(gfs_context *ctx, int *err);
 void gfs_sort_unstable(gfs_context *ctx, int *err);
 /* Tuning switches.  option 0: fast-P2G variant, 1 = brick tiles in shared memory (default), 0 = global atomics
- * only; both produce bit-identical grids. */
+ * only; both produce bit-identical grids.  option 1: fast-G2P variant, 1 = TMA-staged brick tiles (default; used
+ * when dx is a power of two and the particles are sorted), 0 = global loads only; bit-identical results. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid

@@ -246,9 +246,10 @@ def test_counting_sort(ctx, oracle, name):
     assert ctx.stats()["out_of_grid"] == int((~inside).sum())
 
 
-def test_p2g_variants_bit_identical(ctx):
+@pytest.mark.parametrize("name", ["small32", "odd20"])
+def test_p2g_variants_bit_identical(ctx, name):
     """Brick-tile P2G (shared-memory hi/lo integer words) == global-atomic P2G, bit for bit, after either sort."""
-    s = scene("small32")
+    s = scene(name)
     out = []
     for variant, stable in ((1, True), (0, True), (1, False), (0, False)):
         load_domain(ctx, s, SOURCES)
@@ -264,7 +265,7 @@ def test_p2g_variants_bit_identical(ctx):
 
 
 def test_p2g_dense_cells(ctx, oracle):
-    """More than 255 particles in one cell: the tile kernel must take its 64-bit path for that brick and still
+    """More than 63 particles in one cell: the tile kernel must take its 64-bit path for that brick and still
     agree with the oracle (the reference caps at 100 per cell, src/fluidsimulation.cpp:3221-3243, so this is
     beyond anything the simulator produces)."""
     s = scene("tiny16")
@@ -303,7 +304,7 @@ def test_fast_substeps_track_oracle(ctx, oracle):
         pos[o], vel[o] = p, vv                # continue the oracle from the GPU state
 
 
-@pytest.mark.parametrize("name,solids", [("tiny16", False), ("slab24", True), ("small32", False)])
+@pytest.mark.parametrize("name,solids", [("tiny16", False), ("slab24", True), ("small32", False), ("odd20", False)])
 def test_p2g(ctx, oracle, name, solids):
     s = scene(name, solids)
     mat_ref = s["material"].copy()
@@ -362,7 +363,7 @@ def test_p2g_reclassifies_and_keeps_solids(ctx, oracle):
 
 
 @pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
-@pytest.mark.parametrize("name", ["tiny16", "slab24"])
+@pytest.mark.parametrize("name", ["tiny16", "slab24", "odd20"])
 def test_g2p_advect(ctx, oracle, name, interp):
     s = scene(name, interior_solids=(name == "slab24"))
     new, saved = rough_fields(s["dims"], 21, 0.3), rough_fields(s["dims"], 22, 0.3)
@@ -398,6 +399,31 @@ def test_g2p_advect(ctx, oracle, name, interp):
     assert_close(v, v_ref[o], "fast picflip velocity")
     assert_close(p, p_ref[o], "fast advected position")
     assert_close(p - s["pos"][o], p_ref[o] - s["pos"][o], "fast displacement", rtol=2e-5)
+
+
+@pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
+@pytest.mark.parametrize("cfl", [0.5, 3.7])
+def test_g2p_brick_tiles_equal_global_loads(ctx, interp, cfl):
+    """TMA-staged brick kernel == global-load kernel, bit for bit (same fp32 arithmetic, different data path),
+    also when RK stage positions leave the staged block (cfl 3.7: fallback taps) and for every RK order."""
+    s = scene("slab24", interior_solids=True)
+    new, saved = rough_fields(s["dims"], 31, 0.5), rough_fields(s["dims"], 32, 0.5)
+    dt = cfl * s["dx"]
+    for order_rk in (1, 2, 3, 4):
+        res = []
+        for variant in (1, 0):
+            load_domain(ctx, s)
+            ctx.set_option(1, variant)
+            ctx.set_field(capi.FIELD_NEW, *new); ctx.set_field(capi.FIELD_SAVED, *saved)
+            ctx.sort()
+            ctx.p2g(capi.FAST)                      # classification -> fluid/solid material for the solid test
+            ctx.g2p_advect(dt, order=order_rk, interp=interp, arith=capi.FAST)
+            res.append(ctx.get_particles() + (ctx.get_particle_order(), ctx.stats()["solid_hits"]))
+        ctx.set_option(1, 1)
+        (p1, v1, o1, h1), (p0, v0, o0, h0) = res
+        assert np.array_equal(o1, o0) and h1 == h0
+        assert np.array_equal(bits(v1), bits(v0)) and np.array_equal(bits(p1), bits(p0))
+        assert np.abs(p1 - s["pos"][o1]).max() > 0.1 * s["dx"]
 
 
 @pytest.mark.parametrize("order_rk", [1, 2, 3])
