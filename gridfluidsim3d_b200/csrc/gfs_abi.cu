@@ -327,9 +327,14 @@ void do_p2g(gfs_context *c, int arith) {
         }
         LAUNCH(c, gfs::k_p2g_finalize, ceil_div(total, 256), 256, g, sp, c->sources, fa);
     }
-    for (int comp = 0; comp < 3; comp++)
-        LAUNCH(c, gfs::k_assemble, grid3(dims[comp][0], dims[comp][1], dims[comp][2]), 128, g, comp, c->material.p,
-               c->val[comp].p, c->setmask[comp].p, c->field[GFS_FIELD_P2G][comp].p);
+    gfs::AssembleArgs aa;
+    long long total_faces = 0;
+    for (int comp = 0; comp < 3; comp++) {
+        aa.val[comp] = c->val[comp].p; aa.setmask[comp] = c->setmask[comp].p; aa.out[comp] = c->field[GFS_FIELD_P2G][comp].p;
+        aa.count[comp] = (long long)c->face_count[comp];
+        total_faces += aa.count[comp];
+    }
+    LAUNCH(c, gfs::k_assemble, ceil_div(total_faces, 256), 256, g, c->material.p, aa);
 }
 
 void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next) {
@@ -434,13 +439,13 @@ void make_brick_maps(gfs_context *c) {
     const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
     for (int a = 0; a < 3; a++) {
         make_field_map(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<0>::nX, gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nY);
+                       gfs::BrickTile<0>::kX, gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nY);
         make_field_map(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<0>::sX, gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sY);
+                       gfs::BrickTile<0>::kX, gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sY);
         make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<1>::nX, gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nY);
+                       gfs::BrickTile<1>::kX, gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nY);
         make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<1>::sX, gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sY);
+                       gfs::BrickTile<1>::kX, gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sY);
     }
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));

@@ -120,11 +120,12 @@ __device__ __forceinline__ float sample_component_exact(const Grid &g, const flo
 // ---- fast (fp32) contraction ---------------------------------------------------------------------
 // Catmull-Rom weights of the four taps for fraction t (same cubic as interpolation.cpp:44-46, regrouped)
 __device__ __forceinline__ void cr_weights(float t, float w[4]) {
-    float t2 = t * t, t3 = t2 * t;
-    w[0] = 0.5f * (-t3 + 2.0f * t2 - t);
-    w[1] = 0.5f * (3.0f * t3 - 5.0f * t2 + 2.0f);
-    w[2] = 0.5f * (-3.0f * t3 + 4.0f * t2 + t);
-    w[3] = 0.5f * (t3 - t2);
+    // explicit roundings: every kernel that samples must produce the same bits, whatever it is inlined into
+    const float t2 = __fmul_rn(t, t), t3 = __fmul_rn(t2, t);
+    w[0] = __fmul_rn(0.5f, __fsub_rn(fmaf(2.0f, t2, -t3), t));
+    w[1] = __fmul_rn(0.5f, fmaf(3.0f, t3, fmaf(-5.0f, t2, 2.0f)));
+    w[2] = __fmul_rn(0.5f, fmaf(-3.0f, t3, fmaf(4.0f, t2, t)));
+    w[3] = __fmul_rn(0.5f, __fsub_rn(t3, t2));
 }
 
 struct AxisIdxF { int i; float t; };
@@ -161,7 +162,7 @@ __device__ __forceinline__ float sample_component_fast(const Grid &g, const floa
 #pragma unroll
                 for (int pj = 0; pj < 4; pj++) {
                     const float *r = base + pitch * ((size_t)pj + (size_t)nj * (size_t)pk);
-                    float sj = wx[0] * __ldg(r);
+                    float sj = __fmul_rn(wx[0], __ldg(r));
                     sj = fmaf(wx[1], __ldg(r + 1), sj);
                     sj = fmaf(wx[2], __ldg(r + 2), sj);
                     sj = fmaf(wx[3], __ldg(r + 3), sj);
@@ -200,10 +201,10 @@ __device__ __forceinline__ float sample_component_fast(const Grid &g, const floa
         p001 = tap(g, a, COMP, i, j, az.i + 1);     p101 = tap(g, a, COMP, i + 1, j, az.i + 1);
         p011 = tap(g, a, COMP, i, j + 1, az.i + 1); p111 = tap(g, a, COMP, i + 1, j + 1, az.i + 1);
     }
-    float c00 = fmaf(tx, p100 - p000, p000), c10 = fmaf(tx, p110 - p010, p010);
-    float c01 = fmaf(tx, p101 - p001, p001), c11 = fmaf(tx, p111 - p011, p011);
-    float c0 = fmaf(ty, c10 - c00, c00), c1 = fmaf(ty, c11 - c01, c01);
-    return fmaf(tz, c1 - c0, c0);
+    float c00 = fmaf(tx, __fsub_rn(p100, p000), p000), c10 = fmaf(tx, __fsub_rn(p110, p010), p010);
+    float c01 = fmaf(tx, __fsub_rn(p101, p001), p001), c11 = fmaf(tx, __fsub_rn(p111, p011), p011);
+    float c0 = fmaf(ty, __fsub_rn(c10, c00), c00), c1 = fmaf(ty, __fsub_rn(c11, c01), c01);
+    return fmaf(tz, __fsub_rn(c1, c0), c0);
 }
 
 // MACVelocityField::evaluateVelocityAtPosition[Linear] (macvelocityfield.cpp:545-575): zero outside the

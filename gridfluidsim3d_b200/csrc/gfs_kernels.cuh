@@ -528,13 +528,24 @@ __device__ __forceinline__ bool cell_is_fluid(const Grid &g, const uint8_t *__re
     return m[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_FLUID;
 }
 
-__global__ void k_assemble(Grid g, int comp, const uint8_t *__restrict__ material, const float *__restrict__ val,
-                           const uint8_t *__restrict__ setmask, float *__restrict__ out) {
-    int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kl = blockIdx.z;
-    if (i >= ni || j >= nj || kl >= nkl) return;
-    int k = kl + g.k0;
-    size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+struct AssembleArgs {
+    const float *val[3];
+    const uint8_t *setmask[3];
+    float *out[3];
+    long long count[3];
+};
+
+// flat over the faces of all three components (one launch)
+__global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restrict__ material, AssembleArgs aa) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int comp = 0;
+    if (t >= aa.count[0]) { t -= aa.count[0]; comp = 1; if (t >= aa.count[1]) { t -= aa.count[1]; comp = 2; if (t >= aa.count[2]) return; } }
+    const int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
+    const size_t node = (size_t)t;
+    const int i = (int)(node % (size_t)ni), j = (int)((node / (size_t)ni) % (size_t)nj), kl = (int)(node / ((size_t)ni * (size_t)nj));
+    const int k = kl + g.k0;
+    const float *__restrict__ val = aa.val[comp];
+    const uint8_t *__restrict__ setmask = aa.setmask[comp];
     int di = comp == 0, dj = comp == 1, dk = comp == 2;
     // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W} (fluidmaterialgrid.cpp:119-143)
     bool borders = cell_is_fluid(g, material, i, j, k) || cell_is_fluid(g, material, i - di, j - dj, k - dk);
@@ -557,7 +568,7 @@ __global__ void k_assemble(Grid g, int comp, const uint8_t *__restrict__ materia
             if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
         }
     }
-    out[(size_t)i + (size_t)g.pitch[comp] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
+    aa.out[comp][(size_t)i + (size_t)g.pitch[comp] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,18 +641,20 @@ struct BrickMaps { CUtensorMap m[6]; };     // NEW u,v,w then SAVED u,v,w
 
 template <int INTERP> struct BrickTile {
     // trilinear: taps c, c+1;  tricubic: taps c-1 .. c+2.  c ranges over [8b-1-M, 8b+7+M] (M = motion margin).
+    // Along y and z the boxes are exactly that; along x (the contiguous axis) TMA needs the box to start on a
+    // 16-byte boundary, so every box starts at node 8b-4 and is 16 nodes wide.
     static constexpr int kMargin = 1;
     static constexpr int kLo = (INTERP == 1) ? 1 : 0, kHi = (INTERP == 1) ? 2 : 1;
-    // NEW box: nodes [8b - 1 - M - kLo, 8b + 7 + M + kHi], x extent rounded up to a multiple of 4 floats (TMA: 16 B)
-    static constexpr int nOrg = 1 + kMargin + kLo;                          // origin = 8b - nOrg
-    static constexpr int nY = 9 + 2 * kMargin + kLo + kHi, nX = (nY + 3) / 4 * 4;
-    // SAVED box (sampled at p0 only, no margin)
-    static constexpr int sOrg = 1 + kLo;
-    static constexpr int sY = 9 + kLo + kHi, sX = (sY + 3) / 4 * 4;
-    static constexpr int nBox = nX * nY * nY, sBox = sX * sY * sY;           // floats per staged box
+    static constexpr int kOrgX = 4, kX = 16;                                // x: nodes [8b-4, 8b+11] for every box
+    static constexpr int nOrg = 1 + kMargin + kLo;                          // NEW y/z origin = 8b - nOrg
+    static constexpr int nY = 9 + 2 * kMargin + kLo + kHi;
+    static constexpr int sOrg = 1 + kLo;                                    // SAVED (sampled at p0 only, no margin)
+    static constexpr int sY = 9 + kLo + kHi;
+    static constexpr int nBox = kX * nY * nY, sBox = kX * sY * sY;           // floats per staged box
     static constexpr int nCount = (nBox + 31) / 32 * 32, sCount = (sBox + 31) / 32 * 32;   // 128-byte aligned slots
     static constexpr uint32_t kTxBytes = 3 * (nBox + sBox) * sizeof(float);
-    static constexpr size_t kSmemBytes = 3 * (nCount + sCount) * sizeof(float);
+    static constexpr size_t kSmemBytes = 3 * (nCount + sCount) * sizeof(float) + 128 + 16;   // + alignment slack + mbarrier
+    static_assert(kOrgX >= nOrg && kX - kOrgX >= 9 + kMargin + kHi, "x box must cover the y/z node range");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -666,7 +679,7 @@ __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const 
 #pragma unroll
             for (int pj = 0; pj < 4; pj++) {
                 const float *q = r + BX * ((pj - 1) + BY * (pk - 1)) - 1;
-                float sj = wx[0] * q[0];
+                float sj = __fmul_rn(wx[0], q[0]);
                 sj = fmaf(wx[1], q[1], sj); sj = fmaf(wx[2], q[2], sj); sj = fmaf(wx[3], q[3], sj);
                 sk = fmaf(wy[pj], sj, sk);
             }
@@ -676,10 +689,10 @@ __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const 
     }
     const float p000 = r[0], p100 = r[1], p010 = r[BX], p110 = r[BX + 1];
     const float p001 = r[BX * BY], p101 = r[BX * BY + 1], p011 = r[BX * BY + BX], p111 = r[BX * BY + BX + 1];
-    float c00 = fmaf(ax.t, p100 - p000, p000), c10 = fmaf(ax.t, p110 - p010, p010);
-    float c01 = fmaf(ax.t, p101 - p001, p001), c11 = fmaf(ax.t, p111 - p011, p011);
-    float c0 = fmaf(ay.t, c10 - c00, c00), c1 = fmaf(ay.t, c11 - c01, c01);
-    return fmaf(az.t, c1 - c0, c0);
+    float c00 = fmaf(ax.t, __fsub_rn(p100, p000), p000), c10 = fmaf(ax.t, __fsub_rn(p110, p010), p010);
+    float c01 = fmaf(ax.t, __fsub_rn(p101, p001), p001), c11 = fmaf(ax.t, __fsub_rn(p111, p011), p011);
+    float c0 = fmaf(ay.t, __fsub_rn(c10, c00), c00), c1 = fmaf(ay.t, __fsub_rn(c11, c01), c01);
+    return fmaf(az.t, __fsub_rn(c1, c0), c0);
 }
 
 // all six index/fraction pairs of a position (fp32-exact for power-of-two dx)
@@ -699,18 +712,17 @@ __device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f,
     typedef BrickTile<INTERP> T;
     if (!(px >= 0.0f && py >= 0.0f && pz >= 0.0f && px < g.xmaxf && py < g.ymaxf && pz < g.zmaxf)) { ox = oy = oz = 0.0f; return; }
     const SampleIdx s = sample_idx(g, px, py, pz);
-    const int x0 = bx - T::nOrg, y0 = by - T::nOrg, z0 = bz - T::nOrg;
-    // c - kLo >= origin and c + kHi <= origin + extent - 1, for the six index variants (y/z extent nY; x uses nY too:
-    // the x padding columns are real data but not guaranteed beyond nY)
-    const int lo = T::kLo, hi = T::nY - 1 - T::kHi;
-    const unsigned span = (unsigned)(hi - lo);
-    bool in = (unsigned)(s.ux.i - x0 - lo) <= span && (unsigned)(s.sx.i - x0 - lo) <= span &&
+    const int x0 = bx - T::kOrgX, y0 = by - T::nOrg, z0 = bz - T::nOrg;
+    // every tap c - kLo .. c + kHi of the six index variants must lie inside the staged box
+    const int lo = T::kLo;
+    const unsigned spanx = (unsigned)(T::kX - 1 - T::kHi - lo), span = (unsigned)(T::nY - 1 - T::kHi - lo);
+    bool in = (unsigned)(s.ux.i - x0 - lo) <= spanx && (unsigned)(s.sx.i - x0 - lo) <= spanx &&
               (unsigned)(s.uy.i - y0 - lo) <= span && (unsigned)(s.sy.i - y0 - lo) <= span &&
               (unsigned)(s.uz.i - z0 - lo) <= span && (unsigned)(s.sz.i - z0 - lo) <= span;
     if (in) {
-        ox = tile_sample<INTERP, T::nX, T::nY>(tile, s.ux, s.sy, s.sz, x0, y0, z0);
-        oy = tile_sample<INTERP, T::nX, T::nY>(tile + T::nCount, s.sx, s.uy, s.sz, x0, y0, z0);
-        oz = tile_sample<INTERP, T::nX, T::nY>(tile + 2 * T::nCount, s.sx, s.sy, s.uz, x0, y0, z0);
+        ox = tile_sample<INTERP, T::kX, T::nY>(tile, s.ux, s.sy, s.sz, x0, y0, z0);
+        oy = tile_sample<INTERP, T::kX, T::nY>(tile + T::nCount, s.sx, s.uy, s.sz, x0, y0, z0);
+        oz = tile_sample<INTERP, T::kX, T::nY>(tile + 2 * T::nCount, s.sx, s.sy, s.uz, x0, y0, z0);
     } else {
         ox = sample_component_fast<0>(g, f.c[0], INTERP, s.ux, s.sy, s.sz);
         oy = sample_component_fast<1>(g, f.c[1], INTERP, s.sx, s.uy, s.sz);
@@ -729,8 +741,11 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
                             unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
                             uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
     typedef BrickTile<INTERP> T;
-    extern __shared__ __align__(128) float tiles[];          // NEW u,v,w [nCount each] then SAVED u,v,w [sCount each]
-    __shared__ __align__(8) uint64_t bar;
+    // dynamic shared memory: [pad to 128 B] NEW u,v,w [nCount each] | SAVED u,v,w [sCount each] | mbarrier.
+    // TMA destinations must be 128-byte aligned: align by hand, static shared variables precede this block.
+    extern __shared__ unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(tiles + 3 * (T::nCount + T::sCount));
     const uint32_t b = blockIdx.x, nbricks = nkeys / kBrickCells;
     // the last CTA takes the overflow bin (particles outside the grid): no tile, global path only
     const bool overflow = b == nbricks;
@@ -748,8 +763,8 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 // z coordinate is local to the stored layers
-                tma_load_3d(tnew + c * T::nCount, &maps.m[c], bx - T::nOrg, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
-                tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], bx - T::sOrg, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
+                tma_load_3d(tnew + c * T::nCount, &maps.m[c], bx - T::kOrgX, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
+                tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], bx - T::kOrgX, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
             }
         }
         __syncthreads();                                     // barrier init visible to the waiters
@@ -765,14 +780,14 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
         if (!overflow) {
             // p0 lies in this brick: NEW and SAVED taps are all staged, and share the index/fraction set
             const SampleIdx s = sample_idx(g, px, py, pz);
-            const int n0x = bx - T::nOrg, n0y = by - T::nOrg, n0z = bz - T::nOrg;
-            k1x = tile_sample<INTERP, T::nX, T::nY>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
-            k1y = tile_sample<INTERP, T::nX, T::nY>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
-            k1z = tile_sample<INTERP, T::nX, T::nY>(tnew + 2 * T::nCount, s.sx, s.sy, s.uz, n0x, n0y, n0z);
-            const int s0x = bx - T::sOrg, s0y = by - T::sOrg, s0z = bz - T::sOrg;
-            sx = tile_sample<INTERP, T::sX, T::sY>(tsav, s.ux, s.sy, s.sz, s0x, s0y, s0z);
-            sy = tile_sample<INTERP, T::sX, T::sY>(tsav + T::sCount, s.sx, s.uy, s.sz, s0x, s0y, s0z);
-            sz = tile_sample<INTERP, T::sX, T::sY>(tsav + 2 * T::sCount, s.sx, s.sy, s.uz, s0x, s0y, s0z);
+            const int n0x = bx - T::kOrgX, n0y = by - T::nOrg, n0z = bz - T::nOrg;
+            k1x = tile_sample<INTERP, T::kX, T::nY>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
+            k1y = tile_sample<INTERP, T::kX, T::nY>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
+            k1z = tile_sample<INTERP, T::kX, T::nY>(tnew + 2 * T::nCount, s.sx, s.sy, s.uz, n0x, n0y, n0z);
+            const int s0y = by - T::sOrg, s0z = bz - T::sOrg;
+            sx = tile_sample<INTERP, T::kX, T::sY>(tsav, s.ux, s.sy, s.sz, n0x, s0y, s0z);
+            sy = tile_sample<INTERP, T::kX, T::sY>(tsav + T::sCount, s.sx, s.uy, s.sz, n0x, s0y, s0z);
+            sz = tile_sample<INTERP, T::kX, T::sY>(tsav + 2 * T::sCount, s.sx, s.sy, s.uz, n0x, s0y, s0z);
         } else {
             evaluate_pow2(g, fnew, INTERP, px, py, pz, k1x, k1y, k1z);
             evaluate_pow2(g, fsaved, INTERP, px, py, pz, sx, sy, sz);
