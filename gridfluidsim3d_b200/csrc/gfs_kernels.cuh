@@ -421,11 +421,12 @@ struct FinalizeArgs {
 };
 
 __global__ void __launch_bounds__(256) k_p2g_finalize(Grid g, SplatParams sp, Sources src, FinalizeArgs fa) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int comp = 0;
-    if (t >= fa.count[0]) { t -= fa.count[0]; comp = 1; if (t >= fa.count[1]) { t -= fa.count[1]; comp = 2; if (t >= fa.count[2]) return; } }
-    const size_t node = (size_t)t;
-    ulonglong2 *a = reinterpret_cast<ulonglong2 *>(fa.acc[comp]) + node;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c0 = fa.count[0], c01 = fa.count[0] + fa.count[1], c012 = c01 + fa.count[2];
+    if (t0 >= c012) return;
+    const int comp = (t0 >= c0) + (t0 >= c01);
+    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)));
+    ulonglong2 *a = reinterpret_cast<ulonglong2 *>(comp == 0 ? fa.acc[0] : (comp == 1 ? fa.acc[1] : fa.acc[2])) + node;
     ulonglong2 v = *a;
     if (v.x | v.y) *a = make_ulonglong2(0ull, 0ull);
     const long long n = (long long)v.x, w = (long long)v.y;
@@ -443,8 +444,8 @@ __global__ void __launch_bounds__(256) k_p2g_finalize(Grid g, SplatParams sp, So
         for (int q = 0; q < src.n; q++)
             if (source_contains(src.s[q], fx, fy, fz)) value = src.s[q].velocity[comp];
     }
-    fa.val[comp][node] = value;
-    fa.setmask[comp][node] = isset ? 1 : 0;
+    (comp == 0 ? fa.val[0] : (comp == 1 ? fa.val[1] : fa.val[2]))[node] = value;
+    (comp == 0 ? fa.setmask[0] : (comp == 1 ? fa.setmask[1] : fa.setmask[2]))[node] = isset ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -537,15 +538,17 @@ struct AssembleArgs {
 
 // flat over the faces of all three components (one launch)
 __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restrict__ material, AssembleArgs aa) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int comp = 0;
-    if (t >= aa.count[0]) { t -= aa.count[0]; comp = 1; if (t >= aa.count[1]) { t -= aa.count[1]; comp = 2; if (t >= aa.count[2]) return; } }
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c0 = aa.count[0], c01 = aa.count[0] + aa.count[1], c012 = c01 + aa.count[2];
+    if (t0 >= c012) return;
+    const int comp = (t0 >= c0) + (t0 >= c01);
+    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)));
     const int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
-    const size_t node = (size_t)t;
     const int i = (int)(node % (size_t)ni), j = (int)((node / (size_t)ni) % (size_t)nj), kl = (int)(node / ((size_t)ni * (size_t)nj));
     const int k = kl + g.k0;
-    const float *__restrict__ val = aa.val[comp];
-    const uint8_t *__restrict__ setmask = aa.setmask[comp];
+    const float *val = comp == 0 ? aa.val[0] : (comp == 1 ? aa.val[1] : aa.val[2]);
+    const uint8_t *setmask = comp == 0 ? aa.setmask[0] : (comp == 1 ? aa.setmask[1] : aa.setmask[2]);
+    float *out = comp == 0 ? aa.out[0] : (comp == 1 ? aa.out[1] : aa.out[2]);
     int di = comp == 0, dj = comp == 1, dk = comp == 2;
     // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W} (fluidmaterialgrid.cpp:119-143)
     bool borders = cell_is_fluid(g, material, i, j, k) || cell_is_fluid(g, material, i - di, j - dj, k - dk);
@@ -568,7 +571,8 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
             if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
         }
     }
-    aa.out[comp][(size_t)i + (size_t)g.pitch[comp] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
+    const int pitch = comp == 0 ? g.pitch[0] : (comp == 1 ? g.pitch[1] : g.pitch[2]);
+    out[(size_t)i + (size_t)pitch * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,8 +20,10 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-5
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture()
 def ctx():
+    """A fresh context (fresh device buffers) per test: nothing computed by an earlier test can leak into a later
+    one through recycled scratch arrays."""
     c = capi.Context(0)
     yield c
     c.close()
@@ -261,7 +263,7 @@ def test_p2g_variants_bit_identical(ctx, name):
     for other in out[1:]:
         for a, b in zip(out[0], other):
             assert np.array_equal(bits(a), bits(b))
-    assert np.count_nonzero(out[0][0]) > 1000
+    assert all(np.count_nonzero(a) > 1000 for a in out[0])
 
 
 def test_p2g_dense_cells(ctx, oracle):
@@ -320,9 +322,12 @@ def test_p2g(ctx, oracle, name, solids):
     for a, b in zip(ctx.get_field(capi.FIELD_P2G), (u_ref, v_ref, w_ref)):
         assert np.array_equal(bits(a), bits(b))                             # exact mode: bit-exact
 
-    # fast mode: tolerance vs the oracle in the ORIGINAL (shuffled) particle order too
+    # fast mode: tolerance vs the oracle in the ORIGINAL (shuffled) particle order too (fresh context: no buffer
+    # of the exact run above can be reused)
     mat2 = s["material"].copy()
     ref2 = oracle.p2g(s["pos"], s["vel"], s["dims"], s["dx"], mat2, SOURCES)
+    ctx.close()
+    ctx = capi.Context(0)
     load_domain(ctx, s, SOURCES)
     ctx.sort()
     ctx.p2g(capi.FAST)
@@ -340,6 +345,7 @@ def test_p2g(ctx, oracle, name, solids):
     ctx.p2g(capi.FAST)
     for a, b in zip(ctx.get_field(capi.FIELD_P2G), fast):
         assert np.array_equal(bits(a), bits(b))
+    ctx.close()
 
 
 def test_p2g_reclassifies_and_keeps_solids(ctx, oracle):
