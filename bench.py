@@ -287,7 +287,7 @@ ALG_BYTES = {   # algorithmic bytes per launch of each hot kernel (SURVEY.md §8
 def run_gfs(args):
     import torch
     import torch.distributed as dist
-    from gridfluidsim3d_b200 import capi, synth
+    from gridfluidsim3d_b200 import capi, slabs, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -298,27 +298,46 @@ def run_gfs(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if world != args.gpus:
+    if world != args.gpus and rank == 0:
         log("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))
     interp = capi.TRILINEAR if args.interp == "trilinear" else capi.TRICUBIC
     dims, dx, _ = synth.CONFIGS[args.workload]
     G = dims[0] * dims[1] * dims[2]
     hbm_gbs, peak_src = measured_peaks()
+    owned = slabs.slab_ranges(dims[2], world)[rank]
 
-    if world > 1:
-        from gridfluidsim3d_b200 import slabs
-        return slabs.bench_main(args, METRIC, UNIT, hbm_gbs, peak_src, make_scene_device, ClockSampler, log)
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     t_gen = time.time()
-    sc = make_scene_device(args.workload, dev)
+    sc = make_scene_device(args.workload, dev, seed=12345 + rank, k_range=owned if world > 1 else None)
     torch.cuda.synchronize()
-    N = sc["aos"].shape[0]
-    log("scene %s: %d particles, %d cells, generated in %.1fs" % (args.workload, N, G, time.time() - t_gen))
+    n_local = sc["aos"].shape[0]
+    N = allsum(n_local)
+    if rank == 0:
+        log("scene %s: %d particles (%d on rank 0), %d cells, generated in %.1fs" % (args.workload, N, n_local, G, time.time() - t_gen))
 
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: events and kernels share it
     torch.cuda.set_stream(stream)
     ctx = capi.Context(local, stream=stream.cuda_stream)
-    log(ctx.device_info())
+    if rank == 0:
+        log(ctx.device_info())
     ctx.domain_init(dims, dx)
     ctx.set_material(sc["material"])
     # pinned host copies: the e2e leg's inputs, and the source of the resident upload
@@ -331,103 +350,131 @@ def run_gfs(args):
     ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])
     ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])
     dt = sc["dt"]
-    host_small = scene_to_host(sc, max_particles=args.cpu_sample * 32)
+    host_small = scene_to_host(sc, max_particles=args.cpu_sample * 32) if (world == 1 and not args.no_cpu_baseline) else None
     del sc["aos"]
     torch.cuda.empty_cache()
 
-    def substep():
-        ctx.substep(dt, order=4, interp=interp, arith=capi.FAST)
+    halo = capi.slab_halo_cells(interp, 0.5 * dx, dx)
+    if world > 1:
+        def make_driver(ip):
+            return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8)), rank, world,
+                                    halo=capi.slab_halo_cells(ip, 0.5 * dx, dx))
+        drv = make_driver(interp)
+        transport = slabs.DistTransport()
+
+        def substep():
+            slabs.substep(drv, transport, dt)
+    else:
+        transport = None
+
+        def substep():
+            ctx.substep(dt, order=4, interp=interp, arith=capi.FAST)
 
     # ---- value: device-resident substeps --------------------------------------------------------------
     for _ in range(args.warmup):
         substep()
-    torch.cuda.synchronize()
+    barrier()
     launches0 = ctx.stats()["kernel_launches"]
+    bytes0 = transport.bytes_sent if transport else 0
     ctx.profile_enable(True)
     ctx.profile_read(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        torch.cuda.synchronize()
+        barrier()
         e0.record(stream)
         for _ in range(args.steps):
             substep()
         e1.record(stream)
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+        barrier()
+    ms = allmax(e0.elapsed_time(e1))
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
     st = ctx.stats()
     launches = st["kernel_launches"] - launches0
+    comm_bytes = (transport.bytes_sent - bytes0) / args.steps if transport else 0
+    n_now = allsum(ctx.num_particles)
+    n_max = allmax(ctx.num_particles)
     ms_per_step = ms / args.steps
     value = N / (ms_per_step * 1e-3)
 
-    # dominant kernel and its roofline
+    # dominant kernel (on this rank) and its roofline: algorithmic bytes of the launch / CUDA-event time of the launch
     ranked = sorted(prof.items(), key=lambda kv: -kv[1][0])
     kernels = {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches_per_step": v[1] / args.steps,
                    "share_of_step": v[0] / ms} for k, v in ranked}
     top = next((k for k, _ in ranked if k in ALG_BYTES), ranked[0][0])
     pb, cb = ALG_BYTES.get(top, (0, 0))
     top_ms = prof[top][0] / max(1, prof[top][1])
-    alg_bytes = pb * N + cb * G
+    G_local = G * (owned[1] - owned[0]) // dims[2]
+    alg_bytes = pb * ctx.num_particles + cb * G_local
     achieved = alg_bytes / (top_ms * 1e-3) / 1e9
     step_alg_bytes = 72 * N + 37 * G
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                 "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_ms,
                 "substep_algorithmic_bytes": step_alg_bytes,
-                "substep_frac": step_alg_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs}
+                "substep_frac": step_alg_bytes / (ms_per_step * 1e-3) / 1e9 / (hbm_gbs * world)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the ncu capture
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and world == 1:
         with open(traffic_file) as f:
             roofline["traffic"] = json.load(f).get(args.workload, {}).get(top)
 
     # ---- e2e: the same substep through host buffers ------------------------------------------------------
-    aos_out = torch.empty_like(aos_host)
+    aos_out = torch.empty((int(n_max) + 1024, 6), dtype=torch.float32, pin_memory=True)
     p2g_out = [np.empty(t.numel(), np.float32) for t in new_host]
     nu, nv, nw = [t.numel() for t in new_host]
-    h2d = N * 24 + 2 * 4 * (nu + nv + nw)
-    d2h = N * 24 + 4 * (nu + nv + nw) + G
+    h2d = n_local * 24 + 2 * 4 * (nu + nv + nw)
+    d2h = n_local * 24 + 4 * (nu + nv + nw) + G
 
     def e2e_step():
         ctx.set_particles_aos(aos_host.numpy())                                  # H2D 24 B/particle
         ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])           # H2D post-pressure field
         ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])       # H2D saved field
         substep()
-        ctx.get_particles_aos(aos_out.numpy().reshape(-1))                       # D2H particles
+        ctx.get_particles_aos(aos_out.numpy().reshape(-1)[: ctx.num_particles * 6])   # D2H particles
         ctx.get_field(capi.FIELD_P2G, out=p2g_out)                               # D2H P2G u,v,w
         ctx.get_material()                                                        # D2H material
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    barrier()
+    e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d), "d2h_bytes_per_step": allsum(d2h),
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "gfs_set_particles + gfs_set_field x2 + gfs_substep + gfs_get_particles + gfs_get_field + gfs_get_material"}
+           "api": "gfs_set_particles + gfs_set_field x2 + substep + gfs_get_particles + gfs_get_field + gfs_get_material"
+                  + (" (per rank; whole fields are moved by every rank)" if world > 1 else "")}
 
-    # ---- tricubic / trilinear variant (the other interpolation), short ------------------------------------
+    # ---- the other interpolation, short --------------------------------------------------------------------
     other = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR
     other_name = "tricubic" if interp == capi.TRILINEAR else "trilinear"
+    ctx.set_particles_aos(aos_host.numpy())
+    if world > 1:
+        drv2 = make_driver(other)
+
+        def substep2():
+            slabs.substep(drv2, transport, dt)
+    else:
+        def substep2():
+            ctx.substep(dt, order=4, interp=other, arith=capi.FAST)
     for _ in range(2):
-        ctx.substep(dt, order=4, interp=other, arith=capi.FAST)
-    torch.cuda.synchronize()
+        substep2()
+    barrier()
     vs = max(3, min(args.steps, 5))
     e0.record(stream)
     for _ in range(vs):
-        ctx.substep(dt, order=4, interp=other, arith=capi.FAST)
+        substep2()
     e1.record(stream)
-    torch.cuda.synchronize()
-    oms = e0.elapsed_time(e1) / vs
+    barrier()
+    oms = allmax(e0.elapsed_time(e1)) / vs
     variants = {other_name: {"value": N / (oms * 1e-3), "ms_per_step": oms,
-                             "substep_frac": step_alg_bytes / (oms * 1e-3) / 1e9 / hbm_gbs}}
+                             "substep_frac": step_alg_bytes / (oms * 1e-3) / 1e9 / (hbm_gbs * world)}}
 
     # ---- cpu baseline (bounded sample, rank 0, N = 1 only) ---------------------------------------------
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if host_small is not None:
         try:
             cpu = CpuHotpath(host_small, interp, args.cpu_sample)
             cpu.N = N
@@ -439,19 +486,27 @@ def run_gfs(args):
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (fp64 index arithmetic, 64-bit fixed-point P2G accumulation)", "data": "synthetic",
         "config": {"workload": args.workload, "grid": list(dims), "dx": dx, "particles": N, "cells": G,
                    "interp": args.interp, "rk_order": 4, "arith": "fast", "cfl": 0.5,
+                   "parallelism": "z-slabs x%d, halo %d layers" % (world, halo) if world > 1 else "single GPU",
                    "l2": "inputs (%.2f GB particles + %.2f GB fields) exceed the 126 MB L2; no flush needed"
                          % (N * 24 / 1e9, 8 * (nu + nv + nw) / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks.summary(), "kernels": kernels, "variants": variants,
         "stats": {k: int(v) for k, v in st.items()},
     }
+    if world > 1:
+        line["multi_gpu"] = {"comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
+                             "particles_mean": n_now / world, "particles_after": n_now}
     ctx.close()
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -25,6 +25,8 @@ SYMBOLS = [
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
+    "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
+    "gfs_extract_particles", "gfs_append_particles_device",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -90,6 +92,15 @@ def load_library():
     L.gfs_p2g.argtypes = [V, I, _err]
     L.gfs_g2p_advect.argtypes = [V, D, D, I, I, I, _err]
     L.gfs_substep.argtypes = [V, D, D, I, I, I, _err]
+    L.gfs_set_owned_layers.argtypes = [V, I, I, _err]
+    L.gfs_p2g_begin.argtypes = [V, I, _err]
+    L.gfs_p2g_end.argtypes = [V, _err]
+    L.gfs_layer_bytes.argtypes = [V, I, _err]
+    L.gfs_layer_bytes.restype = L64
+    L.gfs_pack_layers.argtypes = [V, I, I, I, V, _err]
+    L.gfs_unpack_layers.argtypes = [V, I, I, I, V, I, _err]
+    L.gfs_extract_particles.argtypes = [V, I, I, V, V, L64, C.POINTER(L64), C.POINTER(L64), _err]
+    L.gfs_append_particles_device.argtypes = [V, V, L64, _err]
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
     L.gfs_resize_particles.argtypes = [V, L64, _err]
@@ -300,6 +311,33 @@ class Context:
 
     def substep(self, dt, ratio=PICFLIP_RATIO, order=4, interp=TRICUBIC, arith=FAST):
         self._call(self.lib.gfs_substep, dt, ratio, order, interp, arith)
+
+    # ---- z-slab sharding primitives (device buffers are raw pointers, e.g. torch tensor.data_ptr()) -----
+    def set_owned_layers(self, k0, k1):
+        self._call(self.lib.gfs_set_owned_layers, int(k0), int(k1))
+
+    def p2g_begin(self, arith=FAST):
+        self._call(self.lib.gfs_p2g_begin, arith)
+
+    def p2g_end(self):
+        self._call(self.lib.gfs_p2g_end)
+
+    def layer_bytes(self, what):
+        return self._call(self.lib.gfs_layer_bytes, what)
+
+    def pack_layers(self, what, k_first, k_count, dst_ptr):
+        self._call(self.lib.gfs_pack_layers, what, int(k_first), int(k_count), dst_ptr)
+
+    def unpack_layers(self, what, k_first, k_count, src_ptr, add=False):
+        self._call(self.lib.gfs_unpack_layers, what, int(k_first), int(k_count), src_ptr, int(add))
+
+    def extract_particles(self, k_lo, k_hi, down_ptr, up_ptr, cap):
+        nd, nu = C.c_int64(), C.c_int64()
+        self._call(self.lib.gfs_extract_particles, int(k_lo), int(k_hi), down_ptr, up_ptr, int(cap), C.byref(nd), C.byref(nu))
+        return nd.value, nu.value
+
+    def append_particles_device(self, aos_ptr, n):
+        self._call(self.lib.gfs_append_particles_device, aos_ptr, int(n))
 
     def device_ptr(self, which):
         return self._call(self.lib.gfs_device_ptr, which)

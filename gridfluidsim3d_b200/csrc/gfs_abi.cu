@@ -128,6 +128,9 @@ struct gfs_context {
     DevBuf<unsigned int> vmax_bits;       // 1 word
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
+    int p2g_arith = 0;
+    int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
+    DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
     int g2p_variant = 1;                  // 1 = TMA-staged brick tiles (default where applicable), 0 = global loads only
     gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
@@ -274,67 +277,106 @@ void do_sort(gfs_context *c, bool stable) {
     c->sorted = true;
 }
 
-void do_p2g(gfs_context *c, int arith) {
+// layer range [lo,hi) of cells the grid kernels process: the owned slab plus one halo layer each side
+void work_layers(gfs_context *c, int *lo, int *hi) {
+    *lo = c->own_k0 > 0 ? c->own_k0 - 1 : 0;
+    *hi = c->own_k1 < c->grid.K ? c->own_k1 + 1 : c->grid.K;
+}
+
+// P2G, first half: classification of the work layers + splat of the resident particles into the accumulators
+void do_p2g_begin(gfs_context *c, int arith) {
     require_domain(c);
     GFS_REQUIRE(c->sorted, "gfs_p2g needs gfs_sort first");
     const Grid &g = c->grid;
     const int kl = g.k1 - g.k0;
     const int b = c->cur;
     gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
+    int lo, hi;
+    work_layers(c, &lo, &hi);
     GFS_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, gfs::k_classify, grid3(g.I, g.J, kl), 128, g, c->cell_start.p, c->material.p, c->counters.p);
+    const long long plane = (long long)g.I * g.J;
+    LAUNCH(c, gfs::k_classify, ceil_div(plane * (hi - lo), 256), 256, g, c->cell_start.p, c->material.p, c->counters.p,
+           plane * lo, plane * (hi - lo), c->own_k0, c->own_k1);
+    c->p2g_arith = arith;
+    if (arith == GFS_EXACT) return;               // the exact gather does everything in do_p2g_end
+    if (c->n > 0) {
+        const bool pow2 = g.pow2 != 0;
+        if (c->p2g_variant == 0) {
+            if (pow2)
+                LAUNCH(c, gfs::k_p2g_scatter<2>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                       c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                       c->acc[0].p, c->acc[1].p, c->acc[2].p);
+            else
+                LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                       c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
+                       c->acc[0].p, c->acc[1].p, c->acc[2].p);
+        } else {
+            const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
+            const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
+            int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
+            if (pow2)
+                gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(
+                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
+            else
+                gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(
+                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
+            c->prof_end(prof_id_);
+            c->launches++;
+            GFS_CUDA(cudaGetLastError());
+        }
+    }
+}
+
+// P2G, second half: normalisation + inflow override + face assembly on the work layers
+void do_p2g_end(gfs_context *c) {
+    require_domain(c);
+    const Grid &g = c->grid;
+    const int kl = g.k1 - g.k0;
+    const int b = c->cur;
+    gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
     const int dims[3][3] = {{g.I + 1, g.J, kl}, {g.I, g.J + 1, kl}, {g.I, g.J, kl + 1}};
-    if (arith == GFS_EXACT) {
+    int lo, hi;
+    work_layers(c, &lo, &hi);
+    const bool whole = lo == 0 && hi == g.K;
+    if (c->p2g_arith == GFS_EXACT) {
+        GFS_REQUIRE(whole, "exact-arithmetic P2G is single-domain only");
         for (int comp = 0; comp < 3; comp++)
             LAUNCH(c, gfs::k_p2g_gather<1>, grid3(dims[comp][0], dims[comp][1], dims[comp][2], 64), 64, g, comp, sp, c->sources,
                    c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3 + comp].p,
                    c->val[comp].p, c->setmask[comp].p);
-    } else {
-        if (c->n > 0) {
-            const bool pow2 = g.pow2 != 0;
-            if (c->p2g_variant == 0) {
-                if (pow2)
-                    LAUNCH(c, gfs::k_p2g_scatter<2>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
-                           c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
-                           c->acc[0].p, c->acc[1].p, c->acc[2].p);
-                else
-                    LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
-                           c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
-                           c->acc[0].p, c->acc[1].p, c->acc[2].p);
-            } else {
-                const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
-                const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
-                int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
-                if (pow2)
-                    gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(
-                        g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
-                        c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
-                else
-                    gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(
-                        g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
-                        c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
-                c->prof_end(prof_id_);
-                c->launches++;
-                GFS_CUDA(cudaGetLastError());
-            }
-        }
+    }
+    // node layers [lo, hi) for u,v and [lo, hi] for w.  Finalize covers them all (it also re-zeroes the accumulators);
+    // assemble only the owned layers' faces -- its 26-neighbourhood reads one finalized layer beyond them.
+    long long plane[3] = {(long long)dims[0][0] * dims[0][1], (long long)dims[1][0] * dims[1][1], (long long)dims[2][0] * dims[2][1]};
+    if (c->p2g_arith != GFS_EXACT) {
         gfs::FinalizeArgs fa;
         long long total = 0;
         for (int comp = 0; comp < 3; comp++) {
             fa.acc[comp] = c->acc[comp].p; fa.val[comp] = c->val[comp].p; fa.setmask[comp] = c->setmask[comp].p;
-            fa.count[comp] = (long long)c->face_count[comp];
+            fa.first[comp] = plane[comp] * lo;
+            fa.count[comp] = plane[comp] * (hi - lo + (comp == 2 ? 1 : 0));
             total += fa.count[comp];
         }
         LAUNCH(c, gfs::k_p2g_finalize, ceil_div(total, 256), 256, g, sp, c->sources, fa);
     }
     gfs::AssembleArgs aa;
     long long total_faces = 0;
+    const int a_lo = whole ? 0 : c->own_k0, a_hi = whole ? g.K : c->own_k1;
     for (int comp = 0; comp < 3; comp++) {
         aa.val[comp] = c->val[comp].p; aa.setmask[comp] = c->setmask[comp].p; aa.out[comp] = c->field[GFS_FIELD_P2G][comp].p;
-        aa.count[comp] = (long long)c->face_count[comp];
+        aa.first[comp] = plane[comp] * a_lo;
+        // the w face layer own_k1 is the upper slab's lower face: it belongs to the upper slab, except the top of the domain
+        aa.count[comp] = plane[comp] * (a_hi - a_lo + ((comp == 2 && a_hi == g.K) ? 1 : 0));
         total_faces += aa.count[comp];
     }
     LAUNCH(c, gfs::k_assemble, ceil_div(total_faces, 256), 256, g, c->material.p, aa);
+}
+
+void do_p2g(gfs_context *c, int arith) {
+    do_p2g_begin(c, arith);
+    do_p2g_end(c);
 }
 
 void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next) {
@@ -505,6 +547,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
+    c->split_counters.release();
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
     c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -698,6 +741,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->has_domain = true;
     c->sorted = false;
     c->have_maps = false;
+    c->own_k0 = 0; c->own_k1 = K;
     if (g.pow2) make_brick_maps(c);
     LAUNCH(c, gfs::k_border_solid, grid3(I, J, kl), 128, g, c->material.p);
     GFS_END()
@@ -855,6 +899,125 @@ void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp,
     do_sort(c, arith == GFS_EXACT);
     do_p2g(c, arith);
     do_g2p(c, dt, ratio, order, interp, arith, arith != GFS_EXACT);
+    GFS_END()
+}
+
+void gfs_p2g_begin(gfs_context *c, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_p2g_begin(c, arith);
+    GFS_END()
+}
+
+void gfs_p2g_end(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_p2g_end(c);
+    GFS_END()
+}
+
+void gfs_set_owned_layers(gfs_context *c, int k0, int k1, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(k0 >= 0 && k1 > k0 && k1 <= c->grid.K, "bad layer range");
+    c->own_k0 = k0; c->own_k1 = k1;
+    GFS_END()
+}
+
+namespace {
+// (pointer, bytes per z-layer, number of z-layers) of a resident grid array; what: 0..2 NEW u,v,w; 3..5 SAVED; 6..8 P2G;
+// 9 material; 10..12 accumulators of u,v,w (two 64-bit integers per node)
+void layer_info(gfs_context *c, int what, unsigned char **base, size_t *bytes, int *layers) {
+    const Grid &g = c->grid;
+    const int kl = g.k1 - g.k0;
+    const int nj[3] = {g.J, g.J + 1, g.J}, ni[3] = {g.I + 1, g.I, g.I};
+    if (what >= 0 && what < 9) {
+        int a = what % 3;
+        *base = (unsigned char *)c->field[what / 3][a].p; *bytes = (size_t)g.pitch[a] * nj[a] * 4; *layers = kl + (a == 2);
+    } else if (what == 9) {
+        *base = (unsigned char *)c->material.p; *bytes = (size_t)g.I * g.J; *layers = kl;
+    } else if (what >= 10 && what < 13) {
+        int a = what - 10;
+        *base = (unsigned char *)c->acc[a].p; *bytes = (size_t)ni[a] * nj[a] * 16; *layers = kl + (a == 2);
+    } else throw GfsError("unknown grid array id");
+}
+}  // namespace
+
+int64_t gfs_layer_bytes(gfs_context *c, int what, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    unsigned char *base; size_t bytes; int layers;
+    layer_info(c, what, &base, &bytes, &layers);
+    return (int64_t)bytes;
+    GFS_END(-1)
+}
+
+void gfs_pack_layers(gfs_context *c, int what, int k_first, int k_count, void *dst_device, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    unsigned char *base; size_t bytes; int layers;
+    layer_info(c, what, &base, &bytes, &layers);
+    GFS_REQUIRE(dst_device && k_first >= 0 && k_count >= 0 && k_first + k_count <= layers, "layer range out of bounds");
+    GFS_CUDA(cudaMemcpyAsync(dst_device, base + bytes * (size_t)k_first, bytes * (size_t)k_count, cudaMemcpyDeviceToDevice, c->stream));
+    GFS_END()
+}
+
+void gfs_unpack_layers(gfs_context *c, int what, int k_first, int k_count, const void *src_device, int add, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    unsigned char *base; size_t bytes; int layers;
+    layer_info(c, what, &base, &bytes, &layers);
+    GFS_REQUIRE(src_device && k_first >= 0 && k_count >= 0 && k_first + k_count <= layers, "layer range out of bounds");
+    if (add) {
+        GFS_REQUIRE(what >= 10 && what < 13, "only the integer accumulators can be added");
+        long long count = (long long)(bytes * (size_t)k_count / 8);
+        if (count > 0)
+            LAUNCH(c, gfs::k_add_u64, ceil_div(count, 256), 256, count, (unsigned long long *)(base + bytes * (size_t)k_first),
+                   (const unsigned long long *)src_device);
+    } else {
+        GFS_CUDA(cudaMemcpyAsync(base + bytes * (size_t)k_first, src_device, bytes * (size_t)k_count, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    GFS_END()
+}
+
+void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
+                           int64_t *n_down, int64_t *n_up, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(n_down && n_up && cap >= 0 && cap < 0x7FFFFFFFll && (cap == 0 || (down_device && up_device)), "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    *n_down = *n_up = 0;
+    if (c->n == 0) return;
+    c->split_counters.reserve(4);
+    GFS_CUDA(cudaMemsetAsync(c->split_counters.p, 0, 4 * sizeof(unsigned int), c->stream));
+    const int src = c->cur, dst = 1 - c->cur;
+    LAUNCH(c, gfs::k_split_by_layer, ceil_div(c->n, 256), 256, c->grid, c->n, k_lo, k_hi, (int)cap,
+           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, c->tag[src].p,
+           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->tag[dst].p,
+           (float *)down_device, (float *)up_device, c->split_counters.p);
+    unsigned int h[4];
+    GFS_CUDA(cudaMemcpyAsync(h, c->split_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_REQUIRE((int64_t)h[1] <= cap && (int64_t)h[2] <= cap, "migration buffer too small");
+    c->n = h[0]; c->cur = dst; c->sorted = false; c->keys_ready = false;
+    *n_down = h[1]; *n_up = h[2];
+    GFS_END()
+}
+
+void gfs_append_particles_device(gfs_context *c, const void *aos_device, int64_t n, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && n >= 0 && (n == 0 || aos_device), "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    const int64_t old = c->n;
+    int e2 = GFS_SUCCESS;
+    gfs_resize_particles(c, old + n, &e2);
+    if (e2 != GFS_SUCCESS) throw GfsError(g_error);
+    const int b = c->cur;
+    LAUNCH(c, gfs::k_append_aos, ceil_div(n, 256), 256, n, old, (const float *)aos_device, c->soa[b][0].p, c->soa[b][1].p,
+           c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p, c->tag[b].p);
     GFS_END()
 }
 

@@ -163,15 +163,16 @@ __global__ void k_reorder(int64_t n, const int32_t *__restrict__ perm,
 // ------------------------------------------------------------------------------------------------
 // K1a: classification  (FluidSimulation::_updateFluidCells marking loop, fluidsimulation.cpp:1998-2017)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_classify(Grid g, const int32_t *__restrict__ cell_start, uint8_t *__restrict__ material,
-                           unsigned long long *__restrict__ counters /* [0]=in_solid particles, [1]=fluid cells */) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y, kl = blockIdx.z;
-    if (i >= g.I) return;
-    int k = kl + g.k0;
+__global__ void __launch_bounds__(256) k_classify(Grid g, const int32_t *__restrict__ cell_start, uint8_t *__restrict__ material,
+                           unsigned long long *__restrict__ counters /* [0]=in_solid particles, [1]=fluid cells */,
+                           long long first_cell, long long ncells, int own_k0, int own_k1) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells) return;
+    const size_t idx = (size_t)(first_cell + t);
+    const int i = (int)(idx % (size_t)g.I), j = (int)((idx / (size_t)g.I) % (size_t)g.J), kl = (int)(idx / ((size_t)g.I * (size_t)g.J));
+    const int k = kl + g.k0;
     uint32_t key = brick_key(g, i, j, kl);
     int cnt = cell_start[key + 1] - cell_start[key];
-    size_t idx = (size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl);
     uint8_t m = material[idx];
     bool interior = i >= 1 && i < g.I - 1 && j >= 1 && j < g.J - 1 && k >= 1 && k < g.K - 1;
     if (interior && m == GFS_FLUID) m = GFS_AIR;
@@ -180,7 +181,7 @@ __global__ void k_classify(Grid g, const int32_t *__restrict__ cell_start, uint8
         else m = GFS_FLUID;
     }
     material[idx] = m;
-    if (m == GFS_FLUID) atomicAdd(&counters[1], 1ull);
+    if (m == GFS_FLUID && k >= own_k0 && k < own_k1) atomicAdd(&counters[1], 1ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,7 +418,8 @@ struct FinalizeArgs {
     unsigned long long *acc[3];
     float *val[3];
     uint8_t *setmask[3];
-    long long count[3];
+    long long first[3];           // first node of the processed layer range, per component
+    long long count[3];           // number of nodes processed, per component
 };
 
 __global__ void __launch_bounds__(256) k_p2g_finalize(Grid g, SplatParams sp, Sources src, FinalizeArgs fa) {
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(256) k_p2g_finalize(Grid g, SplatParams sp, So
     const long long c0 = fa.count[0], c01 = fa.count[0] + fa.count[1], c012 = c01 + fa.count[2];
     if (t0 >= c012) return;
     const int comp = (t0 >= c0) + (t0 >= c01);
-    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)));
+    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)) + (comp == 0 ? fa.first[0] : (comp == 1 ? fa.first[1] : fa.first[2])));
     ulonglong2 *a = reinterpret_cast<ulonglong2 *>(comp == 0 ? fa.acc[0] : (comp == 1 ? fa.acc[1] : fa.acc[2])) + node;
     ulonglong2 v = *a;
     if (v.x | v.y) *a = make_ulonglong2(0ull, 0ull);
@@ -533,6 +535,7 @@ struct AssembleArgs {
     const float *val[3];
     const uint8_t *setmask[3];
     float *out[3];
+    long long first[3];
     long long count[3];
 };
 
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
     const long long c0 = aa.count[0], c01 = aa.count[0] + aa.count[1], c012 = c01 + aa.count[2];
     if (t0 >= c012) return;
     const int comp = (t0 >= c0) + (t0 >= c01);
-    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)));
+    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)) + (comp == 0 ? aa.first[0] : (comp == 1 ? aa.first[1] : aa.first[2])));
     const int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
     const int i = (int)(node % (size_t)ni), j = (int)((node / (size_t)ni) % (size_t)nj), kl = (int)(node / ((size_t)ni * (size_t)nj));
     const int k = kl + g.k0;
@@ -956,6 +959,45 @@ __global__ void k_soa_to_aos(int64_t n, const float *x, const float *y, const fl
     if (r >= n) return;
     float *p = aos + 6 * r;
     p[0] = x[r]; p[1] = y[r]; p[2] = z[r]; p[3] = vx[r]; p[4] = vy[r]; p[5] = vz[r];
+}
+
+// acc[first .. first+count) += src  (integer adds: the slab partial sums merge bit-exactly in any order)
+__global__ void k_add_u64(long long count, unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) dst[t] += src[t];
+}
+
+// Split the resident particles by the cell layer of their position: k < k_lo -> `down` (AoS, 6 floats), k >= k_hi ->
+// `up`, the rest compacted into the other SoA buffer.  counters[0..2] = kept, down, up.  (A NaN position has
+// no layer: it stays.)  Order inside each output is unspecified -- the next substep re-bins anyway.
+__global__ void __launch_bounds__(256) k_split_by_layer(Grid g, int64_t n, int k_lo, int k_hi, int cap,
+                                 const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                                 const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                                 const int32_t *__restrict__ tag,
+                                 float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
+                                 float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, int32_t *__restrict__ otag,
+                                 float *__restrict__ down, float *__restrict__ up, unsigned int *__restrict__ counters) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float pz = z[r];
+    int k = cell_floor((double)pz, g.invdx);
+    int dest = (pz == pz) ? (k < k_lo ? 1 : (k >= k_hi ? 2 : 0)) : 0;
+    unsigned int slot = atomicAdd(&counters[dest], 1u);
+    if (dest == 0) {
+        ox[slot] = x[r]; oy[slot] = y[r]; oz[slot] = pz; ovx[slot] = vx[r]; ovy[slot] = vy[r]; ovz[slot] = vz[r]; otag[slot] = tag[r];
+    } else if ((int)slot < cap) {
+        float *o = (dest == 1 ? down : up) + 6 * (size_t)slot;
+        o[0] = x[r]; o[1] = y[r]; o[2] = pz; o[3] = vx[r]; o[4] = vy[r]; o[5] = vz[r];
+    }
+}
+
+__global__ void k_append_aos(int64_t n, int64_t at, const float *__restrict__ aos, float *x, float *y, float *z,
+                             float *vx, float *vy, float *vz, int32_t *tag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float *p = aos + 6 * r;
+    x[at + r] = p[0]; y[at + r] = p[1]; z[at + r] = p[2]; vx[at + r] = p[3]; vy[at + r] = p[4]; vz[at + r] = p[5];
+    tag[at + r] = -1;
 }
 
 __global__ void k_border_solid(Grid g, uint8_t *__restrict__ material) {

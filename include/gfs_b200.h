@@ -170,6 +170,26 @@ void gfs_g2p_advect(gfs_context *ctx, double dt, double ratio_picflip, int order
 /* gfs_sort + gfs_p2g + gfs_g2p_advect, stream-ordered, no host synchronisation. */
 void gfs_substep(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
 
+/* ---- z-slab sharding across GPUs (one context per GPU; the exchange itself is the caller's: NCCL) ----------
+ * Every rank allocates the whole grid but OWNS the cell layers [k0,k1): its particles are those whose cell lies in
+ * them, and its grid kernels only touch the owned layers plus one halo layer.  A sharded P2G is
+ *   gfs_sort_unstable; gfs_p2g_begin;  exchange(accumulator layers: add; material layers: copy);  gfs_p2g_end
+ * Partial sums are 64-bit integers, so the merged grid is bit-identical to the single-GPU one.
+ * Layer arrays (`what`): 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..12 accumulators of u,v,w. */
+void gfs_set_owned_layers(gfs_context *ctx, int k0, int k1, int *err);
+void gfs_p2g_begin(gfs_context *ctx, int arith, int *err);
+void gfs_p2g_end(gfs_context *ctx, int *err);
+int64_t gfs_layer_bytes(gfs_context *ctx, int what, int *err);
+/* copy z-layers [k_first, k_first+k_count) of a resident array to / from a caller-owned DEVICE buffer; add != 0
+ * (accumulators only) adds the buffer as 64-bit integers instead of overwriting */
+void gfs_pack_layers(gfs_context *ctx, int what, int k_first, int k_count, void *dst_device, int *err);
+void gfs_unpack_layers(gfs_context *ctx, int what, int k_first, int k_count, const void *src_device, int add, int *err);
+/* particle migration: remove the particles whose cell layer is < k_lo (written as MarkerParticle_t AoS to down_device)
+ * or >= k_hi (to up_device); cap = capacity of each buffer in particles.  Synchronises to return the counts. */
+void gfs_extract_particles(gfs_context *ctx, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
+                           int64_t *n_down, int64_t *n_up, int *err);
+void gfs_append_particles_device(gfs_context *ctx, const void *aos_device, int64_t n, int *err);
+
 /* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).
  * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz. */
 void *gfs_device_ptr(gfs_context *ctx, int which, int *err);

@@ -363,21 +363,13 @@ static int source_contains(const orc_source_t *s, const float p[3]) {
  *   in range and "set" -- U tests fabs(value) > 0 (:2630), V and W test isValueSet (:2675, :2720).
  *   out must hold the face array; it is fully overwritten (cleared first, :2598).
  * ---------------------------------------------------------------------------------------- */
-void orc_p2g_component(const float *pos, const float *vel, long n, int dir, int I, int J, int K, double dx,
-                       const unsigned char *material, const orc_source_t *sources, int nsources,
-                       float *out) {
+/* Everything of A6/A7 after the splat: `field`/`weight` hold the raw sums (they are normalised in place). */
+void orc_finish_component(float *field, const float *weight, int dir, int I, int J, int K, double dx,
+                          const unsigned char *material, const orc_source_t *sources, int nsources, float *out) {
     int ni = I + (dir == 0), nj = J + (dir == 1), nk = K + (dir == 2);
     size_t count = (size_t)ni * nj * nk;
-    float *field = (float *)calloc(count, sizeof(float));
-    float *weight = (float *)calloc(count, sizeof(float));
     unsigned char *isset = (unsigned char *)calloc(count, 1);
 
-    float offset[3];
-    offset[0] = (float)(dir == 0 ? 0.0 : 0.5 * dx);
-    offset[1] = (float)(dir == 1 ? 0.0 : 0.5 * dx);
-    offset[2] = (float)(dir == 2 ? 0.0 : 0.5 * dx);
-
-    orc_splat(pos, vel + dir, 3, n, dx, offset, dx, ni, nj, nk, field, weight);
     orc_apply_weight(field, weight, (long)count);
 
     double eps = 1e-9;
@@ -417,8 +409,25 @@ void orc_p2g_component(const float *pos, const float *vel, long n, int dir, int 
                         }
                 if (wsum > 0.0) out[idx] = (float)(avg / wsum);
             }
+    free(isset);
+}
 
-    free(field); free(weight); free(isset);
+void orc_p2g_component(const float *pos, const float *vel, long n, int dir, int I, int J, int K, double dx,
+                       const unsigned char *material, const orc_source_t *sources, int nsources,
+                       float *out) {
+    int ni = I + (dir == 0), nj = J + (dir == 1), nk = K + (dir == 2);
+    size_t count = (size_t)ni * nj * nk;
+    float *field = (float *)calloc(count, sizeof(float));
+    float *weight = (float *)calloc(count, sizeof(float));
+
+    float offset[3];
+    offset[0] = (float)(dir == 0 ? 0.0 : 0.5 * dx);
+    offset[1] = (float)(dir == 1 ? 0.0 : 0.5 * dx);
+    offset[2] = (float)(dir == 2 ? 0.0 : 0.5 * dx);
+
+    orc_splat(pos, vel + dir, 3, n, dx, offset, dx, ni, nj, nk, field, weight);
+    orc_finish_component(field, weight, dir, I, J, K, dx, material, sources, nsources, out);
+    free(field); free(weight);
 }
 
 /* Stage 1 + stage 5 of FluidSimulation::_stepFluid for a given particle set:

@@ -70,6 +70,9 @@ void orc_p2g_component(const float *pos, const float *vel, long n, int dir, int 
                        const unsigned char *material, const orc_source_t *sources, int nsources,
                        float *out);
 
+void orc_finish_component(float *field, const float *weight, int dir, int I, int J, int K, double dx,
+                          const unsigned char *material, const orc_source_t *sources, int nsources, float *out);
+
 void orc_p2g(const float *pos, const float *vel, long n, int I, int J, int K, double dx,
              unsigned char *material, const orc_source_t *sources, int nsources,
              float *u, float *v, float *w);

@@ -86,6 +86,7 @@ class Oracle:
         L.orc_classify.restype = C.c_long
         L.orc_p2g_component.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                         _u8, C.c_void_p, C.c_int, _f32]
+        L.orc_finish_component.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _u8, C.c_void_p, C.c_int, _f32]
         L.orc_p2g.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double,
                               _u8, C.c_void_p, C.c_int, _f32, _f32, _f32]
         L.orc_solid_test.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, _u8, _u8]
@@ -148,6 +149,20 @@ class Oracle:
         u, v, w = np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32)
         self.lib.orc_p2g(pos, vel, len(pos), *dims, dx, material, C.cast(src, C.c_void_p), ns, u, v, w)
         return u, v, w
+
+    def splat_component(self, pos, vel, comp, dims, dx, field, weight):
+        """accumulate velocity component `comp` of the particles into raw (un-normalised) node sums"""
+        nd = face_dims(*dims)[comp]
+        off = np.array([0.0 if comp == 0 else 0.5 * dx, 0.0 if comp == 1 else 0.5 * dx, 0.0 if comp == 2 else 0.5 * dx], np.float32)
+        pos = _c(pos)
+        vals = np.ascontiguousarray(_c(vel)[:, comp])
+        self.lib.orc_splat(pos, vals, 1, len(pos), dx, off, dx, *nd, field, weight)
+
+    def finish_component(self, field, weight, comp, dims, dx, material, sources=()):
+        src, ns = make_sources(list(sources))
+        out = np.empty_like(field)
+        self.lib.orc_finish_component(field, weight, comp, *dims, dx, material, C.cast(src, C.c_void_p), ns, out)
+        return out
 
     def g2p_advect(self, pos, vel, new, saved, dims, dx, dt, ratio=float(np.float32(0.05)), order=4, mode=1,
                    material=None):

@@ -527,3 +527,58 @@ def test_hello_world_64_full_parity(ctx, oracle):
     # everywhere (a 1e-7 position difference can only flip a cell for a particle sitting on a face)
     ca, cb = oracle.cell_index(p, s["dx"]), oracle.cell_index(p_ref[o], s["dx"])
     assert (ca != cb).any(1).mean() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# z-slab sharding on ONE device: several virtual slabs in one process (slabs.LoopbackWorld)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,name,interp", [(2, "small32", capi.TRILINEAR), (4, "small32", capi.TRICUBIC), (3, "slab24", capi.TRILINEAR)])
+def test_virtual_slabs_equal_single_domain(oracle, world, name, interp):
+    """Sharded == unsharded: after each of 3 substeps the material and the P2G fields of every slab's owned layers are
+    bit-identical to the single-context run (integer partial sums), and the union of the slabs' particles is the
+    single-context particle set, bit for bit."""
+    import torch
+    from gridfluidsim3d_b200 import slabs
+    s = scene(name, interior_solids=(name == "slab24"))
+    s["new"] = (s["new"][0], s["new"][1], (s["new"][2] + np.float32(0.6)).astype(np.float32))   # +z drift: cross the cuts
+    I, J, K = s["dims"]
+    dt = 1.5 * s["dt"]
+    single = capi.Context(0)
+    load_domain(single, s)
+    single.set_field(capi.FIELD_NEW, *s["new"]); single.set_field(capi.FIELD_SAVED, *s["saved"])
+    ranges = slabs.slab_ranges(K, world)
+    kcell = oracle.cell_index(s["pos"], s["dx"])[:, 2]
+    ctxs, drivers = [], []
+    for r, (k0, k1) in enumerate(ranges):
+        c = capi.Context(0)
+        c.domain_init(s["dims"], s["dx"]); c.set_material(s["material"]); c.set_sources([])
+        mine = (kcell >= k0) & (kcell < k1)
+        c.set_particles(s["pos"][mine], s["vel"][mine])
+        c.set_field(capi.FIELD_NEW, *s["new"]); c.set_field(capi.FIELD_SAVED, *s["saved"])
+        ctxs.append(c)
+        drivers.append(slabs.SlabDriver(slabs.CudaSlabBackend(c, s["dims"], (k0, k1), interp), r, world, halo=3))
+    world_ = slabs.LoopbackWorld(drivers)
+
+    def rows(p, v):
+        a = np.ascontiguousarray(np.concatenate([p, v], 1))
+        return np.sort(a.view([("f%d" % i, "f4") for i in range(6)]).reshape(-1), order=["f%d" % i for i in range(6)])
+    moved = 0
+    for step in range(3):
+        single.substep(dt, interp=interp, arith=capi.FAST)
+        moved += world_.substep(dt)
+        torch.cuda.synchronize()
+        ref_mat = single.get_material().reshape(K, J, I)
+        ref_f = single.get_field(capi.FIELD_P2G)
+        for c, (k0, k1) in zip(ctxs, ranges):
+            assert np.array_equal(c.get_material().reshape(K, J, I)[k0:k1], ref_mat[k0:k1])
+            for got, ref, (ni, nj, nk) in zip(c.get_field(capi.FIELD_P2G), ref_f, synth.face_dims(s["dims"])):
+                assert np.array_equal(bits(got.reshape(nk, nj, ni)[k0:k1]), bits(ref.reshape(nk, nj, ni)[k0:k1]))
+        ps = [c.get_particles() for c in ctxs]
+        allp, allv = np.concatenate([p for p, _ in ps]), np.concatenate([v for _, v in ps])
+        assert np.array_equal(rows(allp, allv), rows(*single.get_particles()))
+        for (p, _), (k0, k1) in zip(ps, ranges):
+            kk = oracle.cell_index(p, s["dx"])[:, 2]
+            assert ((kk >= k0) & (kk < k1)).all()
+    assert moved > 0
+    for c in ctxs + [single]:
+        c.close()
