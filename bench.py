@@ -274,7 +274,7 @@ def run_reference(args):
         "gpu_launches": 0, "wall_s": wall,
     }
     cpu.close()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -503,13 +503,27 @@ def run_gfs(args):
                              "particles_mean": n_now / world, "particles_after": n_now}
     ctx.close()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints to fd 1 during the
+    run (NCCL's version banner, for one) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(JSON_FD if JSON_FD is not None else 1, data)
+
+
 def main():
+    global JSON_FD
+    sys.stdout.flush()
+    JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -977,12 +977,34 @@ __global__ void __launch_bounds__(256) k_split_by_layer(Grid g, int64_t n, int k
                                  float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
                                  float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, int32_t *__restrict__ otag,
                                  float *__restrict__ down, float *__restrict__ up, unsigned int *__restrict__ counters) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const float pz = z[r];
-    int k = cell_floor((double)pz, g.invdx);
-    int dest = (pz == pz) ? (k < k_lo ? 1 : (k >= k_hi ? 2 : 0)) : 0;
-    unsigned int slot = atomicAdd(&counters[dest], 1u);
+    // one global atomic per block and destination (a per-thread ticket on a single counter serialises 10^8 atomics);
+    // slots inside a block follow thread order, so the stayers keep their (nearly sorted) order
+    __shared__ unsigned int s_warp[8][3], s_base[3];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int dest = -1;
+    float pz = 0.0f;
+    if (r < n) {
+        pz = z[r];
+        int k = cell_floor((double)pz, g.invdx);
+        dest = (pz == pz) ? (k < k_lo ? 1 : (k >= k_hi ? 2 : 0)) : 0;
+    }
+    unsigned int m[3], before = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        m[d] = __ballot_sync(0xffffffffu, dest == d);
+        if (dest == d) before = __popc(m[d] & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[warp][d] = __popc(m[d]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned int tot = 0;
+        for (int w = 0; w < 8; w++) { unsigned int c = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = tot; tot += c; }
+        s_base[threadIdx.x] = tot ? atomicAdd(&counters[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+    if (dest < 0) return;
+    const unsigned int slot = s_base[dest] + s_warp[warp][dest] + before;
     if (dest == 0) {
         ox[slot] = x[r]; oy[slot] = y[r]; oz[slot] = pz; ovx[slot] = vx[r]; ovy[slot] = vy[r]; ovz[slot] = vz[r]; otag[slot] = tag[r];
     } else if ((int)slot < cap) {
