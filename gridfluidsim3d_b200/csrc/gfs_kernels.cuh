@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(256) k_classify(Grid g, const int32_t *__restr
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncells) return;
     const size_t idx = (size_t)(first_cell + t);
-    const int i = (int)(idx % (size_t)g.I), j = (int)((idx / (size_t)g.I) % (size_t)g.J), kl = (int)(idx / ((size_t)g.I * (size_t)g.J));
+    const uint32_t idx32 = (uint32_t)idx;                       // cell counts fit 31 bits (checked at domain_init)
+    const int i = (int)(idx32 % (uint32_t)g.I), j = (int)((idx32 / (uint32_t)g.I) % (uint32_t)g.J), kl = (int)(idx32 / ((uint32_t)g.I * (uint32_t)g.J));
     const int k = kl + g.k0;
     uint32_t key = brick_key(g, i, j, kl);
     int cnt = cell_start[key + 1] - cell_start[key];
@@ -547,7 +548,8 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
     const int comp = (t0 >= c0) + (t0 >= c01);
     const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)) + (comp == 0 ? aa.first[0] : (comp == 1 ? aa.first[1] : aa.first[2])));
     const int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
-    const int i = (int)(node % (size_t)ni), j = (int)((node / (size_t)ni) % (size_t)nj), kl = (int)(node / ((size_t)ni * (size_t)nj));
+    const uint32_t n32 = (uint32_t)node;                        // node counts fit 31 bits
+    const int i = (int)(n32 % (uint32_t)ni), j = (int)((n32 / (uint32_t)ni) % (uint32_t)nj), kl = (int)(n32 / ((uint32_t)ni * (uint32_t)nj));
     const int k = kl + g.k0;
     const float *val = comp == 0 ? aa.val[0] : (comp == 1 ? aa.val[1] : aa.val[2]);
     const uint8_t *setmask = comp == 0 ? aa.setmask[0] : (comp == 1 ? aa.setmask[1] : aa.setmask[2]);
@@ -738,7 +740,7 @@ __device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f,
 }
 
 template <int INTERP>
-__global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
+__global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
                             const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start, int order, RkCoef rk,
                             float ratio_pic, float ratio_flip, int64_t n,
                             const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
@@ -751,7 +753,9 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
     // dynamic shared memory: [pad to 128 B] NEW u,v,w [nCount each] | SAVED u,v,w [sCount each] | mbarrier.
     // TMA destinations must be 128-byte aligned: align by hand, static shared variables precede this block.
     extern __shared__ unsigned char smem_raw[];
-    float *tiles = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler must keep knowing this is
+    // shared memory, or every tap becomes a generic LD instead of an LDS)
+    float *tiles = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     uint64_t &bar = *reinterpret_cast<uint64_t *>(tiles + 3 * (T::nCount + T::sCount));
     const uint32_t b = blockIdx.x, nbricks = nkeys / kBrickCells;
     // the last CTA takes the overflow bin (particles outside the grid): no tile, global path only
@@ -781,8 +785,21 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
                          : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
     }
     float m = 0.0f;
-    for (int r = start + threadIdx.x; r < end; r += blockDim.x) {
-        const float px = x[r], py = y[r], pz = z[r];
+    // software pipeline: the next particle is loaded while this one is processed, and the ticket returned by the
+    // binning atomic of this particle is only stored during the next iteration (neither latency is waited on)
+    int r = start + threadIdx.x;
+    float nx_ = 0.f, ny_ = 0.f, nz_ = 0.f, nvx = 0.f, nvy = 0.f, nvz = 0.f;
+    if (r < end) { nx_ = x[r]; ny_ = y[r]; nz_ = z[r]; nvx = vx[r]; nvy = vy[r]; nvz = vz[r]; }
+    int pend_r = -1;
+    uint32_t pend_rank = 0;
+    for (; r < end; r += blockDim.x) {
+        const float px = nx_, py = ny_, pz = nz_;
+        const float ux = nvx, uy = nvy, uz = nvz;
+        {
+            const int rn = r + blockDim.x;
+            if (rn < end) { nx_ = x[rn]; ny_ = y[rn]; nz_ = z[rn]; nvx = vx[rn]; nvy = vy[rn]; nvz = vz[rn]; }
+        }
+        if (pend_r >= 0) rank_out[pend_r] = pend_rank;
         float k1x, k1y, k1z, sx, sy, sz;
         if (!overflow) {
             // p0 lies in this brick: NEW and SAVED taps are all staged, and share the index/fraction set
@@ -802,7 +819,6 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
         float nx = k1x, ny = k1y, nz = k1z;
         validate3(nx, ny, nz);
         validate3(sx, sy, sz);
-        const float ux = vx[r], uy = vy[r], uz = vz[r];
         const float wx = __fadd_rn(__fmul_rn(nx, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(ux, nx), sx), ratio_flip));
         const float wy = __fadd_rn(__fmul_rn(ny, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uy, ny), sy), ratio_flip));
         const float wz = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
@@ -849,13 +865,20 @@ __global__ void __launch_bounds__(256) k_g2p_brick(Grid g, const __grid_constant
         }
         ox[r] = qx; oy[r] = qy; oz[r] = qz;
         if (keys_out) {
-            uint32_t key = position_key(g, nkeys, qx, qy, qz);
+            // cell key of the advected position in fp32 (exact here, same value as position_key)
+            uint32_t key = nkeys;
+            if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {
+                const int i = (int)floorf(__fmul_rn(qx, g.invdxf)), j = (int)floorf(__fmul_rn(qy, g.invdxf)), k = (int)floorf(__fmul_rn(qz, g.invdxf));
+                if (k >= g.k0 && k < g.k1) key = brick_key(g, i, j, k - g.k0);
+            }
             keys_out[r] = key;
-            rank_out[r] = atomicAdd(counts + key, 1u);
+            pend_rank = atomicAdd(counts + key, 1u);
+            pend_r = r;
             float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (mm < 3.0e38f) m = fmaxf(m, mm);
         }
     }
+    if (pend_r >= 0) rank_out[pend_r] = pend_rank;
     if (keys_out) block_vmax(m, vmax_bits);
 }
 
