@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgfsref.so")
+DROPIN_SO = os.path.join(HERE, "_ref", "libgfsref_dropin.so")   # the reference simulator + the CUDA drop-in classes
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -179,9 +180,10 @@ class Oracle:
 class Reference:
     """The unmodified reference, driven through oracle/ref_harness.cpp."""
 
-    def __init__(self, build=True):
-        path = build_reference() if build else (REF_SO if os.path.exists(REF_SO) else None)
+    def __init__(self, build=True, path=None):
         if path is None:
+            path = build_reference() if build else (REF_SO if os.path.exists(REF_SO) else None)
+        if path is None or not os.path.exists(path):
             raise FileNotFoundError("oracle/_ref/libgfsref.so is not built and /root/reference is absent")
         self.lib = L = C.CDLL(path)
         V = C.c_void_p
@@ -197,6 +199,7 @@ class Reference:
         for name in ("ref_sim_initialize", "ref_sim_destroy", "ref_sim_update_fluid_cells",
                      "ref_sim_advect_velocity_field", "ref_sim_update_particle_velocities"):
             getattr(L, name).argtypes = [V]
+        L.ref_sim_set_accel.argtypes = [V, C.c_int, C.c_int]
         L.ref_sim_add_fluid_sphere.argtypes = [V, C.c_float, C.c_float, C.c_float, C.c_double]
         L.ref_sim_add_fluid_cuboid.argtypes = [V, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double]
         L.ref_sim_add_body_force.argtypes = [V, C.c_float, C.c_float, C.c_float]
@@ -299,6 +302,9 @@ class RefSim:
     def initialize(self):
         self.lib.ref_sim_initialize(self.h)
         self._init = True
+
+    def set_accel(self, particle_advection, scalar_field):
+        self.lib.ref_sim_set_accel(self.h, int(particle_advection), int(scalar_field))
 
     @property
     def n(self):
