@@ -70,7 +70,7 @@ def test_whole_simulator_with_cuda_accelerators(libs, fast):
         out.append((p, v, sim.get_material(), sim.get_fields()))
         sim.close()
     (p0, v0, m0, f0), (p1, v1, m1, f1) = out
-    assert len(p0) == len(p1) > 40000
+    assert len(p0) == len(p1) > 20000
     # two frames through P2G -> pressure solve -> extrapolation -> G2P: fp32-level differences in the splat are
     # carried through the solver, so compare at 1e-4 of the field scale (positions: of the cell size)
     assert np.abs(p0 - p1).max() < 1e-4 * 0.25
