@@ -1,17 +1,17 @@
 // TMA probe (kept as evidence for DESIGN.md section 8): tiled cp.async.bulk.tensor loads need a 16-byte aligned INNER box
 // coordinate.  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 profiles/tma_alignment_probe.cu; run: ./a.out 2 <flags>
-//#include <cuda.h>
-//#include <cuda_runtime.h>
-//#include <cstdio>
-//#include <cstdint>
-//#include <cstdlib>
-//#include <vector>
-//__device__ __forceinline__ uint32_t s32(const void*p){return (uint32_t)__cvta_generic_to_shared(p);}
-//// MODE 0: 1-D bulk copy (no tensor map); MODE 1: 2-D tensor map; MODE 2: 3-D tensor map
-//template<int MODE>
-//__global__ void k(const __grid_constant__ CUtensorMap map, const float* g, float* out, int flags){ int cx = (flags>>8)-64, cy = ((flags>>16)&255)-64;
-//  __shared__ __align__(128) float ts[4096];
-//  __shared__ __align__(8) uint64_t bars;
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+__device__ __forceinline__ uint32_t s32(const void*p){return (uint32_t)__cvta_generic_to_shared(p);}
+// MODE 0: 1-D bulk copy (no tensor map); MODE 1: 2-D tensor map; MODE 2: 3-D tensor map
+template<int MODE>
+__global__ void k(const __grid_constant__ CUtensorMap map, const float* g, float* out, int flags){ int cx = ((flags>>8)&255)-64, cy = ((flags>>16)&255)-64;
+  __shared__ __align__(128) float ts[4096];
+  __shared__ __align__(8) uint64_t bars;
   extern __shared__ unsigned char raw[];
   float* td = (float*)(((uintptr_t)raw+127)&~(uintptr_t)127);
   float* t = (flags&2) ? td : ts;
