@@ -824,34 +824,27 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
         const float wz = __fadd_rn(__fmul_rn(nz, ratio_pic), __fmul_rn(__fsub_rn(__fadd_rn(uz, nz), sz), ratio_flip));
         ovx[r] = wx; ovy[r] = wy; ovz[r] = wz;
 
-        // RK (particleadvector.cpp:1045-1078); stage positions sample the NEW tile (or global memory beyond it)
+        // RK (particleadvector.cpp:1045-1078) as ONE stage loop (one sampling site keeps the kernel inside the
+        // instruction cache): stage s samples at p0 + a_s * k_{s-1}; the sum b_0 k1 + b_1 k2 + ... is built left
+        // to right exactly as the reference writes it (RK4: ((k1 + 2k2) + 2k3) + k4, RK3: (2k1 + 3k2) + 4k3).
         float qx, qy, qz;
-        if (order == 1) { qx = axpy(px, rk.dt, k1x); qy = axpy(py, rk.dt, k1y); qz = axpy(pz, rk.dt, k1z); }
-        else {
-            float k2x, k2y, k2z;
-            if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, rk.half_dt, k1x), axpy(py, rk.half_dt, k1y), axpy(pz, rk.half_dt, k1z), k2x, k2y, k2z);
-            else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, rk.half_dt, k1x), axpy(py, rk.half_dt, k1y), axpy(pz, rk.half_dt, k1z), k2x, k2y, k2z);
-            if (order == 2) { qx = axpy(px, rk.dt, k2x); qy = axpy(py, rk.dt, k2y); qz = axpy(pz, rk.dt, k2z); }
-            else {
-                const float c3 = order == 3 ? rk.three_quarter_dt : rk.half_dt;
-                float k3x, k3y, k3z;
-                if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, c3, k2x), axpy(py, c3, k2y), axpy(pz, c3, k2z), k3x, k3y, k3z);
-                else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, c3, k2x), axpy(py, c3, k2y), axpy(pz, c3, k2z), k3x, k3y, k3z);
-                if (order == 3) {
-                    float ax_ = __fadd_rn(__fadd_rn(__fmul_rn(k1x, 2.0f), __fmul_rn(k2x, 3.0f)), __fmul_rn(k3x, 4.0f));
-                    float ay_ = __fadd_rn(__fadd_rn(__fmul_rn(k1y, 2.0f), __fmul_rn(k2y, 3.0f)), __fmul_rn(k3y, 4.0f));
-                    float az_ = __fadd_rn(__fadd_rn(__fmul_rn(k1z, 2.0f), __fmul_rn(k2z, 3.0f)), __fmul_rn(k3z, 4.0f));
-                    qx = axpy(px, rk.dt_over_9, ax_); qy = axpy(py, rk.dt_over_9, ay_); qz = axpy(pz, rk.dt_over_9, az_);
-                } else {
-                    float k4x, k4y, k4z;
-                    if (overflow) evaluate_pow2(g, fnew, INTERP, axpy(px, rk.dt, k3x), axpy(py, rk.dt, k3y), axpy(pz, rk.dt, k3z), k4x, k4y, k4z);
-                    else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, axpy(px, rk.dt, k3x), axpy(py, rk.dt, k3y), axpy(pz, rk.dt, k3z), k4x, k4y, k4z);
-                    float ax_ = __fadd_rn(__fadd_rn(__fadd_rn(k1x, __fmul_rn(k2x, 2.0f)), __fmul_rn(k3x, 2.0f)), k4x);
-                    float ay_ = __fadd_rn(__fadd_rn(__fadd_rn(k1y, __fmul_rn(k2y, 2.0f)), __fmul_rn(k3y, 2.0f)), k4y);
-                    float az_ = __fadd_rn(__fadd_rn(__fadd_rn(k1z, __fmul_rn(k2z, 2.0f)), __fmul_rn(k3z, 2.0f)), k4z);
-                    qx = axpy(px, rk.dt_over_6, ax_); qy = axpy(py, rk.dt_over_6, ay_); qz = axpy(pz, rk.dt_over_6, az_);
-                }
+        {
+            const float a1 = rk.half_dt, a2 = order == 3 ? rk.three_quarter_dt : rk.half_dt, a3 = rk.dt;
+            const float b0 = order == 3 ? 2.0f : 1.0f, b1 = order == 3 ? 3.0f : 2.0f, b2 = order == 3 ? 4.0f : 2.0f;
+            float kx = k1x, ky = k1y, kz = k1z;
+            float sx_ = __fmul_rn(k1x, b0), sy_ = __fmul_rn(k1y, b0), sz_ = __fmul_rn(k1z, b0);     // k*1.0f == k
+#pragma unroll 1
+            for (int st = 1; st < order; st++) {
+                const float a = st == 1 ? a1 : (st == 2 ? a2 : a3);
+                const float b = st == 1 ? b1 : (st == 2 ? b2 : 1.0f);
+                const float ex = axpy(px, a, kx), ey = axpy(py, a, ky), ez = axpy(pz, a, kz);
+                if (overflow) evaluate_pow2(g, fnew, INTERP, ex, ey, ez, kx, ky, kz);
+                else evaluate_tile<INTERP>(g, fnew, tnew, bx, by, bz, ex, ey, ez, kx, ky, kz);
+                sx_ = __fadd_rn(sx_, __fmul_rn(kx, b)); sy_ = __fadd_rn(sy_, __fmul_rn(ky, b)); sz_ = __fadd_rn(sz_, __fmul_rn(kz, b));
             }
+            if (order <= 2) { sx_ = kx; sy_ = ky; sz_ = kz; }          // RK1: dt*k1, RK2 (midpoint): dt*k2
+            const float h = order == 4 ? rk.dt_over_6 : (order == 3 ? rk.dt_over_9 : rk.dt);
+            qx = axpy(px, h, sx_); qy = axpy(py, h, sy_); qz = axpy(pz, h, sz_);
         }
         if (material) {
             // cell of the advected position (fp32-exact here); out of range reads as solid, NaN compares false -> solid
