@@ -26,7 +26,7 @@ SYMBOLS = [
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
-    "gfs_extract_particles", "gfs_append_particles_device",
+    "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -100,6 +100,8 @@ def load_library():
     L.gfs_pack_layers.argtypes = [V, I, I, I, V, _err]
     L.gfs_unpack_layers.argtypes = [V, I, I, I, V, I, _err]
     L.gfs_extract_particles.argtypes = [V, I, I, V, V, L64, C.POINTER(L64), C.POINTER(L64), _err]
+    L.gfs_extract_particles_async.argtypes = [V, I, I, V, V, L64, V, _err]
+    L.gfs_extract_commit.argtypes = [V, L64, _err]
     L.gfs_append_particles_device.argtypes = [V, V, L64, _err]
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
@@ -335,6 +337,12 @@ class Context:
         nd, nu = C.c_int64(), C.c_int64()
         self._call(self.lib.gfs_extract_particles, int(k_lo), int(k_hi), down_ptr, up_ptr, int(cap), C.byref(nd), C.byref(nu))
         return nd.value, nu.value
+
+    def extract_particles_async(self, k_lo, k_hi, down_ptr, up_ptr, cap, counters_ptr):
+        self._call(self.lib.gfs_extract_particles_async, int(k_lo), int(k_hi), down_ptr, up_ptr, int(cap), counters_ptr)
+
+    def extract_commit(self, n_kept):
+        self._call(self.lib.gfs_extract_commit, int(n_kept))
 
     def append_particles_device(self, aos_ptr, n):
         self._call(self.lib.gfs_append_particles_device, aos_ptr, int(n))

@@ -982,6 +982,16 @@ void gfs_unpack_layers(gfs_context *c, int what, int k_first, int k_count, const
     GFS_END()
 }
 
+// split kernel launch shared by the synchronous and the asynchronous entry points
+static void launch_split(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap, unsigned int *counters) {
+    GFS_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), c->stream));
+    const int src = c->cur, dst = 1 - c->cur;
+    LAUNCH(c, gfs::k_split_by_layer, ceil_div(c->n, 256), 256, c->grid, c->n, k_lo, k_hi, (int)cap,
+           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, c->tag[src].p,
+           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->tag[dst].p,
+           (float *)down_device, (float *)up_device, counters);
+}
+
 void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
                            int64_t *n_down, int64_t *n_up, int *err) {
     GFS_BEGIN
@@ -991,18 +1001,36 @@ void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device
     *n_down = *n_up = 0;
     if (c->n == 0) return;
     c->split_counters.reserve(4);
-    GFS_CUDA(cudaMemsetAsync(c->split_counters.p, 0, 4 * sizeof(unsigned int), c->stream));
-    const int src = c->cur, dst = 1 - c->cur;
-    LAUNCH(c, gfs::k_split_by_layer, ceil_div(c->n, 256), 256, c->grid, c->n, k_lo, k_hi, (int)cap,
-           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, c->tag[src].p,
-           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->tag[dst].p,
-           (float *)down_device, (float *)up_device, c->split_counters.p);
+    launch_split(c, k_lo, k_hi, down_device, up_device, cap, c->split_counters.p);
     unsigned int h[4];
     GFS_CUDA(cudaMemcpyAsync(h, c->split_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_REQUIRE((int64_t)h[1] <= cap && (int64_t)h[2] <= cap, "migration buffer too small");
-    c->n = h[0]; c->cur = dst; c->sorted = false; c->keys_ready = false;
+    c->n = h[0]; c->cur = 1 - c->cur; c->sorted = false; c->keys_ready = false;
     *n_down = h[1]; *n_up = h[2];
+    GFS_END()
+}
+
+/* Asynchronous variant: the three counts (kept, down, up, + one spare word) are left in caller-owned DEVICE memory and
+ * nothing is synchronised; the caller ships the counts to its neighbours, reads everything back in one go and then
+ * calls gfs_extract_commit with the number of kept particles. */
+void gfs_extract_particles_async(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
+                                 void *counters_device, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(counters_device && cap >= 0 && cap < 0x7FFFFFFFll && (cap == 0 || (down_device && up_device)), "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (c->n == 0) { GFS_CUDA(cudaMemsetAsync(counters_device, 0, 4 * sizeof(unsigned int), c->stream)); return; }
+    launch_split(c, k_lo, k_hi, down_device, up_device, cap, (unsigned int *)counters_device);
+    GFS_END()
+}
+
+void gfs_extract_commit(gfs_context *c, int64_t n_kept, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(n_kept >= 0 && n_kept <= c->n, "bad kept count");
+    if (c->n > 0) c->cur = 1 - c->cur;
+    c->n = n_kept; c->sorted = false; c->keys_ready = false;
     GFS_END()
 }
 

@@ -9,20 +9,23 @@ sides of a cut; each rank's grid kernels only touch its own layers plus one halo
        -> C1: add the neighbour's partial accumulators on the two node layers either side of each cut
               (64-bit integers: the merged sums are bit-identical to the single-GPU ones), and copy the
               neighbour's freshly classified boundary material layer
+          C2: copy H halo layers of the NEW and SAVED fields from each neighbour (what a sharded pressure solve
+              would have to hand over; H = stencil radius + displacement in cells) -- same message as C1 when
+              nothing sits between P2G and G2P (the synthetic substep), its own message otherwise
        -> P2G normalise + assemble on the owned layers
-       -> C2: copy H halo layers of the NEW and SAVED fields from each neighbour (what a sharded pressure solve
-              would have to hand over; H = stencil radius + displacement in cells)
        -> PIC/FLIP + RK4
-       -> C3: migrate the particles whose new cell layer left the slab (count-prefixed send/recv)
+       -> C3: migrate the particles whose new cell layer left the slab: counts travel device-to-device, are read
+              back with ONE host synchronisation per substep, then the payloads
 
-All exchanges are neighbour-only.  Transport is either torch.distributed point-to-point batches (NCCL over NVLink
-on GPUs; gloo in the CPU tests, which drive this same code with a numpy backend) or, for single-process tests, an
-in-process loopback between several drivers.  `backend` is duck-typed:
+All exchanges are neighbour-only, one batch of isend/irecv each, out of persistent buffers the backend packs into.
+Transport is torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests, which drive this same code with a
+numpy backend) or, for single-process tests, an in-process loopback between several drivers.  `backend` is duck-typed:
 
-  owned = (k0, k1);  K;  sort(); p2g_begin(); p2g_end(); g2p_advect(dt)
+  owned = (k0, k1);  K;  device;  sort(); p2g_begin(); p2g_end(); g2p_advect(dt);  num_particles
   layer_bytes(what) -> int
-  pack(what, k_first, k_count) -> uint8 tensor;   unpack(what, k_first, k_count, uint8 tensor, add)
-  extract(k_lo, k_hi) -> (down, up) float32 tensors [n,6];   append(float32 tensor [n,6]);   num_particles
+  pack_into(what, k_first, k_count, uint8 tensor, offset);   unpack_from(what, k_first, k_count, uint8 tensor, offset, add)
+  extract_async(k_lo, k_hi) -> (down [cap,6] f32, up [cap,6] f32, counts int32[4] = kept, n_down, n_up, spare)
+  extract_commit(n_kept);  append(float32 tensor [n,6])
 """
 import torch
 import torch.distributed as dist
@@ -49,68 +52,71 @@ class SlabDriver:
         self.K = backend.K
         self.peer = {"down": rank - 1 if rank > 0 else None, "up": rank + 1 if rank + 1 < world else None}
         assert world == 1 or self.k1 - self.k0 >= max(self.halo, 2), "slab thinner than the halo"
+        self._plans, self._bufs = {}, {}
 
     def sides(self):
         return [s for s in SIDES if self.peer[s] is not None]
 
-    def _cut_layers(self, side):
-        """node layers either side of the cut shared with the neighbour on `side`: (k-1, k) for the cut at cell k."""
-        return (self.k0 if side == "down" else self.k1) - 1, 2
+    # ---- what travels: lists of (what, send_first, send_count, recv_first, recv_count, add) per side --------------
+    def _items(self, side, phase):
+        if phase == "partials":                  # C1
+            cut = self.k0 if side == "down" else self.k1
+            items = [(w, cut - 1, 2, cut - 1, 2, True) for w in ACC]       # node layers (k-1, k) either side of the cut
+            mine, theirs = (self.k0, self.k0 - 1) if side == "down" else (self.k1 - 1, self.k1)
+            items.append((MATERIAL, mine, 1, theirs, 1, False))            # my boundary layer -> its halo layer
+            return items
+        if phase == "halos":                     # C2
+            H = self.halo
+            if side == "down":
+                s, r = (self.k0, min(H, self.k1 - self.k0)), (max(self.k0 - H, 0), self.k0 - max(self.k0 - H, 0))
+            else:
+                s, r = (max(self.k1 - H, self.k0), self.k1 - max(self.k1 - H, self.k0)), (self.k1, min(self.k1 + H, self.K) - self.k1)
+            return [(w, s[0], s[1], r[0], r[1], False) for w in NEW + SAVED]
+        raise ValueError(phase)
 
-    # ---- C1: P2G partial sums + boundary material ----------------------------------------------------------
-    def partials_send(self):
-        out = {}
-        for side in self.sides():
-            first, count = self._cut_layers(side)
-            parts = [self.b.pack(what, first, count) for what in ACC]
-            parts.append(self.b.pack(MATERIAL, self.k0 if side == "down" else self.k1 - 1, 1))   # my boundary layer
-            out[side] = torch.cat(parts)
-        return out
+    def plan(self, phases):
+        """{side: (items, send offsets, send bytes, recv offsets, recv bytes)}, cached"""
+        key = tuple(phases)
+        if key not in self._plans:
+            out = {}
+            for side in self.sides():
+                items = [it for ph in phases for it in self._items(side, ph)]
+                so, ro, sb, rb = [], [], 0, 0
+                for (w, sf, sc, rf, rc, add) in items:
+                    so.append(sb); ro.append(rb)
+                    sb += self.b.layer_bytes(w) * sc
+                    rb += self.b.layer_bytes(w) * rc
+                out[side] = (items, so, sb, ro, rb)
+            self._plans[key] = out
+        return self._plans[key]
 
-    def partials_recv_sizes(self):
-        return {side: sum(self.b.layer_bytes(w) * 2 for w in ACC) + self.b.layer_bytes(MATERIAL) for side in self.sides()}
+    def buffers(self, phases):
+        key = tuple(phases)
+        if key not in self._bufs:
+            dev = self.b.device
+            self._bufs[key] = ({s: torch.empty(p[2], dtype=torch.uint8, device=dev) for s, p in self.plan(phases).items()},
+                               {s: torch.empty(p[4], dtype=torch.uint8, device=dev) for s, p in self.plan(phases).items()})
+        return self._bufs[key]
 
-    def partials_recv(self, recv):
-        for side, buf in recv.items():
-            first, count = self._cut_layers(side)
-            sizes = [self.b.layer_bytes(w) * count for w in ACC] + [self.b.layer_bytes(MATERIAL)]
-            chunks = torch.split(buf, sizes)
-            for what, chunk in zip(ACC, chunks[:3]):
-                self.b.unpack(what, first, count, chunk, add=True)
-            # the neighbour's boundary layer is my halo layer
-            self.b.unpack(MATERIAL, self.k0 - 1 if side == "down" else self.k1, 1, chunks[3], add=False)
+    def pack(self, phases):
+        send, _ = self.buffers(phases)
+        for side, (items, so, sb, ro, rb) in self.plan(phases).items():
+            for (w, sf, sc, rf, rc, add), off in zip(items, so):
+                self.b.pack_into(w, sf, sc, send[side], off)
+        return send
 
-    # ---- C2: field halos -------------------------------------------------------------------------------------
-    def _halo_ranges(self, side):
-        H = self.halo
-        if side == "down":
-            return (self.k0, min(H, self.k1 - self.k0)), (max(self.k0 - H, 0), self.k0 - max(self.k0 - H, 0))
-        return (max(self.k1 - H, self.k0), self.k1 - max(self.k1 - H, self.k0)), (self.k1, min(self.k1 + H, self.K) - self.k1)
-
-    def halos_send(self, whats=NEW + SAVED):
-        out = {}
-        for side in self.sides():
-            (first, count), _ = self._halo_ranges(side)
-            out[side] = torch.cat([self.b.pack(what, first, count) for what in whats])
-        return out
-
-    def halos_recv_sizes(self, whats=NEW + SAVED):
-        return {side: sum(self.b.layer_bytes(w) * self._halo_ranges(side)[1][1] for w in whats) for side in self.sides()}
-
-    def halos_recv(self, recv, whats=NEW + SAVED):
-        for side, buf in recv.items():
-            _, (first, count) = self._halo_ranges(side)
-            for what, chunk in zip(whats, torch.split(buf, [self.b.layer_bytes(w) * count for w in whats])):
-                self.b.unpack(what, first, count, chunk, add=False)
+    def unpack(self, phases, recv):
+        for side, (items, so, sb, ro, rb) in self.plan(phases).items():
+            for (w, sf, sc, rf, rc, add), off in zip(items, ro):
+                self.b.unpack_from(w, rf, rc, recv[side], off, add)
 
     # ---- C3: particle migration --------------------------------------------------------------------------------
-    def migrate_send(self):
+    def migrate_begin(self):
         k_lo = self.k0 if self.peer["down"] is not None else INT_MIN
         k_hi = self.k1 if self.peer["up"] is not None else INT_MAX
-        down, up = self.b.extract(k_lo, k_hi)
-        return {s: t for s, t in (("down", down), ("up", up)) if self.peer[s] is not None}
+        return self.b.extract_async(k_lo, k_hi)
 
-    def migrate_recv(self, recv):
+    def migrate_end(self, recv):
         n = 0
         for side, t in recv.items():
             if t.shape[0] > 0:
@@ -139,35 +145,45 @@ class DistTransport:
                 req.wait()
         return recv
 
-    def fixed(self, drv, send, sizes):
-        some = next(iter(send.values())) if send else None
-        recv = {s: torch.empty(sizes[s], dtype=torch.uint8, device=some.device) for s in send}
-        return self.exchange(drv, send, recv)
+    def layers(self, drv, phases):
+        send = drv.pack(phases)
+        _, recv = drv.buffers(phases)
+        drv.unpack(phases, self.exchange(drv, send, recv))
 
-    def variable(self, drv, send):
-        """count-prefixed exchange of [n,6] float32 particle blocks"""
-        if not send:
-            return {}
-        dev = next(iter(send.values())).device
-        cnt_s = {s: torch.tensor([send[s].shape[0]], dtype=torch.int64, device=dev) for s in send}
-        cnt_r = self.exchange(drv, cnt_s, {s: torch.zeros(1, dtype=torch.int64, device=dev) for s in send})
-        recv = {s: torch.empty((int(cnt_r[s].item()), 6), dtype=torch.float32, device=dev) for s in send}
-        flat = self.exchange(drv, {s: send[s].reshape(-1) for s in send}, {s: recv[s].reshape(-1) for s in recv})
-        return {s: flat[s].reshape(-1, 6) for s in flat}
+    def migrate(self, drv):
+        down, up, counts = drv.migrate_begin()
+        sides = drv.sides()
+        if not sides:
+            kept = int(counts.cpu()[0])
+            drv.b.extract_commit(kept)
+            return 0, 0
+        slot = {"down": 1, "up": 2}
+        theirs = torch.zeros(4, dtype=counts.dtype, device=counts.device)
+        self.exchange(drv, {s: counts[slot[s]:slot[s] + 1] for s in sides}, {s: theirs[slot[s]:slot[s] + 1] for s in sides})
+        host = torch.cat([counts, theirs]).cpu().tolist()          # the one host synchronisation of the substep
+        kept, n_out, n_in = host[0], {"down": host[1], "up": host[2]}, {"down": host[5], "up": host[6]}
+        drv.b.extract_commit(kept)
+        out = {"down": down, "up": up}
+        send = {s: out[s][: n_out[s]].reshape(-1) for s in sides}
+        recv = {s: torch.empty((n_in[s], 6), dtype=torch.float32, device=counts.device) for s in sides}
+        self.exchange(drv, send, {s: recv[s].reshape(-1) for s in sides})
+        return sum(n_out[s] for s in sides), drv.migrate_end(recv)
 
 
-def substep(drv, transport, dt, exchange_fields=True):
+def substep(drv, transport, dt, pressure_solve_between=False):
     """One sharded substep of one rank.  Returns (particles sent away, particles received)."""
     b = drv.b
     b.sort()
     b.p2g_begin()
-    drv.partials_recv(transport.fixed(drv, drv.partials_send(), drv.partials_recv_sizes()))
-    b.p2g_end()
-    if exchange_fields:
-        drv.halos_recv(transport.fixed(drv, drv.halos_send(), drv.halos_recv_sizes()))
+    if pressure_solve_between:
+        transport.layers(drv, ("partials",))
+        b.p2g_end()
+        transport.layers(drv, ("halos",))          # the fields a solver produced after P2G
+    else:
+        transport.layers(drv, ("partials", "halos"))
+        b.p2g_end()
     b.g2p_advect(dt)
-    out = drv.migrate_send()
-    return sum(t.shape[0] for t in out.values()), drv.migrate_recv(transport.variable(drv, out))
+    return transport.migrate(drv)
 
 
 class LoopbackWorld:
@@ -178,8 +194,9 @@ class LoopbackWorld:
     def __init__(self, drivers):
         self.drv = list(drivers)
 
-    def _swap(self, sends):
-        recv = [dict() for _ in self.drv]
+    @staticmethod
+    def _swap(sends):
+        recv = [dict() for _ in sends]
         for r, s in enumerate(sends):
             if "up" in s:
                 recv[r + 1]["down"] = s["up"].clone()
@@ -187,22 +204,34 @@ class LoopbackWorld:
                 recv[r - 1]["up"] = s["down"].clone()
         return recv
 
-    def substep(self, dt, exchange_fields=True):
+    def _layers(self, phases):
+        for d, rcv in zip(self.drv, self._swap([d.pack(phases) for d in self.drv])):
+            d.unpack(phases, rcv)
+
+    def substep(self, dt, pressure_solve_between=False):
         for d in self.drv:
             d.b.sort()
             d.b.p2g_begin()
-        for d, rcv in zip(self.drv, self._swap([d.partials_send() for d in self.drv])):
-            d.partials_recv(rcv)
-        for d in self.drv:
-            d.b.p2g_end()
-        if exchange_fields:
-            for d, rcv in zip(self.drv, self._swap([d.halos_send() for d in self.drv])):
-                d.halos_recv(rcv)
+        if pressure_solve_between:
+            self._layers(("partials",))
+            for d in self.drv:
+                d.b.p2g_end()
+            self._layers(("halos",))
+        else:
+            self._layers(("partials", "halos"))
+            for d in self.drv:
+                d.b.p2g_end()
         for d in self.drv:
             d.b.g2p_advect(dt)
+        sends = []
+        for d in self.drv:
+            down, up, counts = d.migrate_begin()
+            c = counts.cpu().tolist()
+            d.b.extract_commit(c[0])
+            sends.append({s: t[:n] for s, t, n in (("down", down, c[1]), ("up", up, c[2])) if d.peer[s] is not None})
         moved = 0
-        for d, rcv in zip(self.drv, self._swap([d.migrate_send() for d in self.drv])):
-            moved += d.migrate_recv(rcv)
+        for d, rcv in zip(self.drv, self._swap(sends)):
+            moved += d.migrate_end(rcv)
         return moved
 
 
@@ -212,10 +241,11 @@ class CudaSlabBackend:
     def __init__(self, ctx, dims, owned, interp, arith=0, order=4, migrate_cap=None):
         self.ctx, self.K, self.owned = ctx, dims[2], tuple(owned)
         self.interp, self.arith, self.order = interp, arith, order
-        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device("cuda", torch.cuda.current_device())
         ctx.set_owned_layers(*owned)
         self.cap = migrate_cap
         self._bufs = None
+        self._counts = torch.zeros(4, dtype=torch.int32, device=self.device)
 
     @property
     def num_particles(self):
@@ -236,27 +266,26 @@ class CudaSlabBackend:
     def layer_bytes(self, what):
         return self.ctx.layer_bytes(what)
 
-    def pack(self, what, k_first, k_count):
-        t = torch.empty(self.layer_bytes(what) * k_count, dtype=torch.uint8, device=self.dev)
+    def pack_into(self, what, k_first, k_count, buf, offset):
         if k_count > 0:
-            self.ctx.pack_layers(what, k_first, k_count, t.data_ptr())
-        return t
+            self.ctx.pack_layers(what, k_first, k_count, buf.data_ptr() + offset)
 
-    def unpack(self, what, k_first, k_count, t, add):
+    def unpack_from(self, what, k_first, k_count, buf, offset, add):
         if k_count > 0:
-            t = t.contiguous()
-            self.ctx.unpack_layers(what, k_first, k_count, t.data_ptr(), add)
-            t.record_stream(torch.cuda.current_stream())
+            self.ctx.unpack_layers(what, k_first, k_count, buf.data_ptr() + offset, add)
 
-    def extract(self, k_lo, k_hi):
+    def extract_async(self, k_lo, k_hi):
         n = self.ctx.num_particles
         cap = self.cap if self.cap is not None else max(1024, n // 4)
         if self._bufs is None or self._bufs[0].shape[0] < cap:
-            self._bufs = (torch.empty((cap, 6), dtype=torch.float32, device=self.dev),
-                          torch.empty((cap, 6), dtype=torch.float32, device=self.dev))
+            self._bufs = (torch.empty((cap, 6), dtype=torch.float32, device=self.device),
+                          torch.empty((cap, 6), dtype=torch.float32, device=self.device))
         down, up = self._bufs
-        nd, nu = self.ctx.extract_particles(k_lo, k_hi, down.data_ptr(), up.data_ptr(), cap)
-        return down[:nd], up[:nu]
+        self.ctx.extract_particles_async(k_lo, k_hi, down.data_ptr(), up.data_ptr(), down.shape[0], self._counts.data_ptr())
+        return down, up, self._counts
+
+    def extract_commit(self, n_kept):
+        self.ctx.extract_commit(n_kept)
 
     def append(self, t):
         t = t.contiguous()

@@ -188,6 +188,11 @@ void gfs_unpack_layers(gfs_context *ctx, int what, int k_first, int k_count, con
  * or >= k_hi (to up_device); cap = capacity of each buffer in particles.  Synchronises to return the counts. */
 void gfs_extract_particles(gfs_context *ctx, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
                            int64_t *n_down, int64_t *n_up, int *err);
+/* the same split without any host synchronisation: counts {kept, down, up, spare} (4 x uint32) stay in caller-owned
+ * DEVICE memory; after reading them back the caller commits the new particle count */
+void gfs_extract_particles_async(gfs_context *ctx, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
+                                 void *counters_device, int *err);
+void gfs_extract_commit(gfs_context *ctx, int64_t n_kept, int *err);
 void gfs_append_particles_device(gfs_context *ctx, const void *aos_device, int64_t n, int *err);
 
 /* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).

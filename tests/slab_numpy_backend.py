@@ -10,6 +10,7 @@ class NumpySlabBackend:
     def __init__(self, oracle, scene, owned, mode=0):
         self.o, self.dims, self.dx, self.owned = oracle, scene["dims"], scene["dx"], tuple(owned)
         self.K = self.dims[2]
+        self.device = torch.device("cpu")
         self.mode = mode
         self.material = scene["material"].copy()
         self.new = [a.copy() for a in scene["new"]]
@@ -71,6 +72,14 @@ class NumpySlabBackend:
         arr, (a, b, _) = self._array(what)
         return a * b * arr.itemsize
 
+    def pack_into(self, what, k_first, k_count, buf, offset):
+        t = self.pack(what, k_first, k_count)
+        buf[offset: offset + t.numel()] = t
+
+    def unpack_from(self, what, k_first, k_count, buf, offset, add):
+        n = self.layer_bytes(what) * k_count
+        self.unpack(what, k_first, k_count, buf[offset: offset + n].clone(), add)
+
     def pack(self, what, k_first, k_count):
         if what >= 10:
             a, b, c = self.fdims[what - 10]
@@ -97,15 +106,20 @@ class NumpySlabBackend:
             arr[a * b * k_first: a * b * (k_first + k_count)] = raw.view(arr.dtype)
 
     # ---- particles
-    def extract(self, k_lo, k_hi):
+    def extract_async(self, k_lo, k_hi):
         k = self.o.cell_index(self.pos, self.dx)[:, 2] if len(self.pos) else np.zeros(0, np.int32)
         down, up = k < k_lo, k >= k_hi
         out = []
         for m in (down, up):
-            out.append(torch.from_numpy(np.concatenate([self.pos[m], self.vel[m]], 1).astype(np.float32)))
+            out.append(torch.from_numpy(np.concatenate([self.pos[m], self.vel[m]], 1).astype(np.float32).reshape(-1, 6)))
         keep = ~(down | up)
-        self.pos, self.vel = self.pos[keep], self.vel[keep]
-        return out[0], out[1]
+        self._kept = (self.pos[keep], self.vel[keep])
+        counts = torch.tensor([int(keep.sum()), int(down.sum()), int(up.sum()), 0], dtype=torch.int32)
+        return out[0], out[1], counts
+
+    def extract_commit(self, n_kept):
+        assert n_kept == len(self._kept[0])
+        self.pos, self.vel = self._kept
 
     def append(self, t):
         a = t.numpy()

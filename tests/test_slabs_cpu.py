@@ -56,7 +56,7 @@ def _worker(rank, world, port, name, steps, outdir):
     tr = slabs.DistTransport()
     moved = 0
     for _ in range(steps):
-        sent, got = slabs.substep(drv, tr, s["dt"] * 1.5)
+        sent, got = slabs.substep(drv, tr, s["dt"] * 1.5, pressure_solve_between=(_ == 1))
         moved += sent
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), pos=b.pos, vel=b.vel, material=b.material,
              u=b.p2g[0], v=b.p2g[1], w=b.p2g[2], owned=np.array(owned), moved=moved, bytes=tr.bytes_sent)
