@@ -357,7 +357,7 @@ def run_gfs(args):
     halo = capi.slab_halo_cells(interp, 0.5 * dx, dx)
     if world > 1:
         def make_driver(ip):
-            return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8)), rank, world,
+            return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8), shared_stream=True), rank, world,
                                     halo=capi.slab_halo_cells(ip, 0.5 * dx, dx))
         drv = make_driver(interp)
         transport = slabs.DistTransport()

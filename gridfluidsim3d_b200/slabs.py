@@ -162,6 +162,8 @@ class DistTransport:
         self.exchange(drv, {s: counts[slot[s]:slot[s] + 1] for s in sides}, {s: theirs[slot[s]:slot[s] + 1] for s in sides})
         host = torch.cat([counts, theirs]).cpu().tolist()          # the one host synchronisation of the substep
         kept, n_out, n_in = host[0], {"down": host[1], "up": host[2]}, {"down": host[5], "up": host[6]}
+        if max(n_out.values()) > down.shape[0]:
+            raise RuntimeError("migration buffer too small: %s leavers, capacity %d" % (n_out, down.shape[0]))
         drv.b.extract_commit(kept)
         out = {"down": down, "up": up}
         send = {s: out[s][: n_out[s]].reshape(-1) for s in sides}
@@ -238,7 +240,11 @@ class LoopbackWorld:
 class CudaSlabBackend:
     """The C-ABI context as a slab backend.  Comm buffers are torch tensors; the library packs / unpacks."""
 
-    def __init__(self, ctx, dims, owned, interp, arith=0, order=4, migrate_cap=None):
+    def __init__(self, ctx, dims, owned, interp, arith=0, order=4, migrate_cap=None, shared_stream=False):
+        """shared_stream: the context was created on torch's current CUDA stream (gfs_create(device, stream)), so the
+        library's kernels and torch's / NCCL's work are already ordered.  Otherwise every hand-over between the two
+        is fenced with a stream synchronisation (correct, slower: what the single-process tests use)."""
+        self.shared_stream = bool(shared_stream)
         self.ctx, self.K, self.owned = ctx, dims[2], tuple(owned)
         self.interp, self.arith, self.order = interp, arith, order
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -266,13 +272,25 @@ class CudaSlabBackend:
     def layer_bytes(self, what):
         return self.ctx.layer_bytes(what)
 
+    def _lib_done(self):          # library work must be visible to torch
+        if not self.shared_stream:
+            self.ctx.sync()
+
+    def _torch_done(self):        # torch work must be visible to the library
+        if not self.shared_stream:
+            torch.cuda.current_stream().synchronize()
+
     def pack_into(self, what, k_first, k_count, buf, offset):
         if k_count > 0:
+            self._torch_done()
             self.ctx.pack_layers(what, k_first, k_count, buf.data_ptr() + offset)
+            self._lib_done()
 
     def unpack_from(self, what, k_first, k_count, buf, offset, add):
         if k_count > 0:
+            self._torch_done()
             self.ctx.unpack_layers(what, k_first, k_count, buf.data_ptr() + offset, add)
+            self._lib_done()
 
     def extract_async(self, k_lo, k_hi):
         n = self.ctx.num_particles
@@ -281,7 +299,9 @@ class CudaSlabBackend:
             self._bufs = (torch.empty((cap, 6), dtype=torch.float32, device=self.device),
                           torch.empty((cap, 6), dtype=torch.float32, device=self.device))
         down, up = self._bufs
+        self._torch_done()
         self.ctx.extract_particles_async(k_lo, k_hi, down.data_ptr(), up.data_ptr(), down.shape[0], self._counts.data_ptr())
+        self._lib_done()
         return down, up, self._counts
 
     def extract_commit(self, n_kept):
@@ -289,5 +309,7 @@ class CudaSlabBackend:
 
     def append(self, t):
         t = t.contiguous()
+        self._torch_done()
         self.ctx.append_particles_device(t.data_ptr(), t.shape[0])
+        self._lib_done()
         t.record_stream(torch.cuda.current_stream())
