@@ -122,7 +122,9 @@ struct gfs_context {
     DevBuf<uint32_t> keys[2];
     DevBuf<uint32_t> rank;
     DevBuf<int32_t> perm[2];
-    bool keys_ready = false;              // keys/rank/counts/vmax of the current buffer were produced by the G2P epilogue
+    bool keys_ready = false;
+    bool indexed = false;                 // sorted order exists only as `index` (sorted slot -> storage slot); see k_build_index
+    DevBuf<int32_t> index;              // keys/rank/counts/vmax of the current buffer were produced by the G2P epilogue
     DevBuf<unsigned char> cub_tmp;
     DevBuf<int32_t> n_valid;              // 1 word
     DevBuf<unsigned int> vmax_bits;       // 1 word
@@ -132,6 +134,7 @@ struct gfs_context {
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
+    int lazy_sort = 1;                    // fused substep: sort by index only (no physical scatter)
     int g2p_variant = 1;                  // 1 = TMA-staged brick tiles (default where applicable), 0 = global loads only
     gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
     bool have_maps = false;
@@ -149,6 +152,7 @@ struct gfs_context {
             perm[b].reserve((size_t)m);
         }
         rank.reserve((size_t)m);
+        index.reserve((size_t)m);
     }
 };
 
@@ -222,7 +226,7 @@ gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
 // cell -- what the exact-arithmetic P2G needs to reproduce the reference's summation order.  stable = false:
 // counting sort (cell histogram with atomic tickets, exclusive scan, scatter); when the previous G2P already
 // binned the advected positions in its epilogue only the scan and the scatter remain.
-void do_sort(gfs_context *c, bool stable) {
+void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     require_domain(c);
     const int64_t n = c->n;
     const int src = c->cur, dst = 1 - c->cur;
@@ -264,6 +268,8 @@ void do_sort(gfs_context *c, bool stable) {
                    c->tag[src].p,
                    c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
                    c->tag[dst].p);
+        } else if (lazy) {
+            LAUNCH(c, gfs::k_build_index, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p, c->index.p);
         } else {
             LAUNCH(c, gfs::k_scatter_sorted, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p,
                    c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
@@ -271,8 +277,9 @@ void do_sort(gfs_context *c, bool stable) {
                    c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
                    c->tag[dst].p);
         }
-        c->cur = dst;
+        if (!(lazy && !stable)) c->cur = dst;
     }
+    c->indexed = lazy && !stable && n > 0;
     c->keys_ready = false;
     c->sorted = true;
 }
@@ -298,16 +305,18 @@ void do_p2g_begin(gfs_context *c, int arith) {
     LAUNCH(c, gfs::k_classify, ceil_div(plane * (hi - lo), 256), 256, g, c->cell_start.p, c->material.p, c->counters.p,
            plane * lo, plane * (hi - lo), c->own_k0, c->own_k1);
     c->p2g_arith = arith;
+    GFS_REQUIRE(!(arith == GFS_EXACT && c->indexed), "internal: exact P2G needs physically sorted particles");
     if (arith == GFS_EXACT) return;               // the exact gather does everything in do_p2g_end
     if (c->n > 0) {
         const bool pow2 = g.pow2 != 0;
+        const int32_t *idx = c->indexed ? c->index.p : nullptr;
         if (c->p2g_variant == 0) {
             if (pow2)
-                LAUNCH(c, gfs::k_p2g_scatter<2>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                LAUNCH(c, gfs::k_p2g_scatter<2>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys, idx,
                        c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
                        c->acc[0].p, c->acc[1].p, c->acc[2].p);
             else
-                LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys,
+                LAUNCH(c, gfs::k_p2g_scatter<0>, ceil_div(c->n, 256), 256, g, sp, c->cell_start.p + c->nkeys, idx,
                        c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
                        c->acc[0].p, c->acc[1].p, c->acc[2].p);
         } else {
@@ -316,11 +325,11 @@ void do_p2g_begin(gfs_context *c, int arith) {
             int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
             if (pow2)
                 gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(
-                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                    g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
                     c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
             else
                 gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(
-                    g, sp, c->cell_start.p, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
+                    g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
                     c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
             c->prof_end(prof_id_);
             c->launches++;
@@ -403,7 +412,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     if (brick) {
         const int nb = (int)(c->nkeys / gfs::kBrickCells) + 1;          // + the overflow-bin CTA
 #define GFS_BRICK_ARGS c->grid, c->maps[interp], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, c->cell_start.p, \
-               order, rk, rp, rf, c->n,                                                                                                  \
+               (c->indexed ? c->index.p : nullptr), c->tag[src].p, c->tag[dst].p, order, rk, rp, rf, c->n,                                                                                                  \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
                c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
@@ -421,8 +430,11 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     else if (c->grid.pow2) LAUNCH(c, gfs::k_g2p_advect<2>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
     else LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
 #undef GFS_G2P_ARGS
-    // tags travel with the slot: the G2P kernel keeps slot order, so copy the tag array across buffers
-    GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    // tags travel with the slot: the per-particle kernels keep slot order (copy the tag array across buffers); the brick
+    // kernel moves the tags itself (it may be reading through the lazy sort index)
+    if (!brick)
+        GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    c->indexed = false;
     c->cur = dst;
     c->sorted = false;          // positions moved: the cell table no longer describes them
     c->keys_ready = bin_next;
@@ -545,7 +557,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 3; s++) for (int a = 0; a < 3; a++) c->field[s][a].release();
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
-    c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release();
+    c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
     c->split_counters.release();
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
@@ -781,7 +793,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_REQUIRE(n < 0x7FFFFFFFll, "particle count must fit int32");
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
-    c->n = n; c->cur = 0; c->sorted = false; c->keys_ready = false;
+    c->n = n; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false;
     if (n > 0) {
         // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
         c->h_pos.reserve((size_t)n * 6);
@@ -869,6 +881,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     GFS_REQUIRE(c, "null context");
     if (option == 0) { GFS_REQUIRE(value == 0 || value == 1, "p2g variant must be 0 or 1"); c->p2g_variant = value; }
     else if (option == 1) { GFS_REQUIRE(value == 0 || value == 1, "g2p variant must be 0 or 1"); c->g2p_variant = value; }
+    else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
     else throw GfsError("gfs_set_option: unknown option");
     GFS_END()
 }
@@ -896,7 +909,7 @@ void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp,
     // exact arithmetic needs the stable order; fast arithmetic is order-independent and uses the counting sort,
     // binned for the following substep by the G2P kernel's epilogue
     if (c->keys_ready && arith == GFS_EXACT) c->keys_ready = false;
-    do_sort(c, arith == GFS_EXACT);
+    do_sort(c, arith == GFS_EXACT, /*lazy=*/arith != GFS_EXACT && c->grid.pow2 && c->have_maps && c->g2p_variant == 1 && c->lazy_sort);
     do_p2g(c, arith);
     do_g2p(c, dt, ratio, order, interp, arith, arith != GFS_EXACT);
     GFS_END()
@@ -1082,6 +1095,7 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
         c->tag[1 - b].release(); c->tag[1 - b].reserve(newcap);
         for (int q = 0; q < 2; q++) { c->keys[q].release(); c->keys[q].reserve(newcap); c->perm[q].release(); c->perm[q].reserve(newcap); }
         c->rank.release(); c->rank.reserve(newcap);
+        c->index.release(); c->index.reserve(newcap);
     }
     c->n = n;
     c->sorted = false;
