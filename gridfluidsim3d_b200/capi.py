@@ -26,7 +26,7 @@ SYMBOLS = [
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
-    "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
+    "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -99,6 +99,7 @@ def load_library():
     L.gfs_layer_bytes.restype = L64
     L.gfs_pack_layers.argtypes = [V, I, I, I, V, _err]
     L.gfs_unpack_layers.argtypes = [V, I, I, I, V, I, _err]
+    L.gfs_copy_layers_batch.argtypes = [V, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(L64), C.POINTER(I), V, _err]
     L.gfs_extract_particles.argtypes = [V, I, I, V, V, L64, C.POINTER(L64), C.POINTER(L64), _err]
     L.gfs_extract_particles_async.argtypes = [V, I, I, V, V, L64, V, _err]
     L.gfs_extract_commit.argtypes = [V, L64, _err]
@@ -332,6 +333,13 @@ class Context:
 
     def unpack_layers(self, what, k_first, k_count, src_ptr, add=False):
         self._call(self.lib.gfs_unpack_layers, what, int(k_first), int(k_count), src_ptr, int(add))
+
+    def copy_layers_batch(self, direction, items, buffer_ptr):
+        """items: [(what, k_first, k_count, byte offset, add)] -- one launch for all of them"""
+        n = len(items)
+        IA, LA = C.c_int * n, C.c_int64 * n
+        self._call(self.lib.gfs_copy_layers_batch, int(direction), n, IA(*[int(i[0]) for i in items]), IA(*[int(i[1]) for i in items]),
+                   IA(*[int(i[2]) for i in items]), LA(*[int(i[3]) for i in items]), IA(*[int(bool(i[4])) for i in items]), buffer_ptr)
 
     def extract_particles(self, k_lo, k_hi, down_ptr, up_ptr, cap):
         nd, nu = C.c_int64(), C.c_int64()

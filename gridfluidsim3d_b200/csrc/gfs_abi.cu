@@ -1005,6 +1005,42 @@ static void launch_split(gfs_context *c, int k_lo, int k_hi, void *down_device, 
            (float *)down_device, (float *)up_device, counters);
 }
 
+/* Batched form of gfs_pack_layers / gfs_unpack_layers: n <= 16 layer ranges to / from one caller-owned device buffer
+ * at the given byte offsets, in ONE kernel launch.  direction 0 = pack (library -> buffer), 1 = unpack (buffer ->
+ * library; add[i] != 0 adds 64-bit integers, accumulators only). */
+void gfs_copy_layers_batch(gfs_context *c, int direction, int n, const int *what, const int *k_first, const int *k_count,
+                           const int64_t *offsets, const int *add, void *buffer_device, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(n >= 0 && n <= 16 && (n == 0 || (what && k_first && k_count && offsets && buffer_device)), "bad arguments");
+    GFS_REQUIRE(direction == 0 || direction == 1, "bad direction");
+    GFS_CUDA(cudaSetDevice(c->device));
+    gfs::CopyBatch cb;
+    cb.n = 0;
+    long long largest = 0;
+    for (int i = 0; i < n; i++) {
+        unsigned char *base; size_t bytes; int layers;
+        layer_info(c, what[i], &base, &bytes, &layers);
+        GFS_REQUIRE(k_first[i] >= 0 && k_count[i] >= 0 && k_first[i] + k_count[i] <= layers, "layer range out of bounds");
+        if (k_count[i] == 0) continue;
+        const bool adding = direction == 1 && add && add[i];
+        GFS_REQUIRE(!adding || (what[i] >= 10 && what[i] < 13), "only the integer accumulators can be added");
+        unsigned char *lib = base + bytes * (size_t)k_first[i], *buf = (unsigned char *)buffer_device + offsets[i];
+        cb.src[cb.n] = direction == 0 ? lib : buf;
+        cb.dst[cb.n] = direction == 0 ? buf : lib;
+        cb.bytes[cb.n] = (long long)(bytes * (size_t)k_count[i]);
+        cb.add[cb.n] = adding ? 1 : 0;
+        if (cb.bytes[cb.n] > largest) largest = cb.bytes[cb.n];
+        cb.n++;
+    }
+    if (cb.n == 0) return;
+    int bx = (int)((largest / 16 + 255) / 256);
+    if (bx < 1) bx = 1;
+    if (bx > 592) bx = 592;                       // 4 waves of 148 SMs; the loops are grid-strided
+    LAUNCH(c, gfs::k_copy_batch, dim3((unsigned)bx, (unsigned)cb.n), 256, cb);
+    GFS_END()
+}
+
 void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,
                            int64_t *n_down, int64_t *n_up, int *err) {
     GFS_BEGIN

@@ -1004,6 +1004,36 @@ __global__ void k_soa_to_aos(int64_t n, const float *x, const float *y, const fl
     p[0] = x[r]; p[1] = y[r]; p[2] = z[r]; p[3] = vx[r]; p[4] = vy[r]; p[5] = vz[r];
 }
 
+// Up to 16 layer-range copies (or 64-bit integer adds) in one launch: the slab exchange packs / unpacks all its
+// arrays with one kernel instead of one memcpy each.  blockIdx.y selects the descriptor.
+struct CopyBatch {
+    int n;
+    const unsigned char *src[16];
+    unsigned char *dst[16];
+    long long bytes[16];
+    int add[16];                  // != 0: dst (uint64[]) += src (uint64[])
+};
+
+__global__ void __launch_bounds__(256) k_copy_batch(CopyBatch cb) {
+    const int d = blockIdx.y;
+    if (d >= cb.n) return;
+    const unsigned char *__restrict__ src = cb.src[d];
+    unsigned char *__restrict__ dst = cb.dst[d];
+    const long long bytes = cb.bytes[d];
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cb.add[d]) {
+        const unsigned long long *s8 = reinterpret_cast<const unsigned long long *>(src);
+        unsigned long long *d8 = reinterpret_cast<unsigned long long *>(dst);
+        for (long long t = t0; t < bytes / 8; t += stride) d8[t] += s8[t];
+    } else if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)bytes) & 15) == 0) {
+        const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+        for (long long t = t0; t < bytes / 16; t += stride) d16[t] = s16[t];
+    } else {
+        for (long long t = t0; t < bytes; t += stride) dst[t] = src[t];
+    }
+}
+
 // acc[first .. first+count) += src  (integer adds: the slab partial sums merge bit-exactly in any order)
 __global__ void k_add_u64(long long count, unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

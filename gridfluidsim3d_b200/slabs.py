@@ -23,7 +23,7 @@ numpy backend) or, for single-process tests, an in-process loopback between seve
 
   owned = (k0, k1);  K;  device;  sort(); p2g_begin(); p2g_end(); g2p_advect(dt);  num_particles
   layer_bytes(what) -> int
-  pack_into(what, k_first, k_count, uint8 tensor, offset);   unpack_from(what, k_first, k_count, uint8 tensor, offset, add)
+  pack_batch([(what, k_first, k_count, offset, _)], uint8 tensor);   unpack_batch([(what, k_first, k_count, offset, add)], uint8 tensor)
   extract_async(k_lo, k_hi) -> (down [cap,6] f32, up [cap,6] f32, counts int32[4] = kept, n_down, n_up, spare)
   extract_commit(n_kept);  append(float32 tensor [n,6])
 """
@@ -101,14 +101,12 @@ class SlabDriver:
     def pack(self, phases):
         send, _ = self.buffers(phases)
         for side, (items, so, sb, ro, rb) in self.plan(phases).items():
-            for (w, sf, sc, rf, rc, add), off in zip(items, so):
-                self.b.pack_into(w, sf, sc, send[side], off)
+            self.b.pack_batch([(w, sf, sc, off, False) for (w, sf, sc, rf, rc, add), off in zip(items, so)], send[side])
         return send
 
     def unpack(self, phases, recv):
         for side, (items, so, sb, ro, rb) in self.plan(phases).items():
-            for (w, sf, sc, rf, rc, add), off in zip(items, ro):
-                self.b.unpack_from(w, rf, rc, recv[side], off, add)
+            self.b.unpack_batch([(w, rf, rc, off, add) for (w, sf, sc, rf, rc, add), off in zip(items, ro)], recv[side])
 
     # ---- C3: particle migration --------------------------------------------------------------------------------
     def migrate_begin(self):
@@ -162,10 +160,11 @@ class DistTransport:
         self.exchange(drv, {s: counts[slot[s]:slot[s] + 1] for s in sides}, {s: theirs[slot[s]:slot[s] + 1] for s in sides})
         host = torch.cat([counts, theirs]).cpu().tolist()          # the one host synchronisation of the substep
         kept, n_out, n_in = host[0], {"down": host[1], "up": host[2]}, {"down": host[5], "up": host[6]}
-        if max(n_out.values()) > down.shape[0]:
-            raise RuntimeError("migration buffer too small: %s leavers, capacity %d" % (n_out, down.shape[0]))
-        drv.b.extract_commit(kept)
         out = {"down": down, "up": up}
+        for s_ in SIDES:
+            if n_out[s_] > out[s_].shape[0]:
+                raise RuntimeError("migration buffer too small: %d leavers %s, capacity %d" % (n_out[s_], s_, out[s_].shape[0]))
+        drv.b.extract_commit(kept)
         send = {s: out[s][: n_out[s]].reshape(-1) for s in sides}
         recv = {s: torch.empty((n_in[s], 6), dtype=torch.float32, device=counts.device) for s in sides}
         self.exchange(drv, send, {s: recv[s].reshape(-1) for s in sides})
@@ -280,17 +279,15 @@ class CudaSlabBackend:
         if not self.shared_stream:
             torch.cuda.current_stream().synchronize()
 
-    def pack_into(self, what, k_first, k_count, buf, offset):
-        if k_count > 0:
-            self._torch_done()
-            self.ctx.pack_layers(what, k_first, k_count, buf.data_ptr() + offset)
-            self._lib_done()
+    def pack_batch(self, items, buf):
+        self._torch_done()
+        self.ctx.copy_layers_batch(0, items, buf.data_ptr())
+        self._lib_done()
 
-    def unpack_from(self, what, k_first, k_count, buf, offset, add):
-        if k_count > 0:
-            self._torch_done()
-            self.ctx.unpack_layers(what, k_first, k_count, buf.data_ptr() + offset, add)
-            self._lib_done()
+    def unpack_batch(self, items, buf):
+        self._torch_done()
+        self.ctx.copy_layers_batch(1, items, buf.data_ptr())
+        self._lib_done()
 
     def extract_async(self, k_lo, k_hi):
         n = self.ctx.num_particles

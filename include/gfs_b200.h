@@ -184,6 +184,10 @@ int64_t gfs_layer_bytes(gfs_context *ctx, int what, int *err);
  * (accumulators only) adds the buffer as 64-bit integers instead of overwriting */
 void gfs_pack_layers(gfs_context *ctx, int what, int k_first, int k_count, void *dst_device, int *err);
 void gfs_unpack_layers(gfs_context *ctx, int what, int k_first, int k_count, const void *src_device, int add, int *err);
+/* the same for up to 16 layer ranges at byte offsets of ONE device buffer, in one kernel launch; direction 0 = pack,
+ * 1 = unpack (add[i] != 0: 64-bit integer add, accumulators only) */
+void gfs_copy_layers_batch(gfs_context *ctx, int direction, int n, const int *what, const int *k_first, const int *k_count,
+                           const int64_t *offsets, const int *add, void *buffer_device, int *err);
 /* particle migration: remove the particles whose cell layer is < k_lo (written as MarkerParticle_t AoS to down_device)
  * or >= k_hi (to up_device); cap = capacity of each buffer in particles.  Synchronises to return the counts. */
 void gfs_extract_particles(gfs_context *ctx, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap,

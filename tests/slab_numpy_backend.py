@@ -72,13 +72,15 @@ class NumpySlabBackend:
         arr, (a, b, _) = self._array(what)
         return a * b * arr.itemsize
 
-    def pack_into(self, what, k_first, k_count, buf, offset):
-        t = self.pack(what, k_first, k_count)
-        buf[offset: offset + t.numel()] = t
+    def pack_batch(self, items, buf):
+        for what, k_first, k_count, offset, _ in items:
+            t = self.pack(what, k_first, k_count)
+            buf[offset: offset + t.numel()] = t
 
-    def unpack_from(self, what, k_first, k_count, buf, offset, add):
-        n = self.layer_bytes(what) * k_count
-        self.unpack(what, k_first, k_count, buf[offset: offset + n].clone(), add)
+    def unpack_batch(self, items, buf):
+        for what, k_first, k_count, offset, add in items:
+            n = self.layer_bytes(what) * k_count
+            self.unpack(what, k_first, k_count, buf[offset: offset + n].clone(), add)
 
     def pack(self, what, k_first, k_count):
         if what >= 10:
