@@ -360,7 +360,12 @@ def run_gfs(args):
             return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8), shared_stream=True), rank, world,
                                     halo=capi.slab_halo_cells(ip, 0.5 * dx, dx))
         drv = make_driver(interp)
-        transport = slabs.DistTransport()
+        if args.transport == "peer":      # neighbours write into each other's HBM over NVLink (gfs_comm_*), no NCCL in the data path
+            other_ip = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR
+            transport = slabs.PeerTransport(drv, particle_cap=max(4096, n_local // 8),
+                                            layer_bytes=slabs.PeerTransport.layer_bytes(make_driver(other_ip)))
+        else:
+            transport = slabs.DistTransport()
 
         def substep():
             slabs.substep(drv, transport, dt)
@@ -499,7 +504,8 @@ def run_gfs(args):
         "stats": {k: int(v) for k, v in st.items()},
     }
     if world > 1:
-        line["multi_gpu"] = {"comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
+        line["multi_gpu"] = {"transport": "peer memory (CUDA IPC, NVLink) written by gfs kernels" if args.transport == "peer"
+                             else "torch.distributed batch_isend_irecv (NCCL)", "comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
                              "particles_mean": n_now / world, "particles_after": n_now}
     ctx.close()
     if rank == 0:
@@ -532,6 +538,8 @@ def main():
     ap.add_argument("--workload", default="splash256")
     ap.add_argument("--interp", default="trilinear", choices=["trilinear", "tricubic"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -27,6 +27,8 @@ SYMBOLS = [
     "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
     "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
+    "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
+    "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -104,6 +106,14 @@ def load_library():
     L.gfs_extract_particles_async.argtypes = [V, I, I, V, V, L64, V, _err]
     L.gfs_extract_commit.argtypes = [V, L64, _err]
     L.gfs_append_particles_device.argtypes = [V, V, L64, _err]
+    L.gfs_comm_alloc.argtypes = [V, L64, L64, _err]
+    L.gfs_comm_export.argtypes = [V, I, C.c_char_p, _err]
+    L.gfs_comm_connect.argtypes = [V, I, C.c_char_p, _err]
+    L.gfs_comm_connect_local.argtypes = [V, I, V, _err]
+    L.gfs_comm_push_layers.argtypes = [V, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(L64), _err]
+    L.gfs_comm_pull_layers.argtypes = [V, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(L64), C.POINTER(I), _err]
+    L.gfs_comm_migrate_begin.argtypes = [V, I, I, _err]
+    L.gfs_comm_migrate_finish.argtypes = [V, C.POINTER(L64), _err]
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
     L.gfs_resize_particles.argtypes = [V, L64, _err]
@@ -354,6 +364,44 @@ class Context:
 
     def append_particles_device(self, aos_ptr, n):
         self._call(self.lib.gfs_append_particles_device, aos_ptr, int(n))
+
+    # ---- peer-memory exchange (CUDA IPC) ---------------------------------------------------------------------
+    def comm_alloc(self, layer_bytes, particle_cap):
+        self._call(self.lib.gfs_comm_alloc, int(layer_bytes), int(particle_cap))
+
+    def comm_export(self, side):
+        buf = C.create_string_buffer(64)
+        self._call(self.lib.gfs_comm_export, int(side), buf)
+        return buf.raw
+
+    def comm_connect(self, side, handle):
+        self._call(self.lib.gfs_comm_connect, int(side), C.create_string_buffer(handle, 64))
+
+    def comm_connect_local(self, side, other):
+        self._call(self.lib.gfs_comm_connect_local, int(side), other.h)
+
+    @staticmethod
+    def _item_arrays(items):
+        n = len(items)
+        IA, LA = C.c_int * n, C.c_int64 * n
+        return (n, IA(*[int(i[0]) for i in items]), IA(*[int(i[1]) for i in items]), IA(*[int(i[2]) for i in items]),
+                LA(*[int(i[3]) for i in items]), IA(*[int(bool(i[4])) for i in items]))
+
+    def comm_push_layers(self, side, items):
+        n, w, f, k, o, _ = self._item_arrays(items)
+        self._call(self.lib.gfs_comm_push_layers, int(side), n, w, f, k, o)
+
+    def comm_pull_layers(self, side, items):
+        n, w, f, k, o, a = self._item_arrays(items)
+        self._call(self.lib.gfs_comm_pull_layers, int(side), n, w, f, k, o, a)
+
+    def comm_migrate_begin(self, has_down, has_up):
+        self._call(self.lib.gfs_comm_migrate_begin, int(bool(has_down)), int(bool(has_up)))
+
+    def comm_migrate_finish(self):
+        moved = (C.c_int64 * 2)()
+        self._call(self.lib.gfs_comm_migrate_finish, moved)
+        return moved[0], moved[1]
 
     def device_ptr(self, which):
         return self._call(self.lib.gfs_device_ptr, which)

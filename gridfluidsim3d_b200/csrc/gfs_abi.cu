@@ -131,6 +131,16 @@ struct gfs_context {
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
     int p2g_arith = 0;
+    // ---- peer-memory exchange (one comm block per side: 0 = down, 1 = up; written by the neighbour on that side)
+    struct CommSide {
+        unsigned char *block = nullptr;       // my block: [flags 256 B][layers buf 0][layers buf 1][arrivals 0][arrivals 1]
+        unsigned char *peer = nullptr;        // the neighbour's block for the opposite side, IPC-mapped
+        unsigned int seq_layers = 0, seq_particles = 0;
+    } comm[2];
+    size_t comm_layer_bytes = 0;          // capacity of one layers buffer
+    int64_t comm_particle_cap = 0;        // capacity (particles) of one arrivals buffer
+    unsigned int *comm_host = nullptr;    // pinned: counts published by k_gather_counts
+    DevBuf<unsigned int> comm_error;
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
@@ -559,7 +569,9 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
-    c->split_counters.release();
+    c->split_counters.release(); c->comm_error.release();
+    for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
+    if (c->comm_host) cudaFreeHost(c->comm_host);
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
     c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1038,6 +1050,188 @@ void gfs_copy_layers_batch(gfs_context *c, int direction, int n, const int *what
     if (bx < 1) bx = 1;
     if (bx > 592) bx = 592;                       // 4 waves of 148 SMs; the loops are grid-strided
     LAUNCH(c, gfs::k_copy_batch, dim3((unsigned)bx, (unsigned)cb.n), 256, cb);
+    GFS_END()
+}
+
+static void launch_split(gfs_context *c, int k_lo, int k_hi, void *down_device, void *up_device, int64_t cap, unsigned int *counters);
+
+/* ---- peer-memory exchange over CUDA IPC (same node; NVLink / NVSwitch) -------------------------------------------
+ * Each context owns one "comm block" per side; the neighbour on that side maps it (gfs_comm_export / gfs_comm_connect)
+ * and WRITES into it directly from its kernels: packed layers, migrating particles and the flag words that announce
+ * them.  No NCCL call, no host round trip except the single count read of gfs_comm_migrate_finish. */
+namespace {
+constexpr size_t kCommFlagBytes = 256;       // uint32 words: [0] layers seq, [1] particles seq, [2] particle count
+size_t comm_block_bytes(gfs_context *c) { return kCommFlagBytes + 2 * c->comm_layer_bytes + 2 * (size_t)c->comm_particle_cap * 24; }
+unsigned char *comm_layers(gfs_context *c, unsigned char *block, unsigned int seq) { return block + kCommFlagBytes + (seq & 1) * c->comm_layer_bytes; }
+unsigned char *comm_arrivals(gfs_context *c, unsigned char *block, unsigned int seq) {
+    return block + kCommFlagBytes + 2 * c->comm_layer_bytes + (seq & 1) * (size_t)c->comm_particle_cap * 24;
+}
+void fill_batch(gfs_context *c, gfs::CopyBatch &cb, int direction, int n, const int *what, const int *k_first, const int *k_count,
+                const int64_t *offsets, const int *add, unsigned char *buffer, long long *largest) {
+    cb.n = 0;
+    *largest = 0;
+    for (int i = 0; i < n; i++) {
+        unsigned char *base; size_t bytes; int layers;
+        layer_info(c, what[i], &base, &bytes, &layers);
+        GFS_REQUIRE(k_first[i] >= 0 && k_count[i] >= 0 && k_first[i] + k_count[i] <= layers, "layer range out of bounds");
+        if (k_count[i] == 0) continue;
+        const bool adding = direction == 1 && add && add[i];
+        GFS_REQUIRE(!adding || (what[i] >= 10 && what[i] < 13), "only the integer accumulators can be added");
+        GFS_REQUIRE((size_t)offsets[i] + bytes * (size_t)k_count[i] <= c->comm_layer_bytes, "comm buffer too small");
+        unsigned char *lib = base + bytes * (size_t)k_first[i], *buf = buffer + offsets[i];
+        cb.src[cb.n] = direction == 0 ? lib : buf;
+        cb.dst[cb.n] = direction == 0 ? buf : lib;
+        cb.bytes[cb.n] = (long long)(bytes * (size_t)k_count[i]);
+        cb.add[cb.n] = adding ? 1 : 0;
+        if (cb.bytes[cb.n] > *largest) *largest = cb.bytes[cb.n];
+        cb.n++;
+    }
+}
+int batch_blocks(long long largest) {
+    long long bx = (largest / 16 + 255) / 256;
+    return (int)(bx < 1 ? 1 : (bx > 592 ? 592 : bx));
+}
+}  // namespace
+
+void gfs_comm_alloc(gfs_context *c, int64_t layer_bytes, int64_t particle_cap, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(layer_bytes >= 0 && particle_cap >= 0 && particle_cap < 0x7FFFFFFFll, "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    c->comm_layer_bytes = ((size_t)layer_bytes + 255) / 256 * 256;
+    c->comm_particle_cap = particle_cap;
+    for (int s = 0; s < 2; s++) {
+        if (c->comm[s].block) GFS_CUDA(cudaFree(c->comm[s].block));
+        GFS_CUDA(cudaMalloc((void **)&c->comm[s].block, comm_block_bytes(c)));
+        GFS_CUDA(cudaMemset(c->comm[s].block, 0, kCommFlagBytes));
+        c->comm[s].seq_layers = c->comm[s].seq_particles = 0;
+        c->comm[s].peer = nullptr;
+    }
+    if (!c->comm_host) GFS_CUDA(cudaHostAlloc((void **)&c->comm_host, 64, cudaHostAllocMapped));
+    c->comm_error.reserve(1);
+    GFS_CUDA(cudaMemset(c->comm_error.p, 0, sizeof(unsigned int)));
+    c->split_counters.reserve(4);
+    GFS_END()
+}
+
+void gfs_comm_export(gfs_context *c, int side, void *handle64, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (side == 0 || side == 1) && handle64 && c->comm[side].block, "gfs_comm_alloc first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GFS_CUDA(cudaIpcGetMemHandle(&h, c->comm[side].block));
+    memcpy(handle64, &h, 64);
+    GFS_END()
+}
+
+/* `side`: where the neighbour sits; handle64: ITS block for the opposite side (the one I write into) */
+void gfs_comm_connect(gfs_context *c, int side, const void *handle64, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (side == 0 || side == 1) && handle64, "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    GFS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->comm[side].peer = (unsigned char *)p;
+    GFS_END()
+}
+
+/* in-process variant for several contexts of one process (tests): connect to another context's block directly */
+void gfs_comm_connect_local(gfs_context *c, int side, gfs_context *neighbour, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && neighbour && (side == 0 || side == 1) && neighbour->comm[1 - side].block, "bad arguments");
+    GFS_REQUIRE(neighbour->comm_layer_bytes == c->comm_layer_bytes && neighbour->comm_particle_cap == c->comm_particle_cap,
+                "both ends must use the same comm sizes");
+    c->comm[side].peer = neighbour->comm[1 - side].block;
+    GFS_END()
+}
+
+/* pack the layer ranges straight into the neighbour's buffer and raise its flag */
+void gfs_comm_push_layers(gfs_context *c, int side, int n, const int *what, const int *k_first, const int *k_count,
+                          const int64_t *offsets, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE((side == 0 || side == 1) && c->comm[side].peer, "gfs_comm_connect first");
+    GFS_REQUIRE(n >= 0 && n <= 16, "at most 16 ranges");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const unsigned int seq = ++c->comm[side].seq_layers;
+    gfs::CopyBatch cb;
+    long long largest;
+    fill_batch(c, cb, 0, n, what, k_first, k_count, offsets, nullptr, comm_layers(c, c->comm[side].peer, seq), &largest);
+    if (cb.n > 0) LAUNCH(c, gfs::k_copy_batch, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb);
+    LAUNCH(c, gfs::k_signal, 1, 1, (volatile unsigned int *)c->comm[side].peer, seq, nullptr, nullptr, 0);
+    GFS_END()
+}
+
+/* wait for the neighbour's layers (device-side spin on my flag) and unpack / add them */
+void gfs_comm_pull_layers(gfs_context *c, int side, int n, const int *what, const int *k_first, const int *k_count,
+                          const int64_t *offsets, const int *add, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE((side == 0 || side == 1) && c->comm[side].block && c->comm[side].peer, "gfs_comm_connect first");
+    GFS_REQUIRE(n >= 1 && n <= 16, "1..16 ranges");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const unsigned int seq = c->comm[side].seq_layers;          // the push of this exchange already advanced it
+    gfs::CopyBatch cb;
+    long long largest;
+    fill_batch(c, cb, 1, n, what, k_first, k_count, offsets, add, comm_layers(c, c->comm[side].block, seq), &largest);
+    GFS_REQUIRE(cb.n > 0, "nothing to unpack");
+    LAUNCH(c, gfs::k_copy_batch_wait, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb,
+           (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p);
+    GFS_END()
+}
+
+/* migration, first half: split the resident particles; leavers are written straight into the neighbours' arrival
+ * buffers, followed by their count and the flag.  has_down / has_up: whether a neighbour exists on that side. */
+void gfs_comm_migrate_begin(gfs_context *c, int has_down, int has_up, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const int k_lo = has_down ? c->own_k0 : (int)0x80000000, k_hi = has_up ? c->own_k1 : 0x7FFFFFFF;
+    unsigned int seq[2];
+    for (int s = 0; s < 2; s++) seq[s] = ++c->comm[s].seq_particles;
+    if (c->n > 0) {
+        launch_split(c, k_lo, k_hi, has_down ? comm_arrivals(c, c->comm[0].peer, seq[0]) : nullptr,
+                     has_up ? comm_arrivals(c, c->comm[1].peer, seq[1]) : nullptr, c->comm_particle_cap, c->split_counters.p);
+    } else {
+        GFS_CUDA(cudaMemsetAsync(c->split_counters.p, 0, 4 * sizeof(unsigned int), c->stream));
+    }
+    const int has[2] = {has_down, has_up};
+    for (int s = 0; s < 2; s++)
+        if (has[s])      // count word [2] then flag word [1] of the neighbour's block
+            LAUNCH(c, gfs::k_signal, 1, 1, (volatile unsigned int *)c->comm[s].peer + 1, seq[s],
+                   (volatile unsigned int *)c->comm[s].peer + 2, c->split_counters.p + 1 + s, 1);
+    LAUNCH(c, gfs::k_gather_counts, 1, 1,
+           has_down ? (const volatile unsigned int *)c->comm[0].block + 1 : nullptr,
+           has_up ? (const volatile unsigned int *)c->comm[1].block + 1 : nullptr, seq[0], c->split_counters.p,
+           (const volatile unsigned int *)c->comm[0].block + 2, (const volatile unsigned int *)c->comm[1].block + 2,
+           c->comm_host, c->comm_error.p);
+    GFS_END()
+}
+
+/* migration, second half: the one host synchronisation of a sharded substep; appends the arrivals.
+ * moved[0] = particles sent away, moved[1] = particles received. */
+void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_CUDA(cudaSetDevice(c->device));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    const unsigned int *h = c->comm_host;
+    GFS_REQUIRE(h[5] == 0, "timed out waiting for a neighbour's particles (peer exchange)");
+    GFS_REQUIRE((int64_t)h[1] <= c->comm_particle_cap && (int64_t)h[2] <= c->comm_particle_cap &&
+                (int64_t)h[3] <= c->comm_particle_cap && (int64_t)h[4] <= c->comm_particle_cap, "migration buffer too small");
+    if (c->n > 0) c->cur = 1 - c->cur;
+    c->n = h[0]; c->sorted = false; c->keys_ready = false; c->indexed = false;
+    const unsigned int n_in[2] = {h[3], h[4]};
+    for (int s = 0; s < 2; s++) {
+        if (n_in[s] == 0) continue;
+        int e2 = GFS_SUCCESS;
+        gfs_append_particles_device(c, comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles), n_in[s], &e2);
+        if (e2 != GFS_SUCCESS) throw GfsError(g_error);
+    }
+    if (moved) { moved[0] = (int64_t)h[1] + h[2]; moved[1] = (int64_t)n_in[0] + n_in[1]; }
     GFS_END()
 }
 

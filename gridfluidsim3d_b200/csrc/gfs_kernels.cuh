@@ -1034,6 +1034,65 @@ __global__ void __launch_bounds__(256) k_copy_batch(CopyBatch cb) {
     }
 }
 
+// ---- peer-memory exchange (CUDA IPC over NVLink): flags written by the neighbour GPU ---------------------------
+// flag words live in the receiver's memory; the sender's k_signal runs after its copy kernel in stream order.
+__global__ void k_signal(volatile unsigned int *peer_flag, unsigned int seq, volatile unsigned int *peer_aux, const unsigned int *aux_src, int naux) {
+    for (int i = 0; i < naux; i++) peer_aux[i] = aux_src[i];
+    __threadfence_system();
+    *peer_flag = seq;
+    __threadfence_system();
+}
+
+// spin until *flag >= seq (written over NVLink by the neighbour); gives up after ~4 s and raises *error
+__device__ __forceinline__ bool wait_flag(const volatile unsigned int *flag, unsigned int seq, unsigned int *error) {
+    const long long t0 = clock64();
+    while ((int)(*flag - seq) < 0) {
+        if (clock64() - t0 > 8000000000ll) { atomicExch(error, 1u); return false; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+    return true;
+}
+
+// the batched layer copy of k_copy_batch, preceded by the wait for the neighbour's data
+__global__ void __launch_bounds__(256) k_copy_batch_wait(CopyBatch cb, const volatile unsigned int *flag, unsigned int seq, unsigned int *error) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = wait_flag(flag, seq, error) ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    const int d = blockIdx.y;
+    if (d >= cb.n) return;
+    const unsigned char *__restrict__ src = cb.src[d];
+    unsigned char *__restrict__ dst = cb.dst[d];
+    const long long bytes = cb.bytes[d];
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cb.add[d]) {
+        const unsigned long long *s8 = reinterpret_cast<const unsigned long long *>(src);
+        unsigned long long *d8 = reinterpret_cast<unsigned long long *>(dst);
+        for (long long t = t0; t < bytes / 8; t += stride) d8[t] += s8[t];
+    } else if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)bytes) & 15) == 0) {
+        const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+        for (long long t = t0; t < bytes / 16; t += stride) d16[t] = s16[t];
+    } else {
+        for (long long t = t0; t < bytes; t += stride) dst[t] = src[t];
+    }
+}
+
+// wait for both neighbours' particle flags, then publish {my kept/down/up counts, arrivals from down, arrivals from up}
+// to pinned host memory: the one word set the host reads per substep
+__global__ void k_gather_counts(const volatile unsigned int *flag_down, const volatile unsigned int *flag_up, unsigned int seq,
+                                const unsigned int *split_counters, const volatile unsigned int *in_down, const volatile unsigned int *in_up,
+                                unsigned int *host_out, unsigned int *error) {
+    bool ok = true;
+    if (flag_down) ok = wait_flag(flag_down, seq, error) && ok;
+    if (flag_up) ok = wait_flag(flag_up, seq, error) && ok;
+    host_out[0] = split_counters[0]; host_out[1] = split_counters[1]; host_out[2] = split_counters[2];
+    host_out[3] = (flag_down && ok) ? *in_down : 0u;
+    host_out[4] = (flag_up && ok) ? *in_up : 0u;
+    host_out[5] = ok ? 0u : 1u;
+}
+
 // acc[first .. first+count) += src  (integer adds: the slab partial sums merge bit-exactly in any order)
 __global__ void k_add_u64(long long count, unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -171,6 +171,95 @@ class DistTransport:
         return sum(n_out[s] for s in sides), drv.migrate_end(recv)
 
 
+SIDE_ID = {"down": 0, "up": 1}
+
+
+class PeerTransport:
+    """Neighbour exchange through peer memory (CUDA IPC over NVLink/NVSwitch), no NCCL in the data path: every rank
+    packs its layers / leavers straight into the neighbour's comm block with its own kernels and raises a flag
+    there; waits are device-side spins (gfs_comm_*).  torch.distributed only ships the 64-byte IPC handles once."""
+
+    @staticmethod
+    def layer_bytes(drv, phases=(("partials", "halos"), ("partials",), ("halos",))):
+        """Bytes of the largest layer message this driver sends or receives on one side."""
+        return max([p[2] for ph in phases for p in drv.plan(ph).values()] +
+                   [p[4] for ph in phases for p in drv.plan(ph).values()] + [256])
+
+    def __init__(self, drv, group=None, particle_cap=None, connect=True, layer_bytes=None):
+        self.ctx = drv.b.ctx
+        self.bytes_sent = 0
+        layer_bytes = max(int(layer_bytes or 0), self.layer_bytes(drv))
+        # both ends of a link must agree on the sizes: take the maxima over all ranks
+        cap = particle_cap if particle_cap is not None else max(4096, drv.b.num_particles // 6)
+        if connect and drv.world > 1:
+            sizes = [None] * drv.world
+            dist.all_gather_object(sizes, (int(layer_bytes), int(cap)), group=group)
+            layer_bytes, cap = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        self.ctx.comm_alloc(layer_bytes, cap)
+        if connect and drv.world > 1:
+            mine = (self.ctx.comm_export(0), self.ctx.comm_export(1))
+            everyone = [None] * drv.world
+            dist.all_gather_object(everyone, mine, group=group)
+            for side in drv.sides():          # the neighbour on my `side` exposes its block for the opposite side
+                self.ctx.comm_connect(SIDE_ID[side], everyone[drv.peer[side]][1 - SIDE_ID[side]])
+            dist.barrier(group=group)
+
+    def layers(self, drv, phases):
+        plan = drv.plan(phases)
+        for side, (items, so, sb, ro, rb) in plan.items():
+            self.ctx.comm_push_layers(SIDE_ID[side], [(w, sf, sc, off, False) for (w, sf, sc, rf, rc, add), off in zip(items, so)])
+            self.bytes_sent += sb
+        for side, (items, so, sb, ro, rb) in plan.items():
+            self.ctx.comm_pull_layers(SIDE_ID[side], [(w, rf, rc, off, add) for (w, sf, sc, rf, rc, add), off in zip(items, ro)])
+
+    def migrate(self, drv):
+        self.ctx.comm_migrate_begin(drv.peer["down"] is not None, drv.peer["up"] is not None)
+        sent, got = self.ctx.comm_migrate_finish()
+        self.bytes_sent += sent * 24
+        return sent, got
+
+
+class PeerLoopbackWorld:
+    """Several slabs of ONE process exchanging through the peer-memory path (comm blocks connected in-process): every
+    context enqueues its pushes before anyone's pull is enqueued, so the device-side waits always find their data."""
+
+    def __init__(self, drivers, particle_cap=None):
+        self.drv = list(drivers)
+        cap = particle_cap or max(4096, max(d.b.num_particles for d in self.drv))
+        self.tr = [PeerTransport(d, particle_cap=cap, connect=False) for d in self.drv]
+        for r, d in enumerate(self.drv):
+            for side in d.sides():
+                d.b.ctx.comm_connect_local(SIDE_ID[side], self.drv[d.peer[side]].b.ctx)
+
+    def _layers(self, phases):
+        plans = [d.plan(phases) for d in self.drv]
+        for d, plan in zip(self.drv, plans):
+            for side, (items, so, sb, ro, rb) in plan.items():
+                d.b.ctx.comm_push_layers(SIDE_ID[side], [(w, sf, sc, off, False) for (w, sf, sc, rf, rc, add), off in zip(items, so)])
+        for d, plan in zip(self.drv, plans):
+            for side, (items, so, sb, ro, rb) in plan.items():
+                d.b.ctx.comm_pull_layers(SIDE_ID[side], [(w, rf, rc, off, add) for (w, sf, sc, rf, rc, add), off in zip(items, ro)])
+
+    def substep(self, dt, pressure_solve_between=False):
+        for d in self.drv:
+            d.b.sort()
+            d.b.p2g_begin()
+        if pressure_solve_between:
+            self._layers(("partials",))
+            for d in self.drv:
+                d.b.p2g_end()
+            self._layers(("halos",))
+        else:
+            self._layers(("partials", "halos"))
+            for d in self.drv:
+                d.b.p2g_end()
+        for d in self.drv:
+            d.b.g2p_advect(dt)
+        for d in self.drv:
+            d.b.ctx.comm_migrate_begin(d.peer["down"] is not None, d.peer["up"] is not None)
+        return sum(d.b.ctx.comm_migrate_finish()[1] for d in self.drv)
+
+
 def substep(drv, transport, dt, pressure_solve_between=False):
     """One sharded substep of one rank.  Returns (particles sent away, particles received)."""
     b = drv.b

@@ -199,6 +199,25 @@ void gfs_extract_particles_async(gfs_context *ctx, int k_lo, int k_hi, void *dow
 void gfs_extract_commit(gfs_context *ctx, int64_t n_kept, int *err);
 void gfs_append_particles_device(gfs_context *ctx, const void *aos_device, int64_t n, int *err);
 
+/* ---- peer-memory exchange (CUDA IPC, one node): the neighbour GPU writes layers / particles / flags straight into
+ * this context's "comm blocks" over NVLink; waits are device-side spins on those flags.  side: 0 = down, 1 = up.
+ *   gfs_comm_alloc(ctx, bytes of the largest layer message, arrival capacity in particles)   once, after domain_init
+ *   gfs_comm_export(ctx, side, handle[64])  -> ship the 64 bytes to the neighbour on that side (any channel)
+ *   gfs_comm_connect(ctx, side, handle[64]) <- the neighbour's handle for ITS opposite side
+ *   per substep:  gfs_comm_push_layers on every side, then gfs_comm_pull_layers on every side   (C1 / C2)
+ *                 gfs_comm_migrate_begin, gfs_comm_migrate_finish (the one host synchronisation)   (C3)
+ * Every rank must issue the same sequence of exchanges. */
+void gfs_comm_alloc(gfs_context *ctx, int64_t layer_bytes, int64_t particle_cap, int *err);
+void gfs_comm_export(gfs_context *ctx, int side, void *handle64, int *err);
+void gfs_comm_connect(gfs_context *ctx, int side, const void *handle64, int *err);
+void gfs_comm_connect_local(gfs_context *ctx, int side, gfs_context *neighbour, int *err);   /* same process (tests) */
+void gfs_comm_push_layers(gfs_context *ctx, int side, int n, const int *what, const int *k_first, const int *k_count,
+                          const int64_t *offsets, int *err);
+void gfs_comm_pull_layers(gfs_context *ctx, int side, int n, const int *what, const int *k_first, const int *k_count,
+                          const int64_t *offsets, const int *add, int *err);
+void gfs_comm_migrate_begin(gfs_context *ctx, int has_down, int has_up, int *err);
+void gfs_comm_migrate_finish(gfs_context *ctx, int64_t *moved2, int *err);
+
 /* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).
  * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz. */
 void *gfs_device_ptr(gfs_context *ctx, int which, int *err);

@@ -532,8 +532,9 @@ def test_hello_world_64_full_parity(ctx, oracle):
 # ---------------------------------------------------------------------------------------------------
 # z-slab sharding on ONE device: several virtual slabs in one process (slabs.LoopbackWorld)
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("transport", ["staged", "peer"])
 @pytest.mark.parametrize("world,name,interp", [(2, "small32", capi.TRILINEAR), (4, "small32", capi.TRICUBIC), (3, "slab24", capi.TRILINEAR)])
-def test_virtual_slabs_equal_single_domain(oracle, world, name, interp):
+def test_virtual_slabs_equal_single_domain(oracle, world, name, interp, transport):
     """Sharded == unsharded: after each of 3 substeps the material and the P2G fields of every slab's owned layers are
     bit-identical to the single-context run (integer partial sums), and the union of the slabs' particles is the
     single-context particle set, bit for bit."""
@@ -557,7 +558,9 @@ def test_virtual_slabs_equal_single_domain(oracle, world, name, interp):
         c.set_field(capi.FIELD_NEW, *s["new"]); c.set_field(capi.FIELD_SAVED, *s["saved"])
         ctxs.append(c)
         drivers.append(slabs.SlabDriver(slabs.CudaSlabBackend(c, s["dims"], (k0, k1), interp), r, world, halo=3))
-    world_ = slabs.LoopbackWorld(drivers)
+    # "staged": pack -> buffer -> unpack (what the torch.distributed transport does); "peer": the gfs_comm_* path, every
+    # slab writing straight into its neighbour's comm block and waiting on device-side flags
+    world_ = slabs.LoopbackWorld(drivers) if transport == "staged" else slabs.PeerLoopbackWorld(drivers)
 
     def rows(p, v):
         a = np.ascontiguousarray(np.concatenate([p, v], 1))
@@ -582,3 +585,17 @@ def test_virtual_slabs_equal_single_domain(oracle, world, name, interp):
     assert moved > 0
     for c in ctxs + [single]:
         c.close()
+
+
+def test_peer_transport_two_gpus():
+    """Real multi-process run (needs >= 2 GPUs, skipped otherwise): the CUDA-IPC peer-memory transport gives the same
+    bits as the torch.distributed transport on every rank (tests/peer_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(here, "peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
