@@ -28,7 +28,9 @@ SYMBOLS = [
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
     "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
-    "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish",
+    "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
+    "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
+    "gfs_comm_allmax_scale", "gfs_sort_index",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -114,6 +116,13 @@ def load_library():
     L.gfs_comm_pull_layers.argtypes = [V, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(L64), C.POINTER(I), _err]
     L.gfs_comm_migrate_begin.argtypes = [V, I, I, _err]
     L.gfs_comm_migrate_finish.argtypes = [V, C.POINTER(L64), _err]
+    L.gfs_comm_g2p_advect.argtypes = [V, C.c_double, C.c_double, I, I, I, I, I, _err]
+    L.gfs_comm_world_alloc.argtypes = [V, I, I, _err]
+    L.gfs_comm_world_export.argtypes = [V, C.c_char_p, _err]
+    L.gfs_comm_world_connect.argtypes = [V, I, C.c_char_p, _err]
+    L.gfs_comm_world_connect_local.argtypes = [V, I, V, _err]
+    L.gfs_comm_allmax_scale.argtypes = [V, _err]
+    L.gfs_sort_index.argtypes = [V, _err]
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
     L.gfs_resize_particles.argtypes = [V, L64, _err]
@@ -313,6 +322,9 @@ class Context:
     def sort_unstable(self):
         self._call(self.lib.gfs_sort_unstable)
 
+    def sort_index(self):
+        self._call(self.lib.gfs_sort_index)
+
     def set_option(self, option, value):
         self._call(self.lib.gfs_set_option, option, value)
 
@@ -397,6 +409,27 @@ class Context:
 
     def comm_migrate_begin(self, has_down, has_up):
         self._call(self.lib.gfs_comm_migrate_begin, int(bool(has_down)), int(bool(has_up)))
+
+    def comm_g2p_advect(self, dt, has_down, has_up, ratio=0.05, order=4, interp=TRICUBIC, arith=FAST):
+        self._call(self.lib.gfs_comm_g2p_advect, float(dt), float(ratio), int(order), int(interp), int(arith),
+                   int(bool(has_down)), int(bool(has_up)))
+
+    def comm_world_alloc(self, rank, world):
+        self._call(self.lib.gfs_comm_world_alloc, int(rank), int(world))
+
+    def comm_world_export(self):
+        buf = C.create_string_buffer(64)
+        self._call(self.lib.gfs_comm_world_export, buf)
+        return buf.raw
+
+    def comm_world_connect(self, rank, handle):
+        self._call(self.lib.gfs_comm_world_connect, int(rank), C.create_string_buffer(handle, 64))
+
+    def comm_world_connect_local(self, rank, other):
+        self._call(self.lib.gfs_comm_world_connect_local, int(rank), other.h)
+
+    def comm_allmax_scale(self):
+        self._call(self.lib.gfs_comm_allmax_scale)
 
     def comm_migrate_finish(self):
         moved = (C.c_int64 * 2)()

@@ -109,12 +109,13 @@ struct gfs_context {
     DevBuf<float> val[3];                 // node grids after normalisation ("ugrid")
     DevBuf<uint8_t> setmask[3];
     DevBuf<unsigned long long> acc[3];    // fixed-point accumulators, 2 per node
-    DevBuf<int32_t> cell_start;           // nkeys + 2: exclusive scan of the per-cell counts (+ overflow bin)
-    DevBuf<uint32_t> counts;              // nkeys + 2
+    DevBuf<int32_t> cell_start;           // nkeys + 3: exclusive scan of the per-cell counts (+ out-of-grid bin, dead bin, end)
+    DevBuf<uint32_t> counts;              // nkeys + 3
     gfs::Sources sources;
 
     // ---- particles (double-buffered SoA: x,y,z,vx,vy,vz) + original-index tags
-    int64_t n = 0;
+    int64_t n = 0;                        // slots in use (includes `dead`)
+    int64_t dead = 0;                     // slots whose particle migrated away in the fused G2P: key nkeys + 1, last in sorted order
     int cur = 0;
     bool sorted = false;
     DevBuf<float> soa[2][6];
@@ -140,6 +141,11 @@ struct gfs_context {
     size_t comm_layer_bytes = 0;          // capacity of one layers buffer
     int64_t comm_particle_cap = 0;        // capacity (particles) of one arrivals buffer
     unsigned int *comm_host = nullptr;    // pinned: counts published by k_gather_counts
+    bool comm_fused = false;              // the pending migration was done by the G2P kernel (leavers are dead slots)
+    int comm_rank = -1, comm_world = 0;   // all-ranks table (k_allmax)
+    unsigned long long *world_table = nullptr;        // mine: [2 parities][16 ranks]
+    unsigned long long *world_peer[16] = {};          // everyone's, IPC-mapped (mine included)
+    unsigned int seq_world = 0;
     DevBuf<unsigned int> comm_error;
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     DevBuf<unsigned int> split_counters;  // kept, down, up
@@ -224,6 +230,7 @@ dim3 grid3(int ni, int nj, int nk, int bx = 128) { return dim3((unsigned)ceil_di
         GFS_CUDA(cudaGetLastError());                                                              \
     } while (0)
 
+void ensure_capacity(gfs_context *c, int64_t n);
 void require_domain(gfs_context *c) { GFS_REQUIRE(c && c->has_domain, "gfs_domain_init has not been called"); }
 
 gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
@@ -236,12 +243,44 @@ gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
 // cell -- what the exact-arithmetic P2G needs to reproduce the reference's summation order.  stable = false:
 // counting sort (cell histogram with atomic tickets, exclusive scan, scatter); when the previous G2P already
 // binned the advected positions in its epilogue only the scan and the scatter remain.
+void scan_counts(gfs_context *c) {
+    const size_t nbins = (size_t)c->nkeys + 3;
+    size_t tmp_bytes = 0;
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
+    c->cub_tmp.reserve(tmp_bytes);
+    int prof_id = c->prof_begin("cub::DeviceScan::ExclusiveSum");
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
+    c->prof_end(prof_id);
+    c->launches += 2;
+}
+
+// Dead slots (particles the fused G2P handed to a neighbour GPU) only make sense to kernels that walk the sorted
+// index; anything else first compacts them away with one physical counting-sort scatter (dead bin = tail).
+void drop_dead(gfs_context *c) {
+    if (c->dead == 0) return;
+    GFS_REQUIRE(c->keys_ready || c->indexed, "internal: dead slots without their keys");
+    if (c->keys_ready) scan_counts(c);          // otherwise cell_start is the scan these keys were indexed with
+    const int src = c->cur, dst = 1 - c->cur;
+    LAUNCH(c, gfs::k_scatter_sorted, ceil_div(c->n, 256), 256, c->n, c->keys[0].p, c->rank.p, c->cell_start.p,
+           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+           c->tag[src].p,
+           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+           c->tag[dst].p);
+    c->cur = dst;
+    c->n -= c->dead;
+    c->dead = 0;
+    c->indexed = false;
+    c->keys_ready = false;
+    c->sorted = true;           // physically sorted now, and cell_start describes it
+}
+
 void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     require_domain(c);
+    if (c->dead > 0 && !(lazy && !stable && c->keys_ready)) { drop_dead(c); c->sorted = false; }
     const int64_t n = c->n;
     const int src = c->cur, dst = 1 - c->cur;
     const int B = 256;
-    const size_t nbins = (size_t)c->nkeys + 2;
+    const size_t nbins = (size_t)c->nkeys + 3;
     if (!c->keys_ready) {
         GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * nbins, c->stream));
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
@@ -250,15 +289,7 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
                    c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->rank.p, c->perm[0].p,
                    c->counts.p, c->vmax_bits.p);
     }
-    {
-        size_t tmp_bytes = 0;
-        GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
-        c->cub_tmp.reserve(tmp_bytes);
-        int prof_id = c->prof_begin("cub::DeviceScan::ExclusiveSum");
-        GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
-        c->prof_end(prof_id);
-        c->launches += 2;
-    }
+    scan_counts(c);
     if (n > 0) {
         if (stable) {
             GFS_REQUIRE(!c->keys_ready, "internal: stable sort after a binning G2P");
@@ -398,10 +429,16 @@ void do_p2g(gfs_context *c, int arith) {
     do_p2g_end(c);
 }
 
-void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next) {
+bool g2p_uses_bricks(gfs_context *c, int arith) {
+    return arith != GFS_EXACT && c->grid.pow2 && c->sorted && c->have_maps && c->g2p_variant == 1;
+}
+
+void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next, const gfs::Migrate *migrate = nullptr) {
     require_domain(c);
     GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
     GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    if (c->dead > 0 && !(g2p_uses_bricks(c, arith) && c->indexed)) drop_dead(c);
+    GFS_REQUIRE(!migrate || (g2p_uses_bricks(c, arith) && bin_next), "internal: fused migration needs the brick kernel");
     if (c->n == 0) return;
     const int src = c->cur, dst = 1 - c->cur;
     gfs::RkCoef rk = make_rk(dt);
@@ -410,7 +447,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     // fast arithmetic: bin the advected positions for the next counting sort in the kernel's epilogue
     uint32_t *keys_out = nullptr, *rank_out = nullptr, *counts = nullptr;
     if (bin_next) {
-        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * ((size_t)c->nkeys + 2), c->stream));
+        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * ((size_t)c->nkeys + 3), c->stream));
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
         keys_out = c->keys[0].p; rank_out = c->rank.p; counts = c->counts.p;
     }
@@ -418,19 +455,25 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
                c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
-    const bool brick = arith != GFS_EXACT && c->grid.pow2 && c->sorted && c->have_maps && c->g2p_variant == 1;
+    const bool brick = g2p_uses_bricks(c, arith);
+    gfs::Migrate mg;
+    if (migrate) mg = *migrate;
+    else { mg.own_lo = (int)0x80000000; mg.own_hi = 0x7FFFFFFF; mg.out[0] = mg.out[1] = nullptr; mg.count = nullptr; mg.cap = 0; }
     if (brick) {
         const int nb = (int)(c->nkeys / gfs::kBrickCells) + 1;          // + the overflow-bin CTA
 #define GFS_BRICK_ARGS c->grid, c->maps[interp], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, c->cell_start.p, \
                (c->indexed ? c->index.p : nullptr), c->tag[src].p, c->tag[dst].p, order, rk, rp, rf, c->n,                                                                                                  \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
-               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg
         int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
-        if (interp == GFS_TRICUBIC)
-            gfs::k_g2p_brick<1><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
-        else
-            gfs::k_g2p_brick<0><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        if (interp == GFS_TRICUBIC) {
+            if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+            else gfs::k_g2p_brick<1, false><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        } else {
+            if (migrate) gfs::k_g2p_brick<0, true><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+            else gfs::k_g2p_brick<0, false><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        }
         c->prof_end(prof_id_);
         c->launches++;
         GFS_CUDA(cudaGetLastError());
@@ -444,6 +487,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     // kernel moves the tags itself (it may be reading through the lazy sort index)
     if (!brick)
         GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    if (brick && c->indexed) { c->n -= c->dead; c->dead = 0; }      // the kernel walked the index: only live slots were written
     c->indexed = false;
     c->cur = dst;
     c->sorted = false;          // positions moved: the cell table no longer describes them
@@ -511,8 +555,10 @@ void make_brick_maps(gfs_context *c) {
         make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
                        gfs::BrickTile<1>::kX, gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sY);
     }
-    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
-    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
     c->have_maps = true;
 }
 
@@ -572,6 +618,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     c->split_counters.release(); c->comm_error.release();
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
+    if (c->world_table) cudaFree(c->world_table);
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
     c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -607,8 +654,8 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     if (c->has_domain && c->sorted)
         GFS_CUDA(cudaMemcpyAsync(&nv, c->cell_start.p + c->nkeys, sizeof(nv), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
-    out->num_particles = c->n;
-    out->out_of_grid = c->sorted ? c->n - nv : 0;
+    out->num_particles = c->n - c->dead;
+    out->out_of_grid = c->sorted ? c->n - c->dead - nv : 0;
     out->in_solid = (int64_t)h[0];
     out->fluid_cells = (int64_t)h[1];
     out->solid_hits = (int64_t)h[2];
@@ -759,8 +806,8 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
         GFS_CUDA(cudaMemsetAsync(c->acc[a].p, 0, 2 * c->face_count[a] * sizeof(unsigned long long), c->stream));
     }
     c->material.reserve(c->cell_count);
-    c->cell_start.reserve((size_t)c->nkeys + 2);
-    c->counts.reserve((size_t)c->nkeys + 2);
+    c->cell_start.reserve((size_t)c->nkeys + 3);
+    c->counts.reserve((size_t)c->nkeys + 3);
     c->keys_ready = false;
     c->has_domain = true;
     c->sorted = false;
@@ -805,7 +852,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_REQUIRE(n < 0x7FFFFFFFll, "particle count must fit int32");
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
-    c->n = n; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false;
+    c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false;
     if (n > 0) {
         // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
         c->h_pos.reserve((size_t)n * 6);
@@ -820,13 +867,15 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
 int64_t gfs_num_particles(gfs_context *c, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
-    return c->n;
+    return c->n - c->dead;
     GFS_END(-1)
 }
 
 void gfs_get_particles(gfs_context *c, gfs_marker_particle_t *particles, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c && (c->n == 0 || particles), "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    drop_dead(c);
     if (c->n == 0) return;
     const int b = c->cur;
     c->h_pos.reserve((size_t)c->n * 6);
@@ -840,6 +889,8 @@ void gfs_get_particles(gfs_context *c, gfs_marker_particle_t *particles, int *er
 void gfs_get_particle_order(gfs_context *c, int32_t *order, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c && (c->n == 0 || order), "bad arguments");
+    GFS_CUDA(cudaSetDevice(c->device));
+    drop_dead(c);
     if (c->n == 0) return;
     GFS_CUDA(cudaMemcpyAsync(order, c->tag[c->cur].p, (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
@@ -885,6 +936,17 @@ void gfs_sort_unstable(gfs_context *c, int *err) {
     GFS_REQUIRE(c, "null context");
     GFS_CUDA(cudaSetDevice(c->device));
     do_sort(c, false);
+    GFS_END()
+}
+
+/* Counting sort that leaves the particles where they are and materialises only the sorted index (P2G and G2P fetch
+ * through it; G2P stores its results in sorted order, so the storage stays nearly sorted from step to step).  Falls
+ * back to gfs_sort_unstable where the brick kernels do not apply. */
+void gfs_sort_index(gfs_context *c, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_sort(c, false, /*lazy=*/c->has_domain && c->grid.pow2 && c->have_maps && c->g2p_variant == 1 && c->p2g_variant == 1 && c->lazy_sort);
     GFS_END()
 }
 
@@ -1182,13 +1244,23 @@ void gfs_comm_pull_layers(gfs_context *c, int side, int n, const int *what, cons
     GFS_END()
 }
 
-/* migration, first half: split the resident particles; leavers are written straight into the neighbours' arrival
- * buffers, followed by their count and the flag.  has_down / has_up: whether a neighbour exists on that side. */
-void gfs_comm_migrate_begin(gfs_context *c, int has_down, int has_up, int *err) {
-    GFS_BEGIN
-    require_domain(c);
-    GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
-    GFS_CUDA(cudaSetDevice(c->device));
+namespace {
+// raise the neighbours' particle flags (count word [2], then flag word [1] of their block) and queue the kernel that
+// waits for theirs and publishes all counts to pinned host memory
+void comm_signal_and_gather(gfs_context *c, const int has[2], const unsigned int seq[2]) {
+    for (int s = 0; s < 2; s++)
+        if (has[s])
+            LAUNCH(c, gfs::k_signal, 1, 1, (volatile unsigned int *)c->comm[s].peer + 1, seq[s],
+                   (volatile unsigned int *)c->comm[s].peer + 2, c->split_counters.p + 1 + s, 1);
+    LAUNCH(c, gfs::k_gather_counts, 1, 1,
+           has[0] ? (const volatile unsigned int *)c->comm[0].block + 1 : nullptr,
+           has[1] ? (const volatile unsigned int *)c->comm[1].block + 1 : nullptr, seq[0], c->split_counters.p,
+           (const volatile unsigned int *)c->comm[0].block + 2, (const volatile unsigned int *)c->comm[1].block + 2,
+           c->comm_host, c->comm_error.p);
+}
+
+void comm_migrate_split(gfs_context *c, int has_down, int has_up) {
+    drop_dead(c);
     const int k_lo = has_down ? c->own_k0 : (int)0x80000000, k_hi = has_up ? c->own_k1 : 0x7FFFFFFF;
     unsigned int seq[2];
     for (int s = 0; s < 2; s++) seq[s] = ++c->comm[s].seq_particles;
@@ -1199,15 +1271,51 @@ void gfs_comm_migrate_begin(gfs_context *c, int has_down, int has_up, int *err) 
         GFS_CUDA(cudaMemsetAsync(c->split_counters.p, 0, 4 * sizeof(unsigned int), c->stream));
     }
     const int has[2] = {has_down, has_up};
-    for (int s = 0; s < 2; s++)
-        if (has[s])      // count word [2] then flag word [1] of the neighbour's block
-            LAUNCH(c, gfs::k_signal, 1, 1, (volatile unsigned int *)c->comm[s].peer + 1, seq[s],
-                   (volatile unsigned int *)c->comm[s].peer + 2, c->split_counters.p + 1 + s, 1);
-    LAUNCH(c, gfs::k_gather_counts, 1, 1,
-           has_down ? (const volatile unsigned int *)c->comm[0].block + 1 : nullptr,
-           has_up ? (const volatile unsigned int *)c->comm[1].block + 1 : nullptr, seq[0], c->split_counters.p,
-           (const volatile unsigned int *)c->comm[0].block + 2, (const volatile unsigned int *)c->comm[1].block + 2,
-           c->comm_host, c->comm_error.p);
+    comm_signal_and_gather(c, has, seq);
+    c->comm_fused = false;
+}
+}  // namespace
+
+/* migration, first half: split the resident particles; leavers are written straight into the neighbours' arrival
+ * buffers, followed by their count and the flag.  has_down / has_up: whether a neighbour exists on that side. */
+void gfs_comm_migrate_begin(gfs_context *c, int has_down, int has_up, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
+    GFS_CUDA(cudaSetDevice(c->device));
+    comm_migrate_split(c, has_down, has_up);
+    GFS_END()
+}
+
+/* G2P + advection with the migration fused into the kernel: a particle that leaves the owned layers is stored by the
+ * G2P kernel itself into the neighbour's arrival buffer and becomes a dead slot here; the stayers are binned for the
+ * next sort in the same epilogue.  Where the brick kernel does not apply (exact arithmetic, dx not a power of two)
+ * this is gfs_g2p_advect followed by gfs_comm_migrate_begin.  Finish with gfs_comm_migrate_finish. */
+void gfs_comm_g2p_advect(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int has_down, int has_up, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const bool fused = g2p_uses_bricks(c, arith) && c->p2g_variant == 1 && c->lazy_sort && c->n - c->dead > 0 && (has_down || has_up);
+    if (!fused) {
+        do_g2p(c, dt, ratio, order, interp, arith, false);
+        comm_migrate_split(c, has_down, has_up);
+        return;
+    }
+    unsigned int seq[2];
+    for (int s = 0; s < 2; s++) seq[s] = ++c->comm[s].seq_particles;
+    GFS_CUDA(cudaMemsetAsync(c->split_counters.p, 0, 4 * sizeof(unsigned int), c->stream));
+    gfs::Migrate mg;
+    mg.own_lo = has_down ? c->own_k0 : (int)0x80000000;
+    mg.own_hi = has_up ? c->own_k1 : 0x7FFFFFFF;
+    mg.out[0] = has_down ? (float *)comm_arrivals(c, c->comm[0].peer, seq[0]) : nullptr;
+    mg.out[1] = has_up ? (float *)comm_arrivals(c, c->comm[1].peer, seq[1]) : nullptr;
+    mg.count = c->split_counters.p + 1;
+    mg.cap = (unsigned int)c->comm_particle_cap;
+    do_g2p(c, dt, ratio, order, interp, arith, true, &mg);
+    const int has[2] = {has_down, has_up};
+    comm_signal_and_gather(c, has, seq);
+    c->comm_fused = true;
     GFS_END()
 }
 
@@ -1222,16 +1330,92 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
     GFS_REQUIRE(h[5] == 0, "timed out waiting for a neighbour's particles (peer exchange)");
     GFS_REQUIRE((int64_t)h[1] <= c->comm_particle_cap && (int64_t)h[2] <= c->comm_particle_cap &&
                 (int64_t)h[3] <= c->comm_particle_cap && (int64_t)h[4] <= c->comm_particle_cap, "migration buffer too small");
-    if (c->n > 0) c->cur = 1 - c->cur;
-    c->n = h[0]; c->sorted = false; c->keys_ready = false; c->indexed = false;
     const unsigned int n_in[2] = {h[3], h[4]};
-    for (int s = 0; s < 2; s++) {
-        if (n_in[s] == 0) continue;
-        int e2 = GFS_SUCCESS;
-        gfs_append_particles_device(c, comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles), n_in[s], &e2);
-        if (e2 != GFS_SUCCESS) throw GfsError(g_error);
+    if (c->comm_fused) {
+        // the leavers stay behind as dead slots (binned last); arrivals go to the end of the arrays, binned like the rest
+        c->dead = (int64_t)h[1] + h[2];
+        const int64_t total = c->n + n_in[0] + n_in[1];
+        GFS_REQUIRE(total < 0x7FFFFFFFll, "particle count must fit int32");
+        ensure_capacity(c, total);
+        const int b = c->cur;
+        for (int s = 0; s < 2; s++) {
+            if (n_in[s] == 0) continue;
+            LAUNCH(c, gfs::k_append_bin, ceil_div((int64_t)n_in[s], 256), 256, c->grid, c->nkeys, (int64_t)n_in[s], c->n,
+                   (const float *)comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles),
+                   c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p, c->tag[b].p,
+                   c->keys[0].p, c->rank.p, c->counts.p);
+            c->n += n_in[s];
+        }
+    } else {
+        if (c->n > 0) c->cur = 1 - c->cur;
+        c->n = h[0]; c->sorted = false; c->keys_ready = false; c->indexed = false;
+        for (int s = 0; s < 2; s++) {
+            if (n_in[s] == 0) continue;
+            int e2 = GFS_SUCCESS;
+            gfs_append_particles_device(c, comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles), n_in[s], &e2);
+            if (e2 != GFS_SUCCESS) throw GfsError(g_error);
+        }
     }
     if (moved) { moved[0] = (int64_t)h[1] + h[2]; moved[1] = (int64_t)n_in[0] + n_in[1]; }
+    GFS_END()
+}
+
+/* ---- all-ranks table: the fixed-point scale of the P2G accumulators comes from max |v| over ALL particles, so the
+ * integer partial sums of different GPUs are commensurable (and equal to the single-GPU run's).  gfs_comm_world_alloc,
+ * exchange the handles, gfs_comm_world_connect for every rank (own rank included), then gfs_comm_allmax_scale once per
+ * substep between the sort and gfs_p2g_begin. */
+void gfs_comm_world_alloc(gfs_context *c, int rank, int world, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && world >= 1 && world <= 16 && rank >= 0 && rank < world, "world size must be 1..16");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (!c->world_table) GFS_CUDA(cudaMalloc((void **)&c->world_table, 2 * 16 * sizeof(unsigned long long)));
+    GFS_CUDA(cudaMemset(c->world_table, 0, 2 * 16 * sizeof(unsigned long long)));
+    c->comm_rank = rank; c->comm_world = world; c->seq_world = 0;
+    for (int r = 0; r < 16; r++) c->world_peer[r] = nullptr;
+    c->world_peer[rank] = c->world_table;
+    c->comm_error.reserve(1);
+    GFS_CUDA(cudaMemset(c->comm_error.p, 0, sizeof(unsigned int)));
+    GFS_END()
+}
+
+void gfs_comm_world_export(gfs_context *c, void *handle64, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && handle64 && c->world_table, "gfs_comm_world_alloc first");
+    cudaIpcMemHandle_t h;
+    GFS_CUDA(cudaIpcGetMemHandle(&h, c->world_table));
+    memcpy(handle64, &h, 64);
+    GFS_END()
+}
+
+void gfs_comm_world_connect(gfs_context *c, int rank, const void *handle64, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && c->world_table && rank >= 0 && rank < c->comm_world && handle64, "bad arguments");
+    if (rank == c->comm_rank) return;
+    GFS_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    GFS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->world_peer[rank] = (unsigned long long *)p;
+    GFS_END()
+}
+
+void gfs_comm_world_connect_local(gfs_context *c, int rank, gfs_context *other, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && other && c->world_table && other->world_table && rank >= 0 && rank < c->comm_world, "bad arguments");
+    c->world_peer[rank] = other->world_table;
+    GFS_END()
+}
+
+void gfs_comm_allmax_scale(gfs_context *c, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(c->world_table, "gfs_comm_world_alloc first");
+    for (int r = 0; r < c->comm_world; r++) GFS_REQUIRE(c->world_peer[r], "gfs_comm_world_connect every rank first");
+    GFS_CUDA(cudaSetDevice(c->device));
+    gfs::AllMaxPeers peers;
+    for (int r = 0; r < 16; r++) peers.table[r] = c->world_peer[r];
+    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p);
     GFS_END()
 }
 
@@ -1242,6 +1426,7 @@ void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device
     GFS_REQUIRE(n_down && n_up && cap >= 0 && cap < 0x7FFFFFFFll && (cap == 0 || (down_device && up_device)), "bad arguments");
     GFS_CUDA(cudaSetDevice(c->device));
     *n_down = *n_up = 0;
+    drop_dead(c);
     if (c->n == 0) return;
     c->split_counters.reserve(4);
     launch_split(c, k_lo, k_hi, down_device, up_device, cap, c->split_counters.p);
@@ -1263,6 +1448,7 @@ void gfs_extract_particles_async(gfs_context *c, int k_lo, int k_hi, void *down_
     require_domain(c);
     GFS_REQUIRE(counters_device && cap >= 0 && cap < 0x7FFFFFFFll && (cap == 0 || (down_device && up_device)), "bad arguments");
     GFS_CUDA(cudaSetDevice(c->device));
+    drop_dead(c);
     if (c->n == 0) { GFS_CUDA(cudaMemsetAsync(counters_device, 0, 4 * sizeof(unsigned int), c->stream)); return; }
     launch_split(c, k_lo, k_hi, down_device, up_device, cap, (unsigned int *)counters_device);
     GFS_END()
@@ -1282,6 +1468,7 @@ void gfs_append_particles_device(gfs_context *c, const void *aos_device, int64_t
     GFS_REQUIRE(c && n >= 0 && (n == 0 || aos_device), "bad arguments");
     GFS_CUDA(cudaSetDevice(c->device));
     if (n == 0) return;
+    drop_dead(c);
     const int64_t old = c->n;
     int e2 = GFS_SUCCESS;
     gfs_resize_particles(c, old + n, &e2);
@@ -1298,6 +1485,7 @@ void *gfs_device_ptr(gfs_context *c, int which, int *err) {
     if (which >= 0 && which < 9) return c->field[which / 3][which % 3].p;
     if (which == 9) return c->material.p;
     if (which >= 10 && which < 16) return c->soa[c->cur][which - 10].p;
+    if (which == 16) return c->vmax_bits.p;
     throw GfsError("gfs_device_ptr: unknown buffer id");
     GFS_END(nullptr)
 }
@@ -1306,6 +1494,18 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c && n >= 0 && n < 0x7FFFFFFFll, "bad arguments");
     GFS_CUDA(cudaSetDevice(c->device));
+    drop_dead(c);
+    ensure_capacity(c, n);
+    c->n = n;
+    c->sorted = false;
+    c->keys_ready = false;
+    GFS_END()
+}
+
+extern "C++" {
+namespace {
+// grow the particle buffers to hold n slots, keeping the current contents (particles, tags and their binning)
+void ensure_capacity(gfs_context *c, int64_t n) {
     if ((size_t)n > c->soa[0][0].cap) {
         // grow both buffer sets, keeping the current contents
         const int b = c->cur;
@@ -1323,15 +1523,21 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
         GFS_CUDA(cudaStreamSynchronize(c->stream));
         c->tag[b].release(); c->tag[b] = nt;
         c->tag[1 - b].release(); c->tag[1 - b].reserve(newcap);
-        for (int q = 0; q < 2; q++) { c->keys[q].release(); c->keys[q].reserve(newcap); c->perm[q].release(); c->perm[q].reserve(newcap); }
-        c->rank.release(); c->rank.reserve(newcap);
+        DevBuf<uint32_t> nk, nr; nk.reserve(newcap); nr.reserve(newcap);
+        if (keep > 0) {
+            GFS_CUDA(cudaMemcpyAsync(nk.p, c->keys[0].p, (size_t)keep * 4, cudaMemcpyDeviceToDevice, c->stream));
+            GFS_CUDA(cudaMemcpyAsync(nr.p, c->rank.p, (size_t)keep * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        GFS_CUDA(cudaStreamSynchronize(c->stream));
+        c->keys[0].release(); c->keys[0] = nk;
+        c->rank.release(); c->rank = nr;
+        c->keys[1].release(); c->keys[1].reserve(newcap);
+        for (int q = 0; q < 2; q++) { c->perm[q].release(); c->perm[q].reserve(newcap); }
         c->index.release(); c->index.reserve(newcap);
     }
-    c->n = n;
-    c->sorted = false;
-    c->keys_ready = false;
-    GFS_END()
 }
+}  // namespace
+}  // extern "C++"
 
 /* ---- z-slab helpers (host arithmetic only) ------------------------------------------------------ */
 

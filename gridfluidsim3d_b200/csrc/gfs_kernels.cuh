@@ -757,7 +757,17 @@ __device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f,
     }
 }
 
-template <int INTERP>
+// Fused migration (z-slab sharding over peer memory): a particle whose advected position lies below / above the layers
+// this GPU owns is written by the G2P kernel itself into the neighbour GPU's arrival buffer (NVLink store), and is
+// binned here into the "dead" bin nkeys + 1 -- behind every cell and the out-of-grid bin, where no kernel looks.
+struct Migrate {
+    int own_lo, own_hi;            // cell layers [own_lo, own_hi) stay; INT_MIN / INT_MAX on a side without neighbour
+    float *out[2];                 // the neighbours' arrival buffers, 6 floats per particle (null: no migration)
+    unsigned int *count;           // count[0], count[1]: leavers down / up (tickets)
+    unsigned int cap;
+};
+
+template <int INTERP, bool MIGRATE>
 __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
                             const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
                             const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
@@ -767,7 +777,8 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
                             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
                             float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
                             unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
-                            uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
+                            uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
+                            Migrate mg) {
     typedef BrickTile<INTERP> T;
     // dynamic shared memory: [pad to 128 B] NEW u,v,w [nCount each] | SAVED u,v,w [sCount each] | mbarrier.
     // TMA destinations must be 128-byte aligned: align by hand, static shared variables precede this block.
@@ -780,7 +791,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
     // the last CTA takes the overflow bin (particles outside the grid): no tile, global path only
     const bool overflow = b == nbricks;
     const int start = cell_start[(size_t)b * kBrickCells];
-    const int end = overflow ? (int)n : cell_start[(size_t)(b + 1) * kBrickCells];
+    const int end = overflow ? cell_start[(size_t)nkeys + 1] : cell_start[(size_t)(b + 1) * kBrickCells];     // the dead bin follows
     if (start >= end) return;
     const int bi = (int)(b % (uint32_t)g.nbi), bj = (int)((b / (uint32_t)g.nbi) % (uint32_t)g.nbj), bk = (int)(b / ((uint32_t)g.nbi * (uint32_t)g.nbj));
     const int bx = bi * kBrick, by = bj * kBrick, bz = bk * kBrick + g.k0;       // global node index of the brick origin
@@ -890,6 +901,17 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
             if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {
                 const int i = (int)floorf(__fmul_rn(qx, g.invdxf)), j = (int)floorf(__fmul_rn(qy, g.invdxf)), k = (int)floorf(__fmul_rn(qz, g.invdxf));
                 if (k >= g.k0 && k < g.k1) key = brick_key(g, i, j, k - g.k0);
+                if (MIGRATE) {
+                    const int side = k < mg.own_lo ? 0 : (k >= mg.own_hi ? 1 : -1);
+                    if (side >= 0) {
+                        const unsigned int slot = atomicAdd(mg.count + side, 1u);
+                        if (slot < mg.cap && mg.out[side]) {
+                            float2 *dst = reinterpret_cast<float2 *>(mg.out[side] + 6 * (size_t)slot);      // 24-byte records: 8-byte aligned
+                            dst[0] = make_float2(qx, qy); dst[1] = make_float2(qz, wx); dst[2] = make_float2(wy, wz);
+                        }
+                        key = nkeys + 1;
+                    }
+                }
             }
             keys_out[r] = key;
             pend_rank = atomicAdd(counts + key, 1u);
@@ -1152,6 +1174,52 @@ __global__ void k_append_aos(int64_t n, int64_t at, const float *__restrict__ ao
     const float *p = aos + 6 * r;
     x[at + r] = p[0]; y[at + r] = p[1]; z[at + r] = p[2]; vx[at + r] = p[3]; vy[at + r] = p[4]; vz[at + r] = p[5];
     tag[at + r] = -1;
+}
+
+// arrivals of the fused migration: AoS -> SoA at the end of the arrays, binned for the next counting sort like the
+// G2P epilogue bins the residents
+__global__ void __launch_bounds__(256) k_append_bin(Grid g, uint32_t nkeys, int64_t n, int64_t at, const float *__restrict__ aos,
+                             float *x, float *y, float *z, float *vx, float *vy, float *vz, int32_t *tag,
+                             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float2 *p = reinterpret_cast<const float2 *>(aos + 6 * r);
+    const float2 a = p[0], b = p[1], c = p[2];
+    x[at + r] = a.x; y[at + r] = a.y; z[at + r] = b.x; vx[at + r] = b.y; vy[at + r] = c.x; vz[at + r] = c.y;
+    tag[at + r] = -1;
+    const uint32_t key = position_key(g, nkeys, a.x, a.y, b.x);
+    keys_out[at + r] = key;
+    rank_out[at + r] = atomicAdd(counts + key, 1u);
+}
+
+// all-ranks maximum of one 32-bit word over peer memory: every rank stores {seq, value} into its slot of every rank's
+// table (NVLink stores, one thread per peer), then waits until all slots of its own table carry seq.  Tables are double
+// buffered by the parity of seq.  value is compared as an unsigned integer (bit patterns of non-negative floats order
+// like the floats).  One CTA of >= world threads.
+struct AllMaxPeers { unsigned long long *table[16]; };
+__global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int seq, unsigned int *value, unsigned int *error) {
+    __shared__ unsigned int s_max;
+    const int t = threadIdx.x;
+    if (t == 0) s_max = 0u;
+    __syncthreads();
+    const unsigned int mine = *value;
+    const size_t base = (size_t)(seq & 1u) * 16;
+    if (t < world) {
+        volatile unsigned long long *slot = peers.table[t] + base + rank;
+        *slot = ((unsigned long long)seq << 32) | mine;
+        __threadfence_system();
+        const volatile unsigned long long *in = peers.table[rank] + base + t;
+        const long long t0 = clock64();
+        unsigned long long v;
+        bool ok = true;
+        while ((unsigned int)((v = *in) >> 32) != seq) {
+            if (clock64() - t0 > 8000000000ll) { atomicExch(error, 1u); ok = false; break; }
+            __nanosleep(100);
+        }
+        if (ok) atomicMax(&s_max, (unsigned int)v);
+    }
+    __syncthreads();
+    if (t == 0) *value = s_max;
 }
 
 __global__ void k_border_solid(Grid g, uint8_t *__restrict__ material) {

@@ -143,6 +143,12 @@ class DistTransport:
                 req.wait()
         return recv
 
+    def agree(self, drv):
+        """max |v| over all ranks -> every rank's fixed-point scale (see gfs_device_ptr(16)); the one collective."""
+        word = drv.b.scale_word() if hasattr(drv.b, "scale_word") else None
+        if word is not None and drv.world > 1:
+            dist.all_reduce(word, op=dist.ReduceOp.MAX, group=self.group)
+
     def layers(self, drv, phases):
         send = drv.pack(phases)
         _, recv = drv.buffers(phases)
@@ -202,7 +208,17 @@ class PeerTransport:
             dist.all_gather_object(everyone, mine, group=group)
             for side in drv.sides():          # the neighbour on my `side` exposes its block for the opposite side
                 self.ctx.comm_connect(SIDE_ID[side], everyone[drv.peer[side]][1 - SIDE_ID[side]])
+            self.ctx.comm_world_alloc(drv.rank, drv.world)
+            tables = [None] * drv.world
+            dist.all_gather_object(tables, self.ctx.comm_world_export(), group=group)
+            for r, h in enumerate(tables):
+                if r != drv.rank:
+                    self.ctx.comm_world_connect(r, h)
             dist.barrier(group=group)
+
+    def agree(self, drv):
+        if drv.world > 1:
+            self.ctx.comm_allmax_scale()
 
     def layers(self, drv, phases):
         plan = drv.plan(phases)
@@ -214,6 +230,15 @@ class PeerTransport:
 
     def migrate(self, drv):
         self.ctx.comm_migrate_begin(drv.peer["down"] is not None, drv.peer["up"] is not None)
+        sent, got = self.ctx.comm_migrate_finish()
+        self.bytes_sent += sent * 24
+        return sent, got
+
+    def advect_and_migrate(self, drv, dt):
+        """G2P + RK with the migration fused into the kernel (gfs_comm_g2p_advect), then the one host sync."""
+        b = drv.b
+        self.ctx.comm_g2p_advect(dt, drv.peer["down"] is not None, drv.peer["up"] is not None,
+                                 order=b.order, interp=b.interp, arith=b.arith)
         sent, got = self.ctx.comm_migrate_finish()
         self.bytes_sent += sent * 24
         return sent, got
@@ -230,6 +255,11 @@ class PeerLoopbackWorld:
         for r, d in enumerate(self.drv):
             for side in d.sides():
                 d.b.ctx.comm_connect_local(SIDE_ID[side], self.drv[d.peer[side]].b.ctx)
+            d.b.ctx.comm_world_alloc(r, len(self.drv))
+        for r, d in enumerate(self.drv):
+            for q, e in enumerate(self.drv):
+                if q != r:
+                    d.b.ctx.comm_world_connect_local(q, e.b.ctx)
 
     def _layers(self, phases):
         plans = [d.plan(phases) for d in self.drv]
@@ -240,9 +270,12 @@ class PeerLoopbackWorld:
             for side, (items, so, sb, ro, rb) in plan.items():
                 d.b.ctx.comm_pull_layers(SIDE_ID[side], [(w, rf, rc, off, add) for (w, sf, sc, rf, rc, add), off in zip(items, ro)])
 
-    def substep(self, dt, pressure_solve_between=False):
+    def substep(self, dt, pressure_solve_between=False, fused=True):
         for d in self.drv:
             d.b.sort()
+        for d in self.drv:
+            d.b.ctx.comm_allmax_scale()
+        for d in self.drv:
             d.b.p2g_begin()
         if pressure_solve_between:
             self._layers(("partials",))
@@ -253,10 +286,15 @@ class PeerLoopbackWorld:
             self._layers(("partials", "halos"))
             for d in self.drv:
                 d.b.p2g_end()
-        for d in self.drv:
-            d.b.g2p_advect(dt)
-        for d in self.drv:
-            d.b.ctx.comm_migrate_begin(d.peer["down"] is not None, d.peer["up"] is not None)
+        if fused:
+            for d in self.drv:
+                d.b.ctx.comm_g2p_advect(dt, d.peer["down"] is not None, d.peer["up"] is not None,
+                                        order=d.b.order, interp=d.b.interp, arith=d.b.arith)
+        else:
+            for d in self.drv:
+                d.b.g2p_advect(dt)
+            for d in self.drv:
+                d.b.ctx.comm_migrate_begin(d.peer["down"] is not None, d.peer["up"] is not None)
         return sum(d.b.ctx.comm_migrate_finish()[1] for d in self.drv)
 
 
@@ -264,6 +302,7 @@ def substep(drv, transport, dt, pressure_solve_between=False):
     """One sharded substep of one rank.  Returns (particles sent away, particles received)."""
     b = drv.b
     b.sort()
+    transport.agree(drv)                           # the fixed-point scale of the partial sums: max |v| over all ranks
     b.p2g_begin()
     if pressure_solve_between:
         transport.layers(drv, ("partials",))
@@ -272,6 +311,8 @@ def substep(drv, transport, dt, pressure_solve_between=False):
     else:
         transport.layers(drv, ("partials", "halos"))
         b.p2g_end()
+    if hasattr(transport, "advect_and_migrate"):
+        return transport.advect_and_migrate(drv, dt)
     b.g2p_advect(dt)
     return transport.migrate(drv)
 
@@ -301,6 +342,13 @@ class LoopbackWorld:
     def substep(self, dt, pressure_solve_between=False):
         for d in self.drv:
             d.b.sort()
+        words = [d.b.scale_word() for d in self.drv if hasattr(d.b, "scale_word")]
+        if words:                                   # max |v| over all slabs -> every slab's fixed-point scale
+            top = torch.stack(words).max()
+            for w in words:
+                w.fill_(top)
+            torch.cuda.current_stream().synchronize()
+        for d in self.drv:
             d.b.p2g_begin()
         if pressure_solve_between:
             self._layers(("partials",))
@@ -346,7 +394,20 @@ class CudaSlabBackend:
         return self.ctx.num_particles
 
     def sort(self):
-        self.ctx.sort_unstable()
+        if self.arith == 0:
+            self.ctx.sort_index()          # fast arithmetic is order independent: no physical reorder
+        else:
+            self.ctx.sort_unstable()
+
+    def scale_word(self):
+        """The device word holding max |v| (float bits) as an int32 tensor (bit patterns of floats >= 0 order like ints)."""
+        class _Word:
+            pass
+        w = _Word()
+        w.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(self.ctx.device_ptr(16)), False), "version": 2}
+        self._torch_done()
+        self._lib_done()
+        return torch.as_tensor(w, device=self.device)
 
     def p2g_begin(self):
         self.ctx.p2g_begin(self.arith)

@@ -156,6 +156,10 @@ void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int
  * counting sort the fast substep uses (the order inside a cell is unspecified; nothing in fast mode depends on it). */
 void gfs_sort(gfs_context *ctx, int *err);
 void gfs_sort_unstable(gfs_context *ctx, int *err);
+/* gfs_sort_index: the counting sort without moving the particles -- only the sorted index is materialised and the
+ * P2G / G2P kernels fetch through it (G2P stores its results in sorted order).  What gfs_substep does internally;
+ * gfs_get_particles afterwards returns the storage order, not the sorted one. */
+void gfs_sort_index(gfs_context *ctx, int *err);
 /* Tuning switches.  option 0: fast-P2G variant, 1 = brick tiles in shared memory (default), 0 = global atomics
  * only; both produce bit-identical grids.  option 1: fast-G2P variant, 1 = TMA-staged brick tiles (default; used
  * when dx is a power of two and the particles are sorted), 0 = global loads only; bit-identical results. */
@@ -216,10 +220,27 @@ void gfs_comm_push_layers(gfs_context *ctx, int side, int n, const int *what, co
 void gfs_comm_pull_layers(gfs_context *ctx, int side, int n, const int *what, const int *k_first, const int *k_count,
                           const int64_t *offsets, const int *add, int *err);
 void gfs_comm_migrate_begin(gfs_context *ctx, int has_down, int has_up, int *err);
+/* gfs_g2p_advect with the migration fused into the G2P kernel (leavers are stored into the neighbour's arrival buffer
+ * by the kernel that advects them; stayers are binned for the next gfs_sort_index).  Replaces gfs_g2p_advect +
+ * gfs_comm_migrate_begin; falls back to exactly that pair where the brick kernel does not apply. */
+void gfs_comm_g2p_advect(gfs_context *ctx, double dt, double picflip_ratio, int rk_order, int interp, int arith,
+                         int has_down, int has_up, int *err);
 void gfs_comm_migrate_finish(gfs_context *ctx, int64_t *moved2, int *err);
 
+/* All-ranks maximum over peer memory (<= 16 GPUs of one node).  The fixed-point scale of the P2G accumulators derives
+ * from max |v| over ALL particles of the domain, so that the integer partial sums of different GPUs are commensurable
+ * and the sharded result equals the single-GPU one bit for bit: call gfs_comm_allmax_scale between the sort and
+ * gfs_p2g_begin.  Setup: world_alloc, ship world_export's 64 bytes to everyone, world_connect for every other rank. */
+void gfs_comm_world_alloc(gfs_context *ctx, int rank, int world, int *err);
+void gfs_comm_world_export(gfs_context *ctx, void *handle64, int *err);
+void gfs_comm_world_connect(gfs_context *ctx, int rank, const void *handle64, int *err);
+void gfs_comm_world_connect_local(gfs_context *ctx, int rank, gfs_context *other, int *err);
+void gfs_comm_allmax_scale(gfs_context *ctx, int *err);
+
 /* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).
- * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz. */
+ * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz;
+ * 16 the word holding max |v| of the resident particles (float bits; the P2G fixed-point scale derives from it --
+ * sharded runs must replace it by the maximum over all ranks between the sort and gfs_p2g_begin). */
 void *gfs_device_ptr(gfs_context *ctx, int which, int *err);
 /* Resize the resident particle set to n (contents of [0,min(old,n)) kept) -- used by slab migration. */
 void gfs_resize_particles(gfs_context *ctx, int64_t n, int *err);
