@@ -30,7 +30,7 @@ SYMBOLS = [
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
-    "gfs_comm_allmax_scale", "gfs_sort_index",
+    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -123,6 +123,9 @@ def load_library():
     L.gfs_comm_world_connect_local.argtypes = [V, I, V, _err]
     L.gfs_comm_allmax_scale.argtypes = [V, _err]
     L.gfs_sort_index.argtypes = [V, _err]
+    PI, PL = C.POINTER(I), C.POINTER(L64)
+    L.gfs_comm_set_plan.argtypes = [V, I, I, PI, PI, PI, PL, I, PI, PI, PI, PL, PI, _err]
+    L.gfs_comm_substep.argtypes = [V, C.c_double, C.c_double, I, I, I, I, I, PL, _err]
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
     L.gfs_resize_particles.argtypes = [V, L64, _err]
@@ -413,6 +416,17 @@ class Context:
     def comm_g2p_advect(self, dt, has_down, has_up, ratio=0.05, order=4, interp=TRICUBIC, arith=FAST):
         self._call(self.lib.gfs_comm_g2p_advect, float(dt), float(ratio), int(order), int(interp), int(arith),
                    int(bool(has_down)), int(bool(has_up)))
+
+    def comm_set_plan(self, side, push_items, pull_items):
+        n, w, f, k, o, _ = self._item_arrays(push_items)
+        m, w2, f2, k2, o2, a2 = self._item_arrays(pull_items)
+        self._call(self.lib.gfs_comm_set_plan, int(side), n, w, f, k, o, m, w2, f2, k2, o2, a2)
+
+    def comm_substep(self, dt, has_down, has_up, ratio=0.05, order=4, interp=TRICUBIC, arith=FAST):
+        moved = (C.c_int64 * 2)()
+        self._call(self.lib.gfs_comm_substep, float(dt), float(ratio), int(order), int(interp), int(arith),
+                   int(bool(has_down)), int(bool(has_up)), moved)
+        return moved[0], moved[1]
 
     def comm_world_alloc(self, rank, world):
         self._call(self.lib.gfs_comm_world_alloc, int(rank), int(world))

@@ -141,6 +141,11 @@ struct gfs_context {
     size_t comm_layer_bytes = 0;          // capacity of one layers buffer
     int64_t comm_particle_cap = 0;        // capacity (particles) of one arrivals buffer
     unsigned int *comm_host = nullptr;    // pinned: counts published by k_gather_counts
+    struct CommPlan {                     // the merged C1+C2 exchange of one side, as gfs_comm_set_plan stored it
+        int n_push = 0, n_pull = 0;
+        int push_what[16], push_first[16], push_count[16], pull_what[16], pull_first[16], pull_count[16], pull_add[16];
+        int64_t push_off[16], pull_off[16];
+    } comm_plan[2];
     bool comm_fused = false;              // the pending migration was done by the G2P kernel (leavers are dead slots)
     int comm_rank = -1, comm_world = 0;   // all-ranks table (k_allmax)
     unsigned long long *world_table = nullptr;        // mine: [2 parities][16 ranks]
@@ -1357,6 +1362,51 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
         }
     }
     if (moved) { moved[0] = (int64_t)h[1] + h[2]; moved[1] = (int64_t)n_in[0] + n_in[1]; }
+    GFS_END()
+}
+
+/* The merged C1 + C2 exchange of one side, stored for gfs_comm_substep (same arguments as push_layers / pull_layers). */
+void gfs_comm_set_plan(gfs_context *c, int side, int n_push, const int *push_what, const int *push_first, const int *push_count,
+                       const int64_t *push_offsets, int n_pull, const int *pull_what, const int *pull_first, const int *pull_count,
+                       const int64_t *pull_offsets, const int *pull_add, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && (side == 0 || side == 1) && n_push >= 0 && n_push <= 16 && n_pull >= 0 && n_pull <= 16, "bad arguments");
+    gfs_context::CommPlan &p = c->comm_plan[side];
+    p.n_push = n_push; p.n_pull = n_pull;
+    for (int i = 0; i < n_push; i++) { p.push_what[i] = push_what[i]; p.push_first[i] = push_first[i]; p.push_count[i] = push_count[i]; p.push_off[i] = push_offsets[i]; }
+    for (int i = 0; i < n_pull; i++) { p.pull_what[i] = pull_what[i]; p.pull_first[i] = pull_first[i]; p.pull_count[i] = pull_count[i]; p.pull_off[i] = pull_offsets[i]; p.pull_add[i] = pull_add[i]; }
+    GFS_END()
+}
+
+/* One sharded substep of this rank as a single call: index sort, agreed scale, P2G with the layer exchange of the stored
+ * plan, G2P + RK with fused migration, and the host synchronisation that appends the arrivals.  Every rank calls it
+ * once per substep.  moved[0] = particles sent away, moved[1] = received. */
+void gfs_comm_substep(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int has_down, int has_up,
+                      int64_t *moved, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_CUDA(cudaSetDevice(c->device));
+    const int has[2] = {has_down, has_up};
+    int e2 = GFS_SUCCESS;
+#define GFS_SUB(call) do { call; if (e2 != GFS_SUCCESS) throw GfsError(g_error); } while (0)
+    if (arith == GFS_EXACT) GFS_SUB(gfs_sort_unstable(c, &e2)); else GFS_SUB(gfs_sort_index(c, &e2));
+    if (c->world_table && c->comm_world > 1) GFS_SUB(gfs_comm_allmax_scale(c, &e2));
+    do_p2g_begin(c, arith);
+    for (int s = 0; s < 2; s++) {
+        if (!has[s]) continue;
+        const gfs_context::CommPlan &p = c->comm_plan[s];
+        GFS_SUB(gfs_comm_push_layers(c, s, p.n_push, p.push_what, p.push_first, p.push_count, p.push_off, &e2));
+    }
+    for (int s = 0; s < 2; s++) {
+        if (!has[s]) continue;
+        const gfs_context::CommPlan &p = c->comm_plan[s];
+        GFS_REQUIRE(p.n_pull > 0, "gfs_comm_set_plan first");
+        GFS_SUB(gfs_comm_pull_layers(c, s, p.n_pull, p.pull_what, p.pull_first, p.pull_count, p.pull_off, p.pull_add, &e2));
+    }
+    do_p2g_end(c);
+    GFS_SUB(gfs_comm_g2p_advect(c, dt, ratio, order, interp, arith, has_down, has_up, &e2));
+    GFS_SUB(gfs_comm_migrate_finish(c, moved, &e2));
+#undef GFS_SUB
     GFS_END()
 }
 

@@ -194,6 +194,7 @@ class PeerTransport:
     def __init__(self, drv, group=None, particle_cap=None, connect=True, layer_bytes=None):
         self.ctx = drv.b.ctx
         self.bytes_sent = 0
+        self._plan_key, self._plan_bytes = None, {}
         layer_bytes = max(int(layer_bytes or 0), self.layer_bytes(drv))
         # both ends of a link must agree on the sizes: take the maxima over all ranks
         cap = particle_cap if particle_cap is not None else max(4096, drv.b.num_particles // 6)
@@ -219,6 +220,22 @@ class PeerTransport:
     def agree(self, drv):
         if drv.world > 1:
             self.ctx.comm_allmax_scale()
+
+    def substep(self, drv, dt):
+        """The whole substep as ONE native call (gfs_comm_substep): same sequence as slabs.substep()."""
+        key = (id(drv), drv.b.interp)
+        if self._plan_key != key:
+            for side, (items, so, sb, ro, rb) in drv.plan(("partials", "halos")).items():
+                self.ctx.comm_set_plan(SIDE_ID[side],
+                                       [(w, sf, sc, off, False) for (w, sf, sc, rf, rc, add), off in zip(items, so)],
+                                       [(w, rf, rc, off, add) for (w, sf, sc, rf, rc, add), off in zip(items, ro)])
+                self._plan_bytes[side] = sb
+            self._plan_key = key
+        b = drv.b
+        sent, got = self.ctx.comm_substep(dt, drv.peer["down"] is not None, drv.peer["up"] is not None,
+                                          order=b.order, interp=b.interp, arith=b.arith)
+        self.bytes_sent += sent * 24 + sum(self._plan_bytes[s] for s in drv.sides())
+        return sent, got
 
     def layers(self, drv, phases):
         plan = drv.plan(phases)
@@ -300,6 +317,8 @@ class PeerLoopbackWorld:
 
 def substep(drv, transport, dt, pressure_solve_between=False):
     """One sharded substep of one rank.  Returns (particles sent away, particles received)."""
+    if hasattr(transport, "substep") and not pressure_solve_between:
+        return transport.substep(drv, dt)          # the same sequence, natively, in one call
     b = drv.b
     b.sort()
     transport.agree(drv)                           # the fixed-point scale of the partial sums: max |v| over all ranks

@@ -226,6 +226,14 @@ void gfs_comm_migrate_begin(gfs_context *ctx, int has_down, int has_up, int *err
 void gfs_comm_g2p_advect(gfs_context *ctx, double dt, double picflip_ratio, int rk_order, int interp, int arith,
                          int has_down, int has_up, int *err);
 void gfs_comm_migrate_finish(gfs_context *ctx, int64_t *moved2, int *err);
+/* The whole sharded substep of one rank in one call (no interpreter between the launches): gfs_comm_set_plan stores the
+ * merged C1 + C2 exchange of a side once (arguments as push_layers / pull_layers), gfs_comm_substep then runs
+ * sort_index, allmax_scale, p2g_begin, push/pull, p2g_end, comm_g2p_advect and migrate_finish. */
+void gfs_comm_set_plan(gfs_context *ctx, int side, int n_push, const int *push_what, const int *push_first, const int *push_count,
+                       const int64_t *push_offsets, int n_pull, const int *pull_what, const int *pull_first, const int *pull_count,
+                       const int64_t *pull_offsets, const int *pull_add, int *err);
+void gfs_comm_substep(gfs_context *ctx, double dt, double picflip_ratio, int rk_order, int interp, int arith,
+                      int has_down, int has_up, int64_t *moved2, int *err);
 
 /* All-ranks maximum over peer memory (<= 16 GPUs of one node).  The fixed-point scale of the P2G accumulators derives
  * from max |v| over ALL particles of the domain, so that the integer partial sums of different GPUs are commensurable
