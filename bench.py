@@ -467,7 +467,9 @@ def run_gfs(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the ncu capture
     if os.path.exists(traffic_file) and world == 1:
         with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get(args.workload, {}).get(top)
+            import re
+            m = re.search(r"(\w+)\s*<\s*(\d+)", top)          # "gfs::k_g2p_brick<0>" -> "k_g2p_brick<0>", as profiles/summarize.py keys it
+            roofline["traffic"] = json.load(f).get(args.workload, {}).get("%s<%s>" % (m.group(1), m.group(2)) if m else top.split("::")[-1])
 
     # ---- e2e: the same substep through host buffers ------------------------------------------------------
     aos_out = torch.empty((int(n_max) + 1024, 6), dtype=torch.float32, pin_memory=True)

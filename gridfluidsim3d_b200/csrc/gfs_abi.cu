@@ -192,7 +192,8 @@ Grid make_grid(int I, int J, int K, double dx, int k0, int k1, bool padded = fal
     int e = 0;
     g.pow2 = (std::frexp(dx, &e) == 0.5 && I < (1 << 20) && J < (1 << 20) && K < (1 << 20) && e > -100 && e < 100) ? 1 : 0;
     const int ni[3] = {I + 1, I, I};
-    for (int a = 0; a < 3; a++) g.pitch[a] = padded ? (ni[a] + 3) / 4 * 4 : ni[a];
+    // resident fields: 4 zero floats in front of every row (gfs::kRowPad), rows padded to whole 32-byte groups
+    for (int a = 0; a < 3; a++) g.pitch[a] = padded ? (ni[a] + gfs::kRowPad + 7) / 8 * 8 : ni[a];
     g.nbi = (I + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbj = (J + 1 + gfs::kBrick - 1) / gfs::kBrick;
     g.nbk = (k1 - k0 + 1 + gfs::kBrick - 1) / gfs::kBrick;
@@ -240,7 +241,7 @@ void require_domain(gfs_context *c) { GFS_REQUIRE(c && c->has_domain, "gfs_domai
 
 gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
     gfs::FieldPtrs f;
-    for (int a = 0; a < 3; a++) f.c[a] = c->field[slot][a].p;
+    for (int a = 0; a < 3; a++) f.c[a] = c->field[slot][a].p + gfs::kRowPad;          // element (0,0,0)
     return f;
 }
 
@@ -417,16 +418,13 @@ void do_p2g_end(gfs_context *c) {
         LAUNCH(c, gfs::k_p2g_finalize, ceil_div(total, 256), 256, g, sp, c->sources, fa);
     }
     gfs::AssembleArgs aa;
-    long long total_faces = 0;
     const int a_lo = whole ? 0 : c->own_k0, a_hi = whole ? g.K : c->own_k1;
     for (int comp = 0; comp < 3; comp++) {
-        aa.val[comp] = c->val[comp].p; aa.setmask[comp] = c->setmask[comp].p; aa.out[comp] = c->field[GFS_FIELD_P2G][comp].p;
-        aa.first[comp] = plane[comp] * a_lo;
-        // the w face layer own_k1 is the upper slab's lower face: it belongs to the upper slab, except the top of the domain
-        aa.count[comp] = plane[comp] * (a_hi - a_lo + ((comp == 2 && a_hi == g.K) ? 1 : 0));
-        total_faces += aa.count[comp];
+        aa.val[comp] = c->val[comp].p; aa.setmask[comp] = c->setmask[comp].p; aa.out[comp] = c->field[GFS_FIELD_P2G][comp].p + gfs::kRowPad;
     }
-    LAUNCH(c, gfs::k_assemble, ceil_div(total_faces, 256), 256, g, c->material.p, aa);
+    // the w face layer own_k1 is the upper slab's lower face: it belongs to the upper slab, except the top of the domain
+    aa.k_lo = a_lo; aa.k_hi = a_hi; aa.k_hi_w = a_hi + (a_hi == g.K ? 1 : 0);
+    LAUNCH(c, gfs::k_assemble, dim3((unsigned)ceil_div((long long)(g.I + 1) * (g.J + 1), 256), (unsigned)(aa.k_hi_w - a_lo)), 256, g, c->material.p, aa);
 }
 
 void do_p2g(gfs_context *c, int arith) {
@@ -531,17 +529,34 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-void make_field_map(CUtensorMap *map, float *base, int ni, int pitch, int nj, int nkl, int bx, int by, int bz) {
-    cuuint64_t dims[3] = {(cuuint64_t)ni, (cuuint64_t)nj, (cuuint64_t)nkl};        // x beyond ni is out of bounds -> 0
+// dense 3-D boxes {x 16, y, z} over the storage columns (trilinear bricks)
+void make_field_map_dense(CUtensorMap *map, float *storage, int pitch, int nj, int nkl, int by, int bz) {
+    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)nj, (cuuint64_t)nkl};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * (cuuint64_t)nj * 4};
-    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    cuuint32_t box[3] = {16, (cuuint32_t)by, (cuuint32_t)bz};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, storage, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char b[160];
-        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d, pitch %d)", (int)r, ni, nj, nkl, pitch);
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d (rows %d, planes %d, pitch %d)", (int)r, nj, nkl, pitch);
+        throw GfsError(b);
+    }
+}
+
+// 4-D view of a resident field for the brick boxes: (x_lo 8 floats, z, x_hi, y), see gfs::BrickTile
+void make_field_map(CUtensorMap *map, float *storage, int pitch, int nj, int nkl, int by, int bz) {
+    cuuint64_t dims[4] = {8, (cuuint64_t)nkl, (cuuint64_t)(pitch / 8), (cuuint64_t)nj};      // outside: zero fill
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * (cuuint64_t)nj * 4, 32, (cuuint64_t)pitch * 4};
+    cuuint32_t box[4] = {8, (cuuint32_t)bz, 2, (cuuint32_t)by};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, storage, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d (rows %d, planes %d, pitch %d)", (int)r, nj, nkl, pitch);
         throw GfsError(b);
     }
 }
@@ -551,14 +566,10 @@ void make_brick_maps(gfs_context *c) {
     const int kl = g.k1 - g.k0;
     const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
     for (int a = 0; a < 3; a++) {
-        make_field_map(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<0>::kX, gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nY);
-        make_field_map(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<0>::kX, gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sY);
-        make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<1>::kX, gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nY);
-        make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, ni[a], g.pitch[a], nj[a], nk[a],
-                       gfs::BrickTile<1>::kX, gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sY);
+        make_field_map_dense(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
+        make_field_map_dense(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
+        make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nZ);
+        make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sZ);
     }
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
@@ -909,7 +920,7 @@ void gfs_set_field(gfs_context *c, int slot, const float *u, const float *v, con
     const float *h[3] = {u, v, w};
     const int ni[3] = {c->grid.I + 1, c->grid.I, c->grid.I};
     for (int a = 0; a < 3; a++)        // reference rows (ni floats) -> resident rows (pitch floats)
-        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p, (size_t)c->grid.pitch[a] * 4, h[a], (size_t)ni[a] * 4, (size_t)ni[a] * 4,
+        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, h[a], (size_t)ni[a] * 4, (size_t)ni[a] * 4,
                                    c->face_count[a] / (size_t)ni[a], cudaMemcpyHostToDevice, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
@@ -922,7 +933,7 @@ void gfs_get_field(gfs_context *c, int slot, float *u, float *v, float *w, int *
     float *h[3] = {u, v, w};
     const int ni[3] = {c->grid.I + 1, c->grid.I, c->grid.I};
     for (int a = 0; a < 3; a++)
-        GFS_CUDA(cudaMemcpy2DAsync(h[a], (size_t)ni[a] * 4, c->field[slot][a].p, (size_t)c->grid.pitch[a] * 4, (size_t)ni[a] * 4,
+        GFS_CUDA(cudaMemcpy2DAsync(h[a], (size_t)ni[a] * 4, c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, (size_t)ni[a] * 4,
                                    c->face_count[a] / (size_t)ni[a], cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
@@ -1532,7 +1543,7 @@ void gfs_append_particles_device(gfs_context *c, const void *aos_device, int64_t
 void *gfs_device_ptr(gfs_context *c, int which, int *err) {
     GFS_BEGIN
     require_domain(c);
-    if (which >= 0 && which < 9) return c->field[which / 3][which % 3].p;
+    if (which >= 0 && which < 9) return c->field[which / 3][which % 3].p + gfs::kRowPad;
     if (which == 9) return c->material.p;
     if (which >= 10 && which < 16) return c->soa[c->cur][which - 10].p;
     if (which == 16) return c->vmax_bits.p;

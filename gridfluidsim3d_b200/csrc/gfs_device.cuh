@@ -16,6 +16,8 @@ constexpr int kBrickCells = 512;
 constexpr uint32_t kKeySentinel = 0xFFFFFFFFu;
 
 // Geometry of the (possibly z-slab-local) grid a kernel works on.
+constexpr int kRowPad = 4;      // zero floats in front of every row of a resident field array (see BrickTile)
+
 struct Grid {
     int I, J, K;          // global cell counts
     int k0, k1;           // cell layers [k0,k1) stored locally (0,K on a single GPU)

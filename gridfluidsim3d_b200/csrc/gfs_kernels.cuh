@@ -176,23 +176,29 @@ __global__ void k_reorder(int64_t n, const int32_t *__restrict__ perm,
 __global__ void __launch_bounds__(256) k_classify(Grid g, const int32_t *__restrict__ cell_start, uint8_t *__restrict__ material,
                            unsigned long long *__restrict__ counters /* [0]=in_solid particles, [1]=fluid cells */,
                            long long first_cell, long long ncells, int own_k0, int own_k1) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncells) return;
-    const size_t idx = (size_t)(first_cell + t);
-    const uint32_t idx32 = (uint32_t)idx;                       // cell counts fit 31 bits (checked at domain_init)
-    const int i = (int)(idx32 % (uint32_t)g.I), j = (int)((idx32 / (uint32_t)g.I) % (uint32_t)g.J), kl = (int)(idx32 / ((uint32_t)g.I * (uint32_t)g.J));
-    const int k = kl + g.k0;
-    uint32_t key = brick_key(g, i, j, kl);
-    int cnt = cell_start[key + 1] - cell_start[key];
-    uint8_t m = material[idx];
-    bool interior = i >= 1 && i < g.I - 1 && j >= 1 && j < g.J - 1 && k >= 1 && k < g.K - 1;
-    if (interior && m == GFS_FLUID) m = GFS_AIR;
-    if (cnt > 0) {
-        if (m == GFS_SOLID) atomicAdd(&counters[0], (unsigned long long)cnt);
-        else m = GFS_FLUID;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool counted = false;
+    if (t < ncells) {
+        const size_t idx = (size_t)(first_cell + t);
+        const uint32_t idx32 = (uint32_t)idx;                       // cell counts fit 31 bits (checked at domain_init)
+        const int i = (int)(idx32 % (uint32_t)g.I), j = (int)((idx32 / (uint32_t)g.I) % (uint32_t)g.J), kl = (int)(idx32 / ((uint32_t)g.I * (uint32_t)g.J));
+        const int k = kl + g.k0;
+        const uint32_t key = brick_key(g, i, j, kl);
+        const int cnt = cell_start[key + 1] - cell_start[key];
+        const uint8_t m0 = material[idx];
+        uint8_t m = m0;
+        const bool interior = i >= 1 && i < g.I - 1 && j >= 1 && j < g.J - 1 && k >= 1 && k < g.K - 1;
+        if (interior && m == GFS_FLUID) m = GFS_AIR;
+        if (cnt > 0) {
+            if (m == GFS_SOLID) atomicAdd(&counters[0], (unsigned long long)cnt);      // rare: particles inside a solid
+            else m = GFS_FLUID;
+        }
+        if (m != m0) material[idx] = m;
+        counted = m == GFS_FLUID && k >= own_k0 && k < own_k1;
     }
-    material[idx] = m;
-    if (m == GFS_FLUID && k >= own_k0 && k < own_k1) atomicAdd(&counters[1], 1ull);
+    // one atomic per block (a ticket per fluid cell on one address serialises ~10^7 atomics)
+    const int nfluid = __syncthreads_count(counted);
+    if (threadIdx.x == 0 && nfluid > 0) atomicAdd(&counters[1], (unsigned long long)nfluid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,27 +560,15 @@ struct AssembleArgs {
     const float *val[3];
     const uint8_t *setmask[3];
     float *out[3];
-    long long first[3];
-    long long count[3];
+    int k_lo, k_hi, k_hi_w;          // cell layers [k_lo, k_hi) for the u, v faces; w face layers [k_lo, k_hi_w)
 };
 
-// flat over the faces of all three components (one launch)
-__global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restrict__ material, AssembleArgs aa) {
-    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c0 = aa.count[0], c01 = aa.count[0] + aa.count[1], c012 = c01 + aa.count[2];
-    if (t0 >= c012) return;
-    const int comp = (t0 >= c0) + (t0 >= c01);
-    const size_t node = (size_t)(t0 - (comp == 0 ? 0 : (comp == 1 ? c0 : c01)) + (comp == 0 ? aa.first[0] : (comp == 1 ? aa.first[1] : aa.first[2])));
-    const int ni = g.I + (comp == 0), nj = g.J + (comp == 1), nkl = g.k1 - g.k0 + (comp == 2);
-    const uint32_t n32 = (uint32_t)node;                        // node counts fit 31 bits
-    const int i = (int)(n32 % (uint32_t)ni), j = (int)((n32 / (uint32_t)ni) % (uint32_t)nj), kl = (int)(n32 / ((uint32_t)ni * (uint32_t)nj));
-    const int k = kl + g.k0;
-    const float *val = comp == 0 ? aa.val[0] : (comp == 1 ? aa.val[1] : aa.val[2]);
-    const uint8_t *setmask = comp == 0 ? aa.setmask[0] : (comp == 1 ? aa.setmask[1] : aa.setmask[2]);
-    float *out = comp == 0 ? aa.out[0] : (comp == 1 ? aa.out[1] : aa.out[2]);
-    int di = comp == 0, dj = comp == 1, dk = comp == 2;
-    // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W} (fluidmaterialgrid.cpp:119-143)
-    bool borders = cell_is_fluid(g, material, i, j, k) || cell_is_fluid(g, material, i - di, j - dj, k - dk);
+template <int COMP>
+__device__ __forceinline__ void assemble_face(const Grid &g, const AssembleArgs &aa, int i, int j, int kl, bool borders) {
+    const int ni = g.I + (COMP == 0), nj = g.J + (COMP == 1), nkl = g.k1 - g.k0 + (COMP == 2);
+    const float *__restrict__ val = aa.val[COMP];
+    const uint8_t *__restrict__ setmask = aa.setmask[COMP];
+    const size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
     float r = 0.0f;
     if (borders) {
         if (setmask[node]) {
@@ -586,16 +580,30 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
                     for (int ni_ = i - 1; ni_ <= i + 1; ni_++) {
                         if (ni_ == i && nj_ == j && nk == kl) continue;
                         if (ni_ < 0 || nj_ < 0 || nk < 0 || ni_ >= ni || nj_ >= nj || nk >= nkl) continue;
-                        size_t nn = (size_t)ni_ + (size_t)ni * ((size_t)nj_ + (size_t)nj * (size_t)nk);
-                        float v = val[nn];
-                        bool ok = comp == 0 ? (fabs((double)v) > 0.0) : (setmask[nn] != 0);
+                        const size_t nn = (size_t)ni_ + (size_t)ni * ((size_t)nj_ + (size_t)nj * (size_t)nk);
+                        const float v = val[nn];
+                        const bool ok = COMP == 0 ? (fabs((double)v) > 0.0) : (setmask[nn] != 0);
                         if (ok) { avg = __dadd_rn(avg, (double)v); cnt += 1.0; }
                     }
             if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
         }
     }
-    const int pitch = comp == 0 ? g.pitch[0] : (comp == 1 ? g.pitch[1] : g.pitch[2]);
-    out[(size_t)i + (size_t)pitch * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
+    aa.out[COMP][(size_t)i + (size_t)g.pitch[COMP] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
+}
+
+// one thread per node (i, j) of the (I+1) x (J+1) plane, blockIdx.y = layer: the u, v and w faces whose lower corner is
+// that node, sharing the four material reads that decide "borders fluid"
+__global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restrict__ material, AssembleArgs aa) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)g.I + 1u;
+    if (t >= w * ((uint32_t)g.J + 1u)) return;
+    const int i = (int)(t % w), j = (int)(t / w);
+    const int k = aa.k_lo + (int)blockIdx.y, kl = k - g.k0;
+    const bool f = cell_is_fluid(g, material, i, j, k);
+    const bool uv = k < aa.k_hi;
+    if (uv && j < g.J) assemble_face<0>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i - 1, j, k));
+    if (uv && i < g.I) assemble_face<1>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i, j - 1, k));
+    if (k < aa.k_hi_w && i < g.I && j < g.J) assemble_face<2>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i, j, k - 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,54 +676,94 @@ struct BrickMaps { CUtensorMap m[6]; };     // NEW u,v,w then SAVED u,v,w
 
 template <int INTERP> struct BrickTile {
     // trilinear: taps c, c+1;  tricubic: taps c-1 .. c+2.  c ranges over [8b-1-M, 8b+7+M] (M = motion margin).
-    // Along y and z the boxes are exactly that; along x (the contiguous axis) TMA needs the box to start on a
-    // 16-byte boundary, so every box starts at node 8b-4 and is 16 nodes wide.
+    // Along y and z the boxes are exactly that (z plus one unused plane, see below); along x (the contiguous axis)
+    // TMA needs the box to start on a 16-byte boundary, so every box starts at node 8b-4 and is 16 nodes wide.
+    //
+    // Shared-memory layout (bank-conflict free for the access pattern of sorted particles).  The resident arrays keep
+    // 4 zero floats in front of every row, so node 8b-4 sits at storage column 8b, and the tensor map views a row as
+    // [x_hi][x_lo = 8 floats].  The 4-D box {x_lo 8, z nZ, x_hi 2, y nY} lands as
+    //     word(x, y, z) = (x & 7) + 8 * (z + nZ * ((x >> 3) + 2 * y)),        x, y, z relative to the box origin
+    // and with nZ ODD the bank is (x & 7) + 8 * (z +- (x >> 3)) + 16 * y  (mod 32): the lanes of a warp -- a few
+    // consecutive cells along x, two candidate rows in y and two in z because of the half-cell stagger -- fall into
+    // four disjoint 8-bank windows.  (The plain [z][y][x 16] box put both z candidates on the same banks: 43 % of all
+    // shared-memory wavefronts of this kernel were bank conflicts, profiles/r01_k_g2p_brick.md.)
     static constexpr int kMargin = 1;
     static constexpr int kLo = (INTERP == 1) ? 1 : 0, kHi = (INTERP == 1) ? 2 : 1;
     static constexpr int kOrgX = 4, kX = 16;                                // x: nodes [8b-4, 8b+11] for every box
     static constexpr int nOrg = 1 + kMargin + kLo;                          // NEW y/z origin = 8b - nOrg
     static constexpr int nY = 9 + 2 * kMargin + kLo + kHi;
+    // (trilinear keeps the dense [z][y][x 16] box: it does 1/7 of the shared loads per sample, is bound by instruction
+    // issue, and the split-column address arithmetic cost it more than the conflicts did -- measured 3.53 -> 3.97 ms.)
+    static constexpr bool kSkew = INTERP == 1;
+    static constexpr int nZ = kSkew ? (nY | 1) : nY;                        // odd plane count (>= nY)
     static constexpr int sOrg = 1 + kLo;                                    // SAVED (sampled at p0 only, no margin)
     static constexpr int sY = 9 + kLo + kHi;
-    static constexpr int nBox = kX * nY * nY, sBox = kX * sY * sY;           // floats per staged box
+    static constexpr int sZ = kSkew ? (sY | 1) : sY;
+    static constexpr int nBox = kX * nY * nZ, sBox = kX * sY * sZ;           // floats per staged box
     static constexpr int nCount = (nBox + 31) / 32 * 32, sCount = (sBox + 31) / 32 * 32;   // 128-byte aligned slots
     static constexpr uint32_t kTxBytes = 3 * (nBox + sBox) * sizeof(float);
     static constexpr size_t kSmemBytes = 3 * (nCount + sCount) * sizeof(float) + 128 + 16;   // + alignment slack + mbarrier
     static_assert(kOrgX >= nOrg && kX - kOrgX >= 9 + kMargin + kHi, "x box must cover the y/z node range");
+    static_assert(!kSkew || ((nZ & 1) && (sZ & 1)), "plane counts must be odd for the bank skew");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// box {x_lo 8, z, x_hi 2, y} of a resident field at (storage column 8 * xh, row y, plane z)
+__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, int z, int xh, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(0), "r"(z), "r"(xh), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// dense box {x 16, y, z} at (storage column x, row y, plane z)
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+// word offset of box column x (0..15) in the skewed layout
+template <int NZ>
+__device__ __forceinline__ int tile_col(int x) { return (x & 7) + 8 * NZ * (x >> 3); }
+
 // one component from a staged tile: ax/ay/az are global node indices + fractions, (ox,oy,oz) the tile origin
-template <int INTERP, int BX, int BY>
+template <int INTERP, int NZ>
 __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const AxisIdxF &ax, const AxisIdxF &ay, const AxisIdxF &az,
                                              int ox, int oy, int oz) {
-    const float *r = t + (ax.i - ox) + BX * ((ay.i - oy) + BY * (az.i - oz));
+    if (INTERP == 0) {          // dense [z][y][x 16] box, NZ = rows per plane
+        const float *r = t + (ax.i - ox) + 16 * ((ay.i - oy) + NZ * (az.i - oz));
+        constexpr int BX = 16, BY = NZ;
+        const float p000 = r[0], p100 = r[1], p010 = r[BX], p110 = r[BX + 1];
+        const float p001 = r[BX * BY], p101 = r[BX * BY + 1], p011 = r[BX * BY + BX], p111 = r[BX * BY + BX + 1];
+        float c00 = fmaf(ax.t, __fsub_rn(p100, p000), p000), c10 = fmaf(ax.t, __fsub_rn(p110, p010), p010);
+        float c01 = fmaf(ax.t, __fsub_rn(p101, p001), p001), c11 = fmaf(ax.t, __fsub_rn(p111, p011), p011);
+        float c0 = fmaf(ay.t, __fsub_rn(c10, c00), c00), c1 = fmaf(ay.t, __fsub_rn(c11, c01), c01);
+        return fmaf(az.t, __fsub_rn(c1, c0), c0);
+    }
+    constexpr int RY = 16 * NZ, RZ = 8;                       // word strides of one row / one plane
+    const int x0 = ax.i - ox;
+    const float *r = t + RY * (ay.i - oy) + RZ * (az.i - oz);
     if (INTERP == 1) {
         float wx[4], wy[4], wz[4];
         cr_weights(ax.t, wx); cr_weights(ay.t, wy); cr_weights(az.t, wz);
+        const int c0 = tile_col<NZ>(x0 - 1), c1 = tile_col<NZ>(x0), c2 = tile_col<NZ>(x0 + 1), c3 = tile_col<NZ>(x0 + 2);
         float acc = 0.0f;
 #pragma unroll
         for (int pk = 0; pk < 4; pk++) {
             float sk = 0.0f;
 #pragma unroll
             for (int pj = 0; pj < 4; pj++) {
-                const float *q = r + BX * ((pj - 1) + BY * (pk - 1)) - 1;
-                float sj = __fmul_rn(wx[0], q[0]);
-                sj = fmaf(wx[1], q[1], sj); sj = fmaf(wx[2], q[2], sj); sj = fmaf(wx[3], q[3], sj);
+                const float *q = r + RY * (pj - 1) + RZ * (pk - 1);
+                float sj = __fmul_rn(wx[0], q[c0]);
+                sj = fmaf(wx[1], q[c1], sj); sj = fmaf(wx[2], q[c2], sj); sj = fmaf(wx[3], q[c3], sj);
                 sk = fmaf(wy[pj], sj, sk);
             }
             acc = fmaf(wz[pk], sk, acc);
         }
         return acc;
     }
-    const float p000 = r[0], p100 = r[1], p010 = r[BX], p110 = r[BX + 1];
-    const float p001 = r[BX * BY], p101 = r[BX * BY + 1], p011 = r[BX * BY + BX], p111 = r[BX * BY + BX + 1];
+    const float *r0 = r + tile_col<NZ>(x0), *r1 = r + tile_col<NZ>(x0 + 1);
+    const float p000 = r0[0], p100 = r1[0], p010 = r0[RY], p110 = r1[RY];
+    const float p001 = r0[RZ], p101 = r1[RZ], p011 = r0[RZ + RY], p111 = r1[RZ + RY];
     float c00 = fmaf(ax.t, __fsub_rn(p100, p000), p000), c10 = fmaf(ax.t, __fsub_rn(p110, p010), p010);
     float c01 = fmaf(ax.t, __fsub_rn(p101, p001), p001), c11 = fmaf(ax.t, __fsub_rn(p111, p011), p011);
     float c0 = fmaf(ay.t, __fsub_rn(c10, c00), c00), c1 = fmaf(ay.t, __fsub_rn(c11, c01), c01);
@@ -747,9 +795,9 @@ __device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f,
               (unsigned)(s.uy.i - y0 - lo) <= span && (unsigned)(s.sy.i - y0 - lo) <= span &&
               (unsigned)(s.uz.i - z0 - lo) <= span && (unsigned)(s.sz.i - z0 - lo) <= span;
     if (in) {
-        ox = tile_sample<INTERP, T::kX, T::nY>(tile, s.ux, s.sy, s.sz, x0, y0, z0);
-        oy = tile_sample<INTERP, T::kX, T::nY>(tile + T::nCount, s.sx, s.uy, s.sz, x0, y0, z0);
-        oz = tile_sample<INTERP, T::kX, T::nY>(tile + 2 * T::nCount, s.sx, s.sy, s.uz, x0, y0, z0);
+        ox = tile_sample<INTERP, T::nZ>(tile, s.ux, s.sy, s.sz, x0, y0, z0);
+        oy = tile_sample<INTERP, T::nZ>(tile + T::nCount, s.sx, s.uy, s.sz, x0, y0, z0);
+        oz = tile_sample<INTERP, T::nZ>(tile + 2 * T::nCount, s.sx, s.sy, s.uz, x0, y0, z0);
     } else {
         ox = sample_component_fast<0>(g, f.c[0], INTERP, s.ux, s.sy, s.sz);
         oy = sample_component_fast<1>(g, f.c[1], INTERP, s.sx, s.uy, s.sz);
@@ -803,9 +851,14 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(T::kTxBytes) : "memory");
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                // z coordinate is local to the stored layers
-                tma_load_3d(tnew + c * T::nCount, &maps.m[c], bx - T::kOrgX, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
-                tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], bx - T::kOrgX, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
+                // z coordinate is local to the stored layers; node 8b-4 is storage column 8 * bi
+                if (T::kSkew) {
+                    tma_load_box(tnew + c * T::nCount, &maps.m[c], bz - g.k0 - T::nOrg, bi, by - T::nOrg, &bar);
+                    tma_load_box(tsav + c * T::sCount, &maps.m[3 + c], bz - g.k0 - T::sOrg, bi, by - T::sOrg, &bar);
+                } else {
+                    tma_load_3d(tnew + c * T::nCount, &maps.m[c], 8 * bi, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
+                    tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], 8 * bi, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
+                }
             }
         }
         __syncthreads();                                     // barrier init visible to the waiters
@@ -843,13 +896,13 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
             // p0 lies in this brick: NEW and SAVED taps are all staged, and share the index/fraction set
             const SampleIdx s = sample_idx(g, px, py, pz);
             const int n0x = bx - T::kOrgX, n0y = by - T::nOrg, n0z = bz - T::nOrg;
-            k1x = tile_sample<INTERP, T::kX, T::nY>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
-            k1y = tile_sample<INTERP, T::kX, T::nY>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
-            k1z = tile_sample<INTERP, T::kX, T::nY>(tnew + 2 * T::nCount, s.sx, s.sy, s.uz, n0x, n0y, n0z);
+            k1x = tile_sample<INTERP, T::nZ>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
+            k1y = tile_sample<INTERP, T::nZ>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
+            k1z = tile_sample<INTERP, T::nZ>(tnew + 2 * T::nCount, s.sx, s.sy, s.uz, n0x, n0y, n0z);
             const int s0y = by - T::sOrg, s0z = bz - T::sOrg;
-            sx = tile_sample<INTERP, T::kX, T::sY>(tsav, s.ux, s.sy, s.sz, n0x, s0y, s0z);
-            sy = tile_sample<INTERP, T::kX, T::sY>(tsav + T::sCount, s.sx, s.uy, s.sz, n0x, s0y, s0z);
-            sz = tile_sample<INTERP, T::kX, T::sY>(tsav + 2 * T::sCount, s.sx, s.sy, s.uz, n0x, s0y, s0z);
+            sx = tile_sample<INTERP, T::sZ>(tsav, s.ux, s.sy, s.sz, n0x, s0y, s0z);
+            sy = tile_sample<INTERP, T::sZ>(tsav + T::sCount, s.sx, s.uy, s.sz, n0x, s0y, s0z);
+            sz = tile_sample<INTERP, T::sZ>(tsav + 2 * T::sCount, s.sx, s.sy, s.uz, n0x, s0y, s0z);
         } else {
             evaluate_pow2(g, fnew, INTERP, px, py, pz, k1x, k1y, k1z);
             evaluate_pow2(g, fsaved, INTERP, px, py, pz, sx, sy, sz);

@@ -37,6 +37,16 @@ KEYS = [
 ]
 
 
+def kernel_key(name):
+    """'void gfs::k_g2p_brick<(int)0, (bool)0>(gfs::Grid, ...)' -> 'k_g2p_brick<0>' (base name + first template integer):
+    the same normalisation bench.py applies to its own kernel names when it looks the traffic up."""
+    import re
+    m = re.search(r"(\w+)\s*<\s*(?:\(\w+\))?\s*(\d+)", name)
+    if m:
+        return "%s<%s>" % (m.group(1), m.group(2))
+    return re.sub(r"\(.*", "", name).replace("void ", "").split("::")[-1].strip()
+
+
 def ncu(args):
     return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
 
@@ -107,8 +117,7 @@ def kernel_report(tag, kernel, workload, traffic):
         v, u = m[k]
         x = float(v.replace(",", ""))
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-    key = name.replace("(int)", "").split("(")[0].replace("void ", "")       # "gfs::k_g2p_brick<0>"
-    traffic.setdefault(workload, {})[key] = \
+    traffic.setdefault(workload, {})[kernel_key(name)] = \
         num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
     print("wrote", kernel, tag)
 
