@@ -316,7 +316,7 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
                    c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
                    c->tag[dst].p);
         } else if (lazy) {
-            LAUNCH(c, gfs::k_build_index, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p, c->index.p);
+            LAUNCH(c, gfs::k_build_index, ceil_div(n, 4 * B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p, c->index.p);
         } else {
             LAUNCH(c, gfs::k_scatter_sorted, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p,
                    c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,

@@ -135,11 +135,25 @@ struct AxisIdxF { int i; float t; };
 __device__ __forceinline__ AxisIdxF to_f(const AxisIdx &a) { AxisIdxF r; r.i = a.i; r.t = (float)a.t; return r; }
 
 // fp32 index + fraction; exact (== axis_index) when dx is a power of two, see Grid::pow2
+// floor of |s| < 2^22 without the conversion pipe: s + 1.5*2^23 rounded toward -inf lands on the integer grid of
+// [2^23, 2^24) (ulp 1), so the sum IS floor(s) + 1.5*2^23 and its mantissa field is the integer.  Same value as
+// floorf / (int)floorf for every in-range argument; F2I / FRND run at a quarter of the FADD rate.
+__device__ __forceinline__ float floor_small(float s, int &i) {
+    const float kMagic = 12582912.0f;                       // 1.5 * 2^23 = 0x4B400000
+    const float m = __fadd_rd(s, kMagic);
+    i = __float_as_int(m) - 0x4B400000;
+    return __fsub_rn(m, kMagic);
+}
+
+// MAGIC: floor through floor_small (same values; pays off in the tricubic brick kernel, costs the register-starved
+// trilinear one two spills -- measured both ways)
+template <bool MAGIC = false>
 __device__ __forceinline__ AxisIdxF axis_index_f(float x, const Grid &g) {
     AxisIdxF r;
     float s = __fmul_rn(x, g.invdxf);
-    float fl = floorf(s);
-    r.i = (int)fl;
+    float fl;
+    if (MAGIC) fl = floor_small(s, r.i);
+    else { fl = floorf(s); r.i = (int)fl; }
     r.t = __fmul_rn(__fsub_rn(x, __fmul_rn(fl, g.dxf)), g.invdxf);
     return r;
 }

@@ -149,9 +149,22 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(int64_t n, const uint32_
 // its results at the sorted slot.  Saves moving 56 bytes per particle once per substep.
 __global__ void __launch_bounds__(256) k_build_index(int64_t n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
                                                      const int32_t *__restrict__ cell_start, int32_t *__restrict__ index) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    index[(int64_t)cell_start[keys[r]] + rank[r]] = (int32_t)r;
+    // four particles per thread, loads first: the key -> cell_start -> store chain is pure latency
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+    uint32_t k[4], q[4];
+    int32_t cs[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int64_t r = r0 + u * 256;
+        if (r < n) { k[u] = keys[r]; q[u] = rank[r]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (r0 + u * 256 < n) cs[u] = cell_start[k[u]];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int64_t r = r0 + u * 256;
+        if (r < n) index[(int64_t)cs[u] + q[u]] = (int32_t)r;
+    }
 }
 
 // K0c (stable path).  sorted SoA <- unsorted SoA through the radix-sorted permutation
@@ -374,9 +387,23 @@ __global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const 
             const int r = index ? index[q] : q;
             splat_pow2<false>(g, sp, ns, x[r], y[r], z[r], vx[r], vy[r], vz[r], tile, ti, tj, tk, accu, accv, accw);
         }
-        else for (int q = start + threadIdx.x; q < end; q += blockDim.x) {
-            const int r = index ? index[q] : q;
-            splat_pow2<true>(g, sp, ns, x[r], y[r], z[r], vx[r], vy[r], vz[r], tile, ti, tj, tk, accu, accv, accw);
+        else {
+            // software pipeline: the next particle is in flight while this one's ~25 shared atomics are issued
+            int q = start + threadIdx.x;
+            float nx = 0.f, ny = 0.f, nz = 0.f, nvx = 0.f, nvy = 0.f, nvz = 0.f;
+            if (q < end) {
+                const int r = index ? index[q] : q;
+                nx = x[r]; ny = y[r]; nz = z[r]; nvx = vx[r]; nvy = vy[r]; nvz = vz[r];
+            }
+            for (; q < end; q += blockDim.x) {
+                const float px = nx, py = ny, pz = nz, ux = nvx, uy = nvy, uz = nvz;
+                const int qn = q + blockDim.x;
+                if (qn < end) {
+                    const int r = index ? index[qn] : qn;
+                    nx = x[r]; ny = y[r]; nz = z[r]; nvx = vx[r]; nvy = vy[r]; nvz = vz[r];
+                }
+                splat_pow2<true>(g, sp, ns, px, py, pz, ux, uy, uz, tile, ti, tj, tk, accu, accv, accw);
+            }
         }
     } else {
         for (int q = start + threadIdx.x; q < end; q += blockDim.x) {
@@ -569,10 +596,13 @@ __device__ __forceinline__ void assemble_face(const Grid &g, const AssembleArgs 
     const float *__restrict__ val = aa.val[COMP];
     const uint8_t *__restrict__ setmask = aa.setmask[COMP];
     const size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+    // both loads are issued before the material-dependent branch (the kernel is a chain of dependent loads otherwise)
+    const uint8_t isset = setmask[node];
+    const float own = val[node];
     float r = 0.0f;
     if (borders) {
-        if (setmask[node]) {
-            r = val[node];
+        if (isset) {
+            r = own;
         } else {
             double avg = 0.0, cnt = 0.0;
             for (int nk = kl - 1; nk <= kl + 1; nk++)
@@ -599,11 +629,13 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
     if (t >= w * ((uint32_t)g.J + 1u)) return;
     const int i = (int)(t % w), j = (int)(t / w);
     const int k = aa.k_lo + (int)blockIdx.y, kl = k - g.k0;
-    const bool f = cell_is_fluid(g, material, i, j, k);
+    // four independent material reads (no short circuit: they overlap)
+    const bool f = cell_is_fluid(g, material, i, j, k), fi = cell_is_fluid(g, material, i - 1, j, k);
+    const bool fj = cell_is_fluid(g, material, i, j - 1, k), fk = cell_is_fluid(g, material, i, j, k - 1);
     const bool uv = k < aa.k_hi;
-    if (uv && j < g.J) assemble_face<0>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i - 1, j, k));
-    if (uv && i < g.I) assemble_face<1>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i, j - 1, k));
-    if (k < aa.k_hi_w && i < g.I && j < g.J) assemble_face<2>(g, aa, i, j, kl, f || cell_is_fluid(g, material, i, j, k - 1));
+    if (uv && j < g.J) assemble_face<0>(g, aa, i, j, kl, f | fi);
+    if (uv && i < g.I) assemble_face<1>(g, aa, i, j, kl, f | fj);
+    if (k < aa.k_hi_w && i < g.I && j < g.J) assemble_face<2>(g, aa, i, j, kl, f | fk);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -673,6 +705,10 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
 // Power-of-two dx only (fp32-exact index arithmetic); other grids use k_g2p_advect.
 // ------------------------------------------------------------------------------------------------
 struct BrickMaps { CUtensorMap m[6]; };     // NEW u,v,w then SAVED u,v,w
+
+#ifndef GFS_TRICUBIC_CTAS
+#define GFS_TRICUBIC_CTAS 2
+#endif
 
 template <int INTERP> struct BrickTile {
     // trilinear: taps c, c+1;  tricubic: taps c-1 .. c+2.  c ranges over [8b-1-M, 8b+7+M] (M = motion margin).
@@ -772,11 +808,12 @@ __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const 
 
 // all six index/fraction pairs of a position (fp32-exact for power-of-two dx)
 struct SampleIdx { AxisIdxF ux, uy, uz, sx, sy, sz; };
+template <bool MAGIC = false>
 __device__ __forceinline__ SampleIdx sample_idx(const Grid &g, float px, float py, float pz) {
     SampleIdx s;
-    s.ux = axis_index_f(px, g); s.uy = axis_index_f(py, g); s.uz = axis_index_f(pz, g);
-    s.sx = axis_index_f(__fsub_rn(px, g.halfdxf), g); s.sy = axis_index_f(__fsub_rn(py, g.halfdxf), g);
-    s.sz = axis_index_f(__fsub_rn(pz, g.halfdxf), g);
+    s.ux = axis_index_f<MAGIC>(px, g); s.uy = axis_index_f<MAGIC>(py, g); s.uz = axis_index_f<MAGIC>(pz, g);
+    s.sx = axis_index_f<MAGIC>(__fsub_rn(px, g.halfdxf), g); s.sy = axis_index_f<MAGIC>(__fsub_rn(py, g.halfdxf), g);
+    s.sz = axis_index_f<MAGIC>(__fsub_rn(pz, g.halfdxf), g);
     return s;
 }
 
@@ -786,7 +823,7 @@ __device__ __forceinline__ void evaluate_tile(const Grid &g, const FieldPtrs &f,
                                               float px, float py, float pz, float &ox, float &oy, float &oz) {
     typedef BrickTile<INTERP> T;
     if (!(px >= 0.0f && py >= 0.0f && pz >= 0.0f && px < g.xmaxf && py < g.ymaxf && pz < g.zmaxf)) { ox = oy = oz = 0.0f; return; }
-    const SampleIdx s = sample_idx(g, px, py, pz);
+    const SampleIdx s = sample_idx<INTERP == 1>(g, px, py, pz);
     const int x0 = bx - T::kOrgX, y0 = by - T::nOrg, z0 = bz - T::nOrg;
     // every tap c - kLo .. c + kHi of the six index variants must lie inside the staged box
     const int lo = T::kLo;
@@ -816,7 +853,7 @@ struct Migrate {
 };
 
 template <int INTERP, bool MIGRATE>
-__global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
+__global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
                             const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
                             const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
                             int order, RkCoef rk, float ratio_pic, float ratio_flip, int64_t n,
@@ -894,7 +931,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
         float k1x, k1y, k1z, sx, sy, sz;
         if (!overflow) {
             // p0 lies in this brick: NEW and SAVED taps are all staged, and share the index/fraction set
-            const SampleIdx s = sample_idx(g, px, py, pz);
+            const SampleIdx s = sample_idx<INTERP == 1>(g, px, py, pz);
             const int n0x = bx - T::kOrgX, n0y = by - T::nOrg, n0z = bz - T::nOrg;
             k1x = tile_sample<INTERP, T::nZ>(tnew, s.ux, s.sy, s.sz, n0x, n0y, n0z);
             k1y = tile_sample<INTERP, T::nZ>(tnew + T::nCount, s.sx, s.uy, s.sz, n0x, n0y, n0z);
@@ -941,7 +978,9 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
             // cell of the advected position (fp32-exact here); out of range reads as solid, NaN compares false -> solid
             bool solid = true;
             if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {
-                const int i = (int)floorf(__fmul_rn(qx, g.invdxf)), j = (int)floorf(__fmul_rn(qy, g.invdxf)), k = (int)floorf(__fmul_rn(qz, g.invdxf));
+                int i, j, k;
+                if (INTERP == 1) { floor_small(__fmul_rn(qx, g.invdxf), i); floor_small(__fmul_rn(qy, g.invdxf), j); floor_small(__fmul_rn(qz, g.invdxf), k); }
+                else { i = (int)floorf(__fmul_rn(qx, g.invdxf)); j = (int)floorf(__fmul_rn(qy, g.invdxf)); k = (int)floorf(__fmul_rn(qz, g.invdxf)); }
                 const int kl = k - g.k0;
                 solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
             }
@@ -952,7 +991,9 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? 2 : 4) k_g2p_brick(Grid g, 
             // cell key of the advected position in fp32 (exact here, same value as position_key)
             uint32_t key = nkeys;
             if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {
-                const int i = (int)floorf(__fmul_rn(qx, g.invdxf)), j = (int)floorf(__fmul_rn(qy, g.invdxf)), k = (int)floorf(__fmul_rn(qz, g.invdxf));
+                int i, j, k;
+                if (INTERP == 1) { floor_small(__fmul_rn(qx, g.invdxf), i); floor_small(__fmul_rn(qy, g.invdxf), j); floor_small(__fmul_rn(qz, g.invdxf), k); }
+                else { i = (int)floorf(__fmul_rn(qx, g.invdxf)); j = (int)floorf(__fmul_rn(qy, g.invdxf)); k = (int)floorf(__fmul_rn(qz, g.invdxf)); }
                 if (k >= g.k0 && k < g.k1) key = brick_key(g, i, j, k - g.k0);
                 if (MIGRATE) {
                     const int side = k < mg.own_lo ? 0 : (k >= mg.own_hi ? 1 : -1);
