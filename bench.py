@@ -551,6 +551,40 @@ def run_gfs(args):
         "clocks": clocks.summary(), "kernels": kernels, "variants": variants,
         "stats": {k: int(v) for k, v in st.items()},
     }
+    # ---- sub-metrics of SURVEY 8(d): P2G only, G2P + RK4 only (from the per-kernel CUDA-event times of the timed steps),
+    # and advection only through the host-pointer operator (C5: uniformly random particles, RK4 through the NEW field)
+    def per_step(names):
+        return sum(kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"] for k in kernels if any(nm in k for nm in names))
+    n_rank = ctx.num_particles
+    p2g_ms = per_step(["ExclusiveSum", "k_build_index", "k_hist", "k_scatter_sorted", "k_classify", "k_p2g_tile", "k_p2g_scatter", "k_p2g_finalize", "k_assemble"])
+    g2p_ms = per_step(["k_g2p_brick", "k_g2p_advect"])
+    sub = {}
+    if p2g_ms > 0:
+        b = 24 * n_rank + 13 * G_local
+        sub["p2g_only"] = {"value": n_rank / (p2g_ms * 1e-3), "unit": UNIT, "ms": p2g_ms, "algorithmic_bytes": b,
+                           "hbm_frac": b / (p2g_ms * 1e-3) / 1e9 / hbm_gbs, "includes": "counting-sort scan + index, classify, splat, finalize, assemble (rank 0)"}
+    if g2p_ms > 0:
+        b = 48 * n_rank + 24 * G_local
+        sub["g2p_rk4_only"] = {"value": n_rank / (g2p_ms * 1e-3), "unit": UNIT, "ms": g2p_ms, "algorithmic_bytes": b,
+                               "hbm_frac": b / (g2p_ms * 1e-3) / 1e9 / hbm_gbs, "includes": "PIC/FLIP update + RK4 + solid test + binning for the next sort (rank 0)"}
+    if world == 1:
+        n_adv = 1 << 24
+        rng = np.random.default_rng(12345 + 24)
+        lo, span = np.float32(1.5 * dx), np.float32((min(dims) - 3) * dx)
+        pos_adv = (lo + span * rng.random((n_adv, 3), dtype=np.float32)).astype(np.float32)
+        ctx.profile_enable(True)
+        ctx.profile_read(reset=True)
+        t0 = time.perf_counter()
+        ctx.advect(pos_adv, *[t.numpy() for t in new_host], dims, dx, dt, order=4, interp=interp, arith=capi.FAST)
+        wall = time.perf_counter() - t0
+        pa = ctx.profile_read(reset=True)
+        ctx.profile_enable(False)
+        k_ms = sum(v[0] for k, v in pa.items() if "k_advect" in k)
+        b = 24 * n_adv + 12 * G
+        sub["advect_only"] = {"particles": n_adv, "kernel_ms": k_ms, "value": n_adv / (k_ms * 1e-3) if k_ms > 0 else None, "unit": "particles/s",
+                              "algorithmic_bytes": b, "hbm_frac": b / (k_ms * 1e-3) / 1e9 / hbm_gbs if k_ms > 0 else None,
+                              "through_host_value": n_adv / wall, "api": "gfs_advect (host pointers, unsorted random positions, global loads)"}
+    line["submetrics"] = sub
     if world > 1:
         line["multi_gpu"] = {"transport": "peer memory (CUDA IPC, NVLink) written by gfs kernels" if args.transport == "peer"
                              else "torch.distributed batch_isend_irecv (NCCL)", "comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),

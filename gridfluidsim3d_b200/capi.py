@@ -30,7 +30,7 @@ SYMBOLS = [
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
-    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep",
+    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -123,6 +123,8 @@ def load_library():
     L.gfs_comm_world_connect_local.argtypes = [V, I, V, _err]
     L.gfs_comm_allmax_scale.argtypes = [V, _err]
     L.gfs_sort_index.argtypes = [V, _err]
+    L.gfs_extrapolate.argtypes = [V, I, I, _err]
+    L.gfs_copy_field.argtypes = [V, I, I, _err]
     PI, PL = C.POINTER(I), C.POINTER(L64)
     L.gfs_comm_set_plan.argtypes = [V, I, I, PI, PI, PI, PL, I, PI, PI, PI, PL, PI, _err]
     L.gfs_comm_substep.argtypes = [V, C.c_double, C.c_double, I, I, I, I, I, PL, _err]
@@ -324,6 +326,12 @@ class Context:
 
     def sort_unstable(self):
         self._call(self.lib.gfs_sort_unstable)
+
+    def extrapolate(self, slot, num_layers):
+        self._call(self.lib.gfs_extrapolate, int(slot), int(num_layers))
+
+    def copy_field(self, dst_slot, src_slot):
+        self._call(self.lib.gfs_copy_field, int(dst_slot), int(src_slot))
 
     def sort_index(self):
         self._call(self.lib.gfs_sort_index)

@@ -129,6 +129,7 @@ struct gfs_context {
     DevBuf<unsigned char> cub_tmp;
     DevBuf<int32_t> n_valid;              // 1 word
     DevBuf<unsigned int> vmax_bits;       // 1 word
+    DevBuf<int8_t> ext_layer;             // gfs_extrapolate: layer index per cell
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
     int p2g_arith = 0;
@@ -631,7 +632,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
-    c->split_counters.release(); c->comm_error.release();
+    c->split_counters.release(); c->comm_error.release(); c->ext_layer.release();
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
     if (c->world_table) cudaFree(c->world_table);
@@ -723,6 +724,7 @@ void gfs_sample(gfs_context *c, const float *pos, int64_t n, const float *u, con
     c->h_pos.reserve((size_t)n * 3); c->h_out.reserve((size_t)n * 3);
     GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     if (arith == GFS_EXACT) LAUNCH(c, gfs::k_sample<1>, ceil_div(n, 128), 128, g, f, interp, validate, n, c->h_pos.p, c->h_out.p);
+    else if (g.pow2) LAUNCH(c, gfs::k_sample<2>, ceil_div(n, 128), 128, g, f, interp, validate, n, c->h_pos.p, c->h_out.p);   // fp32-exact index math
     else LAUNCH(c, gfs::k_sample<0>, ceil_div(n, 128), 128, g, f, interp, validate, n, c->h_pos.p, c->h_out.p);
     GFS_CUDA(cudaMemcpyAsync(out, c->h_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
@@ -744,6 +746,7 @@ void gfs_advect(gfs_context *c, const float *pos, int64_t n, const float *u, con
     GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     gfs::RkCoef rk = make_rk(dt);
     if (arith == GFS_EXACT) LAUNCH(c, gfs::k_advect<1>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
+    else if (g.pow2) LAUNCH(c, gfs::k_advect<2>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
     else LAUNCH(c, gfs::k_advect<0>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
     GFS_CUDA(cudaMemcpyAsync(out, c->h_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
@@ -936,6 +939,42 @@ void gfs_get_field(gfs_context *c, int slot, float *u, float *v, float *w, int *
         GFS_CUDA(cudaMemcpy2DAsync(h[a], (size_t)ni[a] * 4, c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, (size_t)ni[a] * 4,
                                    c->face_count[a] / (size_t)ni[a], cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+/* MACVelocityField::extrapolateVelocityField(materialGrid, numLayers) (src/macvelocityfield.cpp:786-798) on a resident
+ * field, with the resident material grid (what FluidSimulation runs on the saved field after P2G and on
+ * the solved field before G2P, src/fluidsimulation.cpp:3067-3070, 3306-3307, 3334). */
+void gfs_extrapolate(gfs_context *c, int slot, int num_layers, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3, "bad field slot");
+    GFS_REQUIRE(num_layers >= 0 && num_layers <= 126, "layer count must be 0..126");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_extrapolate is single-domain only (no slab exchange of the layer grid yet)");
+    GFS_CUDA(cudaSetDevice(c->device));
+    c->ext_layer.reserve(c->cell_count);
+    gfs::FieldRW f;
+    for (int a = 0; a < 3; a++) f.c[a] = c->field[slot][a].p + gfs::kRowPad;
+    const unsigned nodes = (unsigned)ceil_div((long long)(g.I + 1) * (g.J + 1), 256), cells = (unsigned)ceil_div((long long)g.I * g.J, 256);
+    LAUNCH(c, gfs::k_extrapolate_reset, dim3(nodes, (unsigned)g.K + 1), 256, g, c->material.p, c->ext_layer.p, f);
+    for (int L = 1; L <= num_layers; L++)
+        LAUNCH(c, gfs::k_extrapolate_mark, dim3(cells, (unsigned)g.K), 256, g, c->material.p, c->ext_layer.p, L);
+    for (int L = 1; L <= num_layers; L++)
+        LAUNCH(c, gfs::k_extrapolate_faces, dim3(nodes, (unsigned)g.K + 1), 256, g, c->material.p, c->ext_layer.p, f, L);
+    GFS_END()
+}
+
+/* dst field slot := src field slot (e.g. "_savedVelocityField = _MACVelocity", src/fluidsimulation.cpp:3306) */
+void gfs_copy_field(gfs_context *c, int dst_slot, int src_slot, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(dst_slot >= 0 && dst_slot < 3 && src_slot >= 0 && src_slot < 3, "bad field slot");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (dst_slot != src_slot)
+        for (int a = 0; a < 3; a++)
+            GFS_CUDA(cudaMemcpyAsync(c->field[dst_slot][a].p, c->field[src_slot][a].p, c->field_floats[a] * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, c->stream));
     GFS_END()
 }
 

@@ -639,6 +639,89 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3: MACVelocityField::extrapolateVelocityField (macvelocityfield.cpp:577-798) on a resident field.
+// The reference's sweeps are sequential and in place; every one of them is order independent (a layer pass only turns
+// -1 cells into L and only reads "== L-1"; a face pass writes faces that do not border layer L-1 and reads faces that
+// do), so each is one flat kernel with the same arithmetic: mean in double over the neighbours in the reference's order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cell_equals(const Grid &g, const int8_t *__restrict__ a, int i, int j, int k, int value) {
+    if (i < 0 || j < 0 || k < 0 || i >= g.I || j >= g.J || k >= g.K) return false;
+    return a[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)k)] == value;
+}
+
+template <int COMP>
+__device__ __forceinline__ bool face_borders(const Grid &g, const int8_t *__restrict__ a, int i, int j, int k, int value) {
+    return cell_equals(g, a, i, j, k, value) || cell_equals(g, a, i - (COMP == 0), j - (COMP == 1), k - (COMP == 2), value);
+}
+
+struct FieldRW { float *c[3]; };
+
+// _resetExtrapolatedFluidVelocities (:748-784) + layer 0 of _updateExtrapolationLayers (:603-613); one thread per node
+__global__ void __launch_bounds__(256) k_extrapolate_reset(Grid g, const uint8_t *__restrict__ material, int8_t *__restrict__ layer, FieldRW f) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)g.I + 1u;
+    if (t >= w * ((uint32_t)g.J + 1u)) return;
+    const int i = (int)(t % w), j = (int)(t / w), k = (int)blockIdx.y;
+    const int8_t *m = reinterpret_cast<const int8_t *>(material);
+    const bool fl = cell_equals(g, m, i, j, k, GFS_FLUID);
+    if (i < g.I && j < g.J && k < g.K) layer[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)k)] = fl ? 0 : -1;
+    if (j < g.J && k < g.K && !(fl || cell_equals(g, m, i - 1, j, k, GFS_FLUID)))
+        f.c[0][(size_t)i + (size_t)g.pitch[0] * ((size_t)j + (size_t)g.J * (size_t)k)] = 0.0f;
+    if (i < g.I && k < g.K && !(fl || cell_equals(g, m, i, j - 1, k, GFS_FLUID)))
+        f.c[1][(size_t)i + (size_t)g.pitch[1] * ((size_t)j + (size_t)(g.J + 1) * (size_t)k)] = 0.0f;
+    if (i < g.I && j < g.J && !(fl || cell_equals(g, m, i, j, k - 1, GFS_FLUID)))
+        f.c[2][(size_t)i + (size_t)g.pitch[2] * ((size_t)j + (size_t)g.J * (size_t)k)] = 0.0f;
+}
+
+// _updateExtrapolationLayer (:577-601), gather form: a -1, non-solid cell with a 6-neighbour in layer L-1 becomes L
+__global__ void __launch_bounds__(256) k_extrapolate_mark(Grid g, const uint8_t *__restrict__ material, int8_t *__restrict__ layer, int L) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)g.I * (uint32_t)g.J) return;
+    const int i = (int)(t % (uint32_t)g.I), j = (int)(t / (uint32_t)g.I), k = (int)blockIdx.y;
+    const size_t c = (size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)k);
+    if (layer[c] != -1 || material[c] == GFS_SOLID) return;
+    // (a layer L-1 >= 1 cell is never solid; layer 0 cells are fluid)
+    const bool hit = cell_equals(g, layer, i - 1, j, k, L - 1) || cell_equals(g, layer, i + 1, j, k, L - 1) ||
+                     cell_equals(g, layer, i, j - 1, k, L - 1) || cell_equals(g, layer, i, j + 1, k, L - 1) ||
+                     cell_equals(g, layer, i, j, k - 1, L - 1) || cell_equals(g, layer, i, j, k + 1, L - 1);
+    if (hit) layer[c] = (int8_t)L;
+}
+
+template <int COMP>
+__device__ __forceinline__ void extrapolate_face(const Grid &g, const uint8_t *__restrict__ material, const int8_t *__restrict__ layer,
+                                                 float *__restrict__ a, int i, int j, int k, int L) {
+    const int ni = g.I + (COMP == 0), nj = g.J + (COMP == 1), nk = g.K + (COMP == 2);
+    if (i >= ni || j >= nj || k >= nk) return;
+    if (!face_borders<COMP>(g, layer, i, j, k, L) || face_borders<COMP>(g, layer, i, j, k, L - 1) ||
+        face_borders<COMP>(g, reinterpret_cast<const int8_t *>(material), i, j, k, GFS_SOLID)) return;
+    const size_t pitch = (size_t)g.pitch[COMP];
+    double sum = 0.0, cnt = 0.0;
+    const int d6[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};       // grid3d.h:205-212
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        const int x = i + d6[q][0], y = j + d6[q][1], z = k + d6[q][2];
+        if (x < 0 || y < 0 || z < 0 || x >= ni || y >= nj || z >= nk) continue;
+        if (face_borders<COMP>(g, layer, x, y, z, L - 1)) {
+            sum = __dadd_rn(sum, (double)a[(size_t)x + pitch * ((size_t)y + (size_t)nj * (size_t)z)]);
+            cnt += 1.0;
+        }
+    }
+    a[(size_t)i + pitch * ((size_t)j + (size_t)nj * (size_t)k)] = sum == 0.0 ? 0.0f : (float)__ddiv_rn(sum, cnt);
+}
+
+// _extrapolateVelocitiesForLayerIndexU/V/W (:692-744); one thread per node, its three faces
+__global__ void __launch_bounds__(256) k_extrapolate_faces(Grid g, const uint8_t *__restrict__ material, const int8_t *__restrict__ layer,
+                                                           FieldRW f, int L) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)g.I + 1u;
+    if (t >= w * ((uint32_t)g.J + 1u)) return;
+    const int i = (int)(t % w), j = (int)(t / w), k = (int)blockIdx.y;
+    extrapolate_face<0>(g, material, layer, f.c[0], i, j, k, L);
+    extrapolate_face<1>(g, material, layer, f.c[1], i, j, k, L);
+    extrapolate_face<2>(g, material, layer, f.c[2], i, j, k, L);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: fused G2P.  One thread per (sorted) particle:
 //   vnew = sample(NEW, p0), vold = sample(SAVED, p0), both validated        (fluidsimulation.cpp:3115-3116)
 //   v   <- (float)ratio*vnew + (float)(1-ratio)*((v + vnew) - vold)         (:3118-3128)
@@ -1026,7 +1109,7 @@ __global__ void k_sample(Grid g, FieldPtrs f, int interp, int validate, int64_t 
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     float ox, oy, oz;
-    evaluate<ARITH>(g, f, interp, pos[3 * r], pos[3 * r + 1], pos[3 * r + 2], ox, oy, oz);
+    evaluate_any<ARITH>(g, f, interp, pos[3 * r], pos[3 * r + 1], pos[3 * r + 2], ox, oy, oz);
     if (validate) validate3(ox, oy, oz);
     out[3 * r] = ox; out[3 * r + 1] = oy; out[3 * r + 2] = oz;
 }
@@ -1037,7 +1120,7 @@ __global__ void k_advect(Grid g, FieldPtrs f, int interp, int order, RkCoef rk, 
     if (r >= n) return;
     float px = pos[3 * r], py = pos[3 * r + 1], pz = pos[3 * r + 2];
     float k1x, k1y, k1z, ox, oy, oz;
-    evaluate<ARITH>(g, f, interp, px, py, pz, k1x, k1y, k1z);
+    evaluate_any<ARITH>(g, f, interp, px, py, pz, k1x, k1y, k1z);
     rk_advance<ARITH>(g, f, interp, order, rk, px, py, pz, k1x, k1y, k1z, ox, oy, oz);
     out[3 * r] = ox; out[3 * r + 1] = oy; out[3 * r + 2] = oz;
 }

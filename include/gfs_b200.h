@@ -156,6 +156,14 @@ void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int
  * counting sort the fast substep uses (the order inside a cell is unspecified; nothing in fast mode depends on it). */
 void gfs_sort(gfs_context *ctx, int *err);
 void gfs_sort_unstable(gfs_context *ctx, int *err);
+
+/* Grid-only neighbours of the path, so that the P2G output and the G2P input can stay on the device:
+ * gfs_extrapolate = MACVelocityField::extrapolateVelocityField(materialGrid, num_layers) (src/macvelocityfield.cpp:786-798)
+ * on the resident field `slot` with the resident material grid; bit-identical to the reference.  FluidSimulation calls
+ * it with num_layers = ceil(CFL + 2) on the saved field after P2G and on the solved field before G2P
+ * (src/fluidsimulation.cpp:3067-3070, 3306-3307, 3334).  gfs_copy_field: dst slot := src slot (":3306"). */
+void gfs_extrapolate(gfs_context *ctx, int slot, int num_layers, int *err);
+void gfs_copy_field(gfs_context *ctx, int dst_slot, int src_slot, int *err);
 /* gfs_sort_index: the counting sort without moving the particles -- only the sorted index is materialised and the
  * P2G / G2P kernels fetch through it (G2P stores its results in sorted order).  What gfs_substep does internally;
  * gfs_get_particles afterwards returns the storage order, not the sorted one. */

@@ -34,9 +34,35 @@ def probes(dims, dx, n, seed):
     return pos.astype(np.float32)
 
 
+def extrapolation_case(seed=301):
+    """A 14 x 11 x 13 domain: solid border, an interior solid block, a fluid blob touching it, rough fields."""
+    dims = (14, 11, 13)
+    I, J, K = dims
+    mat = synth.border_material(dims).reshape(K, J, I).copy()
+    mat[4:7, 2:5, 6:9] = synth.SOLID
+    kk, jj, ii = np.meshgrid(np.arange(K), np.arange(J), np.arange(I), indexing="ij")
+    blob = ((ii - 5.5) ** 2 + (jj - 4.5) ** 2 + (kk - 6.0) ** 2 < 9.5) & (mat != synth.SOLID)
+    mat[blob] = synth.FLUID
+    mat[10, 8, 11] = synth.FLUID                     # an isolated fluid cell near the corner
+    return dims, 0.25, mat.reshape(-1), rough_fields(dims, seed)
+
+
+def golden_extrapolate(ref):
+    dims, dx, mat, (u, v, w) = extrapolation_case()
+    g = dict(dims=np.array(dims, np.int32), dx=np.float64(dx), material=mat, u=u, v=v, w=w)
+    for nl in (1, 3, 7):
+        a, b, c = ref.extrapolate(u, v, w, dims, dx, mat, nl)
+        g["u_%d" % nl], g["v_%d" % nl], g["w_%d" % nl] = a, b, c
+    np.savez_compressed(os.path.join(OUT, "extrapolate.npz"), **g)
+
+
 def main():
     ref = Reference()
     os.makedirs(OUT, exist_ok=True)
+    if "--only-extrapolate" in sys.argv:             # added after the other fixtures were committed
+        golden_extrapolate(ref)
+        return
+    golden_extrapolate(ref)
 
     # ---- primitives: index, sampling, RK1-4, splat ---------------------------------------------
     dims, dx = (10, 8, 12), 0.25

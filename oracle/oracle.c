@@ -475,3 +475,72 @@ void orc_g2p_advect(const float *pos, const float *vel, long n,
     orc_advect(pos, n, u, v, w, I, J, K, dx, dt, order, mode, pos_out);
     if (material) orc_solid_test(pos, pos_out, n, I, J, K, dx, material, flags);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f) rank 1.  MACVelocityField::extrapolateVelocityField   src/macvelocityfield.cpp:786-798
+ *   _resetExtrapolatedFluidVelocities :748-784   faces not bordering a fluid cell := 0
+ *   _updateExtrapolationLayers        :603-619   layer 0 = fluid cells, layer L = non-solid cells still at -1 that are a
+ *                                                6-neighbour of a non-solid layer L-1 cell (:577-601, in-place sweep)
+ *   _extrapolateVelocitiesForLayerIndexU/V/W :692-744  a face that borders layer L, does not border layer L-1 and does
+ *                                                not border a solid cell takes the mean (double; 0 when the sum is 0,
+ *                                                :637-641) of its in-range 6 face neighbours, in the order
+ *                                                (i-1,i+1,j-1,j+1,k-1,k+1) of grid3d.h:205-212, that border layer L-1
+ *   "borders" on a boundary face looks at the one existing cell (macvelocityfield.h:159-173, fluidmaterialgrid.cpp:119-143)
+ * ---------------------------------------------------------------------------------------- */
+static int ext_cell_eq(const int *g, int I, int J, int K, int i, int j, int k, int value) {
+    if (i < 0 || j < 0 || k < 0 || i >= I || j >= J || k >= K) return 0;
+    return g[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)] == value;
+}
+
+/* face (i,j,k) of direction dir borders a cell whose grid value equals `value` */
+static int ext_face_borders(const int *g, int I, int J, int K, int dir, int i, int j, int k, int value) {
+    return ext_cell_eq(g, I, J, K, i, j, k, value) ||
+           ext_cell_eq(g, I, J, K, i - (dir == 0), j - (dir == 1), k - (dir == 2), value);
+}
+
+void orc_extrapolate(float *u, float *v, float *w, int I, int J, int K, const unsigned char *material, int nlayers) {
+    size_t cells = (size_t)I * J * K;
+    int *mat = (int *)malloc(cells * sizeof(int));
+    int *layer = (int *)malloc(cells * sizeof(int));
+    for (size_t c = 0; c < cells; c++) { mat[c] = material[c]; layer[c] = material[c] == ORC_FLUID ? 0 : -1; }
+    float *fld[3] = {u, v, w};
+    for (int dir = 0; dir < 3; dir++) {
+        int ni = I + (dir == 0), nj = J + (dir == 1), nk = K + (dir == 2);
+        for (int k = 0; k < nk; k++) for (int j = 0; j < nj; j++) for (int i = 0; i < ni; i++)
+            if (!ext_face_borders(mat, I, J, K, dir, i, j, k, ORC_FLUID))
+                fld[dir][(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * k)] = 0.0f;
+    }
+    static const int d6[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    for (int L = 1; L <= nlayers; L++)
+        for (int k = 0; k < K; k++) for (int j = 0; j < J; j++) for (int i = 0; i < I; i++) {
+            size_t c = (size_t)i + (size_t)I * ((size_t)j + (size_t)J * k);
+            if (layer[c] != L - 1 || mat[c] == ORC_SOLID) continue;
+            for (int q = 0; q < 6; q++) {
+                int a = i + d6[q][0], b = j + d6[q][1], d = k + d6[q][2];
+                if (a < 0 || b < 0 || d < 0 || a >= I || b >= J || d >= K) continue;
+                size_t n = (size_t)a + (size_t)I * ((size_t)b + (size_t)J * d);
+                if (layer[n] == -1 && mat[n] != ORC_SOLID) layer[n] = L;
+            }
+        }
+    for (int L = 1; L <= nlayers; L++)
+        for (int dir = 0; dir < 3; dir++) {
+            int ni = I + (dir == 0), nj = J + (dir == 1), nk = K + (dir == 2);
+            float *f = fld[dir];
+            for (int k = 0; k < nk; k++) for (int j = 0; j < nj; j++) for (int i = 0; i < ni; i++) {
+                if (!(ext_face_borders(layer, I, J, K, dir, i, j, k, L) && !ext_face_borders(layer, I, J, K, dir, i, j, k, L - 1) &&
+                      !ext_face_borders(mat, I, J, K, dir, i, j, k, ORC_SOLID))) continue;
+                double sum = 0.0, weightsum = 0.0;
+                for (int q = 0; q < 6; q++) {
+                    int a = i + d6[q][0], b = j + d6[q][1], d = k + d6[q][2];
+                    if (a < 0 || b < 0 || d < 0 || a >= ni || b >= nj || d >= nk) continue;
+                    if (ext_face_borders(layer, I, J, K, dir, a, b, d, L - 1)) {
+                        sum += f[(size_t)a + (size_t)ni * ((size_t)b + (size_t)nj * d)];
+                        weightsum++;
+                    }
+                }
+                double val = sum == 0.0 ? 0.0 : sum / weightsum;
+                f[(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * k)] = (float)val;
+            }
+        }
+    free(mat); free(layer);
+}

@@ -86,6 +86,9 @@ void orc_g2p_advect(const float *pos, const float *vel, long n,
                     int I, int J, int K, double dx, double ratio, double dt, int order, int mode,
                     const unsigned char *material, float *pos_out, float *vel_out, unsigned char *flags);
 
+/* MACVelocityField::extrapolateVelocityField (src/macvelocityfield.cpp:577-798), in place on u, v, w */
+void orc_extrapolate(float *u, float *v, float *w, int I, int J, int K, const unsigned char *material, int nlayers);
+
 #ifdef __cplusplus
 }
 #endif

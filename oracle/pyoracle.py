@@ -102,6 +102,13 @@ class Oracle:
         self.lib.orc_cell_index(pos, len(pos), dx, out)
         return out
 
+    def extrapolate(self, u, v, w, dims, material, nlayers):
+        """MACVelocityField::extrapolateVelocityField on copies of u, v, w."""
+        u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
+        self.lib.orc_extrapolate.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int, _u8, C.c_int]
+        self.lib.orc_extrapolate(u, v, w, *dims, np.ascontiguousarray(material, np.uint8).reshape(-1), int(nlayers))
+        return u, v, w
+
     def sample(self, pos, u, v, w, dims, dx, mode, validate=True):
         pos = _c(pos)
         out = np.empty_like(pos)
@@ -240,6 +247,12 @@ class Reference:
         out = np.empty_like(pos)
         self.lib.ref_advect(pos, len(pos), _c(u), _c(v), _c(w), *dims, dx, dt, order, out)
         return out
+
+    def extrapolate(self, u, v, w, dims, dx, material, nlayers):
+        u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
+        self.lib.ref_extrapolate.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double, _u8, C.c_int]
+        self.lib.ref_extrapolate(u, v, w, *dims, dx, np.ascontiguousarray(material, np.uint8).reshape(-1), int(nlayers))
+        return u, v, w
 
     def add_point_values(self, pos, values, radius, offset, dx, ndims):
         pos, values = _c(pos), _c(values)

@@ -603,3 +603,42 @@ def test_peer_transport_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29531", os.path.join(here, "peer_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PEER_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------------
+# velocity extrapolation on the resident fields
+# ---------------------------------------------------------------------------------------------------
+def test_extrapolate_matches_reference_fixture():
+    """gfs_extrapolate against the outputs of the unmodified reference (tests/golden/extrapolate.npz): bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "extrapolate.npz"))
+    dims, dx = tuple(int(x) for x in g["dims"]), float(g["dx"])
+    for nl in (1, 3, 7):
+        c = capi.Context(0)
+        c.domain_init(dims, dx); c.set_material(g["material"])
+        c.set_field(capi.FIELD_SAVED, g["u"], g["v"], g["w"])
+        c.extrapolate(capi.FIELD_SAVED, nl)
+        for got, name in zip(c.get_field(capi.FIELD_SAVED), "uvw"):
+            assert np.array_equal(bits(got), bits(g["%s_%d" % (name, nl)])), (name, nl)
+        c.close()
+
+
+@pytest.mark.parametrize("name,nlayers", [("small32", 3), ("odd20", 7), ("slab24", 2)])
+def test_p2g_then_extrapolate_equals_oracle(oracle, name, nlayers):
+    """The reference's stage 5 tail on the device: P2G -> "_savedVelocityField = _MACVelocity" -> extrapolate
+    (fluidsimulation.cpp:3305-3307).  Extrapolating the SAME input is bit-exact; the P2G input itself is within the
+    fast-arithmetic tolerance, so the chain is compared with the oracle fed the GPU's own P2G field."""
+    s = scene(name, interior_solids=(name != "small32"))
+    c = capi.Context(0)
+    load_domain(c, s)
+    c.sort_unstable(); c.p2g(capi.FAST)
+    c.copy_field(capi.FIELD_SAVED, capi.FIELD_P2G)
+    p2g = c.get_field(capi.FIELD_P2G)
+    mat = c.get_material()
+    c.extrapolate(capi.FIELD_SAVED, nlayers)
+    want = oracle.extrapolate(*p2g, s["dims"], mat, nlayers)
+    for got, ref in zip(c.get_field(capi.FIELD_SAVED), want):
+        assert np.array_equal(bits(got), bits(ref))
+    assert any((a != b).any() for a, b in zip(want, p2g))          # it did extend the field
+    for a, b in zip(c.get_field(capi.FIELD_P2G), p2g):              # and left the source slot alone
+        assert np.array_equal(bits(a), bits(b))
+    c.close()

@@ -108,3 +108,13 @@ def test_uniform_field_properties(oracle):
         assert np.allclose(s, np.array(c, np.float32), rtol=0, atol=1e-6)
         out = oracle.advect(pos, u, v, w, dims, dx, 0.25, 4, mode)
         assert np.allclose(out - pos, 0.25 * np.array(c), rtol=0, atol=2e-6)
+
+
+def test_extrapolate_golden(oracle):
+    """MACVelocityField::extrapolateVelocityField outputs of the unmodified reference (oracle/make_golden.py)."""
+    g = load("extrapolate.npz")
+    dims = tuple(int(x) for x in g["dims"])
+    for nl in (1, 3, 7):
+        out = oracle.extrapolate(g["u"], g["v"], g["w"], dims, g["material"], nl)
+        for got, name in zip(out, "uvw"):
+            assert np.array_equal(bits(got), bits(g["%s_%d" % (name, nl)]))

@@ -154,3 +154,23 @@ def test_picflip_and_rk4_bit_exact(oracle, reference, name):
     assert flags.sum() == 0
     assert np.array_equal(vel.view(np.uint32), vel_ref.view(np.uint32))
     assert np.array_equal(pos.view(np.uint32), pos_ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("nlayers", [0, 1, 3, 7])
+def test_extrapolate_bit_exact(oracle, reference, nlayers):
+    """SURVEY 8(f) rank 1: MACVelocityField::extrapolateVelocityField, with interior solids, a fluid blob against the
+    solid border and isolated fluid cells; rough fields so that every averaged neighbour matters."""
+    dims = (13, 9, 11)
+    I, J, K = dims
+    rng = np.random.default_rng(40 + nlayers)
+    mat = synth.border_material(dims).reshape(K, J, I).copy()
+    mat[3:6, 2:4, 5:8] = synth.SOLID
+    fluid = (rng.random((K, J, I)) < 0.18) & (mat != synth.SOLID)
+    fluid[4:8, 3:7, 2:6] |= mat[4:8, 3:7, 2:6] != synth.SOLID
+    mat[fluid] = synth.FLUID
+    u, v, w = rough_fields(dims, 41)
+    a = oracle.extrapolate(u, v, w, dims, mat, nlayers)
+    b = reference.extrapolate(u, v, w, dims, 0.25, mat, nlayers)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    assert any((x != y.reshape(-1)).any() for x, y in zip(a, (u, v, w)))
