@@ -130,6 +130,9 @@ struct gfs_context {
     DevBuf<int32_t> n_valid;              // 1 word
     DevBuf<unsigned int> vmax_bits;       // 1 word
     DevBuf<int8_t> ext_layer;             // gfs_extrapolate: layer index per cell
+    DevBuf<float4> coll_list;             // particles advected into a solid cell: {slot, p1}, resolved by k_resolve_collisions
+    DevBuf<unsigned int> coll_count;
+    int resolve_collisions = 1;           // option 3: 1 = the reference's collision resolve, 0 = solid test only (keep p0)
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
     int p2g_arith = 0;
@@ -285,6 +288,10 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     require_domain(c);
     if (c->dead > 0 && !(lazy && !stable && c->keys_ready)) { drop_dead(c); c->sorted = false; }
     const int64_t n = c->n;
+    if (c->resolve_collisions) {
+        if ((size_t)(n / 16 + 4096) > c->coll_list.cap) c->coll_list.reserve((size_t)(n / 16 + 4096) + (size_t)n / 64);
+        c->coll_count.reserve(1);
+    }
     const int src = c->cur, dst = 1 - c->cur;
     const int B = 256;
     const size_t nbins = (size_t)c->nkeys + 3;
@@ -458,8 +465,20 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
 #define GFS_G2P_ARGS c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, interp, order, rk, rp, rf, c->n, \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
-               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, coll
     const bool brick = g2p_uses_bricks(c, arith);
+    gfs::CollList coll;
+    coll.list = nullptr; coll.count = nullptr; coll.cap = 0;
+    if (c->resolve_collisions) {
+        // colliders are rare (a few per thousand at CFL 0.5 next to walls); a full list falls back to "keep p0"
+        // (sized by do_sort at the start of the step: no allocation -- an implicit device synchronisation -- here,
+        // between the device-side waits of a sharded substep)
+        if (c->coll_list.cap == 0) c->coll_list.reserve((size_t)(c->n / 16 + 4096));
+        const size_t cap = c->coll_list.cap;
+        c->coll_count.reserve(1);
+        GFS_CUDA(cudaMemsetAsync(c->coll_count.p, 0, sizeof(unsigned int), c->stream));
+        coll.list = c->coll_list.p; coll.count = c->coll_count.p; coll.cap = (unsigned int)cap;
+    }
     gfs::Migrate mg;
     if (migrate) mg = *migrate;
     else { mg.own_lo = (int)0x80000000; mg.own_hi = 0x7FFFFFFF; mg.out[0] = mg.out[1] = nullptr; mg.count = nullptr; mg.cap = 0; }
@@ -469,7 +488,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
                (c->indexed ? c->index.p : nullptr), c->tag[src].p, c->tag[dst].p, order, rk, rp, rf, c->n,                                                                                                  \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
-               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg, coll
         int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
         if (interp == GFS_TRICUBIC) {
             if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
@@ -487,6 +506,9 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     else if (c->grid.pow2) LAUNCH(c, gfs::k_g2p_advect<2>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
     else LAUNCH(c, gfs::k_g2p_advect<0>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
 #undef GFS_G2P_ARGS
+    if (coll.list)
+        LAUNCH(c, gfs::k_resolve_collisions, 64, 128, c->grid, c->material.p, coll, c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p,
+               c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->nkeys, keys_out, rank_out, counts, mg);
     // tags travel with the slot: the per-particle kernels keep slot order (copy the tag array across buffers); the brick
     // kernel moves the tags itself (it may be reading through the lazy sort index)
     if (!brick)
@@ -632,7 +654,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
-    c->split_counters.release(); c->comm_error.release(); c->ext_layer.release();
+    c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release();
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
     if (c->world_table) cudaFree(c->world_table);
@@ -1011,6 +1033,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     if (option == 0) { GFS_REQUIRE(value == 0 || value == 1, "p2g variant must be 0 or 1"); c->p2g_variant = value; }
     else if (option == 1) { GFS_REQUIRE(value == 0 || value == 1, "g2p variant must be 0 or 1"); c->g2p_variant = value; }
     else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
+    else if (option == 3) { GFS_REQUIRE(value == 0 || value == 1, "collision resolve must be 0 or 1"); c->resolve_collisions = value; }
     else throw GfsError("gfs_set_option: unknown option");
     GFS_END()
 }

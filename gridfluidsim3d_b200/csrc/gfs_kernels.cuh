@@ -722,6 +722,87 @@ __global__ void __launch_bounds__(256) k_extrapolate_faces(Grid g, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// A14, the resolve routine: FluidSimulation::_resolveParticleSolidCellCollision
+// (fluidsimulation.cpp:3145-3179) = Collision::getLineSegmentVoxelIntersection (collision.cpp:303-400) + normalize +
+// Collision::rayIntersectsAABB (:404-448, including its dir.x-for-dir.z slip) + back-off by 0.05 dx.  The G2P kernels
+// only LIST the (rare) particles whose advected cell is solid -- slot and advected position -- and leave p0 in place;
+// k_resolve_collisions then runs the reference's arithmetic on the list (float vec3 operations with explicit
+// roundings, double voxel walk and slab test, exactly as oracle/oracle.c restates them) and bins the result.
+// ------------------------------------------------------------------------------------------------
+struct CollList {
+    float4 *list;                  // {slot as int bits, p1.x, p1.y, p1.z}; null = keep p0 (solid test only)
+    unsigned int *count;
+    unsigned int cap;
+};
+
+__device__ __forceinline__ bool cell_solid_or_outside(const Grid &g, const uint8_t *__restrict__ m, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i >= g.I || j >= g.J || k >= g.K) return true;      // fluidmaterialgrid.cpp:25-29
+    return m[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)(k - g.k0))] == GFS_SOLID;
+}
+
+__device__ inline void resolve_collision(const Grid &g, const uint8_t *__restrict__ material, const float p0[3], const float p1[3], float out[3]) {
+    out[0] = p0[0]; out[1] = p0[1]; out[2] = p0[2];
+    const float s = (float)g.invdx;                                  // vec3 *= (float)invdx, vmath.cpp:79-84
+    float a0[3], a1[3];
+    int g1[3], st[3], c[3];
+    double gp[3], v[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        a0[a] = __fmul_rn(p0[a], s); a1[a] = __fmul_rn(p1[a], s);
+        const int g0 = (int)floor((double)a0[a]);
+        g1[a] = (int)floor((double)a1[a]);
+        st[a] = g1[a] > g0 ? 1 : (g1[a] < g0 ? -1 : 0);
+        c[a] = g0;
+        gp[a] = (double)(g0 + (g1[a] > g0 ? 1 : 0));
+        v[a] = a1[a] == a0[a] ? 1.0 : (double)__fsub_rn(a1[a], a0[a]);
+    }
+    const double vxvy = __dmul_rn(v[0], v[1]), vxvz = __dmul_rn(v[0], v[2]), vyvz = __dmul_rn(v[1], v[2]);
+    double ex = __dmul_rn(__dsub_rn(gp[0], (double)a0[0]), vyvz), ey = __dmul_rn(__dsub_rn(gp[1], (double)a0[1]), vxvz),
+           ez = __dmul_rn(__dsub_rn(gp[2], (double)a0[2]), vxvy);
+    const double dex = __dmul_rn((double)st[0], vyvz), dey = __dmul_rn((double)st[1], vxvz), dez = __dmul_rn((double)st[2], vxvy);
+    bool found = false;
+    for (int iter = 0; iter < 1000000; iter++) {
+        if (c[0] >= 0 && c[1] >= 0 && c[2] >= 0 && c[0] < g.I && c[1] < g.J && c[2] < g.K &&
+            material[(size_t)c[0] + (size_t)g.I * ((size_t)c[1] + (size_t)g.J * (size_t)(c[2] - g.k0))] == GFS_SOLID) { found = true; break; }
+        if (c[0] == g1[0] && c[1] == g1[1] && c[2] == g1[2]) break;
+        const double xr = fabs(ex), yr = fabs(ey), zr = fabs(ez);
+        if (st[0] != 0 && (st[1] == 0 || xr < yr) && (st[2] == 0 || xr < zr)) { c[0] += st[0]; ex = __dadd_rn(ex, dex); }
+        else if (st[1] != 0 && (st[2] == 0 || yr < zr)) { c[1] += st[1]; ey = __dadd_rn(ey, dey); }
+        else if (st[2] != 0) { c[2] += st[2]; ez = __dadd_rn(ez, dez); }
+    }
+    if (!found) return;
+    // raynorm = normalize(p1 - p0)   (vmath.h:81-92: float length, inv = (float)(1.0 / len))
+    const float d0 = __fsub_rn(p1[0], p0[0]), d1 = __fsub_rn(p1[1], p0[1]), d2 = __fsub_rn(p1[2], p0[2]);
+    const float lensq = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+    const float len = (float)__dsqrt_rn((double)lensq);
+    const float inv = (float)__ddiv_rn(1.0, (double)len);
+    const float rn[3] = {__fmul_rn(d0, inv), __fmul_rn(d1, inv), __fmul_rn(d2, inv)};
+    const double eps = 1e-10;
+    float dir[3] = {rn[0], rn[1], rn[2]};
+    if (fabs((double)dir[0]) < eps) dir[0] = (float)(dir[0] < 0 ? -eps : eps);
+    if (fabs((double)dir[1]) < eps) dir[1] = (float)(dir[1] < 0 ? -eps : eps);
+    if (fabs((double)dir[0]) < eps) dir[2] = (float)(dir[2] < 0 ? -eps : eps);       // sic (collision.cpp:417)
+    double tmin = 0.0, tmax = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float bmin = (float)__dmul_rn((double)(float)c[a], g.dx);               // GridIndexToPosition, grid3d.h:83-85
+        const float bmax = __fadd_rn(bmin, (float)g.dx);                              // aabb.cpp:481-483
+        const float dinv = (float)__ddiv_rn(1.0, (double)dir[a]);
+        const double t1 = (double)__fmul_rn(__fsub_rn(bmin, p0[a]), dinv), t2 = (double)__fmul_rn(__fsub_rn(bmax, p0[a]), dinv);
+        if (a == 0) { tmin = fmin(t1, t2); tmax = fmax(t1, t2); }
+        else { tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2)); }
+    }
+    if (!(tmax > fmax(tmin, 0.0))) return;
+    const float tm = (float)tmin, back = (float)__dmul_rn(0.05, g.dx);
+    float r[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) r[a] = __fsub_rn(__fadd_rn(p0[a], __fmul_rn(dir[a], tm)), __fmul_rn(rn[a], back));
+    const int i = cell_floor((double)r[0], g.invdx), j = cell_floor((double)r[1], g.invdx), k = cell_floor((double)r[2], g.invdx);
+    if (cell_solid_or_outside(g, material, i, j, k)) return;
+    out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: fused G2P.  One thread per (sorted) particle:
 //   vnew = sample(NEW, p0), vold = sample(SAVED, p0), both validated        (fluidsimulation.cpp:3115-3116)
 //   v   <- (float)ratio*vnew + (float)(1-ratio)*((v + vnew) - vold)         (:3118-3128)
@@ -737,7 +818,7 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
                              float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
                              unsigned long long *__restrict__ counters /* [2] = solid hits */,
                              uint32_t nkeys, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out,
-                             uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
+                             uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits, CollList coll) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (r < n) {
@@ -756,6 +837,7 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
 
         float qx, qy, qz;
         rk_advance<ARITH>(g, fnew, interp, order, rk, px, py, pz, k1x, k1y, k1z, qx, qy, qz);
+        bool deferred = false;
         if (material) {
             int i = cell_floor((double)qx, g.invdx), j = cell_floor((double)qy, g.invdx), k = cell_floor((double)qz, g.invdx);
             bool solid = true;                                   // NaN -> huge negative index -> out of range -> solid
@@ -764,13 +846,22 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
                 // a particle that leaves this slab's stored layers is not judged here: it migrates first
                 solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
             }
-            if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
+            if (solid) {
+                atomicAdd(&counters[2], 1ull);
+                if (coll.list) {
+                    const unsigned int tk = atomicAdd(coll.count, 1u);
+                    if (tk < coll.cap) { coll.list[tk] = make_float4(__int_as_float((int)r), qx, qy, qz); deferred = true; }
+                }
+                qx = px; qy = py; qz = pz;
+            }
         }
         ox[r] = qx; oy[r] = qy; oz[r] = qz;
         if (keys_out) {          // bin for the next substep's counting sort while the position is in registers
-            uint32_t key = position_key(g, nkeys, qx, qy, qz);
-            keys_out[r] = key;
-            rank_out[r] = atomicAdd(counts + key, 1u);
+            if (!deferred) {
+                uint32_t key = position_key(g, nkeys, qx, qy, qz);
+                keys_out[r] = key;
+                rank_out[r] = atomicAdd(counts + key, 1u);
+            }
             m = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (!(m < 3.0e38f)) m = 0.0f;
         }
@@ -935,6 +1026,40 @@ struct Migrate {
     unsigned int cap;
 };
 
+// the listed colliders: reference resolve, final position, and the binning / migration the G2P kernel skipped for them
+__global__ void __launch_bounds__(128) k_resolve_collisions(Grid g, const uint8_t *__restrict__ material, CollList coll,
+                                                            float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
+                                                            const float *__restrict__ ovx, const float *__restrict__ ovy, const float *__restrict__ ovz,
+                                                            uint32_t nkeys, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out,
+                                                            uint32_t *__restrict__ counts, Migrate mg) {
+    const unsigned int n = min(*coll.count, coll.cap);
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const float4 e = coll.list[t];
+        const int r = __float_as_int(e.x);
+        const float p0[3] = {ox[r], oy[r], oz[r]}, p1[3] = {e.y, e.z, e.w};
+        float q[3];
+        resolve_collision(g, material, p0, p1, q);
+        ox[r] = q[0]; oy[r] = q[1]; oz[r] = q[2];
+        if (keys_out) {
+            uint32_t key = position_key(g, nkeys, q[0], q[1], q[2]);
+            if (key < nkeys && (mg.out[0] || mg.out[1])) {
+                const int k = cell_floor((double)q[2], g.invdx);
+                const int side = k < mg.own_lo ? 0 : (k >= mg.own_hi ? 1 : -1);
+                if (side >= 0) {
+                    const unsigned int slot = atomicAdd(mg.count + side, 1u);
+                    if (slot < mg.cap && mg.out[side]) {
+                        float2 *dst = reinterpret_cast<float2 *>(mg.out[side] + 6 * (size_t)slot);
+                        dst[0] = make_float2(q[0], q[1]); dst[1] = make_float2(q[2], ovx[r]); dst[2] = make_float2(ovy[r], ovz[r]);
+                    }
+                    key = nkeys + 1;
+                }
+            }
+            keys_out[r] = key;
+            rank_out[r] = atomicAdd(counts + key, 1u);
+        }
+    }
+}
+
 template <int INTERP, bool MIGRATE>
 __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
                             const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
@@ -946,7 +1071,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2
                             float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
                             unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
                             uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
-                            Migrate mg) {
+                            Migrate mg, CollList coll) {
     typedef BrickTile<INTERP> T;
     // dynamic shared memory: [pad to 128 B] NEW u,v,w [nCount each] | SAVED u,v,w [sCount each] | mbarrier.
     // TMA destinations must be 128-byte aligned: align by hand, static shared variables precede this block.
@@ -1057,6 +1182,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2
             const float h = order == 4 ? rk.dt_over_6 : (order == 3 ? rk.dt_over_9 : rk.dt);
             qx = axpy(px, h, sx_); qy = axpy(py, h, sy_); qz = axpy(pz, h, sz_);
         }
+        bool deferred = false;
         if (material) {
             // cell of the advected position (fp32-exact here); out of range reads as solid, NaN compares false -> solid
             bool solid = true;
@@ -1067,10 +1193,21 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2
                 const int kl = k - g.k0;
                 solid = (kl >= 0 && kl < g.k1 - g.k0) ? material[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)kl)] == GFS_SOLID : false;
             }
-            if (solid) { qx = px; qy = py; qz = pz; atomicAdd(&counters[2], 1ull); }
+            if (solid) {
+                atomicAdd(&counters[2], 1ull);
+                if (coll.list) {               // listed for k_resolve_collisions, which also bins it; p0 stays for now
+                    const unsigned int tk = atomicAdd(coll.count, 1u);
+                    if (tk < coll.cap) { coll.list[tk] = make_float4(__int_as_float(r), qx, qy, qz); deferred = true; }
+                }
+                qx = px; qy = py; qz = pz;
+            }
         }
         ox[r] = qx; oy[r] = qy; oz[r] = qz;
-        if (keys_out) {
+        if (keys_out && deferred) {            // its velocity still steers the fixed-point scale
+            float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
+            if (mm < 3.0e38f) m = fmaxf(m, mm);
+        }
+        if (keys_out && !deferred) {
             // cell key of the advected position in fp32 (exact here, same value as position_key)
             uint32_t key = nkeys;
             if (qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && qx < g.xmaxf && qy < g.ymaxf && qz < g.zmaxf) {

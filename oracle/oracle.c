@@ -544,3 +544,116 @@ void orc_extrapolate(float *u, float *v, float *w, int I, int J, int K, const un
         }
     free(mat); free(layer);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * A14, the resolve routine.
+ * FluidSimulation::_resolveParticleSolidCellCollision   src/fluidsimulation.cpp:3145-3179
+ *   Collision::getLineSegmentVoxelIntersection           src/collision.cpp:303-400   (voxel walk p0 -> p1)
+ *   vmath::normalize                                     src/vmath.h:81-92, vmath.cpp:90-93
+ *   Grid3d::GridIndexToPosition                          src/grid3d.h:83-85
+ *   AABB::getMinPoint / getMaxPoint                      src/aabb.cpp:477-483
+ *   Collision::rayIntersectsAABB                         src/collision.cpp:404-448   (incl. its dir.x-for-dir.z slip)
+ * Every vmath::vec3 operation is a float operation (vec3 * double narrows the scalar first: vmath.cpp:71-84); the
+ * voxel walk and the slab test run in double, as written.  Out-of-range cells read as solid (fluidmaterialgrid.cpp:25-29).
+ * ---------------------------------------------------------------------------------------- */
+static int cell_solid(const unsigned char *m, int I, int J, int K, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i >= I || j >= J || k >= K) return 1;
+    return m[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)] == ORC_SOLID;
+}
+
+void orc_resolve_collision(const float *p0, const float *p1, int I, int J, int K, double dx,
+                           const unsigned char *material, float *out) {
+    out[0] = p0[0]; out[1] = p0[1]; out[2] = p0[2];
+    /* --- getLineSegmentVoxelIntersection: p0 *= invdx is vec3 *= float */
+    double invdx = 1.0 / dx;
+    float s = (float)invdx;
+    float a0[3] = {p0[0] * s, p0[1] * s, p0[2] * s}, a1[3] = {p1[0] * s, p1[1] * s, p1[2] * s};
+    int g0[3], g1[3], st[3], g[3];
+    double gp[3], v[3];
+    for (int a = 0; a < 3; a++) {
+        g0[a] = (int)floor(a0[a]); g1[a] = (int)floor(a1[a]);
+        st[a] = g1[a] > g0[a] ? 1 : (g1[a] < g0[a] ? -1 : 0);
+        g[a] = g0[a];
+        gp[a] = g0[a] + (g1[a] > g0[a] ? 1 : 0);
+        v[a] = a1[a] == a0[a] ? 1 : a1[a] - a0[a];          /* float subtraction, widened */
+    }
+    double vxvy = v[0] * v[1], vxvz = v[0] * v[2], vyvz = v[1] * v[2];
+    double err[3] = {(gp[0] - a0[0]) * vyvz, (gp[1] - a0[1]) * vxvz, (gp[2] - a0[2]) * vxvy};
+    double derr[3] = {st[0] * vyvz, st[1] * vxvz, st[2] * vxvy};
+    int found = 0, vox[3] = {0, 0, 0};
+    for (long iter = 0; iter < 1000000; iter++) {
+        if (g[0] >= 0 && g[1] >= 0 && g[2] >= 0 && g[0] < I && g[1] < J && g[2] < K &&
+            material[(size_t)g[0] + (size_t)I * ((size_t)g[1] + (size_t)J * g[2])] == ORC_SOLID) {
+            vox[0] = g[0]; vox[1] = g[1]; vox[2] = g[2]; found = 1; break;
+        }
+        if (g[0] == g1[0] && g[1] == g1[1] && g[2] == g1[2]) break;
+        double xr = fabs(err[0]), yr = fabs(err[1]), zr = fabs(err[2]);
+        if (st[0] != 0 && (st[1] == 0 || xr < yr) && (st[2] == 0 || xr < zr)) { g[0] += st[0]; err[0] += derr[0]; }
+        else if (st[1] != 0 && (st[2] == 0 || yr < zr)) { g[1] += st[1]; err[1] += derr[1]; }
+        else if (st[2] != 0) { g[2] += st[2]; err[2] += derr[2]; }
+    }
+    if (!found) return;
+    /* --- raynorm = normalize(p1 - p0) */
+    float d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    float lensq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    float len = (float)sqrt((double)lensq);
+    float inv = (float)(1.0 / len);
+    float rn[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+    /* --- voxel box */
+    float bmin[3], bmax[3];
+    for (int a = 0; a < 3; a++) { bmin[a] = (float)((float)vox[a] * dx); bmax[a] = bmin[a] + (float)dx; }
+    /* --- rayIntersectsAABB */
+    double eps = 1e-10;
+    float dir[3] = {rn[0], rn[1], rn[2]};
+    if (fabs(dir[0]) < eps) dir[0] = (float)(dir[0] < 0 ? -eps : eps);
+    if (fabs(dir[1]) < eps) dir[1] = (float)(dir[1] < 0 ? -eps : eps);
+    if (fabs(dir[0]) < eps) dir[2] = (float)(dir[2] < 0 ? -eps : eps);      /* sic: tests dir.x (collision.cpp:417) */
+    float dirinv[3] = {(float)(1.0 / dir[0]), (float)(1.0 / dir[1]), (float)(1.0 / dir[2])};
+    double t1 = (bmin[0] - p0[0]) * dirinv[0], t2 = (bmax[0] - p0[0]) * dirinv[0];
+    double tmin = fmin(t1, t2), tmax = fmax(t1, t2);
+    t1 = (bmin[1] - p0[1]) * dirinv[1]; t2 = (bmax[1] - p0[1]) * dirinv[1];
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    t1 = (bmin[2] - p0[2]) * dirinv[2]; t2 = (bmax[2] - p0[2]) * dirinv[2];
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    if (!(tmax > fmax(tmin, 0.0))) return;
+    float tm = (float)tmin;
+    float cp[3] = {p0[0] + dir[0] * tm, p0[1] + dir[1] * tm, p0[2] + dir[2] * tm};
+    /* --- back off 0.05 dx along the ray */
+    float back = (float)(0.05 * dx);
+    float r[3] = {cp[0] - rn[0] * back, cp[1] - rn[1] * back, cp[2] - rn[2] * back};
+    int i, j, k;
+    cell_of(r, dx, &i, &j, &k);
+    if (cell_solid(material, I, J, K, i, j, k)) return;
+    out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+
+/* _advanceRangeOfMarkerParticles' post-pass (src/fluidsimulation.cpp:3198-3208) with the resolve: a particle whose
+ * advected cell is solid goes through _resolveParticleSolidCellCollision.  flags as orc_solid_test.  Returns hits. */
+long orc_collide(const float *p0, float *p1, long n, int I, int J, int K, double dx,
+                 const unsigned char *material, unsigned char *flags) {
+    long hits = 0;
+    for (long p = 0; p < n; p++) {
+        int i, j, k;
+        cell_of(p1 + 3 * p, dx, &i, &j, &k);
+        int solid = cell_solid(material, I, J, K, i, j, k);
+        if (flags) flags[p] = (unsigned char)solid;
+        if (solid) {
+            float r[3];
+            orc_resolve_collision(p0 + 3 * p, p1 + 3 * p, I, J, K, dx, material, r);
+            p1[3 * p] = r[0]; p1[3 * p + 1] = r[1]; p1[3 * p + 2] = r[2];
+            hits++;
+        }
+    }
+    return hits;
+}
+
+/* orc_g2p_advect with the collision resolve instead of the bare solid test */
+void orc_g2p_advect_resolve(const float *pos, const float *vel, long n,
+                            const float *u, const float *v, const float *w,
+                            const float *us, const float *vs, const float *ws,
+                            int I, int J, int K, double dx, double ratio, double dt, int order, int mode,
+                            const unsigned char *material, float *pos_out, float *vel_out, unsigned char *flags) {
+    orc_picflip(pos, vel, n, u, v, w, us, vs, ws, I, J, K, dx, ratio, mode, vel_out);
+    orc_advect(pos, n, u, v, w, I, J, K, dx, dt, order, mode, pos_out);
+    if (material) orc_collide(pos, pos_out, n, I, J, K, dx, material, flags);
+}

@@ -86,6 +86,17 @@ void orc_g2p_advect(const float *pos, const float *vel, long n,
                     int I, int J, int K, double dx, double ratio, double dt, int order, int mode,
                     const unsigned char *material, float *pos_out, float *vel_out, unsigned char *flags);
 
+/* A14 with FluidSimulation::_resolveParticleSolidCellCollision (src/fluidsimulation.cpp:3145-3179) */
+void orc_resolve_collision(const float *p0, const float *p1, int I, int J, int K, double dx,
+                           const unsigned char *material, float *out);
+long orc_collide(const float *p0, float *p1, long n, int I, int J, int K, double dx,
+                 const unsigned char *material, unsigned char *flags);
+void orc_g2p_advect_resolve(const float *pos, const float *vel, long n,
+                            const float *u, const float *v, const float *w,
+                            const float *us, const float *vs, const float *ws,
+                            int I, int J, int K, double dx, double ratio, double dt, int order, int mode,
+                            const unsigned char *material, float *pos_out, float *vel_out, unsigned char *flags);
+
 /* MACVelocityField::extrapolateVelocityField (src/macvelocityfield.cpp:577-798), in place on u, v, w */
 void orc_extrapolate(float *u, float *v, float *w, int I, int J, int K, const unsigned char *material, int nlayers);
 

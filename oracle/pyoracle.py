@@ -102,6 +102,15 @@ class Oracle:
         self.lib.orc_cell_index(pos, len(pos), dx, out)
         return out
 
+    def collide(self, p0, p1, dims, dx, material):
+        """The post-advection pass with the collision resolve; returns (positions, flags)."""
+        p0, p1 = _c(p0), np.array(p1, np.float32, copy=True)
+        flags = np.zeros(len(p0), np.uint8)
+        self.lib.orc_collide.argtypes = [_f32, _f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, _u8, _u8]
+        self.lib.orc_collide.restype = C.c_long
+        self.lib.orc_collide(p0, p1, len(p0), *dims, dx, np.ascontiguousarray(material, np.uint8).reshape(-1), flags)
+        return p1, flags
+
     def extrapolate(self, u, v, w, dims, material, nlayers):
         """MACVelocityField::extrapolateVelocityField on copies of u, v, w."""
         u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
@@ -173,12 +182,16 @@ class Oracle:
         return out
 
     def g2p_advect(self, pos, vel, new, saved, dims, dx, dt, ratio=float(np.float32(0.05)), order=4, mode=1,
-                   material=None):
+                   material=None, resolve=True):
+        """resolve=True (the reference's behaviour): particles advected into a solid cell go through
+        _resolveParticleSolidCellCollision (fluidsimulation.cpp:3145-3179); False: they just keep p0."""
         pos, vel = _c(pos), _c(vel)
         pos_out, vel_out = np.empty_like(pos), np.empty_like(vel)
         flags = np.zeros(len(pos), np.uint8)
         mptr = material.ctypes.data_as(C.c_void_p) if material is not None else None
-        self.lib.orc_g2p_advect(pos, vel, len(pos), *[_c(a) for a in new], *[_c(a) for a in saved],
+        fn = self.lib.orc_g2p_advect_resolve if resolve else self.lib.orc_g2p_advect
+        fn.argtypes = self.lib.orc_g2p_advect.argtypes
+        fn(pos, vel, len(pos), *[_c(a) for a in new], *[_c(a) for a in saved],
                                 *dims, dx, ratio, dt, order, mode, mptr, pos_out, vel_out,
                                 flags.ctypes.data_as(C.c_void_p))
         return pos_out, vel_out, flags

@@ -500,9 +500,9 @@ def test_golden_fixtures_through_cuda(ctx):
     o = ctx.get_particle_order()
     p, vv = ctx.get_particles()
     assert np.array_equal(bits(vv), bits(g["vel_out"][o]))
-    hit = ~np.all(bits(p) == bits(g["pos_out"][o]), 1)
-    assert hit.sum() == 1 and ctx.stats()["solid_hits"] == 1       # the one collision case of the fixture
-    assert np.array_equal(bits(p[hit]), bits(g["pos"][o][hit]))
+    # the one particle of the fixture that ends in a solid cell went through the collision resolve, as in the reference
+    assert ctx.stats()["solid_hits"] == 1
+    assert np.array_equal(bits(p), bits(g["pos_out"][o]))
 
 
 def test_hello_world_64_full_parity(ctx, oracle):
@@ -641,4 +641,57 @@ def test_p2g_then_extrapolate_equals_oracle(oracle, name, nlayers):
     assert any((a != b).any() for a, b in zip(want, p2g))          # it did extend the field
     for a, b in zip(c.get_field(capi.FIELD_P2G), p2g):              # and left the source slot alone
         assert np.array_equal(bits(a), bits(b))
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the collision resolve (A14's second half)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,scale,interp", [("slab24", 4.0, capi.TRICUBIC), ("slab24", 1.5, capi.TRILINEAR), ("small32", 8.0, capi.TRILINEAR), ("odd20", 6.0, capi.TRILINEAR)])
+def test_collision_resolve_exact(oracle, name, scale, interp):
+    """A step large enough that hundreds of particles are advected into solid cells (border + interior block): exact
+    arithmetic is bit-identical to the oracle's restatement of _resolveParticleSolidCellCollision (itself pinned against
+    the reference, tests/test_oracle_vs_ref.py::test_collision_resolve_bit_exact); option 3 = 0 restores "keep p0";
+    and the binning done by k_resolve_collisions feeds the next counting sort correctly."""
+    s = scene(name, interior_solids=True)
+    new, saved = rough_fields(s["dims"], 31), rough_fields(s["dims"], 32)
+    dt = scale * s["dx"]
+    mat = s["material"].copy()
+    oracle.classify(s["pos"], s["dims"], s["dx"], mat)
+    want = {r: oracle.g2p_advect(s["pos"], s["vel"], new, saved, s["dims"], s["dx"], dt, mode=interp, material=mat, resolve=r) for r in (True, False)}
+    assert want[True][2].sum() > 20 and not np.array_equal(want[True][0], want[False][0])
+    for resolve in (True, False):
+        c = capi.Context(0)
+        load_domain(c, s)
+        c.set_option(3, int(resolve))
+        c.set_material(mat)
+        c.set_field(capi.FIELD_NEW, *new); c.set_field(capi.FIELD_SAVED, *saved)
+        c.sort()
+        c.g2p_advect(dt, interp=interp, arith=capi.EXACT)
+        o = c.get_particle_order()
+        p, v = c.get_particles()
+        assert np.array_equal(bits(v), bits(want[resolve][1][o]))
+        assert np.array_equal(bits(p), bits(want[resolve][0][o]))
+        assert c.stats()["solid_hits"] == int(want[resolve][2].sum())
+        c.close()
+    # fast arithmetic through the fused substep (brick kernel where dx is a power of two): colliders are binned by
+    # k_resolve_collisions; the following sort must see every particle exactly once, in the cell of its resolved position
+    c = capi.Context(0)
+    load_domain(c, s)
+    c.set_material(mat)
+    c.set_field(capi.FIELD_NEW, *new); c.set_field(capi.FIELD_SAVED, *saved)
+    c.substep(dt, interp=interp, arith=capi.FAST)
+    hits = c.stats()["solid_hits"]
+    assert abs(hits - int(want[True][2].sum())) <= max(3, hits // 50)
+    c.sort_unstable()
+    p, _ = c.get_particles()
+    assert len(p) == len(s["pos"])
+    cells = oracle.cell_index(p, s["dx"])
+    I, J, K = s["dims"]
+    inside = ((cells >= 0) & (cells < np.array([I, J, K]))).all(1)
+    flat = cells[inside, 0] + I * (cells[inside, 1] + J * cells[inside, 2])
+    assert not (mat[flat] == synth.SOLID).any()                      # nobody ended inside a solid cell
+    key = np.where(inside, cells[:, 2].astype(np.int64) * 10**6 + cells[:, 1] * 10**3 + cells[:, 0], 10**12)
+    o = c.get_particle_order()
+    assert len(np.unique(o)) == len(o)
     c.close()

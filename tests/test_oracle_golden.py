@@ -54,12 +54,13 @@ def test_stages_golden(oracle):
     saved = (g["saved_u"], g["saved_v"], g["saved_w"])
     pos, vel, flags = oracle.g2p_advect(g["pos"], g["vel"], new, saved, dims, dx, float(g["dt"]), material=mat)
     assert np.array_equal(bits(vel), bits(g["vel_out"]))
-    # exactly one particle of this fixture ends in a solid cell; the reference then runs its collision
-    # resolve (src/fluidsimulation.cpp:3145-3179, outside this scope), the oracle keeps p0 and flags it
+    # exactly one particle of this fixture ends in a solid cell and goes through the reference's collision resolve
+    # (src/fluidsimulation.cpp:3145-3179): the fixture holds the reference's resolved position for it
     assert flags.sum() == 1
-    ok = flags == 0
-    assert np.array_equal(bits(pos[ok]), bits(g["pos_out"][ok]))
-    assert np.array_equal(bits(pos[~ok]), bits(g["pos"][~ok]))
+    assert np.array_equal(bits(pos), bits(g["pos_out"]))
+    kept, _, _ = oracle.g2p_advect(g["pos"], g["vel"], new, saved, dims, dx, float(g["dt"]), material=mat, resolve=False)
+    hit = flags == 1
+    assert np.array_equal(bits(kept[hit]), bits(g["pos"][hit])) and not np.array_equal(bits(kept[hit]), bits(pos[hit]))
 
 
 def test_whole_simulator_frame_golden(oracle):

@@ -174,3 +174,29 @@ def test_extrapolate_bit_exact(oracle, reference, nlayers):
     for x, y in zip(a, b):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
     assert any((x != y.reshape(-1)).any() for x, y in zip(a, (u, v, w)))
+
+
+@pytest.mark.parametrize("name,scale", [("slab24", 1.0), ("slab24", 4.0), ("tiny16", 2.5)])
+def test_collision_resolve_bit_exact(oracle, reference, name, scale):
+    """stage 12 with a step large enough that many particles are advected into solid cells (the
+    border and an interior block), so FluidSimulation::_resolveParticleSolidCellCollision runs: voxel walk, ray/box
+    intersection, back-off, and every "return p0" branch.  orc_g2p_advect_resolve must reproduce it bit for bit."""
+    s = _scene(name, interior_solids=True)
+    new, saved = rough_fields(s["dims"], 31), rough_fields(s["dims"], 32)
+    dt = scale * s["dx"]
+    sim = _ref_sim(reference, s)
+    sim.update_fluid_cells()
+    sim.set_fields(new, saved)
+    sim.update_particle_velocities()
+    sim.advance_particles(dt)
+    pos_ref, vel_ref = sim.get_particles()
+    mat = sim.get_material()
+    sim.close()
+
+    pos, vel, flags = oracle.g2p_advect(s["pos"], s["vel"], new, saved, s["dims"], s["dx"], dt, material=mat, resolve=True)
+    assert flags.sum() > 20                                             # the resolve really ran
+    assert np.array_equal(vel.view(np.uint32), vel_ref.view(np.uint32))
+    assert np.array_equal(pos.view(np.uint32), pos_ref.view(np.uint32))
+    hit = flags.astype(bool)
+    moved = (pos[hit] != s["pos"][hit]).any(1)
+    assert moved.any()                                                  # resolved positions, not just "keep p0"
