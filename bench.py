@@ -473,7 +473,9 @@ def run_gfs(args):
 
     # ---- e2e: the same substep through host buffers ------------------------------------------------------
     aos_out = torch.empty((int(n_max) + 1024, 6), dtype=torch.float32, pin_memory=True)
-    p2g_out = [np.empty(t.numel(), np.float32) for t in new_host]
+    p2g_pinned = [torch.empty(t.numel(), dtype=torch.float32, pin_memory=True) for t in new_host]     # every host buffer of the
+    p2g_out = [t.numpy() for t in p2g_pinned]                                                         # e2e leg is pinned
+    mat_pinned = torch.empty(G, dtype=torch.uint8, pin_memory=True)
     nu, nv, nw = [t.numel() for t in new_host]
     h2d = n_local * 24 + 2 * 4 * (nu + nv + nw)
     d2h = n_local * 24 + 4 * (nu + nv + nw) + G
@@ -485,7 +487,7 @@ def run_gfs(args):
         substep()
         ctx.get_particles_aos(aos_out.numpy().reshape(-1)[: ctx.num_particles * 6])   # D2H particles
         ctx.get_field(capi.FIELD_P2G, out=p2g_out)                               # D2H P2G u,v,w
-        ctx.get_material()                                                        # D2H material
+        ctx.get_material(out=mat_pinned.numpy())                                  # D2H material
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()

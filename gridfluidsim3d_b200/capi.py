@@ -269,8 +269,8 @@ class Context:
     def set_material(self, material):
         self._call(self.lib.gfs_set_material, _c(material, np.uint8))
 
-    def get_material(self):
-        m = np.empty(self.dims[0] * self.dims[1] * self.dims[2], np.uint8)
+    def get_material(self, out=None):
+        m = np.empty(self.dims[0] * self.dims[1] * self.dims[2], np.uint8) if out is None else out
         self._call(self.lib.gfs_get_material, m)
         return m
 
