@@ -589,8 +589,13 @@ void make_brick_maps(gfs_context *c) {
     const int kl = g.k1 - g.k0;
     const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
     for (int a = 0; a < 3; a++) {
-        make_field_map_dense(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
-        make_field_map_dense(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
+        if (gfs::BrickTile<0>::kSkew) {
+            make_field_map(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
+            make_field_map(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
+        } else {
+            make_field_map_dense(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
+            make_field_map_dense(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
+        }
         make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nZ);
         make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sZ);
     }

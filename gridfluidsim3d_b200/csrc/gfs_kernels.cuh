@@ -904,7 +904,10 @@ template <int INTERP> struct BrickTile {
     static constexpr int nY = 9 + 2 * kMargin + kLo + kHi;
     // (trilinear keeps the dense [z][y][x 16] box: it does 1/7 of the shared loads per sample, is bound by instruction
     // issue, and the split-column address arithmetic cost it more than the conflicts did -- measured 3.53 -> 3.97 ms.)
-    static constexpr bool kSkew = INTERP == 1;
+#ifndef GFS_SKEW_TRILINEAR
+#define GFS_SKEW_TRILINEAR 0
+#endif
+    static constexpr bool kSkew = INTERP == 1 || GFS_SKEW_TRILINEAR;
     static constexpr int nZ = kSkew ? (nY | 1) : nY;                        // odd plane count (>= nY)
     static constexpr int sOrg = 1 + kLo;                                    // SAVED (sampled at p0 only, no margin)
     static constexpr int sY = 9 + kLo + kHi;
@@ -933,13 +936,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 
 // word offset of box column x (0..15) in the skewed layout
 template <int NZ>
-__device__ __forceinline__ int tile_col(int x) { return (x & 7) + 8 * NZ * (x >> 3); }
+__device__ __forceinline__ int tile_col(int x) { return x + (x >> 3) * (8 * NZ - 8); }      // x in [0, 16)
 
 // one component from a staged tile: ax/ay/az are global node indices + fractions, (ox,oy,oz) the tile origin
 template <int INTERP, int NZ>
 __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const AxisIdxF &ax, const AxisIdxF &ay, const AxisIdxF &az,
                                              int ox, int oy, int oz) {
-    if (INTERP == 0) {          // dense [z][y][x 16] box, NZ = rows per plane
+    if (INTERP == 0 && !GFS_SKEW_TRILINEAR) {          // dense [z][y][x 16] box, NZ = rows per plane
         const float *r = t + (ax.i - ox) + 16 * ((ay.i - oy) + NZ * (az.i - oz));
         constexpr int BX = 16, BY = NZ;
         const float p000 = r[0], p100 = r[1], p010 = r[BX], p110 = r[BX + 1];
@@ -982,12 +985,25 @@ __device__ __forceinline__ float tile_sample(const float *__restrict__ t, const 
 
 // all six index/fraction pairs of a position (fp32-exact for power-of-two dx)
 struct SampleIdx { AxisIdxF ux, uy, uz, sx, sy, sz; };
+// Power-of-two dx: u = x / dx is exact in fp32, the staggered coordinate is u - 0.5 (also exact), and the fraction
+// (x - floor(u) dx) / dx of axis_index_f equals u - floor(u) -- same bits, a third of the operations (scaling by a
+// power of two commutes with every rounding involved).
+template <bool MAGIC>
+__device__ __forceinline__ void axis_pair(float x, const Grid &g, AxisIdxF &plain, AxisIdxF &stag) {
+    const float u = __fmul_rn(x, g.invdxf), us = __fsub_rn(u, 0.5f);
+    float fu, fs;
+    if (MAGIC) { fu = floor_small(u, plain.i); fs = floor_small(us, stag.i); }
+    else { fu = floorf(u); plain.i = (int)fu; fs = floorf(us); stag.i = (int)fs; }
+    plain.t = __fsub_rn(u, fu);
+    stag.t = __fsub_rn(us, fs);
+}
+
 template <bool MAGIC = false>
 __device__ __forceinline__ SampleIdx sample_idx(const Grid &g, float px, float py, float pz) {
     SampleIdx s;
-    s.ux = axis_index_f<MAGIC>(px, g); s.uy = axis_index_f<MAGIC>(py, g); s.uz = axis_index_f<MAGIC>(pz, g);
-    s.sx = axis_index_f<MAGIC>(__fsub_rn(px, g.halfdxf), g); s.sy = axis_index_f<MAGIC>(__fsub_rn(py, g.halfdxf), g);
-    s.sz = axis_index_f<MAGIC>(__fsub_rn(pz, g.halfdxf), g);
+    axis_pair<MAGIC>(px, g, s.ux, s.sx);
+    axis_pair<MAGIC>(py, g, s.uy, s.sy);
+    axis_pair<MAGIC>(pz, g, s.uz, s.sz);
     return s;
 }
 
