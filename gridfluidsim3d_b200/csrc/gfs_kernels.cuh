@@ -880,6 +880,9 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
 // ------------------------------------------------------------------------------------------------
 struct BrickMaps { CUtensorMap m[6]; };     // NEW u,v,w then SAVED u,v,w
 
+#ifndef GFS_TRILINEAR_CTAS
+#define GFS_TRILINEAR_CTAS 3
+#endif
 #ifndef GFS_TRICUBIC_CTAS
 #define GFS_TRICUBIC_CTAS 2
 #endif
@@ -1077,7 +1080,7 @@ __global__ void __launch_bounds__(128) k_resolve_collisions(Grid g, const uint8_
 }
 
 template <int INTERP, bool MIGRATE>
-__global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : 4) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
+__global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : GFS_TRILINEAR_CTAS) k_g2p_brick(Grid g, const __grid_constant__ BrickMaps maps, FieldPtrs fnew, FieldPtrs fsaved,
                             const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
                             const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
                             int order, RkCoef rk, float ratio_pic, float ratio_flip, int64_t n,
