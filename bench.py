@@ -350,7 +350,13 @@ def run_gfs(args):
     dims, dx, _ = synth.CONFIGS[args.workload]
     G = dims[0] * dims[1] * dims[2]
     hbm_gbs, peak_src = measured_peaks()
-    owned = slabs.slab_ranges(dims[2], world)[rank]
+    if world > 1 and args.cuts == "weighted":
+        # cuts that balance particles per slab (8 per seeded cell); every rank computes the same cuts from the scene
+        layer_counts = synth.fluid_cells(synth.CONFIGS[args.workload][2], dims, synth.border_material(dims)).reshape(dims[2], -1).sum(1)
+        ranges = slabs.slab_ranges_weighted(layer_counts, world, min_layers=max(4, capi.slab_halo_cells(capi.TRICUBIC, 0.5 * dx, dx)))
+    else:
+        ranges = slabs.slab_ranges(dims[2], world)
+    owned = ranges[rank]
 
     def allmax(x):
         if world == 1:
@@ -546,7 +552,7 @@ def run_gfs(args):
         "dtype": "f32 (fp64 index arithmetic, 64-bit fixed-point P2G accumulation)", "data": "synthetic",
         "config": {"workload": args.workload, "grid": list(dims), "dx": dx, "particles": N, "cells": G,
                    "interp": args.interp, "rk_order": 4, "arith": "fast", "cfl": 0.5,
-                   "parallelism": "z-slabs x%d, halo %d layers" % (world, halo) if world > 1 else "single GPU",
+                   "parallelism": "z-slabs x%d (%s cuts: %s), halo %d layers" % (world, args.cuts, ranges, halo) if world > 1 else "single GPU",
                    "l2": "inputs (%.2f GB particles + %.2f GB fields) exceed the 126 MB L2; no flush needed"
                          % (N * 24 / 1e9, 8 * (nu + nv + nw) / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
@@ -622,6 +628,8 @@ def main():
     ap.add_argument("--workload", default="splash256")
     ap.add_argument("--interp", default="trilinear", choices=["trilinear", "tricubic"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cuts", default="weighted", choices=["weighted", "uniform"],
+                    help="N>1 slab cuts: weighted = balance particles per slab, uniform = equal layer counts")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")

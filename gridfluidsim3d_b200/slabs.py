@@ -43,6 +43,32 @@ def slab_ranges(K, world):
     return [(K * r // world, K * (r + 1) // world) for r in range(world)]
 
 
+def slab_ranges_weighted(layer_counts, world, min_layers=4):
+    """[(k0,k1)] for every rank with cuts that balance the PARTICLES, not the layers: layer_counts[k] = particles in
+    cell layer k (efficiency is governed by particles per slab).  Cut r is placed after the layer where the
+    running count reaches r/world of the total; every slab keeps at least min_layers layers (the halo)."""
+    counts = [float(c) for c in layer_counts]
+    K, total = len(counts), sum(counts)
+    if world == 1 or total <= 0 or K < world * min_layers:
+        return slab_ranges(K, world)
+    cuts, run, k = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while k < K and run + counts[k] <= target:
+            run += counts[k]
+            k += 1
+        # the layer straddling the target goes to whichever side leaves the smaller error
+        if k < K and (run + counts[k] - target) < (target - run):
+            run += counts[k]
+            k += 1
+        k = max(k, cuts[-1] + min_layers)
+        k = min(k, K - (world - r) * min_layers)
+        run = sum(counts[:k])
+        cuts.append(k)
+    cuts.append(K)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class SlabDriver:
     """The per-rank half of every exchange: what to send to each neighbour, what to do with what arrives."""
 

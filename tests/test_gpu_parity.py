@@ -538,6 +538,17 @@ def test_virtual_slabs_equal_single_domain(oracle, world, name, interp, transpor
     """Sharded == unsharded: after each of 3 substeps the material and the P2G fields of every slab's owned layers are
     bit-identical to the single-context run (integer partial sums), and the union of the slabs' particles is the
     single-context particle set, bit for bit."""
+    _virtual_slabs(oracle, world, name, interp, transport, None)
+
+
+@pytest.mark.parametrize("transport", ["staged", "peer"])
+@pytest.mark.parametrize("ranges,interp", [([(0, 11), (11, 21), (21, 32)], capi.TRILINEAR), ([(0, 13), (13, 32)], capi.TRICUBIC)])
+def test_virtual_slabs_unaligned_cuts(oracle, ranges, interp, transport):
+    """Cuts that are not multiples of the 8-layer bricks (what particle-weighted cuts produce, slabs.slab_ranges_weighted)."""
+    _virtual_slabs(oracle, len(ranges), "small32", interp, transport, ranges)
+
+
+def _virtual_slabs(oracle, world, name, interp, transport, ranges):
     import torch
     from gridfluidsim3d_b200 import slabs
     s = scene(name, interior_solids=(name == "slab24"))
@@ -550,7 +561,7 @@ def test_virtual_slabs_equal_single_domain(oracle, world, name, interp, transpor
     single = capi.Context(0)
     load_domain(single, s)
     single.set_field(capi.FIELD_NEW, *s["new"]); single.set_field(capi.FIELD_SAVED, *s["saved"])
-    ranges = slabs.slab_ranges(K, world)
+    ranges = ranges or slabs.slab_ranges(K, world)
     kcell = oracle.cell_index(s["pos"], s["dx"])[:, 2]
     ctxs, drivers = [], []
     for r, (k0, k1) in enumerate(ranges):

@@ -97,3 +97,15 @@ def test_sharded_substeps_equal_unsharded(oracle, world, name):
             a, b = got.reshape(nk, nj, ni)[k0:k1], ref.reshape(nk, nj, ni)[k0:k1]
             assert np.abs(a - b).max() <= 2e-5 * np.abs(ref).max()
             assert np.array_equal(a != 0, b != 0)
+
+
+def test_weighted_slab_ranges_balance_particles():
+    from gridfluidsim3d_b200 import slabs
+    counts = np.array([0, 10, 10, 10, 10, 40, 40, 40, 40, 10, 10, 10, 10, 10, 10, 0] * 2)
+    for world in (2, 3, 4):
+        r = slabs.slab_ranges_weighted(counts, world, min_layers=2)
+        assert r[0][0] == 0 and r[-1][1] == len(counts) and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(b - a >= 2 for a, b in r)
+        load = [counts[a:b].sum() for a, b in r]
+        uni = [counts[a:b].sum() for a, b in slabs.slab_ranges(len(counts), world)]
+        assert max(load) <= max(uni)
