@@ -74,6 +74,20 @@ def launches(tag):
                 "compare SHARES, not absolutes.\n\n| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n" % tag)
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.1f | %.1f | %.1f %% |\n" % (name[:90], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / tot))
+        # the kernels of ONE trilinear substep, by mean launch time: the shares to compare with bench.py's "kernels" block
+        step = ["k_p2g_tile<2>", "k_g2p_brick<0, 0>", "k_build_index", "k_assemble", "k_p2g_finalize", "k_classify",
+                "DeviceScanKernel", "k_resolve_collisions"]
+        rows = []
+        for key in step:
+            hit = [(n, v) for n, v in per.items() if key in n and "at_cuda_detail" not in n.split("DeviceScanKernel")[0][:0]]
+            if hit:
+                n, v = hit[0]
+                rows.append((key, sorted(v)[len(v) // 2]))          # median: the first launch after an upload sorts physically
+        tot_step = sum(m for _, m in rows) or 1.0
+        f.write("\n## one trilinear substep (median launch time of each of its kernels)\n\n| kernel | median us | share of the substep |\n|---|---:|---:|\n")
+        for key, m in rows:
+            f.write("| `%s` | %.1f | %.1f %% |\n" % (key, m, 100 * m / tot_step))
+        f.write("| total | %.1f | |\n" % tot_step)
     print("wrote launches for", tag, "kernels:", len(per))
 
 
