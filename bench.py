@@ -110,7 +110,7 @@ def make_scene_device(name, device, seed=12345, k_range=None):
 # clocks during the timed region
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (one sample per ~4 ms; the timed
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (one sample per ~1 ms; the timed
     region of a short run lasts tens of ms), with `nvidia-smi -lms` as the fallback when NVML is not importable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -152,7 +152,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def __enter__(self):
         if self.nvml is not None:
