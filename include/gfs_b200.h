@@ -170,7 +170,11 @@ void gfs_copy_field(gfs_context *ctx, int dst_slot, int src_slot, int *err);
 void gfs_sort_index(gfs_context *ctx, int *err);
 /* Tuning switches.  option 0: fast-P2G variant, 1 = brick tiles in shared memory (default), 0 = global atomics
  * only; both produce bit-identical grids.  option 1: fast-G2P variant, 1 = TMA-staged brick tiles (default; used
- * when dx is a power of two and the particles are sorted), 0 = global loads only; bit-identical results. */
+ * when dx is a power of two and the particles are sorted), 0 = global loads only; bit-identical results.
+ * option 2: 1 = gfs_substep / gfs_sort_index sort by index only once the storage is nearly sorted (default), 0 = always
+ * move the particles.  option 3: 1 = particles advected into a solid cell go through the reference's collision resolve
+ * (FluidSimulation::_resolveParticleSolidCellCollision, src/fluidsimulation.cpp:3145-3179; default), 0 = they keep
+ * their old position (bare solid test).  gfs_stats_t.solid_hits counts them either way. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
