@@ -56,13 +56,28 @@ def golden_extrapolate(ref):
     np.savez_compressed(os.path.join(OUT, "extrapolate.npz"), **g)
 
 
+def golden_state(ref):
+    """A save state written by the reference's FluidSimulationSaveState: 10 x 8 x 9 cells, a fluid ball (the
+    simulator seeds and jitters the particles itself, glibc rand() with its default seed) and four interior solid cells."""
+    sim = ref.sim((10, 8, 9), 0.25)
+    sim.add_fluid_sphere((1.25, 1.0, 1.1), 0.6)
+    sim.add_solid_cells(np.array([[6, 2, 3], [6, 3, 3], [7, 2, 3], [2, 5, 6]], np.int32))
+    sim.initialize()
+    sim.save_state(os.path.join(OUT, "reference_small.state"))
+    sim.close()
+
+
 def main():
     ref = Reference()
     os.makedirs(OUT, exist_ok=True)
     if "--only-extrapolate" in sys.argv:             # added after the other fixtures were committed
         golden_extrapolate(ref)
         return
+    if "--only-state" in sys.argv:
+        golden_state(ref)
+        return
     golden_extrapolate(ref)
+    golden_state(ref)
 
     # ---- primitives: index, sampling, RK1-4, splat ---------------------------------------------
     dims, dx = (10, 8, 12), 0.25

@@ -274,6 +274,34 @@ class Reference:
         self.lib.ref_add_point_values(pos, values, len(pos), radius, _c(offset), dx, *ndims, field, weight)
         return field, weight
 
+    # -- save states (src/fluidsimulationsavestate.cpp)
+    def state_read(self, path):
+        """The reference's own reader on `path`: dict(dims, dx, frame, n_diffuse, pos, vel, solid_ijk) or None."""
+        L = self.lib
+        L.ref_state_read.argtypes = [C.c_char_p, _i32, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_state_read.restype = C.c_int
+        hdr, dx = np.zeros(7, np.int32), C.c_double()
+        if not L.ref_state_read(path.encode(), hdr, C.byref(dx), None, None, None):
+            return None
+        pos, vel = np.empty((hdr[4], 3), np.float32), np.empty((hdr[4], 3), np.float32)
+        solid = np.empty((hdr[6], 3), np.int32)
+        L.ref_state_read(path.encode(), hdr, C.byref(dx), pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p),
+                         solid.ctypes.data_as(C.c_void_p))
+        return dict(dims=tuple(int(x) for x in hdr[:3]), dx=dx.value, frame=int(hdr[3]), n_diffuse=int(hdr[5]),
+                    pos=pos, vel=vel, solid_ijk=solid)
+
+    def sim_from_state(self, path):
+        """FluidSimulation(FluidSimulationSaveState&) on `path`, wrapped as a RefSim (already initialised)."""
+        self.lib.ref_sim_create_from_state.restype = C.c_void_p
+        self.lib.ref_sim_create_from_state.argtypes = [C.c_char_p]
+        h = self.lib.ref_sim_create_from_state(path.encode())
+        if not h:
+            return None
+        st = self.state_read(path)
+        sim = RefSim.__new__(RefSim)
+        sim.lib, sim.dims, sim.dx, sim.h, sim._init = self.lib, st["dims"], st["dx"], h, True
+        return sim
+
     # -- simulation-level
     def sim(self, dims, dx):
         return RefSim(self.lib, dims, dx)
@@ -371,6 +399,10 @@ class RefSim:
 
     def advance_particles(self, dt):
         self.lib.ref_sim_advance_particles(self.h, dt)
+
+    def save_state(self, path):
+        self.lib.ref_sim_save_state.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.ref_sim_save_state(self.h, path.encode())
 
     def update(self, dt):
         self.lib.ref_sim_update(self.h, dt)

@@ -706,3 +706,22 @@ def test_collision_resolve_exact(oracle, name, scale, interp):
     o = c.get_particle_order()
     assert len(np.unique(o)) == len(o)
     c.close()
+
+
+def test_reference_save_state_loads_into_the_resident_domain(oracle):
+    """A state file written by the unmodified reference (tests/golden/reference_small.state) -> gfs_domain_init /
+    gfs_set_material / gfs_set_particles -> one P2G: classification and splat equal the oracle's on the same data."""
+    from gridfluidsim3d_b200 import savestate
+    st = savestate.read_state(os.path.join(os.path.dirname(__file__), "golden", "reference_small.state"))
+    mat0 = savestate.material_from_state(st)
+    c = capi.Context(0)
+    c.domain_init(st["dims"], st["dx"]); c.set_material(mat0); c.set_sources([])
+    vel = (st["pos"] * np.float32(0.3) - np.float32(0.2)).astype(np.float32)      # the fixture's velocities are all zero
+    c.set_particles(st["pos"], vel)
+    c.sort(); c.p2g(capi.EXACT)
+    mat = mat0.copy()
+    want = oracle.p2g(st["pos"][c.get_particle_order()], vel[c.get_particle_order()], st["dims"], st["dx"], mat, [])
+    assert np.array_equal(c.get_material(), mat) and (mat == synth.FLUID).sum() > 0
+    for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
+        assert np.array_equal(bits(got), bits(ref))
+    c.close()

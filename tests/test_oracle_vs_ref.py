@@ -200,3 +200,41 @@ def test_collision_resolve_bit_exact(oracle, reference, name, scale):
     hit = flags.astype(bool)
     moved = (pos[hit] != s["pos"][hit]).any(1)
     assert moved.any()                                                  # resolved positions, not just "keep p0"
+
+
+def test_save_state_both_directions(reference, tmp_path):
+    """SURVEY 8(f) rank 4 (wire format): a state written by the reference's FluidSimulationSaveState is read field for
+    field by gridfluidsim3d_b200/savestate.py, and a state written by savestate.py is accepted by the reference's reader and
+    by FluidSimulation(FluidSimulationSaveState&) with the same particles and solid cells."""
+    from gridfluidsim3d_b200 import savestate
+    s = _scene("slab24", interior_solids=True)
+    sim = _ref_sim(reference, s)
+    ref_path = str(tmp_path / "ref.state")
+    sim.save_state(ref_path)
+    p_ref, v_ref = sim.get_particles()
+    mat_ref = sim.get_material()
+    sim.close()
+
+    st = savestate.read_state(ref_path)
+    assert st["dims"] == tuple(s["dims"]) and st["dx"] == s["dx"] and st["frame"] == 0
+    assert np.array_equal(st["pos"].view(np.uint32), p_ref.view(np.uint32))
+    assert np.array_equal(st["vel"].view(np.uint32), v_ref.view(np.uint32))
+    assert len(st["diffuse_pos"]) == 0 and st["brick_blob"] is None
+    solid = savestate.material_from_state(st)
+    assert np.array_equal(solid == synth.SOLID, mat_ref == synth.SOLID)
+    assert np.array_equal(st["solid_ijk"], savestate.solid_ijk_from_material(mat_ref, s["dims"]))
+
+    ours = str(tmp_path / "ours.state")
+    savestate.write_state(ours, s["dims"], s["dx"], s["pos"], s["vel"], st["solid_ijk"], frame=3)
+    back = reference.state_read(ours)
+    assert back is not None and back["dims"] == tuple(s["dims"]) and back["dx"] == s["dx"] and back["frame"] == 3
+    assert np.array_equal(back["pos"].view(np.uint32), s["pos"].view(np.uint32))
+    assert np.array_equal(back["vel"].view(np.uint32), s["vel"].view(np.uint32))
+    assert np.array_equal(back["solid_ijk"], st["solid_ijk"])
+    assert open(ours, "rb").read()[37:] == open(ref_path, "rb").read()[37:]          # byte-identical payload
+    sim2 = reference.sim_from_state(ours)
+    assert sim2 is not None and sim2.n == len(s["pos"])
+    p2, v2 = sim2.get_particles()
+    assert np.array_equal(p2.view(np.uint32), s["pos"].view(np.uint32))
+    assert np.array_equal(sim2.get_material() == synth.SOLID, mat_ref == synth.SOLID)
+    sim2.close()
