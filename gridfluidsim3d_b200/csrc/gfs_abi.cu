@@ -133,6 +133,18 @@ struct gfs_context {
     DevBuf<int8_t> ext_layer;             // gfs_extrapolate: layer index per cell
     DevBuf<float4> coll_list;             // particles advected into a solid cell: {slot, p1}, resolved by k_resolve_collisions
     DevBuf<unsigned int> coll_count;
+    // ---- CUDA graphs of the fused single-domain substep: one per buffer parity, replayed while nothing it baked in changes
+    struct SubstepGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t epoch = 0;               // graph_epoch at capture
+        int64_t n = -1, launches = 0;
+        double dt = 0, ratio = 0;
+        int order = 0, interp = 0;
+        const void *scratch[3] = {nullptr, nullptr, nullptr};       // lazily sized buffers the capture saw
+    } graphs[2];
+    uint64_t graph_epoch = 1;             // bumped by every call that changes what a captured substep baked in
+    int use_graphs = 1;                   // option 4
+    int64_t graph_replays = 0;
     int resolve_collisions = 1;           // option 3: 1 = the reference's collision resolve, 0 = solid test only (keep p0)
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
@@ -669,6 +681,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
     if (c->world_table) cudaFree(c->world_table);
+    for (int gi = 0; gi < 2; gi++) if (c->graphs[gi].exec) cudaGraphExecDestroy(c->graphs[gi].exec);
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
     c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -710,6 +723,7 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     out->fluid_cells = (int64_t)h[1];
     out->solid_hits = (int64_t)h[2];
     out->kernel_launches = c->launches;
+    out->graph_replays = c->graph_replays;
     GFS_END()
 }
 
@@ -834,6 +848,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     GFS_REQUIRE(c, "null context");
     GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
     GFS_CUDA(cudaSetDevice(c->device));
+    c->graph_epoch++;
     c->grid = make_grid(I, J, K, dx, 0, K, true);
     const Grid &g = c->grid;
     const int kl = g.k1 - g.k0;
@@ -895,6 +910,7 @@ void gfs_set_sources(gfs_context *c, const gfs_source_t *sources, int nsources, 
     GFS_REQUIRE(nsources == 0 || sources, "null pointer");
     c->sources.n = nsources;
     for (int i = 0; i < nsources; i++) c->sources.s[i] = sources[i];
+    c->graph_epoch++;
     GFS_END()
 }
 
@@ -905,6 +921,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
     c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false; c->storage_sorted = false;
+    c->graph_epoch++;
     if (n > 0) {
         // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
         c->h_pos.reserve((size_t)n * 6);
@@ -1045,7 +1062,9 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 1) { GFS_REQUIRE(value == 0 || value == 1, "g2p variant must be 0 or 1"); c->g2p_variant = value; }
     else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
     else if (option == 3) { GFS_REQUIRE(value == 0 || value == 1, "collision resolve must be 0 or 1"); c->resolve_collisions = value; }
+    else if (option == 4) { GFS_REQUIRE(value == 0 || value == 1, "graph replay must be 0 or 1"); c->use_graphs = value; }
     else throw GfsError("gfs_set_option: unknown option");
+    c->graph_epoch++;
     GFS_END()
 }
 
@@ -1065,16 +1084,67 @@ void gfs_g2p_advect(gfs_context *c, double dt, double ratio, int order, int inte
     GFS_END()
 }
 
-void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int *err) {
-    GFS_BEGIN
-    GFS_REQUIRE(c, "null context");
-    GFS_CUDA(cudaSetDevice(c->device));
+namespace {
+void substep_body(gfs_context *c, double dt, double ratio, int order, int interp, int arith) {
     // exact arithmetic needs the stable order; fast arithmetic is order-independent and uses the counting sort,
     // binned for the following substep by the G2P kernel's epilogue
     if (c->keys_ready && arith == GFS_EXACT) c->keys_ready = false;
     do_sort(c, arith == GFS_EXACT, /*lazy=*/arith != GFS_EXACT && c->grid.pow2 && c->have_maps && c->g2p_variant == 1 && c->lazy_sort);
     do_p2g(c, arith);
     do_g2p(c, dt, ratio, order, interp, arith, arith != GFS_EXACT);
+}
+
+// steady state of the fused fast substep: everything the launch sequence depends on is either baked into the graph key
+// or guarded by graph_epoch, and the host-side state transition of one substep is fixed (the buffer parity flips)
+bool substep_graph_eligible(gfs_context *c, int arith) {
+    return c->use_graphs && !c->profiling && arith != GFS_EXACT && c->has_domain && c->grid.pow2 && c->have_maps &&
+           c->g2p_variant == 1 && c->p2g_variant == 1 && c->lazy_sort && c->storage_sorted && c->keys_ready && !c->sorted &&
+           !c->indexed && c->dead == 0 && c->n > 0 && c->own_k0 == 0 && c->own_k1 == c->grid.K;
+}
+}  // namespace
+
+void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c, "null context");
+    GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
+    GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (!substep_graph_eligible(c, arith)) { substep_body(c, dt, ratio, order, interp, arith); return; }
+    gfs_context::SubstepGraph &g = c->graphs[c->cur];
+    const void *scratch[3] = {c->cub_tmp.p, c->coll_list.p, c->coll_count.p};
+    const bool fresh = g.exec && g.epoch == c->graph_epoch && g.n == c->n && g.dt == dt && g.ratio == ratio && g.order == order &&
+                       g.interp == interp && g.scratch[0] == scratch[0] && g.scratch[1] == scratch[1] && g.scratch[2] == scratch[2];
+    if (fresh) {
+        // replay; then the host-side state transition the captured calls made: sort (index) -> p2g -> g2p (parity flips)
+        GFS_CUDA(cudaGraphLaunch(g.exec, c->stream));
+        c->p2g_arith = arith;
+        c->cur = 1 - c->cur;
+        c->sorted = false; c->indexed = false; c->keys_ready = true;
+        c->launches += g.launches;
+        c->graph_replays++;
+        return;
+    }
+    // scratch buffers are sized lazily by the first steps: capture only once they exist (no allocation inside a capture)
+    if (!scratch[0] || (c->resolve_collisions && (!scratch[1] || !scratch[2]))) { substep_body(c, dt, ratio, order, interp, arith); return; }
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    const int64_t launches0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    GFS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        substep_body(c, dt, ratio, order, interp, arith);
+    } catch (...) {
+        cudaStreamEndCapture(c->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    GFS_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g.exec = nullptr; throw GfsError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    g.epoch = c->graph_epoch; g.n = c->n; g.dt = dt; g.ratio = ratio; g.order = order; g.interp = interp;
+    g.launches = c->launches - launches0;
+    for (int i = 0; i < 3; i++) g.scratch[i] = scratch[i];
+    GFS_CUDA(cudaGraphLaunch(g.exec, c->stream));          // the capture recorded the step, this performs it
     GFS_END()
 }
 
@@ -1099,6 +1169,7 @@ void gfs_set_owned_layers(gfs_context *c, int k0, int k1, int *err) {
     require_domain(c);
     GFS_REQUIRE(k0 >= 0 && k1 > k0 && k1 <= c->grid.K, "bad layer range");
     c->own_k0 = k0; c->own_k1 = k1;
+    c->graph_epoch++;
     GFS_END()
 }
 
@@ -1641,6 +1712,7 @@ namespace {
 // grow the particle buffers to hold n slots, keeping the current contents (particles, tags and their binning)
 void ensure_capacity(gfs_context *c, int64_t n) {
     if ((size_t)n > c->soa[0][0].cap) {
+        c->graph_epoch++;
         // grow both buffer sets, keeping the current contents
         const int b = c->cur;
         int64_t keep = c->n < n ? c->n : n;

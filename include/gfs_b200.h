@@ -80,9 +80,10 @@ typedef struct gfs_stats_t {
     int64_t num_particles;        /* particles currently resident                                   */
     int64_t out_of_grid;          /* particles whose cell lies outside the grid (ignored by P2G)     */
     int64_t in_solid;             /* particles whose cell is solid at classification (src/fluidsimulation.cpp:2015 asserts 0) */
-    int64_t solid_hits;           /* particles whose advected position fell in a solid cell (kept at p0) */
+    int64_t solid_hits;           /* particles whose advected position fell in a solid cell (resolved, or kept at p0 with option 3 = 0) */
     int64_t fluid_cells;          /* cells classified fluid by the last P2G                         */
-    int64_t kernel_launches;      /* CUDA kernels launched by this context since creation           */
+    int64_t kernel_launches;      /* CUDA kernels launched by this context since creation (kernels inside replayed graphs included) */
+    int64_t graph_replays;        /* substeps performed by replaying a captured CUDA graph (gfs_substep, steady state) */
 } gfs_stats_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -174,7 +175,9 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * option 2: 1 = gfs_substep / gfs_sort_index sort by index only once the storage is nearly sorted (default), 0 = always
  * move the particles.  option 3: 1 = particles advected into a solid cell go through the reference's collision resolve
  * (FluidSimulation::_resolveParticleSolidCellCollision, src/fluidsimulation.cpp:3145-3179; default), 0 = they keep
- * their old position (bare solid test).  gfs_stats_t.solid_hits counts them either way. */
+ * their old position (bare solid test).  gfs_stats_t.solid_hits counts them either way.  option 4: 1 = gfs_substep
+ * captures its launch sequence into a CUDA graph (one per buffer parity) and replays it while the particle count, the
+ * step parameters and every buffer stay the same (default), 0 = always launch kernel by kernel; identical results. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid

@@ -725,3 +725,41 @@ def test_reference_save_state_loads_into_the_resident_domain(oracle):
     for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
         assert np.array_equal(bits(got), bits(ref))
     c.close()
+
+
+@pytest.mark.parametrize("name,interp", [("small32", capi.TRILINEAR), ("tiny16", capi.TRICUBIC)])
+def test_substep_graph_replay_is_identical(name, interp):
+    """gfs_substep replays a captured CUDA graph once the step is in steady state (option 4): same grids and the same
+    particle set, bit for bit, as launching kernel by kernel -- across a change of dt (re-capture), a source change
+    (epoch bump) and a particle re-upload."""
+    s = scene(name)
+
+    def run(use_graphs):
+        c = capi.Context(0)
+        load_domain(c, s)
+        c.set_option(4, int(use_graphs))
+        c.set_field(capi.FIELD_NEW, *s["new"]); c.set_field(capi.FIELD_SAVED, *s["saved"])
+        out = []
+        for step in range(14):
+            dt = s["dt"] * (1.0 if step < 8 else 0.5)                          # step 8: new dt -> both parities re-captured
+            if step == 11:
+                c.set_sources([SOURCES[0]])                                    # epoch bump -> re-captured again
+            c.substep(dt, interp=interp, arith=capi.FAST)
+            p, v = c.get_particles() if step in (6, 13) else (None, None)      # get_particles is a plain read: no state change
+            out.append((c.get_material().copy(), [bits(a).copy() for a in c.get_field(capi.FIELD_P2G)], p, v))
+        replays = c.stats()["graph_replays"]
+        c.close()
+        return out, replays
+
+    def rows(p, v):
+        a = np.ascontiguousarray(np.concatenate([p, v], 1))
+        return np.sort(a.view([("f%d" % i, "f4") for i in range(6)]).reshape(-1), order=["f%d" % i for i in range(6)])
+    a, ra = run(True)
+    b, rb = run(False)
+    assert ra >= 6 and rb == 0          # steps 3..7 and step 10 replay; 1, 2, 8, 9, 11, 12 capture
+    for (ma, fa, pa, va), (mb, fb, pb, vb) in zip(a, b):
+        assert np.array_equal(ma, mb)
+        for x, y in zip(fa, fb):
+            assert np.array_equal(x, y)
+        if pa is not None:
+            assert np.array_equal(rows(pa, va), rows(pb, vb))
