@@ -546,6 +546,26 @@ def run_gfs(args):
     oms = allmax(e0.elapsed_time(e1)) / vs
     variants = {other_name: {"value": N / (oms * 1e-3), "ms_per_step": oms,
                              "substep_frac": step_alg_bytes / (oms * 1e-3) / 1e9 / (hbm_gbs * world)}}
+    # The tricubic G2P kernel is bound by shared-memory bandwidth, not HBM: 5 samples x 3 components x 64 taps
+    # x 4 B = 3840 B of shared-memory reads per particle against 128 B/clk/SM.  Two profiled steps give its kernel time.
+    ctx.profile_enable(True)
+    ctx.profile_read(reset=True)
+    for _ in range(2):
+        (substep2 if other == capi.TRICUBIC else substep)()
+    barrier()
+    pc = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    cubic = [v for k, v in pc.items() if "k_g2p_brick<1>" in k]
+    if cubic and cubic[0][1] > 0:
+        k_ms = cubic[0][0] / cubic[0][1]
+        sm_count, clk_ghz = 148, (clocks.summary()["sm_mhz"] or 1965.0) / 1e3
+        smem_tbs = sm_count * 128 * clk_ghz / 1e3
+        smem_bytes = 3840.0 * ctx.num_particles
+        tc = variants["tricubic"] if "tricubic" in variants else variants.setdefault("tricubic_kernel", {})
+        tc["g2p_kernel_ms"] = k_ms
+        tc["smem_bound"] = {"bytes_per_particle": 3840, "peak_tb_s": smem_tbs, "achieved_tb_s": smem_bytes / (k_ms * 1e-3) / 1e12,
+                            "frac": smem_bytes / (k_ms * 1e-3) / 1e12 / smem_tbs,
+                            "note": "k_g2p_brick<1> on rank 0; peak = 148 SMs x 128 B/clk x SM clock; ncu: 87 % of LSU wavefront peak (profiles/r01_k_g2p_brick_tricubic.md)"}
 
     # ---- cpu baseline (bounded sample, rank 0, N = 1 only) ---------------------------------------------
     cpu_baseline = None
