@@ -30,7 +30,7 @@ SYMBOLS = [
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
-    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field",
+    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -124,6 +124,7 @@ def load_library():
     L.gfs_comm_allmax_scale.argtypes = [V, _err]
     L.gfs_sort_index.argtypes = [V, _err]
     L.gfs_extrapolate.argtypes = [V, I, I, _err]
+    L.gfs_extrapolate_field.argtypes = [V, _f32, _f32, _f32, I, I, I, _u8, I, _err]
     L.gfs_copy_field.argtypes = [V, I, I, _err]
     PI, PL = C.POINTER(I), C.POINTER(L64)
     L.gfs_comm_set_plan.argtypes = [V, I, I, PI, PI, PI, PL, I, PI, PI, PI, PL, PI, _err]
@@ -326,6 +327,12 @@ class Context:
 
     def sort_unstable(self):
         self._call(self.lib.gfs_sort_unstable)
+
+    def extrapolate_field(self, u, v, w, dims, material, num_layers):
+        """Host-pointer operator: returns extrapolated copies of u, v, w."""
+        u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
+        self._call(self.lib.gfs_extrapolate_field, u, v, w, *dims, np.ascontiguousarray(material, np.uint8).reshape(-1), int(num_layers))
+        return u, v, w
 
     def extrapolate(self, slot, num_layers):
         self._call(self.lib.gfs_extrapolate, int(slot), int(num_layers))

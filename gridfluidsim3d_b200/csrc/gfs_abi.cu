@@ -180,6 +180,8 @@ struct gfs_context {
 
     // ---- scratch for host-pointer operators
     DevBuf<float> h_pos, h_out, h_val, h_fld, h_wgt, h_field[3];
+    DevBuf<uint8_t> h_mat;
+    DevBuf<int8_t> h_layer;
     DevBuf<unsigned long long> h_acc;
 
     void reserve_particles(int64_t m) {
@@ -677,7 +679,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
-    c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release();
+    c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release(); c->h_mat.release(); c->h_layer.release();
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
     if (c->world_table) cudaFree(c->world_table);
@@ -796,6 +798,37 @@ void gfs_advect(gfs_context *c, const float *pos, int64_t n, const float *u, con
     else if (g.pow2) LAUNCH(c, gfs::k_advect<2>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
     else LAUNCH(c, gfs::k_advect<0>, ceil_div(n, 128), 128, g, f, interp, order, rk, n, c->h_pos.p, c->h_out.p);
     GFS_CUDA(cudaMemcpyAsync(out, c->h_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+/* MACVelocityField::extrapolateVelocityField (src/macvelocityfield.cpp:786-798) on caller-owned host arrays, in place:
+ * the body a maintainer would put into that method (u, v, w = getRawArrayU/V/W(), material = one byte per cell). */
+void gfs_extrapolate_field(gfs_context *c, float *u, float *v, float *w, int I, int J, int K, const uint8_t *material,
+                           int num_layers, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && u && v && w && material, "bad arguments");
+    GFS_REQUIRE(I > 0 && J > 0 && K > 0, "bad grid");
+    GFS_REQUIRE(num_layers >= 0 && num_layers <= 126, "layer count must be 0..126");
+    GFS_CUDA(cudaSetDevice(c->device));
+    Grid g = make_grid(I, J, K, 1.0, 0, K);                 // unpadded rows; dx plays no role in the extrapolation
+    gfs::FieldPtrs fp = upload_field(c, u, v, w, I, J, K);
+    gfs::FieldRW f;
+    for (int a = 0; a < 3; a++) f.c[a] = const_cast<float *>(fp.c[a]);
+    const size_t cells = (size_t)I * J * K;
+    c->h_mat.reserve(cells);
+    c->h_layer.reserve(cells);
+    GFS_CUDA(cudaMemcpyAsync(c->h_mat.p, material, cells, cudaMemcpyHostToDevice, c->stream));
+    const unsigned nodes = (unsigned)ceil_div((long long)(I + 1) * (J + 1), 256), percell = (unsigned)ceil_div((long long)I * J, 256);
+    LAUNCH(c, gfs::k_extrapolate_reset, dim3(nodes, (unsigned)K + 1), 256, g, c->h_mat.p, c->h_layer.p, f);
+    for (int L = 1; L <= num_layers; L++)
+        LAUNCH(c, gfs::k_extrapolate_mark, dim3(percell, (unsigned)K), 256, g, c->h_mat.p, c->h_layer.p, L);
+    for (int L = 1; L <= num_layers; L++)
+        LAUNCH(c, gfs::k_extrapolate_faces, dim3(nodes, (unsigned)K + 1), 256, g, c->h_mat.p, c->h_layer.p, f, L);
+    const size_t cnt[3] = {(size_t)(I + 1) * J * K, (size_t)I * (J + 1) * K, (size_t)I * J * (K + 1)};
+    float *h[3] = {u, v, w};
+    for (int a = 0; a < 3; a++)
+        GFS_CUDA(cudaMemcpyAsync(h[a], f.c[a], cnt[a] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }

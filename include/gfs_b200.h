@@ -124,6 +124,12 @@ void gfs_advect(gfs_context *ctx, const float *pos, int64_t n,
                 const float *u, const float *v, const float *w, int isize, int jsize, int ksize, double dx,
                 double dt, int order, int interp, int arith, float *out, int *err);
 
+/* MACVelocityField::extrapolateVelocityField(materialGrid, numLayers) (src/macvelocityfield.cpp:786-798) on the
+ * caller's own arrays, in place: u, v, w are MACVelocityField::getRawArrayU/V/W() ((I+1)JK, I(J+1)K, IJ(K+1) floats),
+ * material one byte per cell with the codes of src/fluidmaterialgrid.h:29-33.  Bit-identical to the reference. */
+void gfs_extrapolate_field(gfs_context *ctx, float *u, float *v, float *w, int isize, int jsize, int ksize,
+                           const uint8_t *material, int num_layers, int *err);
+
 /* CLScalarField::addPointValues(points, values, radius, offset, dx, scalarfield, weightfield)
  * (src/clscalarfield.cpp:200-267) == ScalarField::addPointValue per point (src/scalarfield.cpp:167-201).
  * field/weight are (ni,nj,nk) float grids; weight may be NULL (the no-weight overload, :147-198).

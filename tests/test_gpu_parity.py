@@ -630,6 +630,9 @@ def test_extrapolate_matches_reference_fixture():
         c.extrapolate(capi.FIELD_SAVED, nl)
         for got, name in zip(c.get_field(capi.FIELD_SAVED), "uvw"):
             assert np.array_equal(bits(got), bits(g["%s_%d" % (name, nl)])), (name, nl)
+        # the host-pointer operator (the body of MACVelocityField::extrapolateVelocityField for a drop-in)
+        for got, name in zip(c.extrapolate_field(g["u"], g["v"], g["w"], dims, g["material"], nl), "uvw"):
+            assert np.array_equal(bits(got), bits(g["%s_%d" % (name, nl)])), (name, nl)
         c.close()
 
 
