@@ -46,7 +46,7 @@ class Source(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("num_particles", "out_of_grid", "in_solid", "solid_hits",
-                                         "fluid_cells", "kernel_launches", "graph_replays")]
+                                         "fluid_cells", "kernel_launches", "graph_replays", "removed_particles")]
 
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")

@@ -145,6 +145,10 @@ struct gfs_context {
     uint64_t graph_epoch = 1;             // bumped by every call that changes what a captured substep baked in
     int use_graphs = 1;                   // option 4
     int64_t graph_replays = 0;
+    int cell_cap = 0;                     // option 5: at most this many particles per cell survive a sort / G2P (0 = no cap)
+    int remove_in_solid = 0;              // option 6: particles found inside solid cells by the binning are removed
+    int64_t removed = 0;                  // particles removed by the two rules since creation
+    unsigned int *removal_host = nullptr; // pinned word: dead-bin count read back after a binning pass
     int resolve_collisions = 1;           // option 3: 1 = the reference's collision resolve, 0 = solid test only (keep p0)
     DevBuf<unsigned long long> counters;  // [0] in_solid, [1] fluid cells, [2] solid hits, [3] spare
     int64_t out_of_grid = 0;
@@ -268,7 +272,20 @@ gfs::FieldPtrs field_ptrs(gfs_context *c, int slot) {
 // cell -- what the exact-arithmetic P2G needs to reproduce the reference's summation order.  stable = false:
 // counting sort (cell histogram with atomic tickets, exclusive scan, scatter); when the previous G2P already
 // binned the advected positions in its epilogue only the scan and the scatter remain.
+// With a removal rule on, a binning pass (k_hist or a G2P epilogue) may have put particles into the dead bin: the host
+// needs their number to keep its slot accounting.  One 4-byte read and a stream synchronisation -- only when a rule is on.
+bool removal_on(const gfs_context *c) { return c->cell_cap > 0 || c->remove_in_solid; }
+
+int64_t read_dead_bin(gfs_context *c) {
+    if (!c->removal_host) GFS_CUDA(cudaHostAlloc((void **)&c->removal_host, 64, cudaHostAllocDefault));
+    GFS_CUDA(cudaMemcpyAsync(c->removal_host, c->counts.p + c->nkeys + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    return (int64_t)*c->removal_host;
+}
+
 void scan_counts(gfs_context *c) {
+    if (c->cell_cap > 0)
+        LAUNCH(c, gfs::k_clamp_counts, ceil_div((long long)c->nkeys, 256), 256, c->nkeys, (uint32_t)c->cell_cap, c->counts.p);
     const size_t nbins = (size_t)c->nkeys + 3;
     size_t tmp_bytes = 0;
     GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
@@ -321,7 +338,8 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
         if (n > 0)
             LAUNCH(c, gfs::k_hist, ceil_div(n, B), B, c->grid, c->nkeys, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
                    c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->rank.p, c->perm[0].p,
-                   c->counts.p, c->vmax_bits.p);
+                   c->counts.p, c->vmax_bits.p, c->remove_in_solid ? c->material.p : (const uint8_t *)nullptr, (uint32_t)c->cell_cap);
+        if (removal_on(c) && n > 0) { c->dead = read_dead_bin(c); c->removed += c->dead; }
     }
     scan_counts(c);
     if (n > 0) {
@@ -352,7 +370,10 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
                    c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
                    c->tag[dst].p);
         }
-        if (!(lazy && !stable)) { c->cur = dst; c->storage_sorted = true; }
+        if (!(lazy && !stable)) {
+            c->cur = dst; c->storage_sorted = true;
+            c->n -= c->dead; c->dead = 0;            // the dead bin is the tail of the physically sorted arrays
+        }
     }
     c->indexed = lazy && !stable && n > 0;
     c->keys_ready = false;
@@ -489,6 +510,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     const bool brick = g2p_uses_bricks(c, arith);
     gfs::CollList coll;
     coll.list = nullptr; coll.count = nullptr; coll.cap = 0;
+    coll.cell_cap = migrate ? 0u : (unsigned int)c->cell_cap;          // (the cap is a single-domain rule so far)
     if (c->resolve_collisions) {
         // colliders are rare (a few per thousand at CFL 0.5 next to walls); a full list falls back to "keep p0"
         // (sized by do_sort at the start of the step: no allocation -- an implicit device synchronisation -- here,
@@ -534,6 +556,10 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     if (!brick)
         GFS_CUDA(cudaMemcpyAsync(c->tag[dst].p, c->tag[src].p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     if (brick && c->indexed) { c->n -= c->dead; c->dead = 0; }      // the kernel walked the index: only live slots were written
+    if (bin_next && c->cell_cap > 0 && !migrate) {                  // particles past the per-cell cap went to the dead bin
+        const int64_t d = read_dead_bin(c);
+        c->dead += d; c->removed += d;
+    }
     c->indexed = false;
     c->cur = dst;
     c->sorted = false;          // positions moved: the cell table no longer describes them
@@ -682,6 +708,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release(); c->h_mat.release(); c->h_layer.release();
     for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
     if (c->comm_host) cudaFreeHost(c->comm_host);
+    if (c->removal_host) cudaFreeHost(c->removal_host);
     if (c->world_table) cudaFree(c->world_table);
     for (int gi = 0; gi < 2; gi++) if (c->graphs[gi].exec) cudaGraphExecDestroy(c->graphs[gi].exec);
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
@@ -726,6 +753,7 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     out->solid_hits = (int64_t)h[2];
     out->kernel_launches = c->launches;
     out->graph_replays = c->graph_replays;
+    out->removed_particles = c->removed;
     GFS_END()
 }
 
@@ -1096,6 +1124,8 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
     else if (option == 3) { GFS_REQUIRE(value == 0 || value == 1, "collision resolve must be 0 or 1"); c->resolve_collisions = value; }
     else if (option == 4) { GFS_REQUIRE(value == 0 || value == 1, "graph replay must be 0 or 1"); c->use_graphs = value; }
+    else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
+    else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else throw GfsError("gfs_set_option: unknown option");
     c->graph_epoch++;
     GFS_END()
@@ -1132,7 +1162,7 @@ void substep_body(gfs_context *c, double dt, double ratio, int order, int interp
 bool substep_graph_eligible(gfs_context *c, int arith) {
     return c->use_graphs && !c->profiling && arith != GFS_EXACT && c->has_domain && c->grid.pow2 && c->have_maps &&
            c->g2p_variant == 1 && c->p2g_variant == 1 && c->lazy_sort && c->storage_sorted && c->keys_ready && !c->sorted &&
-           !c->indexed && c->dead == 0 && c->n > 0 && c->own_k0 == 0 && c->own_k1 == c->grid.K;
+           !c->indexed && c->dead == 0 && c->n > 0 && c->own_k0 == 0 && c->own_k1 == c->grid.K && !removal_on(c);
 }
 }  // namespace
 

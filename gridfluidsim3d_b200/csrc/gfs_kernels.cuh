@@ -107,19 +107,41 @@ __device__ __forceinline__ uint32_t position_key(const Grid &g, uint32_t nkeys, 
     return nkeys;
 }
 
+// Ticket of a particle in its cell; with a per-cell cap (FluidSimulation::_removeMarkerParticles,
+// fluidsimulation.cpp:3221-3243: at most _maxMarkerParticlesPerCell particles survive per cell, WHICH ones is decided
+// by the reference's rand() shuffle and here by the ticket order -- equally arbitrary) a particle whose ticket is past
+// the cap is re-binned into the dead bin nkeys + 1.  The cell counter is left over-incremented; k_clamp_counts trims
+// it before the scan.
+__device__ __forceinline__ uint32_t take_ticket(uint32_t *__restrict__ counts, uint32_t nkeys, uint32_t cap, uint32_t &key) {
+    uint32_t t = atomicAdd(counts + key, 1u);
+    if (cap && key < nkeys && t >= cap) { key = nkeys + 1; t = atomicAdd(counts + key, 1u); }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_clamp_counts(uint32_t nkeys, uint32_t cap, uint32_t *__restrict__ counts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nkeys && counts[t] > cap) counts[t] = cap;
+}
+
 // K0a.  One thread per particle: key, rank inside its cell (atomic ticket on the cell counter -- the count
 // is deterministic, the ticket order is not and does not need to be: the fast P2G is order-independent),
-// identity permutation for the stable path, and max |velocity|.
+// identity permutation for the stable path, and max |velocity|.  solid != null: a particle inside a solid cell goes to
+// the dead bin (FluidSimulation::_removeMarkerParticlesInSolidCells, fluidsimulation.cpp:1933-1957).
 __global__ void __launch_bounds__(256) k_hist(Grid g, uint32_t nkeys, const float *__restrict__ x, const float *__restrict__ y,
                        const float *__restrict__ z, const float *__restrict__ vx, const float *__restrict__ vy,
                        const float *__restrict__ vz, int64_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ rank,
-                       int32_t *__restrict__ perm, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits) {
+                       int32_t *__restrict__ perm, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
+                       const uint8_t *__restrict__ solid, uint32_t cap) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (r < n) {
         uint32_t key = position_key(g, nkeys, x[r], y[r], z[r]);
+        if (solid && key < nkeys) {
+            const int i = cell_floor((double)x[r], g.invdx), j = cell_floor((double)y[r], g.invdx), k = cell_floor((double)z[r], g.invdx);
+            if (solid[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)(k - g.k0))] == GFS_SOLID) key = nkeys + 1;
+        }
+        rank[r] = take_ticket(counts, nkeys, cap, key);
         keys[r] = key;
-        rank[r] = atomicAdd(counts + key, 1u);
         perm[r] = (int32_t)r;
         m = fmaxf(fabsf(vx[r]), fmaxf(fabsf(vy[r]), fabsf(vz[r])));
         if (!(m < 3.0e38f)) m = 0.0f;          // NaN/Inf velocities do not steer the scale
@@ -733,6 +755,7 @@ struct CollList {
     float4 *list;                  // {slot as int bits, p1.x, p1.y, p1.z}; null = keep p0 (solid test only)
     unsigned int *count;
     unsigned int cap;
+    unsigned int cell_cap;         // per-cell particle cap applied while binning (0 = none), see take_ticket
 };
 
 __device__ __forceinline__ bool cell_solid_or_outside(const Grid &g, const uint8_t *__restrict__ m, int i, int j, int k) {
@@ -859,8 +882,8 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
         if (keys_out) {          // bin for the next substep's counting sort while the position is in registers
             if (!deferred) {
                 uint32_t key = position_key(g, nkeys, qx, qy, qz);
+                rank_out[r] = take_ticket(counts, nkeys, coll.cell_cap, key);
                 keys_out[r] = key;
-                rank_out[r] = atomicAdd(counts + key, 1u);
             }
             m = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (!(m < 3.0e38f)) m = 0.0f;
@@ -1073,8 +1096,8 @@ __global__ void __launch_bounds__(128) k_resolve_collisions(Grid g, const uint8_
                     key = nkeys + 1;
                 }
             }
+            rank_out[r] = take_ticket(counts, nkeys, coll.cell_cap, key);
             keys_out[r] = key;
-            rank_out[r] = atomicAdd(counts + key, 1u);
         }
     }
 }
@@ -1246,8 +1269,8 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : GFS_TRI
                     }
                 }
             }
+            pend_rank = take_ticket(counts, nkeys, coll.cell_cap, key);
             keys_out[r] = key;
-            pend_rank = atomicAdd(counts + key, 1u);
             pend_r = r;
             float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (mm < 3.0e38f) m = fmaxf(m, mm);

@@ -84,6 +84,7 @@ typedef struct gfs_stats_t {
     int64_t fluid_cells;          /* cells classified fluid by the last P2G                         */
     int64_t kernel_launches;      /* CUDA kernels launched by this context since creation (kernels inside replayed graphs included) */
     int64_t graph_replays;        /* substeps performed by replaying a captured CUDA graph (gfs_substep, steady state) */
+    int64_t removed_particles;    /* particles removed by options 5 and 6 since creation                */
 } gfs_stats_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -183,7 +184,13 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * (FluidSimulation::_resolveParticleSolidCellCollision, src/fluidsimulation.cpp:3145-3179; default), 0 = they keep
  * their old position (bare solid test).  gfs_stats_t.solid_hits counts them either way.  option 4: 1 = gfs_substep
  * captures its launch sequence into a CUDA graph (one per buffer parity) and replays it while the particle count, the
- * step parameters and every buffer stay the same (default), 0 = always launch kernel by kernel; identical results. */
+ * step parameters and every buffer stay the same (default), 0 = always launch kernel by kernel; identical results.
+ * option 5: per-cell particle cap, FluidSimulation::_removeMarkerParticles (src/fluidsimulation.cpp:3221-3243; the
+ * reference uses 100): every binning pass keeps at most `value` particles per cell and removes the rest -- which ones
+ * is arbitrary, as with the reference's rand() shuffle; 0 = no cap (default).  option 6: 1 = a particle found inside a
+ * solid cell by a sort is removed (FluidSimulation::_removeMarkerParticlesInSolidCells, :1933-1957), 0 = it is kept and
+ * counted in gfs_stats_t.in_solid (default).  Both cost one 4-byte read-back per binning pass and apply to the
+ * single-domain entry points (gfs_sort*, gfs_substep, gfs_g2p_advect); gfs_stats_t.removed_particles counts. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid

@@ -723,7 +723,8 @@ def test_reference_save_state_loads_into_the_resident_domain(oracle):
     c.set_particles(st["pos"], vel)
     c.sort(); c.p2g(capi.EXACT)
     mat = mat0.copy()
-    want = oracle.p2g(st["pos"][c.get_particle_order()], vel[c.get_particle_order()], st["dims"], st["dx"], mat, [])
+    lin = linear_cell_order(oracle, st["pos"], st["dims"], st["dx"])
+    want = oracle.p2g(st["pos"][lin], vel[lin], st["dims"], st["dx"], mat, [])
     assert np.array_equal(c.get_material(), mat) and (mat == synth.FLUID).sum() > 0
     for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
         assert np.array_equal(bits(got), bits(ref))
@@ -809,3 +810,98 @@ def test_dambreak128_size_independent_properties(oracle):
     assert np.array_equal(bits(p), bits(s["pos"][o]))
     assert np.array_equal(bits(v), bits((s["vel"][o] * np.float32(1.0 - np.float32(0.05))).astype(np.float32)))
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rank 3, the removal rules: per-cell cap and particles inside solid cells
+# ---------------------------------------------------------------------------------------------------
+def _rows6(p, v):
+    a = np.ascontiguousarray(np.concatenate([p, v], 1))
+    return a.view([("f%d" % i, "f4") for i in range(6)]).reshape(-1)
+
+
+@pytest.mark.parametrize("name", ["tiny16", "small32", "odd20"])
+def test_per_cell_cap(oracle, name):
+    """Option 5 = FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:3221-3243) without its rand(): after every
+    binning pass no cell holds more than the cap, exactly sum(max(0, count - cap)) particles are gone, the survivors are
+    original particles, and the sorted structure stays consistent (exact P2G of the survivors == oracle, bit for bit)."""
+    s = scene(name)
+    cap = 3
+    I, J, K = s["dims"]
+
+    def per_cell(p):
+        c = oracle.cell_index(p, s["dx"])
+        return np.unique(c[:, 0].astype(np.int64) + I * (c[:, 1] + J * c[:, 2].astype(np.int64)), return_counts=True)[1]
+    before = per_cell(s["pos"])
+    assert before.max() > cap
+    c = capi.Context(0)
+    load_domain(c, s)
+    c.set_option(5, cap)
+    c.sort()
+    p, v = c.get_particles()
+    assert len(p) == int(np.minimum(before, cap).sum()) == c.num_particles
+    assert c.stats()["removed_particles"] == len(s["pos"]) - len(p)
+    assert per_cell(p).max() == cap
+    assert np.isin(_rows6(p, v), _rows6(s["pos"], s["vel"])).all()
+    c.p2g(capi.EXACT)
+    mat = s["material"].copy()
+    lin = linear_cell_order(oracle, p, s["dims"], s["dx"])       # the exact gather sums in ascending (k,j,i) cell order
+    want = oracle.p2g(p[lin], v[lin], s["dims"], s["dx"], mat, [])
+    assert np.array_equal(c.get_material(), mat)
+    for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
+        assert np.array_equal(bits(got), bits(ref))
+    c.close()
+
+    # through the fused fast substep: a converging field piles particles up, the cap trims every step
+    c = capi.Context(0)
+    load_domain(c, s)
+    c.set_option(5, cap + 2)
+    ext = np.array(s["dims"]) * s["dx"]
+    sink = []
+    for comp, (ni, nj, nk) in enumerate(synth.face_dims(s["dims"])):
+        idx = np.arange([ni, nj, nk][comp], dtype=np.float32) * np.float32(s["dx"]) - np.float32(0.5 * ext[comp])
+        shape = [1, 1, 1]; shape[2 - comp] = -1
+        sink.append(np.broadcast_to((-0.8 * idx).reshape(shape), (nk, nj, ni)).astype(np.float32).reshape(-1).copy())
+    c.set_field(capi.FIELD_NEW, *sink); c.set_field(capi.FIELD_SAVED, *sink)
+    n_prev, removed_prev = len(s["pos"]), 0
+    for step in range(4):
+        c.substep(2.0 * s["dt"], interp=capi.TRILINEAR, arith=capi.FAST)
+        p, _ = c.get_particles()
+        st = c.stats()
+        assert per_cell(p).max() <= cap + 2
+        assert len(p) == c.num_particles == n_prev - (st["removed_particles"] - removed_prev)
+        n_prev, removed_prev = len(p), st["removed_particles"]
+    assert removed_prev > 0 and c.stats()["graph_replays"] == 0
+    c.close()
+
+
+def test_particles_in_solid_cells_are_removed(oracle):
+    """Option 6 = FluidSimulation::_removeMarkerParticlesInSolidCells (fluidsimulation.cpp:1933-1957): solids added after
+    the particles were seeded swallow the particles inside them at the next sort."""
+    s = scene("slab24")
+    I, J, K = s["dims"]
+    mat = s["material"].copy().reshape(K, J, I)
+    mat[6:12, 3:9, 2:8] = synth.SOLID                       # a block dropped into the fluid
+    mat = mat.reshape(-1)
+    cells = oracle.cell_index(s["pos"], s["dx"])
+    inside = mat[cells[:, 0] + I * (cells[:, 1] + J * cells[:, 2])] == synth.SOLID
+    assert 50 < inside.sum() < len(inside)
+    for option, kept in ((0, len(inside)), (1, int((~inside).sum()))):
+        c = capi.Context(0)
+        c.domain_init(s["dims"], s["dx"]); c.set_material(mat); c.set_sources([])
+        c.set_option(6, option)
+        c.set_particles(s["pos"], s["vel"])
+        c.sort(); c.p2g(capi.EXACT)
+        st = c.stats()
+        assert st["num_particles"] == kept and st["removed_particles"] == len(inside) - kept
+        assert st["in_solid"] == (0 if option else int(inside.sum()))
+        if option:
+            p, v = c.get_particles()
+            assert np.array_equal(np.sort(_rows6(p, v)), np.sort(_rows6(s["pos"][~inside], s["vel"][~inside])))
+            m2 = mat.copy()
+            lin = linear_cell_order(oracle, p, s["dims"], s["dx"])
+            want = oracle.p2g(p[lin], v[lin], s["dims"], s["dx"], m2, [])
+            assert np.array_equal(c.get_material(), m2)
+            for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
+                assert np.array_equal(bits(got), bits(ref))
+        c.close()
