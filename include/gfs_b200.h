@@ -196,10 +196,12 @@ void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
  * assembly (:2526-2730).  Result in slot GFS_FIELD_P2G; material updated.  Requires gfs_sort. */
 void gfs_p2g(gfs_context *ctx, int arith, int *err);
-/* K2: stage 11 + stage 12 (src/fluidsimulation.cpp:3104-3129, :3181-3209; no shuffle/cap): PIC/FLIP
- * velocity update from slots NEW and SAVED, RK advance through NEW, solid test. */
+/* K2: stage 11 + stage 12 (src/fluidsimulation.cpp:3104-3129, :3181-3209): PIC/FLIP velocity update from slots NEW
+ * and SAVED, RK advance through NEW, solid test + collision resolve (:3145-3179, option 3).  The reference's shuffle
+ * is not reproduced; its per-cell cap is option 5. */
 void gfs_g2p_advect(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
-/* gfs_sort + gfs_p2g + gfs_g2p_advect, stream-ordered, no host synchronisation. */
+/* gfs_sort + gfs_p2g + gfs_g2p_advect, stream-ordered, no host synchronisation (fast arithmetic: index-only counting sort
+ * binned by the previous call's G2P epilogue; the steady-state launch sequence is replayed from a CUDA graph, option 4). */
 void gfs_substep(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
 
 /* ---- z-slab sharding across GPUs (one context per GPU; the exchange itself is the caller's: NCCL) ----------
