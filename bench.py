@@ -52,58 +52,11 @@ def measured_peaks():
 # synthetic workload on the device (same construction as gridfluidsim3d_b200/synth.py, generated with torch so
 # that the 100 M-particle scene takes seconds, not minutes)
 # ---------------------------------------------------------------------------------------------------------
-def vortex_t(x, y, z, ext):
-    import torch
-    pi = float(np.pi)
-    xh, yh, zh = x / ext[0], y / ext[1], z / ext[2]
-    u = -torch.sin(pi * xh) ** 2 * torch.sin(2 * pi * yh) * torch.cos(pi * zh)
-    v = torch.sin(2 * pi * xh) * torch.sin(pi * yh) ** 2 * torch.cos(pi * zh)
-    w = 0.5 * torch.sin(2 * pi * xh) * torch.sin(2 * pi * zh) * torch.sin(pi * yh)
-    return u, v, w
-
-
 def make_scene_device(name, device, seed=12345, k_range=None):
-    """Particles (AoS float32 [N,6]), new/saved fields and material of workload `name` as torch tensors on
-    `device`.  k_range=(k0,k1) keeps only particles whose cell layer is in [k0,k1) (slab ownership)."""
-    import torch
+    """Counter-based scene (gridfluidsim3d_b200/synth.py:make_scene_torch): the particle SET depends on (name, seed)
+    only -- every rank of a sharded run generates its own layers of the very scene the single-GPU run uses."""
     from gridfluidsim3d_b200 import synth
-    dims, dx, shape = synth.CONFIGS[name]
-    I, J, K = dims
-    material = synth.border_material(dims)
-    mask = torch.from_numpy(synth.fluid_cells(shape, dims, material)).to(device)
-    if k_range is not None:
-        keep = torch.zeros(K, dtype=torch.bool, device=device)
-        keep[k_range[0]:k_range[1]] = True
-        mask &= keep[:, None, None]
-    kk, jj, ii = torch.nonzero(mask, as_tuple=True)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    centre = (torch.stack([ii, jj, kk], 1).to(torch.float32) + 0.5) * dx
-    q = 0.25 * dx
-    sub = torch.tensor([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1],
-                        [-1, 1, -1], [1, 1, -1], [1, 1, 1], [-1, 1, 1]], dtype=torch.float32, device=device) * q
-    pos = (centre[:, None, :] + sub[None, :, :]).reshape(-1, 3)
-    del centre
-    jit = 0.25 * 0.1 * dx
-    pos += (torch.rand(pos.shape, generator=gen, device=device, dtype=torch.float32) * 2 - 1) * jit
-    perm = torch.randperm(pos.shape[0], generator=gen, device=device)      # the reference shuffles every step
-    pos = pos[perm].contiguous()
-    del perm
-    ext = (I * dx, J * dx, K * dx)
-    u, v, w = vortex_t(pos[:, 0], pos[:, 1], pos[:, 2], ext)
-    aos = torch.cat([pos, torch.stack([u, v, w], 1)], 1).contiguous()
-    del pos, u, v, w
-    new = []
-    for comp, (ni, nj, nk) in enumerate(synth.face_dims(dims)):
-        i = torch.arange(ni, device=device, dtype=torch.float32)[None, None, :]
-        j = torch.arange(nj, device=device, dtype=torch.float32)[None, :, None]
-        k = torch.arange(nk, device=device, dtype=torch.float32)[:, None, None]
-        x = (i + (0.0 if comp == 0 else 0.5)) * dx
-        y = (j + (0.0 if comp == 1 else 0.5)) * dx
-        z = (k + (0.0 if comp == 2 else 0.5)) * dx
-        new.append(vortex_t(x, y, z, ext)[comp].expand(nk, nj, ni).contiguous().reshape(-1))
-    saved = [a * 0.9 for a in new]
-    return dict(name=name, dims=dims, dx=dx, dt=synth.cfl_dt(dx), material=material, aos=aos, new=new, saved=saved)
+    return synth.make_scene_torch(name, device, seed=seed, k_range=k_range)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -378,7 +331,7 @@ def run_gfs(args):
         torch.cuda.synchronize()
 
     t_gen = time.time()
-    sc = make_scene_device(args.workload, dev, seed=12345 + rank, k_range=owned if world > 1 else None)
+    sc = make_scene_device(args.workload, dev, seed=12345, k_range=owned if world > 1 else None)
     torch.cuda.synchronize()
     n_local = sc["aos"].shape[0]
     N = allsum(n_local)
@@ -461,6 +414,20 @@ def run_gfs(args):
     prof_ms = p0.elapsed_time(p1)
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
+    # ---- verification (outside every timed region): order- and distribution-independent hashes of the state after
+    # warmup + 2 x steps substeps.  The sharded result is designed to be bit-identical to the single-GPU one, so these
+    # five numbers must be the same at every GPU count for the same --steps / --warmup.
+    local_hash = ctx.state_hash()
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local_hash)
+    else:
+        gathered = [local_hash]
+    hashes = [sum(h[i] for h in gathered) & ((1 << 64) - 1) for i in range(5)]
+    verify = {"after_substeps": args.warmup + 2 * args.steps, "seed": 12345,
+              "hash_material": "%016x" % hashes[0], "hash_p2g_u": "%016x" % hashes[1], "hash_p2g_v": "%016x" % hashes[2],
+              "hash_p2g_w": "%016x" % hashes[3], "hash_particles": "%016x" % hashes[4],
+              "note": "gfs_state_hash summed over ranks mod 2^64; identical for every --gpus N by construction of the path"}
     st = ctx.stats()
     launches = launches_timed
     n_now = allsum(ctx.num_particles)
@@ -591,7 +558,7 @@ def run_gfs(args):
                          % (N * 24 / 1e9, 8 * (nu + nv + nw) / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks.summary(), "kernels": kernels, "variants": variants,
-        "stats": {k: int(v) for k, v in st.items()},
+        "stats": {k: int(v) for k, v in st.items()}, "verify": verify,
         "launch": {"graph_replays_in_timed_region": int(graph_replays), "kernels_per_step": launches_timed / args.steps,
                    "note": "gfs_substep replays a captured CUDA graph in steady state (single GPU); gpu_launches counts the kernels inside"},
     }
@@ -634,6 +601,16 @@ def run_gfs(args):
                              else "torch.distributed batch_isend_irecv (NCCL)", "comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
                              "particles_mean": n_now / world, "particles_after": n_now}
     ctx.close()
+    if world > 1 and not args.no_peer_check:
+        # the CUDA-IPC peer transport against the torch.distributed (NCCL) one on a small sharded scene, across these very
+        # processes: owned P2G layers, material and particle rows bit for bit after every substep (tests/peer_check.py)
+        try:
+            from tests import peer_check
+            torch.cuda.set_stream(torch.cuda.default_stream(dev))
+            ok, n_chk = peer_check.check(rank, world, local, dev, "small32" if world <= 4 else "tall64")
+            line["verify"]["peer_vs_nccl"] = {"ok": bool(ok), "scene_particles": n_chk, "ranks": world}
+        except Exception as e:          # never lose the measurement to the check
+            line["verify"]["peer_vs_nccl"] = {"ok": False, "error": repr(e)[:300]}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -670,6 +647,7 @@ def main():
                     help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-check", action="store_true", help="N>1: skip the peer-memory vs NCCL transport cross-check after the timed runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gfs" else args.warmup
     if args.impl == "reference":

@@ -21,7 +21,7 @@ AIR, FLUID, SOLID = 0, 1, 2
 SYMBOLS = [
     "gfs_get_error_message", "gfs_create", "gfs_destroy", "gfs_device_info", "gfs_sync", "gfs_get_stats",
     "gfs_profile_enable", "gfs_profile_read",
-    "gfs_sample", "gfs_advect", "gfs_add_point_values",
+    "gfs_sample", "gfs_advect", "gfs_add_point_values", "gfs_add_points",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
@@ -31,7 +31,7 @@ SYMBOLS = [
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
     "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
-    "gfs_device_ptr", "gfs_resize_particles", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
+    "gfs_device_ptr", "gfs_resize_particles", "gfs_state_hash", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
 
@@ -46,7 +46,8 @@ class Source(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("num_particles", "out_of_grid", "in_solid", "solid_hits",
-                                         "fluid_cells", "kernel_launches", "graph_replays", "removed_particles")]
+                                         "fluid_cells", "kernel_launches", "graph_replays", "removed_particles",
+                                         "collision_overflow")]
 
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -79,6 +80,8 @@ def load_library():
     L.gfs_sample.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, I, I, I, _f32, _err]
     L.gfs_advect.argtypes = [V, _f32, L64, _f32, _f32, _f32, I, I, I, D, D, I, I, I, _f32, _err]
     L.gfs_add_point_values.argtypes = [V, _f32, _f32, L64, D, _f32, D, I, I, I, _f32, V, I, I, _err]
+    L.gfs_add_points.argtypes = [V, _f32, L64, D, _f32, D, I, I, I, _f32, I, I, C.c_float, I, _err]
+    L.gfs_state_hash.argtypes = [V, C.POINTER(C.c_uint64), _err]
     L.gfs_domain_init.argtypes = [V, I, I, I, D, _err]
     L.gfs_set_material.argtypes = [V, _u8, _err]
     L.gfs_get_material.argtypes = [V, _u8, _err]
@@ -261,6 +264,20 @@ class Context:
         self._call(self.lib.gfs_add_point_values, pos, values, len(pos), radius, _c(offset), dx, *ndims,
                    field, wptr, int(accumulate), arith)
         return field, weight
+
+    def add_points(self, pos, radius, offset, dx, ndims, field=None, accumulate=True, threshold=None, arith=FAST):
+        """CLScalarField::addPoints; threshold = the mesher's max-scalar-field-value threshold (None: not set)."""
+        pos = _c(pos)
+        field = np.zeros(ndims[0] * ndims[1] * ndims[2], np.float32) if field is None else field
+        self._call(self.lib.gfs_add_points, pos, len(pos), radius, _c(offset), dx, *ndims, field, int(accumulate),
+                   int(threshold is not None), float(threshold or 0.0), arith)
+        return field
+
+    def state_hash(self):
+        """-> [material, p2g_u, p2g_v, p2g_w, particles] order/distribution-independent 64-bit hashes (ints)."""
+        out = (C.c_uint64 * 5)()
+        self._call(self.lib.gfs_state_hash, out)
+        return [int(v) for v in out]
 
     # ---- device-resident domain ---------------------------------------------------------------------
     def domain_init(self, dims, dx):

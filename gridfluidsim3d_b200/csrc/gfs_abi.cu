@@ -158,6 +158,7 @@ struct gfs_context {
         unsigned char *block = nullptr;       // my block: [flags 256 B][layers buf 0][layers buf 1][arrivals 0][arrivals 1]
         unsigned char *peer = nullptr;        // the neighbour's block for the opposite side, IPC-mapped
         unsigned int seq_layers = 0, seq_particles = 0;
+        bool peer_ipc = false;                // `peer` came from cudaIpcOpenMemHandle (closed by gfs_destroy)
     } comm[2];
     size_t comm_layer_bytes = 0;          // capacity of one layers buffer
     int64_t comm_particle_cap = 0;        // capacity (particles) of one arrivals buffer
@@ -171,8 +172,11 @@ struct gfs_context {
     int comm_rank = -1, comm_world = 0;   // all-ranks table (k_allmax)
     unsigned long long *world_table = nullptr;        // mine: [2 parities][16 ranks]
     unsigned long long *world_peer[16] = {};          // everyone's, IPC-mapped (mine included)
+    bool world_peer_ipc[16] = {};
     unsigned int seq_world = 0;
     DevBuf<unsigned int> comm_error;
+    long long comm_timeout_cycles = 8000000000ll;     // option 7: device-side wait limit (SM clocks; ~4 s)
+    int64_t coll_cap_user = 0;                          // option 8: collision list capacity in particles (0 = n/16 + 4096)
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
@@ -326,7 +330,8 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     if (c->dead > 0 && !(lazy && !stable && c->keys_ready)) { drop_dead(c); c->sorted = false; }
     const int64_t n = c->n;
     if (c->resolve_collisions) {
-        if ((size_t)(n / 16 + 4096) > c->coll_list.cap) c->coll_list.reserve((size_t)(n / 16 + 4096) + (size_t)n / 64);
+        const size_t want = c->coll_cap_user > 0 ? (size_t)c->coll_cap_user : (size_t)(n / 16 + 4096);
+        if (want > c->coll_list.cap) c->coll_list.reserve(c->coll_cap_user > 0 ? want : want + (size_t)n / 64);
         c->coll_count.reserve(1);
     }
     const int src = c->cur, dst = 1 - c->cur;
@@ -391,7 +396,6 @@ void do_p2g_begin(gfs_context *c, int arith) {
     require_domain(c);
     GFS_REQUIRE(c->sorted, "gfs_p2g needs gfs_sort first");
     const Grid &g = c->grid;
-    const int kl = g.k1 - g.k0;
     const int b = c->cur;
     gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
     int lo, hi;
@@ -515,7 +519,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
         // colliders are rare (a few per thousand at CFL 0.5 next to walls); a full list falls back to "keep p0"
         // (sized by do_sort at the start of the step: no allocation -- an implicit device synchronisation -- here,
         // between the device-side waits of a sharded substep)
-        if (c->coll_list.cap == 0) c->coll_list.reserve((size_t)(c->n / 16 + 4096));
+        if (c->coll_list.cap == 0) c->coll_list.reserve(c->coll_cap_user > 0 ? (size_t)c->coll_cap_user : (size_t)(c->n / 16 + 4096));
         const size_t cap = c->coll_list.cap;
         c->coll_count.reserve(1);
         GFS_CUDA(cudaMemsetAsync(c->coll_count.p, 0, sizeof(unsigned int), c->stream));
@@ -633,7 +637,7 @@ void make_field_map(CUtensorMap *map, float *storage, int pitch, int nj, int nkl
 void make_brick_maps(gfs_context *c) {
     const Grid &g = c->grid;
     const int kl = g.k1 - g.k0;
-    const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
+    const int nj[3] = {g.J, g.J + 1, g.J}, nk[3] = {kl, kl, kl + 1};
     for (int a = 0; a < 3; a++) {
         if (gfs::BrickTile<0>::kSkew) {
             make_field_map(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
@@ -677,7 +681,7 @@ gfs_context *gfs_create(int device, void *stream, int *err) {
     GFS_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     GFS_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    if (!(prop.major == 10 && prop.minor == 0)) {      // the library carries sm_100a SASS only (no PTX): sm_103 / sm_120 parts cannot run it
         char b[256];
         snprintf(b, sizeof(b), "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; kernels are built for sm_100a only",
                  device, prop.name, prop.major, prop.minor);
@@ -706,7 +710,13 @@ void gfs_destroy(gfs_context *c, int *err) {
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
     c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release(); c->h_mat.release(); c->h_layer.release();
-    for (int sd = 0; sd < 2; sd++) if (c->comm[sd].block) cudaFree(c->comm[sd].block);
+    for (int sd = 0; sd < 2; sd++) {
+        if (c->comm[sd].peer && c->comm[sd].peer_ipc) cudaIpcCloseMemHandle(c->comm[sd].peer);
+        if (c->comm[sd].block) cudaFree(c->comm[sd].block);
+    }
+    for (int r = 0; r < 16; r++) if (c->world_peer[r] && c->world_peer_ipc[r]) cudaIpcCloseMemHandle(c->world_peer[r]);
+    for (size_t i = 0; i < c->prof_spans.size(); i++) { cudaEventDestroy(c->prof_spans[i].a); cudaEventDestroy(c->prof_spans[i].b); }
+    for (size_t i = 0; i < c->prof_pool.size(); i++) cudaEventDestroy(c->prof_pool[i]);
     if (c->comm_host) cudaFreeHost(c->comm_host);
     if (c->removal_host) cudaFreeHost(c->removal_host);
     if (c->world_table) cudaFree(c->world_table);
@@ -754,6 +764,7 @@ void gfs_get_stats(gfs_context *c, gfs_stats_t *out, int *err) {
     out->kernel_launches = c->launches;
     out->graph_replays = c->graph_replays;
     out->removed_particles = c->removed;
+    out->collision_overflow = (int64_t)h[3];
     GFS_END()
 }
 
@@ -861,11 +872,11 @@ void gfs_extrapolate_field(gfs_context *c, float *u, float *v, float *w, int I, 
     GFS_END()
 }
 
-void gfs_add_point_values(gfs_context *c, const float *pos, const float *values, int64_t n, double radius,
-                          const float *offset3, double dx, int ni, int nj, int nk, float *field, float *weight,
-                          int accumulate, int arith, int *err) {
-    GFS_BEGIN
-    GFS_REQUIRE(c && field && offset3 && (n == 0 || (pos && values)), "bad arguments");
+namespace {
+void splat_points_host(gfs_context *c, const float *pos, const float *values, int64_t n, double radius,
+                       const float *offset3, double dx, int ni, int nj, int nk, float *field, float *weight,
+                       int accumulate, int arith, int use_threshold, float threshold) {
+    GFS_REQUIRE(c && field && offset3 && (n == 0 || pos), "bad arguments");
     GFS_REQUIRE(ni > 0 && nj > 0 && nk > 0 && dx > 0 && radius > 0, "bad grid");
     GFS_CUDA(cudaSetDevice(c->device));
     const size_t count = (size_t)ni * nj * nk;
@@ -873,8 +884,8 @@ void gfs_add_point_values(gfs_context *c, const float *pos, const float *values,
     c->h_fld.reserve(count); c->h_wgt.reserve(count);
     GFS_CUDA(cudaMemsetAsync(c->h_acc.p, 0, 2 * count * sizeof(unsigned long long), c->stream));
     // numerator scale from the largest |value| (order-independent, so the result stays order-independent)
-    float vmax = 0.0f;
-    for (int64_t i = 0; i < n; i++) { float a = std::fabs(values[i]); if (a < 3.0e38f && a > vmax) vmax = a; }
+    float vmax = values ? 0.0f : 1.0f;                    // values == NULL: every point carries 1 (ScalarField::addPoint)
+    if (values) for (int64_t i = 0; i < n; i++) { float a = std::fabs(values[i]); if (a < 3.0e38f && a > vmax) vmax = a; }
     int vexp = 0;
     if (vmax > 0.0f) { int e; std::frexp(vmax, &e); vexp = e; }      // vmax < 2^e
     vexp = vexp < -24 ? -24 : (vexp > 40 ? 40 : vexp);
@@ -882,23 +893,47 @@ void gfs_add_point_values(gfs_context *c, const float *pos, const float *values,
     if (n > 0) {
         c->h_pos.reserve((size_t)n * 3); c->h_val.reserve((size_t)n);
         GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
-        GFS_CUDA(cudaMemcpyAsync(c->h_val.p, values, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (values) GFS_CUDA(cudaMemcpyAsync(c->h_val.p, values, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         if (arith == GFS_EXACT)
             LAUNCH(c, gfs::k_splat_points<1>, ceil_div(n, 128), 128, sp, vexp, dx, offset3[0], offset3[1], offset3[2], ni, nj, nk, n,
-                   c->h_pos.p, c->h_val.p, c->h_acc.p);
+                   c->h_pos.p, values ? c->h_val.p : nullptr, c->h_acc.p);
         else
             LAUNCH(c, gfs::k_splat_points<0>, ceil_div(n, 128), 128, sp, vexp, dx, offset3[0], offset3[1], offset3[2], ni, nj, nk, n,
-                   c->h_pos.p, c->h_val.p, c->h_acc.p);
+                   c->h_pos.p, values ? c->h_val.p : nullptr, c->h_acc.p);
     }
     if (accumulate) {
         GFS_CUDA(cudaMemcpyAsync(c->h_fld.p, field, count * 4, cudaMemcpyHostToDevice, c->stream));
         if (weight) GFS_CUDA(cudaMemcpyAsync(c->h_wgt.p, weight, count * 4, cudaMemcpyHostToDevice, c->stream));
     }
     LAUNCH(c, gfs::k_splat_points_store, ceil_div((int64_t)count, 256), 256, (int64_t)count, vexp, c->h_acc.p, c->h_fld.p,
-           weight ? c->h_wgt.p : nullptr, accumulate);
+           weight ? c->h_wgt.p : nullptr, accumulate, use_threshold, threshold);
     GFS_CUDA(cudaMemcpyAsync(field, c->h_fld.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
     if (weight) GFS_CUDA(cudaMemcpyAsync(weight, c->h_wgt.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
+}
+}  // namespace
+
+void gfs_add_point_values(gfs_context *c, const float *pos, const float *values, int64_t n, double radius,
+                          const float *offset3, double dx, int ni, int nj, int nk, float *field, float *weight,
+                          int accumulate, int arith, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(n == 0 || values, "null values");
+    splat_points_host(c, pos, values, n, radius, offset3, dx, ni, nj, nk, field, weight, accumulate, arith, 0, 0.0f);
+    GFS_END()
+}
+
+/* CLScalarField::addPoints (src/clscalarfield.cpp:62-145): every point carries the value 1.  use_threshold: the caller
+ * set a max-scalar-field-value threshold (IsotropicParticleMesher, src/isotropicparticlemesher.cpp:334-359).  The
+ * reference honours it three different ways -- ScalarField::addPoint skips a node whose RUNNING value exceeds it
+ * (src/scalarfield.cpp:182-184, order dependent), the OpenCL path skips whole 8^3 chunks whose minimum already does
+ * (src/clscalarfield.cpp:1002-1010), and the class's own CPU path ignores it (:1490-1505) -- all of which leave the
+ * iso-surface level (0.5 < threshold 1.0) where it is.  Here: a node whose value BEFORE this batch already exceeds the
+ * threshold receives nothing from the batch (the per-node form of the chunk rule; order independent). */
+void gfs_add_points(gfs_context *c, const float *pos, int64_t n, double radius, const float *offset3, double dx,
+                    int ni, int nj, int nk, float *field, int accumulate, int use_threshold, float threshold, int arith, int *err) {
+    GFS_BEGIN
+    splat_points_host(c, pos, nullptr, n, radius, offset3, dx, ni, nj, nk, field, nullptr, accumulate, arith,
+                      (use_threshold && accumulate) ? 1 : 0, threshold);
     GFS_END()
 }
 
@@ -909,6 +944,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     GFS_REQUIRE(c, "null context");
     GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
     GFS_CUDA(cudaSetDevice(c->device));
+    if (c->has_domain && c->dead > 0) drop_dead(c);          // dead slots are only defined by the OLD domain's keys
     c->graph_epoch++;
     c->grid = make_grid(I, J, K, dx, 0, K, true);
     const Grid &g = c->grid;
@@ -936,9 +972,9 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->material.reserve(c->cell_count);
     c->cell_start.reserve((size_t)c->nkeys + 3);
     c->counts.reserve((size_t)c->nkeys + 3);
-    c->keys_ready = false;
+    // a new domain invalidates every key, index and cell table of the old one
+    c->keys_ready = false; c->indexed = false; c->storage_sorted = false; c->sorted = false;
     c->has_domain = true;
-    c->sorted = false;
     c->have_maps = false;
     c->own_k0 = 0; c->own_k1 = K;
     if (g.pow2) make_brick_maps(c);
@@ -950,6 +986,12 @@ void gfs_set_material(gfs_context *c, const uint8_t *material, int *err) {
     GFS_BEGIN
     require_domain(c);
     GFS_REQUIRE(material, "null pointer");
+    if (c->remove_in_solid) {
+        // option 6 is applied by the binning pass that reads the positions (k_hist): keys binned by a G2P epilogue
+        // against the OLD material must not be reused, or particles inside newly added solids would survive
+        if (c->dead > 0) drop_dead(c);
+        c->keys_ready = false;
+    }
     GFS_CUDA(cudaMemcpyAsync(c->material.p, material, c->cell_count, cudaMemcpyHostToDevice, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
@@ -1012,7 +1054,16 @@ void gfs_get_particles(gfs_context *c, gfs_marker_particle_t *particles, int *er
     LAUNCH(c, gfs::k_soa_to_aos, ceil_div(c->n, 256), 256, c->n, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p,
            c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p, c->h_pos.p);
     GFS_CUDA(cudaMemcpyAsync(particles, c->h_pos.p, (size_t)c->n * 24, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long overflow = 0;
+    GFS_CUDA(cudaMemcpyAsync(&overflow, c->counters.p + 3, sizeof(overflow), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
+    if (overflow) {         // a silent parity break otherwise: those particles kept p0 instead of the reference's resolved position
+        GFS_CUDA(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned long long), c->stream));
+        char b[256];
+        snprintf(b, sizeof(b), "%llu particles advected into solid cells did not fit the collision list (capacity %zu) and kept their old "
+                 "position; raise it with gfs_set_option(ctx, 8, capacity)", overflow, c->coll_list.cap);
+        throw GfsError(b);
+    }
     GFS_END()
 }
 
@@ -1126,6 +1177,8 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 4) { GFS_REQUIRE(value == 0 || value == 1, "graph replay must be 0 or 1"); c->use_graphs = value; }
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
+    else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 8) { GFS_REQUIRE(value >= 0, "collision list capacity must be >= 0"); c->coll_cap_user = value; c->coll_list.release(); }
     else throw GfsError("gfs_set_option: unknown option");
     c->graph_epoch++;
     GFS_END()
@@ -1390,7 +1443,8 @@ void gfs_comm_alloc(gfs_context *c, int64_t layer_bytes, int64_t particle_cap, i
         GFS_CUDA(cudaMalloc((void **)&c->comm[s].block, comm_block_bytes(c)));
         GFS_CUDA(cudaMemset(c->comm[s].block, 0, kCommFlagBytes));
         c->comm[s].seq_layers = c->comm[s].seq_particles = 0;
-        c->comm[s].peer = nullptr;
+        if (c->comm[s].peer && c->comm[s].peer_ipc) cudaIpcCloseMemHandle(c->comm[s].peer);
+        c->comm[s].peer = nullptr; c->comm[s].peer_ipc = false;
     }
     if (!c->comm_host) GFS_CUDA(cudaHostAlloc((void **)&c->comm_host, 64, cudaHostAllocMapped));
     c->comm_error.reserve(1);
@@ -1418,7 +1472,9 @@ void gfs_comm_connect(gfs_context *c, int side, const void *handle64, int *err) 
     memcpy(&h, handle64, 64);
     void *p = nullptr;
     GFS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c->comm[side].peer && c->comm[side].peer_ipc) cudaIpcCloseMemHandle(c->comm[side].peer);
     c->comm[side].peer = (unsigned char *)p;
+    c->comm[side].peer_ipc = true;
     GFS_END()
 }
 
@@ -1429,6 +1485,7 @@ void gfs_comm_connect_local(gfs_context *c, int side, gfs_context *neighbour, in
     GFS_REQUIRE(neighbour->comm_layer_bytes == c->comm_layer_bytes && neighbour->comm_particle_cap == c->comm_particle_cap,
                 "both ends must use the same comm sizes");
     c->comm[side].peer = neighbour->comm[1 - side].block;
+    c->comm[side].peer_ipc = false;
     GFS_END()
 }
 
@@ -1463,7 +1520,7 @@ void gfs_comm_pull_layers(gfs_context *c, int side, int n, const int *what, cons
     fill_batch(c, cb, 1, n, what, k_first, k_count, offsets, add, comm_layers(c, c->comm[side].block, seq), &largest);
     GFS_REQUIRE(cb.n > 0, "nothing to unpack");
     LAUNCH(c, gfs::k_copy_batch_wait, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb,
-           (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p);
+           (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p, c->comm_timeout_cycles);
     GFS_END()
 }
 
@@ -1479,7 +1536,7 @@ void comm_signal_and_gather(gfs_context *c, const int has[2], const unsigned int
            has[0] ? (const volatile unsigned int *)c->comm[0].block + 1 : nullptr,
            has[1] ? (const volatile unsigned int *)c->comm[1].block + 1 : nullptr, seq[0], c->split_counters.p,
            (const volatile unsigned int *)c->comm[0].block + 2, (const volatile unsigned int *)c->comm[1].block + 2,
-           c->comm_host, c->comm_error.p);
+           c->comm_host, c->comm_error.p, c->comm_timeout_cycles);
 }
 
 void comm_migrate_split(gfs_context *c, int has_down, int has_up) {
@@ -1518,6 +1575,7 @@ void gfs_comm_g2p_advect(gfs_context *c, double dt, double ratio, int order, int
     GFS_BEGIN
     require_domain(c);
     GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
+    GFS_REQUIRE(!removal_on(c), "options 5 and 6 (per-cell cap, removal in solids) are single-domain rules: switch them off for sharded runs");
     GFS_CUDA(cudaSetDevice(c->device));
     const bool fused = g2p_uses_bricks(c, arith) && c->p2g_variant == 1 && c->lazy_sort && c->n - c->dead > 0 && (has_down || has_up);
     if (!fused) {
@@ -1550,7 +1608,17 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
     GFS_CUDA(cudaSetDevice(c->device));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     const unsigned int *h = c->comm_host;
-    GFS_REQUIRE(h[5] == 0, "timed out waiting for a neighbour's particles (peer exchange)");
+    if (h[5] != 0) {
+        // the exchange of this substep is incomplete (missing partial sums, stale halos or a local-only fixed-point scale):
+        // the sharded result is NOT the single-domain one.  Clear the word so that the caller can retry or shut down.
+        const unsigned int why = h[5];
+        cudaMemsetAsync(c->comm_error.p, 0, sizeof(unsigned int), c->stream);
+        cudaStreamSynchronize(c->stream);
+        throw GfsError(std::string("peer exchange timed out: ") +
+                       ((why & 2u) ? "a neighbour's grid layers or the all-ranks scale did not arrive (C1/C2/C0)" : "") +
+                       ((why & 3u) == 3u ? "; " : "") + ((why & 1u) ? "a neighbour's migrating particles did not arrive (C3)" : "") +
+                       " -- raise the limit with gfs_set_option(ctx, 7, seconds)");
+    }
     GFS_REQUIRE((int64_t)h[1] <= c->comm_particle_cap && (int64_t)h[2] <= c->comm_particle_cap &&
                 (int64_t)h[3] <= c->comm_particle_cap && (int64_t)h[4] <= c->comm_particle_cap, "migration buffer too small");
     const unsigned int n_in[2] = {h[3], h[4]};
@@ -1604,6 +1672,7 @@ void gfs_comm_substep(gfs_context *c, double dt, double ratio, int order, int in
     GFS_BEGIN
     require_domain(c);
     GFS_CUDA(cudaSetDevice(c->device));
+    GFS_REQUIRE(!removal_on(c), "options 5 and 6 (per-cell cap, removal in solids) are single-domain rules: switch them off for sharded runs");
     const int has[2] = {has_down, has_up};
     int e2 = GFS_SUCCESS;
 #define GFS_SUB(call) do { call; if (e2 != GFS_SUCCESS) throw GfsError(g_error); } while (0)
@@ -1665,6 +1734,7 @@ void gfs_comm_world_connect(gfs_context *c, int rank, const void *handle64, int 
     void *p = nullptr;
     GFS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->world_peer[rank] = (unsigned long long *)p;
+    c->world_peer_ipc[rank] = true;
     GFS_END()
 }
 
@@ -1683,7 +1753,7 @@ void gfs_comm_allmax_scale(gfs_context *c, int *err) {
     GFS_CUDA(cudaSetDevice(c->device));
     gfs::AllMaxPeers peers;
     for (int r = 0; r < 16; r++) peers.table[r] = c->world_peer[r];
-    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p);
+    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles);
     GFS_END()
 }
 
@@ -1756,6 +1826,46 @@ void *gfs_device_ptr(gfs_context *c, int which, int *err) {
     if (which == 16) return c->vmax_bits.p;
     throw GfsError("gfs_device_ptr: unknown buffer id");
     GFS_END(nullptr)
+}
+
+/* Verification hook: order- and distribution-independent 64-bit hashes of the resident state.  out[0] material of the
+ * owned cell layers, out[1..3] the P2G u, v, w faces of the owned layers (w: the top face layer with the last slab),
+ * out[4] the particle set (sum over particles of a hash of position + velocity bits).  Every value is a sum mod 2^64 of
+ * per-element hashes keyed by the element's GLOBAL index, so the hashes of a sharded run, added over the ranks, equal
+ * the single-GPU run's -- bench.py prints them at every GPU count.  Synchronises. */
+void gfs_state_hash(gfs_context *c, uint64_t *out5, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(out5, "null pointer");
+    GFS_CUDA(cudaSetDevice(c->device));
+    drop_dead(c);
+    const Grid &g = c->grid;
+    DevBuf<unsigned long long> d;
+    d.reserve(5);
+    GFS_CUDA(cudaMemsetAsync(d.p, 0, 5 * sizeof(unsigned long long), c->stream));
+    const int k0 = c->own_k0, k1 = c->own_k1;
+    const int nblk = 148 * 8;
+    LAUNCH(c, gfs::k_hash_grid, nblk, 256, c->material.p + (size_t)g.I * g.J * (size_t)(k0 - g.k0), 1, (long long)g.I, (long long)g.I,
+           (long long)g.J * k0, (long long)g.J * (k1 - k0), 0x6d6174ull, d.p);
+    const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J};
+    for (int a = 0; a < 3; a++) {
+        const int layers = (k1 - k0) + ((a == 2 && k1 == g.K) ? 1 : 0);
+        const float *base = c->field[GFS_FIELD_P2G][a].p + gfs::kRowPad + (size_t)g.pitch[a] * nj[a] * (size_t)(k0 - g.k0);
+        LAUNCH(c, gfs::k_hash_grid, nblk, 256, base, 4, (long long)ni[a], (long long)g.pitch[a], (long long)nj[a] * k0,
+               (long long)nj[a] * layers, 0x750000ull + (unsigned long long)a, d.p + 1 + a);
+    }
+    if (c->n > 0) {
+        const int b = c->cur;
+        LAUNCH(c, gfs::k_hash_particles, nblk, 256, c->n, (const uint32_t *)c->soa[b][0].p, (const uint32_t *)c->soa[b][1].p,
+               (const uint32_t *)c->soa[b][2].p, (const uint32_t *)c->soa[b][3].p, (const uint32_t *)c->soa[b][4].p,
+               (const uint32_t *)c->soa[b][5].p, d.p + 4);
+    }
+    unsigned long long h[5];
+    GFS_CUDA(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    d.release();
+    for (int i = 0; i < 5; i++) out5[i] = (uint64_t)h[i];
+    GFS_END()
 }
 
 void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {

@@ -874,6 +874,7 @@ __global__ void __launch_bounds__(256) k_g2p_advect(Grid g, FieldPtrs fnew, Fiel
                 if (coll.list) {
                     const unsigned int tk = atomicAdd(coll.count, 1u);
                     if (tk < coll.cap) { coll.list[tk] = make_float4(__int_as_float((int)r), qx, qy, qz); deferred = true; }
+                    else atomicAdd(&counters[3], 1ull);                  // list full: reported, see gfs_stats_t.collision_overflow
                 }
                 qx = px; qy = py; qz = pz;
             }
@@ -1240,6 +1241,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : GFS_TRI
                 if (coll.list) {               // listed for k_resolve_collisions, which also bins it; p0 stays for now
                     const unsigned int tk = atomicAdd(coll.count, 1u);
                     if (tk < coll.cap) { coll.list[tk] = make_float4(__int_as_float(r), qx, qy, qz); deferred = true; }
+                    else atomicAdd(&counters[3], 1ull);                  // list full: reported, see gfs_stats_t.collision_overflow
                 }
                 qx = px; qy = py; qz = pz;
             }
@@ -1314,7 +1316,7 @@ __global__ void k_splat_points(SplatParams sp, int vexp, double dx, float offx, 
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     float q[3] = {__fsub_rn(pos[3 * r], offx), __fsub_rn(pos[3 * r + 1], offy), __fsub_rn(pos[3 * r + 2], offz)};
-    float value = values[r];
+    float value = values ? values[r] : 1.0f;
     double inv = 1.0 / dx;
     float num_scale = num_scale_f(vexp);
     int lo[3], hi[3];
@@ -1358,9 +1360,11 @@ __global__ void k_splat_points(SplatParams sp, int vexp, double dx, float offx, 
 
 // field[n] (+)= fixed-point num, weight[n] (+)= fixed-point weight  -- epilogue of gfs_add_point_values
 __global__ void k_splat_points_store(int64_t count, int vexp, const unsigned long long *__restrict__ acc,
-                                     float *__restrict__ field, float *__restrict__ weight, int accumulate) {
+                                     float *__restrict__ field, float *__restrict__ weight, int accumulate,
+                                     int use_threshold, float threshold) {
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= count) return;
+    if (use_threshold && field[n] > threshold) return;       // saturated before this batch: see gfs_add_points
     float nf = (float)((double)(long long)acc[2 * n] * inv_num_scale_d(vexp));
     float wf = (float)((double)(long long)acc[2 * n + 1] * (1.0 / kWeightScaleD));
     field[n] = accumulate ? __fadd_rn(field[n], nf) : nf;
@@ -1422,10 +1426,10 @@ __global__ void k_signal(volatile unsigned int *peer_flag, unsigned int seq, vol
 }
 
 // spin until *flag >= seq (written over NVLink by the neighbour); gives up after ~4 s and raises *error
-__device__ __forceinline__ bool wait_flag(const volatile unsigned int *flag, unsigned int seq, unsigned int *error) {
+__device__ __forceinline__ bool wait_flag(const volatile unsigned int *flag, unsigned int seq, unsigned int *error, long long timeout) {
     const long long t0 = clock64();
     while ((int)(*flag - seq) < 0) {
-        if (clock64() - t0 > 8000000000ll) { atomicExch(error, 1u); return false; }
+        if (clock64() - t0 > timeout) { atomicExch(error, 1u); return false; }
         __nanosleep(200);
     }
     __threadfence_system();
@@ -1433,9 +1437,9 @@ __device__ __forceinline__ bool wait_flag(const volatile unsigned int *flag, uns
 }
 
 // the batched layer copy of k_copy_batch, preceded by the wait for the neighbour's data
-__global__ void __launch_bounds__(256) k_copy_batch_wait(CopyBatch cb, const volatile unsigned int *flag, unsigned int seq, unsigned int *error) {
+__global__ void __launch_bounds__(256) k_copy_batch_wait(CopyBatch cb, const volatile unsigned int *flag, unsigned int seq, unsigned int *error, long long timeout) {
     __shared__ int ok;
-    if (threadIdx.x == 0) ok = wait_flag(flag, seq, error) ? 1 : 0;
+    if (threadIdx.x == 0) ok = wait_flag(flag, seq, error, timeout) ? 1 : 0;
     __syncthreads();
     if (!ok) return;
     const int d = blockIdx.y;
@@ -1461,14 +1465,16 @@ __global__ void __launch_bounds__(256) k_copy_batch_wait(CopyBatch cb, const vol
 // to pinned host memory: the one word set the host reads per substep
 __global__ void k_gather_counts(const volatile unsigned int *flag_down, const volatile unsigned int *flag_up, unsigned int seq,
                                 const unsigned int *split_counters, const volatile unsigned int *in_down, const volatile unsigned int *in_up,
-                                unsigned int *host_out, unsigned int *error) {
+                                unsigned int *host_out, unsigned int *error, long long timeout) {
     bool ok = true;
-    if (flag_down) ok = wait_flag(flag_down, seq, error) && ok;
-    if (flag_up) ok = wait_flag(flag_up, seq, error) && ok;
+    if (flag_down) ok = wait_flag(flag_down, seq, error, timeout) && ok;
+    if (flag_up) ok = wait_flag(flag_up, seq, error, timeout) && ok;
     host_out[0] = split_counters[0]; host_out[1] = split_counters[1]; host_out[2] = split_counters[2];
     host_out[3] = (flag_down && ok) ? *in_down : 0u;
     host_out[4] = (flag_up && ok) ? *in_up : 0u;
-    host_out[5] = ok ? 0u : 1u;
+    // bit 0: this kernel's own wait timed out; bit 1: an earlier wait of the substep did (k_copy_batch_wait, k_allmax raise
+    // *error in stream order before this kernel runs) -- the host reads the word in gfs_comm_migrate_finish
+    host_out[5] = (ok ? 0u : 1u) | (*(volatile unsigned int *)error ? 2u : 0u);
 }
 
 // acc[first .. first+count) += src  (integer adds: the slab partial sums merge bit-exactly in any order)
@@ -1553,7 +1559,7 @@ __global__ void __launch_bounds__(256) k_append_bin(Grid g, uint32_t nkeys, int6
 // buffered by the parity of seq.  value is compared as an unsigned integer (bit patterns of non-negative floats order
 // like the floats).  One CTA of >= world threads.
 struct AllMaxPeers { unsigned long long *table[16]; };
-__global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int seq, unsigned int *value, unsigned int *error) {
+__global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int seq, unsigned int *value, unsigned int *error, long long timeout) {
     __shared__ unsigned int s_max;
     const int t = threadIdx.x;
     if (t == 0) s_max = 0u;
@@ -1569,13 +1575,52 @@ __global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int se
         unsigned long long v;
         bool ok = true;
         while ((unsigned int)((v = *in) >> 32) != seq) {
-            if (clock64() - t0 > 8000000000ll) { atomicExch(error, 1u); ok = false; break; }
+            if (clock64() - t0 > timeout) { atomicExch(error, 1u); ok = false; break; }
             __nanosleep(100);
         }
         if (ok) atomicMax(&s_max, (unsigned int)v);
     }
     __syncthreads();
     if (t == 0) *value = s_max;
+}
+
+// ---- order-independent 64-bit state hashes (verification hook, gfs_state_hash) ---------------------------------
+// Each element contributes splitmix64(position-in-the-GLOBAL-array, value bits); contributions are summed mod 2^64, so
+// the hash of a grid does not depend on which rank owns which layers, and the hash of the particle set (a sum over
+// particles of a hash of their six words) does not depend on their order or distribution.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ void hash_commit(unsigned long long h, unsigned long long *out) {
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
+// rows of `ni` elements at pitch `pitch` (elements), `rows` rows starting at global row `row0`; elem_bytes 1 or 4
+__global__ void __launch_bounds__(256) k_hash_grid(const void *__restrict__ base, int elem_bytes, long long ni, long long pitch, long long row0,
+                                                   long long rows, unsigned long long salt, unsigned long long *out) {
+    unsigned long long h = 0;
+    const long long total = ni * rows;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / ni, i = t - r * ni;
+        const unsigned long long v = elem_bytes == 1 ? (unsigned long long)((const uint8_t *)base)[r * pitch + i]
+                                                      : (unsigned long long)((const uint32_t *)base)[r * pitch + i];
+        h += mix64(mix64((unsigned long long)((row0 + r) * ni + i) ^ salt) ^ v);
+    }
+    hash_commit(h, out);
+}
+__global__ void __launch_bounds__(256) k_hash_particles(int64_t n, const uint32_t *__restrict__ x, const uint32_t *__restrict__ y, const uint32_t *__restrict__ z,
+                                                        const uint32_t *__restrict__ vx, const uint32_t *__restrict__ vy, const uint32_t *__restrict__ vz,
+                                                        unsigned long long *out) {
+    unsigned long long h = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long a = mix64(((unsigned long long)y[r] << 32) | x[r]);
+        a = mix64(a ^ (((unsigned long long)vx[r] << 32) | z[r]));
+        h += mix64(a ^ (((unsigned long long)vz[r] << 32) | vy[r]));
+    }
+    hash_commit(h, out);
 }
 
 __global__ void k_border_solid(Grid g, uint8_t *__restrict__ material) {

@@ -62,9 +62,16 @@ void CLScalarField::_splat(std::vector<vmath::vec3> &points, const float *values
 
 void CLScalarField::addPoints(std::vector<vmath::vec3> &points, double radius, vmath::vec3 offset, double dx,
                               Array3d<float> *field) {
-    _check(_isMaxScalarFieldValueThresholdSet ? GFS_FAIL : GFS_SUCCESS,
-           "addPoints with a max scalar field value threshold (surface mesher path) is not supported");
-    _splat(points, NULL, radius, offset, dx, field, NULL);
+    // IsotropicParticleMesher sets a threshold before every batch (src/isotropicparticlemesher.cpp:334-359); see
+    // gfs_add_points for how the reference's three different skip rules map onto one order-independent rule
+    _check(_isInitialized ? GFS_SUCCESS : GFS_FAIL, "initialize() has not been called");
+    float off[3] = {offset.x, offset.y, offset.z};
+    int err;
+    gfs_add_points(_ctx, points.empty() ? NULL : reinterpret_cast<const float *>(&points[0]), (int64_t)points.size(), radius, off, dx,
+                   field->width, field->height, field->depth, field->getRawArray(), _isOpenCLEnabled ? 1 : 0,
+                   _isMaxScalarFieldValueThresholdSet ? 1 : 0, _maxScalarFieldValueThreshold,
+                   _isOpenCLEnabled ? GFS_FAST : GFS_EXACT, &err);
+    _check(err, "gfs_add_points");
 }
 
 void CLScalarField::addPoints(std::vector<vmath::vec3> &points, double radius, vmath::vec3 offset, double dx,

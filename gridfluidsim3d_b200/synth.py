@@ -22,6 +22,7 @@ CONFIGS = {
     "tiny16": ((16, 16, 16), 0.5, "sphere"),             # test-only
     "small32": ((32, 32, 32), 0.25, "sphere"),           # test-only
     "slab24": ((24, 20, 28), 0.25, "dam"),               # test-only, non-cubic
+    "tall64": ((32, 32, 64), 0.25, "sphere"),            # test-only: enough layers for 8 slabs
     "odd20": ((20, 18, 22), 0.3, "sphere"),              # test-only, dx not a power of two (fp64 index path)
 }
 
@@ -55,8 +56,8 @@ def fluid_cells(shape, dims, material=None):
         ball2 = (cx - 0.7) ** 2 + (cy - 0.85) ** 2 + (cz - 0.7) ** 2 < 0.12 ** 2
         mask = (cy < 0.72) | ball1 | ball2
         mask = mask & (cx > -1) & (cz > -1)
-    elif shape == "river":           # channel y < 0.47 H
-        mask = (cy < 0.47) & (cx > -1) & (cz > -1)
+    elif shape == "river":           # channel y < 0.93 H: ~245 M particles at 512x256x256 (BASELINE configs[3]: "~250M")
+        mask = (cy < 0.93) & (cx > -1) & (cz > -1)
     elif shape == "full":
         mask = (cx > -1) & (cy > -1) & (cz > -1)
     else:
@@ -138,3 +139,125 @@ def make_scene(name, seed=12345, shuffle=True, max_particles=None):
     new, saved = make_fields(dims, dx)
     return dict(name=name, dims=dims, dx=dx, material=material, pos=pos, vel=vel, new=new, saved=saved,
                 dt=cfl_dt(dx))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Counter-based scene generation with torch (CPU or CUDA): every particle's jitter is a pure function of
+# (seed, global cell index, sub-cell slot, axis), so a slab-sharded run generates -- rank by rank, from its own
+# layers only -- exactly the particle set the single-GPU run generates.  Used by bench.py and by the parity tests at
+# the BASELINE sizes (numpy takes minutes at 10^8 particles).
+# ---------------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _s64(x):
+    """Python int -> the signed 64-bit value with the same bits (torch has no uint64 arithmetic)."""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(x, s):
+    """logical right shift of an int64 tensor"""
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def splitmix64_t(x):
+    """splitmix64 finaliser on an int64 tensor (wrap-around arithmetic); same bits as splitmix64_np."""
+    z = x + _s64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _s64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+def splitmix64_np(x):
+    with np.errstate(over="ignore"):
+        z = x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+SUB_CELL = np.array([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1],
+                     [-1, 1, -1], [1, 1, -1], [1, 1, 1], [-1, 1, 1]], np.float64)
+
+
+def hashed_positions_np(cell_ijk, dims, dx, seed=12345, jitter_factor=0.1):
+    """float32 positions of the 8 particles of each listed cell (numpy twin of the torch generator, for tests)."""
+    I, J, K = dims
+    c = np.asarray(cell_ijk, np.int64)
+    lin = c[:, 0] + I * (c[:, 1] + J * c[:, 2])
+    pid = (lin[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    centre = (np.repeat(c, 8, 0).astype(np.float64) + 0.5) * dx + np.tile(SUB_CELL, (len(c), 1)) * (0.25 * dx)
+    jit = 0.25 * jitter_factor * dx
+    out = np.empty((len(pid), 3), np.float64)
+    for a in range(3):
+        h = splitmix64_np((pid * 3 + a).astype(np.uint64) ^ splitmix64_np(np.array([seed], np.uint64)))
+        u = (h >> np.uint64(40)).astype(np.float64) * (1.0 / (1 << 24))
+        out[:, a] = centre[:, a] + (2.0 * u - 1.0) * jit
+    return out.astype(np.float32)
+
+
+def vortex_t(x, y, z, ext):
+    import torch
+    pi = float(np.pi)
+    xh, yh, zh = x / ext[0], y / ext[1], z / ext[2]
+    u = -torch.sin(pi * xh) ** 2 * torch.sin(2 * pi * yh) * torch.cos(pi * zh)
+    v = torch.sin(2 * pi * xh) * torch.sin(pi * yh) ** 2 * torch.cos(pi * zh)
+    w = 0.5 * torch.sin(2 * pi * xh) * torch.sin(2 * pi * zh) * torch.sin(pi * yh)
+    return u, v, w
+
+
+def make_scene_torch(name, device, seed=12345, k_range=None, shuffle=True, fields=True):
+    """Particles (AoS float32 [N,6]), new/saved fields and material of workload `name` as torch tensors on `device`.
+    k_range=(k0,k1) keeps only the particles seeded in cell layers [k0,k1): the union over a partition of the layers is
+    the particle SET of the unrestricted call, bit for bit (only the order differs: the reference shuffles its particles
+    every step, src/fluidsimulation.cpp:3211-3219, so the arrays are handed over shuffled)."""
+    import torch
+    dims, dx, shape = CONFIGS[name]
+    I, J, K = dims
+    material = border_material(dims)
+    mask = torch.from_numpy(fluid_cells(shape, dims, material)).to(device)
+    if k_range is not None:
+        keep = torch.zeros(K, dtype=torch.bool, device=device)
+        keep[k_range[0]:k_range[1]] = True
+        mask &= keep[:, None, None]
+    kk, jj, ii = torch.nonzero(mask, as_tuple=True)
+    del mask
+    lin = ii + I * (jj + J * kk)                                              # int64 global cell index
+    ncell = lin.shape[0]
+    sub = torch.tensor(SUB_CELL, dtype=torch.float64, device=device) * (0.25 * dx)
+    key = splitmix64_t(torch.tensor([_s64(seed)], dtype=torch.int64, device=device))
+    pid = (lin[:, None] * 8 + torch.arange(8, device=device, dtype=torch.int64)[None, :]).reshape(-1)
+    jit = 0.25 * 0.1 * dx
+    pos = torch.empty((ncell * 8, 3), dtype=torch.float32, device=device)
+    for a, idx in enumerate((ii, jj, kk)):
+        centre = ((idx.to(torch.float64) + 0.5) * dx)[:, None] + sub[None, :, a]          # (ncell, 8)
+        h = splitmix64_t((pid * 3 + a) ^ key)
+        u = _lsr(h, 40).to(torch.float64) * (1.0 / (1 << 24))
+        pos[:, a] = (centre.reshape(-1) + (2.0 * u - 1.0) * jit).to(torch.float32)
+        del centre, h, u
+    del pid, lin, ii, jj, kk
+    if shuffle:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        perm = torch.randperm(pos.shape[0], generator=gen, device=device)
+        pos = pos[perm].contiguous()
+        del perm
+    ext = (I * dx, J * dx, K * dx)
+    u, v, w = vortex_t(pos[:, 0], pos[:, 1], pos[:, 2], ext)
+    aos = torch.cat([pos, torch.stack([u, v, w], 1)], 1).contiguous()
+    del pos, u, v, w
+    out = dict(name=name, dims=dims, dx=dx, dt=cfl_dt(dx), material=material, aos=aos)
+    if fields:
+        new = []
+        for comp, (ni, nj, nk) in enumerate(face_dims(dims)):
+            i = torch.arange(ni, device=device, dtype=torch.float32)[None, None, :]
+            j = torch.arange(nj, device=device, dtype=torch.float32)[None, :, None]
+            k = torch.arange(nk, device=device, dtype=torch.float32)[:, None, None]
+            x = (i + (0.0 if comp == 0 else 0.5)) * dx
+            y = (j + (0.0 if comp == 1 else 0.5)) * dx
+            z = (k + (0.0 if comp == 2 else 0.5)) * dx
+            new.append(vortex_t(x, y, z, ext)[comp].expand(nk, nj, ni).contiguous().reshape(-1))
+        out["new"] = new
+        out["saved"] = [a * 0.9 for a in new]
+    return out

@@ -85,6 +85,9 @@ typedef struct gfs_stats_t {
     int64_t kernel_launches;      /* CUDA kernels launched by this context since creation (kernels inside replayed graphs included) */
     int64_t graph_replays;        /* substeps performed by replaying a captured CUDA graph (gfs_substep, steady state) */
     int64_t removed_particles;    /* particles removed by options 5 and 6 since creation                */
+    int64_t collision_overflow;   /* colliders that did not fit the collision list since creation (they kept their old
+                                     position instead of going through the reference's resolve); gfs_get_particles fails
+                                     while it is non-zero -- raise option 8 */
 } gfs_stats_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -140,6 +143,15 @@ void gfs_add_point_values(gfs_context *ctx, const float *pos, const float *value
                           double radius, const float *offset3, double dx, int ni, int nj, int nk,
                           float *field, float *weight, int accumulate, int arith, int *err);
 
+/* CLScalarField::addPoints(points, radius, offset, dx, field) (src/clscalarfield.cpp:62-145): gfs_add_point_values with
+ * value 1 for every point and no weight grid.  use_threshold != 0 mirrors setMaxScalarFieldValueThreshold(threshold)
+ * (src/clscalarfield.cpp:303-310; set by IsotropicParticleMesher, src/isotropicparticlemesher.cpp:334-359): a node whose
+ * value before this call already exceeds `threshold` receives nothing from it -- the per-node, order-independent form of
+ * the reference's skip rules (src/scalarfield.cpp:182-184 on the CPU, whole chunks at src/clscalarfield.cpp:1002-1010 in
+ * OpenCL; its own no-OpenCL body ignores the threshold, :1490-1505).  Needs accumulate != 0 to have a "before". */
+void gfs_add_points(gfs_context *ctx, const float *pos, int64_t n, double radius, const float *offset3, double dx,
+                    int ni, int nj, int nk, float *field, int accumulate, int use_threshold, float threshold, int arith, int *err);
+
 /* ---- device-resident domain (particles, fields and material stay in HBM between calls) -------- */
 
 /* Allocate grids for an isize x jsize x ksize domain of cell size dx (FluidSimulation(isize,jsize,ksize,dx),
@@ -190,7 +202,10 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * is arbitrary, as with the reference's rand() shuffle; 0 = no cap (default).  option 6: 1 = a particle found inside a
  * solid cell by a sort is removed (FluidSimulation::_removeMarkerParticlesInSolidCells, :1933-1957), 0 = it is kept and
  * counted in gfs_stats_t.in_solid (default).  Both cost one 4-byte read-back per binning pass and apply to the
- * single-domain entry points (gfs_sort*, gfs_substep, gfs_g2p_advect); gfs_stats_t.removed_particles counts. */
+ * single-domain entry points (gfs_sort*, gfs_substep, gfs_g2p_advect; the sharded gfs_comm_* entry points refuse to run
+ * with them on); gfs_stats_t.removed_particles counts.  option 7: limit, in seconds (default 4), of the device-side
+ * waits of the peer exchange; a wait that exceeds it fails gfs_comm_migrate_finish / gfs_comm_substep.  option 8:
+ * capacity of the collision list in particles (default 0 = n/16 + 4096); see gfs_stats_t.collision_overflow. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
@@ -280,6 +295,11 @@ void gfs_comm_allmax_scale(gfs_context *ctx, int *err);
  * 16 the word holding max |v| of the resident particles (float bits; the P2G fixed-point scale derives from it --
  * sharded runs must replace it by the maximum over all ranks between the sort and gfs_p2g_begin). */
 void *gfs_device_ptr(gfs_context *ctx, int which, int *err);
+/* Verification hook: order- and distribution-independent 64-bit hashes of the resident state.  out5[0] = material of the
+ * owned cell layers, out5[1..3] = P2G u, v, w faces of the owned layers, out5[4] = the particle set.  Each is a sum mod
+ * 2^64 of per-element hashes keyed by GLOBAL element index (particles: by their six words), so the per-rank hashes of a
+ * z-slab run add up to the single-GPU run's.  Synchronises; compacts dead slots like gfs_get_particles. */
+void gfs_state_hash(gfs_context *ctx, uint64_t *out5, int *err);
 /* Resize the resident particle set to n (contents of [0,min(old,n)) kept) -- used by slab migration. */
 void gfs_resize_particles(gfs_context *ctx, int64_t n, int *err);
 

@@ -357,6 +357,22 @@ class RefSim:
         self.lib.ref_sim_initialize(self.h)
         self._init = True
 
+    def enable_mesh_output(self):
+        """Stock output settings of the reference (surface mesh + isotropic reconstruction on); -> output directory."""
+        self.lib.ref_sim_enable_mesh_output.restype = C.c_char_p
+        self.lib.ref_sim_enable_mesh_output.argtypes = [C.c_void_p]
+        return self.lib.ref_sim_enable_mesh_output(self.h).decode()
+
+    def mesh_particles(self, use_accelerator, cap=4000000):
+        """IsotropicParticleMesher::meshParticles on the current state -> (vertices (n,3), triangle count)."""
+        fn = self.lib.ref_sim_mesh_particles
+        fn.restype = C.c_long
+        fn.argtypes = [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_long, C.POINTER(C.c_long)]
+        verts = np.empty((cap, 3), np.float32)
+        ntris = C.c_long(0)
+        nv = fn(self.h, int(use_accelerator), verts, cap, C.byref(ntris))
+        return verts[:min(nv, cap)].copy(), int(ntris.value)
+
     def set_accel(self, particle_advection, scalar_field):
         self.lib.ref_sim_set_accel(self.h, int(particle_advection), int(scalar_field))
 

@@ -2,7 +2,8 @@
 
 Every rank steps the same sharded scene twice, once per transport, and the owned P2G layers, the material and the
 sorted particle rows must agree bit for bit after every substep.  Prints "PEER_CHECK_OK" on rank 0.
-Used by tests/test_gpu_parity.py::test_peer_transport_two_gpus and by hand:
+Used by tests/test_gpu_parity.py::test_peer_transport_two_gpus, by bench.py at every --gpus N > 1 (check(), after its
+timed regions: the result is the line's verify.peer_vs_nccl) and by hand:
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/peer_check.py
 """
 import os
@@ -16,12 +17,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from gridfluidsim3d_b200 import capi, slabs, synth  # noqa: E402
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    name = os.environ.get("PEER_CHECK_SCENE", "small32")
+def check(rank, world, local, dev, name=None):
+    """-> (ok on every rank, particles of the last peer run); needs an initialised process group."""
+    name = name or os.environ.get("PEER_CHECK_SCENE", "small32")
     s = synth.make_scene(name, seed=7)
     s["new"] = (s["new"][0], s["new"][1], (s["new"][2] + np.float32(0.6)).astype(np.float32))
     I, J, K = s["dims"]
@@ -66,10 +64,19 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     moved = torch.tensor([len(results[("peer", capi.TRILINEAR)][-1][0])], device=dev)
     dist.all_reduce(moved)
+    return int(t.item()) == 1, int(moved.item())
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok, n = check(rank, world, local, dev)
     if rank == 0:
-        print("PEER_CHECK_OK" if int(t.item()) == 1 else "PEER_CHECK_FAILED", "particles", int(moved.item()), flush=True)
+        print("PEER_CHECK_OK" if ok else "PEER_CHECK_FAILED", "particles", n, flush=True)
     dist.destroy_process_group()
-    sys.exit(0 if int(t.item()) == 1 else 1)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

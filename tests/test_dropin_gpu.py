@@ -78,3 +78,49 @@ def test_whole_simulator_with_cuda_accelerators(libs, fast):
     assert (m0 != m1).mean() < 1e-3
     for a, b in zip(f0, f1):
         assert np.abs(a - b).max() < 1e-4 * max(1.0, np.abs(a).max())
+
+
+def test_whole_simulator_stock_settings_with_surface_mesher(libs):
+    """The reference's stock scene (src/main.cpp:8-21 at 32^3) with surface-mesh output and isotropic reconstruction ON:
+    IsotropicParticleMesher sets the max-scalar-field threshold and calls CLScalarField::addPoints every frame
+    (src/isotropicparticlemesher.cpp:334-359).  The drop-in must run it (round 1 aborted here), leave the particle
+    state where the CPU classes leave it, write its surface meshes, and produce the surface the mesher's own CPU loop
+    produces.  (The plain reference build cannot run this setting with OpenCL disabled: CLScalarField::addPoints lacks a
+    `return` after its NoCL branch, src/clscalarfield.cpp:75-77, and falls into the OpenCL path -- so the CPU side of
+    the comparison is the run without mesh output plus IsotropicParticleMesher without an accelerator.)"""
+    ref, drop = libs
+    libc = ctypes.CDLL(None)
+    out = []
+    for lib in (ref, drop):
+        libc.srand(1)
+        sim = lib.sim((32, 32, 32), 0.25)
+        sim.add_fluid_sphere((4.0, 4.0, 4.0), 5.0)
+        sim.add_body_force((0.0, -25.0, 0.0))
+        files = []
+        if lib is drop:
+            bakedir = sim.enable_mesh_output()
+            sim.set_accel(True, True)
+        sim.initialize()
+        if lib is drop and os.path.isdir(bakedir):
+            for f in os.listdir(bakedir):
+                if f.endswith(".ply"):
+                    os.remove(os.path.join(bakedir, f))
+        for _ in range(2):
+            sim.update(1.0 / 30.0)
+        if lib is drop:
+            files = sorted((f, os.path.getsize(os.path.join(bakedir, f))) for f in os.listdir(bakedir) if f.endswith(".ply"))
+        p, v = sim.get_particles()
+        mesh = sim.mesh_particles(use_accelerator=lib is drop)
+        out.append((p, v, files, mesh))
+        sim.close()
+    (p0, v0, _, (mv0, mt0)), (p1, v1, files, (mv1, mt1)) = out
+    assert len(p0) == len(p1) > 20000
+    assert np.abs(p0 - p1).max() < 1e-4 * 0.25
+    assert np.abs(v0 - v1).max() < 1e-4 * max(1.0, np.abs(v0).max())
+    assert len(files) >= 2 and all(sz > 1000 for _, sz in files), files           # one surface mesh per frame was written
+    # same iso-surface: the threshold (1.0) only limits how far ABOVE the iso level (0.5) a node may grow, and the rules
+    # differ between the reference's own paths (gfs_add_points); topology and extent must agree, vertex positions to a
+    # fraction of a cell
+    assert mt0 > 1000 and abs(mt0 - mt1) <= 0.05 * mt0, (mt0, mt1)
+    assert np.abs(mv0.min(0) - mv1.min(0)).max() < 0.25 * 0.5 and np.abs(mv0.max(0) - mv1.max(0)).max() < 0.25 * 0.5
+    assert np.abs(mv0.mean(0) - mv1.mean(0)).max() < 0.25 * 0.1
