@@ -279,6 +279,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 ALG_BYTES = {   # algorithmic bytes per launch of each hot kernel: (per particle, per cell)
     "gfs::k_p2g_scatter<0>": (24, 13), "gfs::k_p2g_tile<0>": (24, 13), "gfs::k_p2g_scatter<2>": (24, 13), "gfs::k_p2g_tile<2>": (24, 13),
+    "gfs::k_p2g_tile2<0>": (24, 13), "gfs::k_p2g_tile2<1>": (24, 13), "gfs::k_g2p_tri<0>": (48, 24), "gfs::k_g2p_tri<1>": (48, 24),
     "gfs::k_g2p_advect<0>": (48, 24), "gfs::k_g2p_advect<1>": (48, 24), "gfs::k_g2p_advect<2>": (48, 24), "gfs::k_g2p_brick<0>": (48, 24), "gfs::k_g2p_brick<1>": (48, 24),
 }
 
@@ -568,7 +569,7 @@ def run_gfs(args):
         return sum(kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"] for k in kernels if any(nm in k for nm in names))
     n_rank = ctx.num_particles
     p2g_ms = per_step(["ExclusiveSum", "k_build_index", "k_hist", "k_scatter_sorted", "k_classify", "k_p2g_tile", "k_p2g_scatter", "k_p2g_finalize", "k_assemble"])
-    g2p_ms = per_step(["k_g2p_brick", "k_g2p_advect"])
+    g2p_ms = per_step(["k_g2p_brick", "k_g2p_advect", "k_g2p_tri", "k_g2p_slow", "k_resolve_collisions"])
     sub = {}
     if p2g_ms > 0:
         b = 24 * n_rank + 13 * G_local

@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "gfs_kernels.cuh"
+#include "gfs_p2g2.cuh"
+#include "gfs_g2p2.cuh"
 
 namespace {
 
@@ -179,10 +181,14 @@ struct gfs_context {
     int64_t coll_cap_user = 0;                          // option 8: collision list capacity in particles (0 = n/16 + 4096)
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     DevBuf<unsigned int> split_counters;  // kept, down, up
-    int p2g_variant = 1;                  // 1 = brick tiles in shared memory (default), 0 = global atomics only
+    int p2g_variant = 3;                  // 0 = global atomics only; brick tiles in shared memory: 1 = round-1 kernel, 2 = round-2
+                                          // kernel, 3 = round-2 kernel with the lane transposition (default)
     int lazy_sort = 1;                    // fused substep: sort by index only (no physical scatter)
-    int g2p_variant = 1;                  // 1 = TMA-staged brick tiles (default where applicable), 0 = global loads only
+    int g2p_variant = 2;                  // 0 = global loads only; TMA-staged brick tiles: 1 = round-1 kernel, 2 = round-2 trilinear
+                                          // kernel on the dense tile (default), 3 = on the bank-skewed tile; tricubic: k_g2p_brick<1>
     gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
+    gfs::BrickMaps maps_tri_skew;         // 4-D (bank-skewed) boxes of the round-2 trilinear kernel
+    DevBuf<unsigned int> slow_count;      // k_g2p_tri's list of particles left to k_g2p_slow (the list itself lives in perm[0])
     bool have_maps = false;
     size_t field_floats[3] = {0, 0, 0};   // padded element counts of the resident u,v,w arrays
 
@@ -422,16 +428,29 @@ void do_p2g_begin(gfs_context *c, int arith) {
         } else {
             const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
             const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
-            int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
-            if (pow2)
-                gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(
-                    g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
-                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
-            else
-                gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(
-                    g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p,
-                    c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p);
-            c->prof_end(prof_id_);
+#define GFS_TILE_ARGS g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, \
+                      c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p
+            if (pow2 && c->p2g_variant == 3) {
+                const size_t smem3 = smem + 6 * gfs::kStageChunk * sizeof(float);
+                static bool attr_set = false;
+                if (!attr_set) {
+                    GFS_CUDA(cudaFuncSetAttribute(gfs::k_p2g_tile2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                    attr_set = true;
+                }
+                int prof_id_ = c->prof_begin("gfs::k_p2g_tile2<1>");
+                gfs::k_p2g_tile2<true><<<nbricks, 512, smem3, c->stream>>>(GFS_TILE_ARGS);
+                c->prof_end(prof_id_);
+            } else if (pow2 && c->p2g_variant == 2) {
+                int prof_id_ = c->prof_begin("gfs::k_p2g_tile2<0>");
+                gfs::k_p2g_tile2<false><<<nbricks, 256, smem, c->stream>>>(GFS_TILE_ARGS);
+                c->prof_end(prof_id_);
+            } else {
+                int prof_id_ = c->prof_begin(pow2 ? "gfs::k_p2g_tile<2>" : "gfs::k_p2g_tile<0>");
+                if (pow2) gfs::k_p2g_tile<2><<<nbricks, 256, smem, c->stream>>>(GFS_TILE_ARGS);
+                else gfs::k_p2g_tile<0><<<nbricks, 256, smem, c->stream>>>(GFS_TILE_ARGS);
+                c->prof_end(prof_id_);
+            }
+#undef GFS_TILE_ARGS
             c->launches++;
             GFS_CUDA(cudaGetLastError());
         }
@@ -486,7 +505,7 @@ void do_p2g(gfs_context *c, int arith) {
 }
 
 bool g2p_uses_bricks(gfs_context *c, int arith) {
-    return arith != GFS_EXACT && c->grid.pow2 && c->sorted && c->have_maps && c->g2p_variant == 1;
+    return arith != GFS_EXACT && c->grid.pow2 && c->sorted && c->have_maps && c->g2p_variant >= 1;
 }
 
 void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int arith, bool bin_next, const gfs::Migrate *migrate = nullptr) {
@@ -529,23 +548,64 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     if (migrate) mg = *migrate;
     else { mg.own_lo = (int)0x80000000; mg.own_hi = 0x7FFFFFFF; mg.out[0] = mg.out[1] = nullptr; mg.count = nullptr; mg.cap = 0; }
     if (brick) {
-        const int nb = (int)(c->nkeys / gfs::kBrickCells) + 1;          // + the overflow-bin CTA
+        const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
+        const int nb = nbricks + 1;          // + the overflow-bin CTA
 #define GFS_BRICK_ARGS c->grid, c->maps[interp], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, c->cell_start.p, \
                (c->indexed ? c->index.p : nullptr), c->tag[src].p, c->tag[dst].p, order, rk, rp, rf, c->n,                                                                                                  \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
                c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg, coll
-        int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
-        if (interp == GFS_TRICUBIC) {
-            if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
-            else gfs::k_g2p_brick<1, false><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+        if (interp == GFS_TRILINEAR && c->g2p_variant >= 2) {
+            // round-2 trilinear kernel: bricks only; the out-of-grid bin goes through k_g2p_brick (one CTA), particles whose
+            // RK stages leave the staged block through k_g2p_slow
+            const bool skew = c->g2p_variant == 3;
+            gfs::SlowList slow;
+            c->slow_count.reserve(1);
+            slow.list = c->perm[0].p; slow.count = c->slow_count.p;
+            GFS_CUDA(cudaMemsetAsync(c->slow_count.p, 0, sizeof(unsigned int), c->stream));
+#define GFS_TRI_ARGS c->grid, (skew ? c->maps_tri_skew : c->maps[0]), c->material.p, c->cell_start.p, (c->indexed ? c->index.p : nullptr), \
+               c->tag[src].p, c->tag[dst].p, order, rk, rp, rf,                                                                         \
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg, coll, slow
+            int prof_id_ = c->prof_begin(skew ? "gfs::k_g2p_tri<1>" : "gfs::k_g2p_tri<0>");
+            if (skew) {
+                if (migrate) gfs::k_g2p_tri<true, true><<<nbricks, 256, gfs::TriTile<true>::kSmemBytes, c->stream>>>(GFS_TRI_ARGS);
+                else gfs::k_g2p_tri<true, false><<<nbricks, 256, gfs::TriTile<true>::kSmemBytes, c->stream>>>(GFS_TRI_ARGS);
+            } else {
+                if (migrate) gfs::k_g2p_tri<false, true><<<nbricks, 256, gfs::TriTile<false>::kSmemBytes, c->stream>>>(GFS_TRI_ARGS);
+                else gfs::k_g2p_tri<false, false><<<nbricks, 256, gfs::TriTile<false>::kSmemBytes, c->stream>>>(GFS_TRI_ARGS);
+            }
+            c->prof_end(prof_id_);
+            GFS_CUDA(cudaGetLastError());
+#undef GFS_TRI_ARGS
+            int prof_id2_ = c->prof_begin("gfs::k_g2p_brick<0> (out-of-grid bin)");
+            if (migrate) gfs::k_g2p_brick<0, true><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks);
+            else gfs::k_g2p_brick<0, false><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks);
+            c->prof_end(prof_id2_);
+            GFS_CUDA(cudaGetLastError());
+#define GFS_SLOW_ARGS c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, (c->indexed ? c->index.p : nullptr), \
+               c->tag[src].p, c->tag[dst].p, interp, order, rk, rp, rf,                                                                 \
+               c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
+               c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
+               c->counters.p, c->nkeys, keys_out, rank_out, counts, c->vmax_bits.p, mg, coll, slow
+            if (migrate) LAUNCH(c, gfs::k_g2p_slow<true>, 296, 128, GFS_SLOW_ARGS);
+            else LAUNCH(c, gfs::k_g2p_slow<false>, 296, 128, GFS_SLOW_ARGS);
+#undef GFS_SLOW_ARGS
+            c->launches += 2;
         } else {
-            if (migrate) gfs::k_g2p_brick<0, true><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
-            else gfs::k_g2p_brick<0, false><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS);
+            int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
+            if (interp == GFS_TRICUBIC) {
+                if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
+                else gfs::k_g2p_brick<1, false><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
+            } else {
+                if (migrate) gfs::k_g2p_brick<0, true><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
+                else gfs::k_g2p_brick<0, false><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
+            }
+            c->prof_end(prof_id_);
+            c->launches++;
+            GFS_CUDA(cudaGetLastError());
         }
-        c->prof_end(prof_id_);
-        c->launches++;
-        GFS_CUDA(cudaGetLastError());
 #undef GFS_BRICK_ARGS
     }
     else if (arith == GFS_EXACT) LAUNCH(c, gfs::k_g2p_advect<1>, ceil_div(c->n, 256), 256, GFS_G2P_ARGS);
@@ -646,6 +706,8 @@ void make_brick_maps(gfs_context *c) {
             make_field_map_dense(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
             make_field_map_dense(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
         }
+        make_field_map(&c->maps_tri_skew.m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::nY, gfs::TriTile<true>::nZ);
+        make_field_map(&c->maps_tri_skew.m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::sY, gfs::TriTile<true>::sZ);
         make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nZ);
         make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sZ);
     }
@@ -653,6 +715,13 @@ void make_brick_maps(gfs_context *c) {
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<0>::kSmemBytes));
     GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_brick<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::BrickTile<1>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_tri<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::TriTile<false>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_tri<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::TriTile<false>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_tri<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::TriTile<true>::kSmemBytes));
+    GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_tri<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::TriTile<true>::kSmemBytes));
+    static_assert(gfs::TriTile<false>::nY == gfs::BrickTile<0>::nY && gfs::TriTile<false>::sY == gfs::BrickTile<0>::sY &&
+                  gfs::TriTile<false>::nOrg == gfs::BrickTile<0>::nOrg && gfs::TriTile<false>::sOrg == gfs::BrickTile<0>::sOrg &&
+                  !gfs::BrickTile<0>::kSkew, "the dense trilinear tile of k_g2p_tri uses the tensor maps of k_g2p_brick<0>");
     c->have_maps = true;
 }
 
@@ -1163,15 +1232,15 @@ void gfs_sort_index(gfs_context *c, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
     GFS_CUDA(cudaSetDevice(c->device));
-    do_sort(c, false, /*lazy=*/c->has_domain && c->grid.pow2 && c->have_maps && c->g2p_variant == 1 && c->p2g_variant == 1 && c->lazy_sort);
+    do_sort(c, false, /*lazy=*/c->has_domain && c->grid.pow2 && c->have_maps && c->g2p_variant >= 1 && c->p2g_variant >= 1 && c->lazy_sort);
     GFS_END()
 }
 
 void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
-    if (option == 0) { GFS_REQUIRE(value == 0 || value == 1, "p2g variant must be 0 or 1"); c->p2g_variant = value; }
-    else if (option == 1) { GFS_REQUIRE(value == 0 || value == 1, "g2p variant must be 0 or 1"); c->g2p_variant = value; }
+    if (option == 0) { GFS_REQUIRE(value >= 0 && value <= 3, "p2g variant must be 0..3"); c->p2g_variant = value; }
+    else if (option == 1) { GFS_REQUIRE(value >= 0 && value <= 3, "g2p variant must be 0..3"); c->g2p_variant = value; }
     else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
     else if (option == 3) { GFS_REQUIRE(value == 0 || value == 1, "collision resolve must be 0 or 1"); c->resolve_collisions = value; }
     else if (option == 4) { GFS_REQUIRE(value == 0 || value == 1, "graph replay must be 0 or 1"); c->use_graphs = value; }
@@ -1205,7 +1274,7 @@ void substep_body(gfs_context *c, double dt, double ratio, int order, int interp
     // exact arithmetic needs the stable order; fast arithmetic is order-independent and uses the counting sort,
     // binned for the following substep by the G2P kernel's epilogue
     if (c->keys_ready && arith == GFS_EXACT) c->keys_ready = false;
-    do_sort(c, arith == GFS_EXACT, /*lazy=*/arith != GFS_EXACT && c->grid.pow2 && c->have_maps && c->g2p_variant == 1 && c->lazy_sort);
+    do_sort(c, arith == GFS_EXACT, /*lazy=*/arith != GFS_EXACT && c->grid.pow2 && c->have_maps && c->g2p_variant >= 1 && c->lazy_sort);
     do_p2g(c, arith);
     do_g2p(c, dt, ratio, order, interp, arith, arith != GFS_EXACT);
 }
@@ -1214,7 +1283,7 @@ void substep_body(gfs_context *c, double dt, double ratio, int order, int interp
 // or guarded by graph_epoch, and the host-side state transition of one substep is fixed (the buffer parity flips)
 bool substep_graph_eligible(gfs_context *c, int arith) {
     return c->use_graphs && !c->profiling && arith != GFS_EXACT && c->has_domain && c->grid.pow2 && c->have_maps &&
-           c->g2p_variant == 1 && c->p2g_variant == 1 && c->lazy_sort && c->storage_sorted && c->keys_ready && !c->sorted &&
+           c->g2p_variant >= 1 && c->p2g_variant >= 1 && c->lazy_sort && c->storage_sorted && c->keys_ready && !c->sorted &&
            !c->indexed && c->dead == 0 && c->n > 0 && c->own_k0 == 0 && c->own_k1 == c->grid.K && !removal_on(c);
 }
 }  // namespace
@@ -1577,7 +1646,7 @@ void gfs_comm_g2p_advect(gfs_context *c, double dt, double ratio, int order, int
     GFS_REQUIRE((!has_down || c->comm[0].peer) && (!has_up || c->comm[1].peer), "gfs_comm_connect first");
     GFS_REQUIRE(!removal_on(c), "options 5 and 6 (per-cell cap, removal in solids) are single-domain rules: switch them off for sharded runs");
     GFS_CUDA(cudaSetDevice(c->device));
-    const bool fused = g2p_uses_bricks(c, arith) && c->p2g_variant == 1 && c->lazy_sort && c->n - c->dead > 0 && (has_down || has_up);
+    const bool fused = g2p_uses_bricks(c, arith) && c->p2g_variant >= 1 && c->lazy_sort && c->n - c->dead > 0 && (has_down || has_up);
     if (!fused) {
         do_g2p(c, dt, ratio, order, interp, arith, false);
         comm_migrate_split(c, has_down, has_up);

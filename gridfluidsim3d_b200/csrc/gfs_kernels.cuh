@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : GFS_TRI
                             float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz,
                             unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
                             uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
-                            Migrate mg, CollList coll) {
+                            Migrate mg, CollList coll, uint32_t brick0) {
     typedef BrickTile<INTERP> T;
     // dynamic shared memory: [pad to 128 B] NEW u,v,w [nCount each] | SAVED u,v,w [sCount each] | mbarrier.
     // TMA destinations must be 128-byte aligned: align by hand, static shared variables precede this block.
@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(256, INTERP == 1 ? GFS_TRICUBIC_CTAS : GFS_TRI
     // shared memory, or every tap becomes a generic LD instead of an LDS)
     float *tiles = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     uint64_t &bar = *reinterpret_cast<uint64_t *>(tiles + 3 * (T::nCount + T::sCount));
-    const uint32_t b = blockIdx.x, nbricks = nkeys / kBrickCells;
+    const uint32_t b = blockIdx.x + brick0, nbricks = nkeys / kBrickCells;      // brick0: first brick of this launch
     // the last CTA takes the overflow bin (particles outside the grid): no tile, global path only
     const bool overflow = b == nbricks;
     const int start = cell_start[(size_t)b * kBrickCells];

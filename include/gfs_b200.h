@@ -188,9 +188,11 @@ void gfs_copy_field(gfs_context *ctx, int dst_slot, int src_slot, int *err);
  * P2G / G2P kernels fetch through it (G2P stores its results in sorted order).  What gfs_substep does internally;
  * gfs_get_particles afterwards returns the storage order, not the sorted one. */
 void gfs_sort_index(gfs_context *ctx, int *err);
-/* Tuning switches.  option 0: fast-P2G variant, 1 = brick tiles in shared memory (default), 0 = global atomics
- * only; both produce bit-identical grids.  option 1: fast-G2P variant, 1 = TMA-staged brick tiles (default; used
- * when dx is a power of two and the particles are sorted), 0 = global loads only; bit-identical results.
+/* Tuning switches.  option 0: fast-P2G variant, 0 = global atomics only; brick tiles in shared memory: 1 = round-1
+ * kernel, 2 = round-2 kernel, 3 = round-2 kernel with lanes transposed through shared memory (default); all produce
+ * bit-identical grids.  option 1: fast-G2P variant, 0 = global loads only; TMA-staged brick tiles (dx a power of two,
+ * sorted particles): 1 = round-1 kernel, 2 = round-2 trilinear kernel (default), 3 = the same on a bank-skewed tile;
+ * bit-identical results.
  * option 2: 1 = gfs_substep / gfs_sort_index sort by index only once the storage is nearly sorted (default), 0 = always
  * move the particles.  option 3: 1 = particles advected into a solid cell go through the reference's collision resolve
  * (FluidSimulation::_resolveParticleSolidCellCollision, src/fluidsimulation.cpp:3145-3179; default), 0 = they keep

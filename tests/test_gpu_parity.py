@@ -250,16 +250,17 @@ def test_counting_sort(ctx, oracle, name):
 
 @pytest.mark.parametrize("name", ["small32", "odd20"])
 def test_p2g_variants_bit_identical(ctx, name):
-    """Brick-tile P2G (shared-memory hi/lo integer words) == global-atomic P2G, bit for bit, after either sort."""
+    """Brick-tile P2G (shared-memory hi/lo integer words; variant 1 = round-1 kernel, 2 = round-2 kernel, 3 = round-2
+    kernel with the lane transposition through shared memory) == global-atomic P2G, bit for bit, after either sort."""
     s = scene(name)
     out = []
-    for variant, stable in ((1, True), (0, True), (1, False), (0, False)):
+    for variant, stable in ((1, True), (0, True), (2, True), (3, True), (1, False), (0, False), (2, False), (3, False)):
         load_domain(ctx, s, SOURCES)
         ctx.set_option(0, variant)
         ctx.sort() if stable else ctx.sort_unstable()
         ctx.p2g(capi.FAST)
         out.append(ctx.get_field(capi.FIELD_P2G))
-    ctx.set_option(0, 1)
+    ctx.set_option(0, 3)
     for other in out[1:]:
         for a, b in zip(out[0], other):
             assert np.array_equal(bits(a), bits(b))
@@ -410,14 +411,15 @@ def test_g2p_advect(ctx, oracle, name, interp):
 @pytest.mark.parametrize("interp", [capi.TRILINEAR, capi.TRICUBIC])
 @pytest.mark.parametrize("cfl", [0.5, 3.7])
 def test_g2p_brick_tiles_equal_global_loads(ctx, interp, cfl):
-    """TMA-staged brick kernel == global-load kernel, bit for bit (same fp32 arithmetic, different data path),
-    also when RK stage positions leave the staged block (cfl 3.7: fallback taps) and for every RK order."""
+    """TMA-staged brick kernels (variant 1 = round-1 kernel; 2 / 3 = round-2 trilinear kernel with the dense / the
+    bank-skewed tile, which hands particles whose RK stages leave the staged block to k_g2p_slow) == global-load kernel,
+    bit for bit (same fp32 arithmetic, different data path), also at cfl 3.7 and for every RK order."""
     s = scene("slab24", interior_solids=True)
     new, saved = rough_fields(s["dims"], 31, 0.5), rough_fields(s["dims"], 32, 0.5)
     dt = cfl * s["dx"]
     for order_rk in (1, 2, 3, 4):
         res = []
-        for variant in (1, 0):
+        for variant in (1, 0, 2, 3):
             load_domain(ctx, s)
             ctx.set_option(1, variant)
             ctx.set_field(capi.FIELD_NEW, *new); ctx.set_field(capi.FIELD_SAVED, *saved)
@@ -425,10 +427,11 @@ def test_g2p_brick_tiles_equal_global_loads(ctx, interp, cfl):
             ctx.p2g(capi.FAST)                      # classification -> fluid/solid material for the solid test
             ctx.g2p_advect(dt, order=order_rk, interp=interp, arith=capi.FAST)
             res.append(ctx.get_particles() + (ctx.get_particle_order(), ctx.stats()["solid_hits"]))
-        ctx.set_option(1, 1)
-        (p1, v1, o1, h1), (p0, v0, o0, h0) = res
-        assert np.array_equal(o1, o0) and h1 == h0
-        assert np.array_equal(bits(v1), bits(v0)) and np.array_equal(bits(p1), bits(p0))
+        ctx.set_option(1, 2)
+        (p1, v1, o1, h1) = res[0]
+        for (p0, v0, o0, h0) in res[1:]:
+            assert np.array_equal(o1, o0) and h1 == h0
+            assert np.array_equal(bits(v1), bits(v0)) and np.array_equal(bits(p1), bits(p0))
         assert np.abs(p1 - s["pos"][o1]).max() > 0.1 * s["dx"]
 
 
