@@ -596,6 +596,8 @@ def run_gfs(args):
         sub["advect_only"] = {"particles": n_adv, "kernel_ms": k_ms, "value": n_adv / (k_ms * 1e-3) if k_ms > 0 else None, "unit": "particles/s",
                               "algorithmic_bytes": b, "hbm_frac": b / (k_ms * 1e-3) / 1e9 / hbm_gbs if k_ms > 0 else None,
                               "through_host_value": n_adv / wall, "api": "gfs_advect (host pointers, unsorted random positions, global loads)"}
+    if world == 1 and not args.no_cpu_baseline and not args.no_dropin:
+        sub["dropin"] = dropin_submetric()
     line["submetrics"] = sub
     if world > 1:
         line["multi_gpu"] = {"transport": "peer memory (CUDA IPC, NVLink) written by gfs kernels" if args.transport == "peer"
@@ -617,6 +619,59 @@ def run_gfs(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dropin_submetric(n=64, frames=1):
+    """FluidSimulation::update() of the UNMODIFIED reference simulator (Hello World scene of README.md:113-117 at 64^3,
+    BASELINE configs[0]) three ways: its own CPU accelerator classes, the CUDA drop-in classes (host-pointer C-ABI calls
+    per stage), and the device-resident stages of dropin/fluidsimulation_resident.cpp.  The libraries are the reference
+    sources compiled where they lie (oracle/Makefile: ref, dropin, resident); particle-substeps/s counts every substep
+    the simulator's own log reports.  The pressure solve, meshing and everything else stay reference CPU code in all
+    three, so this is the speed-up a user of the reference sees today, not the kernel speed-up."""
+    import ctypes
+    from oracle import pyoracle
+    from oracle.pyoracle import RefSim
+    out = {"scene": "%d^3 sphere drop, %d frame(s) of 1/30 s" % (n, frames), "unit": UNIT}
+    libs = (("cpu_classes", pyoracle.REF_SO, False), ("cuda_classes", pyoracle.DROPIN_SO, True), ("cuda_resident", pyoracle.RESIDENT_SO, True))
+    for name, path, cuda in libs:
+        if not os.path.exists(path):
+            out[name] = {"unavailable": "%s not built" % os.path.basename(path)}
+            continue
+        try:
+            lib = pyoracle.Reference(build=False, path=path)
+            ctypes.CDLL(None).srand(1)
+            sim = lib.sim((n, n, n), 8.0 / n)
+            sim.add_fluid_sphere((4.0, 4.0, 4.0), 6.0)
+            sim.add_body_force((0.0, -25.0, 0.0))
+            if cuda:
+                sim.set_accel(True, True)
+            log_path = sim.log_path()
+            if os.path.exists(log_path):
+                os.remove(log_path)
+            sim.initialize()
+            if cuda:                      # context creation, first allocations and the first kernel loads are not the steady state
+                sim.update(1.0 / 30.0)
+                if os.path.exists(log_path):
+                    os.remove(log_path)
+            t0 = time.perf_counter()
+            for _ in range(frames):
+                sim.update(1.0 / 30.0)
+            wall = time.perf_counter() - t0
+            stages, substeps = RefSim.stage_times(log_path)
+            npart = sim.n
+            sim.close()
+            hot = sum(stages.get(k, 0.0) for k in ("Update Fluid Cells", "Advect Velocity Field", "Update PIC/FLIP Velocities", "Advance Marker Particles"))
+            out[name] = {"value": npart * max(1, substeps) / wall, "seconds": wall, "substeps": substeps, "particles": npart,
+                         "hot_path_stage_seconds": hot, "hot_path_value": npart * max(1, substeps) / hot if hot > 0 else None,
+                         "stage_seconds": {k: round(v, 4) for k, v in stages.items()}}
+        except Exception as e:
+            out[name] = {"unavailable": repr(e)[:200]}
+    try:
+        out["speedup_whole_update"] = out["cuda_resident"]["value"] / out["cpu_classes"]["value"]
+        out["speedup_hot_path_stages"] = out["cuda_resident"]["hot_path_value"] / out["cpu_classes"]["hot_path_value"]
+    except (KeyError, TypeError, ZeroDivisionError):
+        pass
+    return out
 
 
 JSON_FD = None
@@ -648,6 +703,7 @@ def main():
                     help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the FluidSimulation::update drop-in sub-metric (64^3, CPU vs CUDA classes)")
     ap.add_argument("--no-peer-check", action="store_true", help="N>1: skip the peer-memory vs NCCL transport cross-check after the timed runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gfs" else args.warmup

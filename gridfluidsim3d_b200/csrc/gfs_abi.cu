@@ -185,9 +185,9 @@ struct gfs_context {
                                           // kernel, 3 = round-2 kernel with the lane transposition (default)
     int lazy_sort = 1;                    // fused substep: sort by index only (no physical scatter)
     int g2p_variant = 2;                  // 0 = global loads only; TMA-staged brick tiles: 1 = round-1 kernel, 2 = round-2 trilinear
-                                          // kernel on the dense tile (default), 3 = on the bank-skewed tile; tricubic: k_g2p_brick<1>
+                                          // kernel on the 16-wide tile (default), 3 = on the 20-wide tile; tricubic: k_g2p_brick<1>
     gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
-    gfs::BrickMaps maps_tri_skew;         // 4-D (bank-skewed) boxes of the round-2 trilinear kernel
+    gfs::BrickMaps maps_tri_wide;         // dense boxes 20 columns wide (k_g2p_tri<true>: bank-conflict free row pitch)
     DevBuf<unsigned int> slow_count;      // k_g2p_tri's list of particles left to k_g2p_slow (the list itself lives in perm[0])
     bool have_maps = false;
     size_t field_floats[3] = {0, 0, 0};   // padded element counts of the resident u,v,w arrays
@@ -563,7 +563,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
             c->slow_count.reserve(1);
             slow.list = c->perm[0].p; slow.count = c->slow_count.p;
             GFS_CUDA(cudaMemsetAsync(c->slow_count.p, 0, sizeof(unsigned int), c->stream));
-#define GFS_TRI_ARGS c->grid, (skew ? c->maps_tri_skew : c->maps[0]), c->material.p, c->cell_start.p, (c->indexed ? c->index.p : nullptr), \
+#define GFS_TRI_ARGS c->grid, (skew ? c->maps_tri_wide : c->maps[0]), c->material.p, c->cell_start.p, (c->indexed ? c->index.p : nullptr), \
                c->tag[src].p, c->tag[dst].p, order, rk, rp, rf,                                                                         \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
@@ -663,10 +663,10 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // dense 3-D boxes {x 16, y, z} over the storage columns (trilinear bricks)
-void make_field_map_dense(CUtensorMap *map, float *storage, int pitch, int nj, int nkl, int by, int bz) {
+void make_field_map_dense(CUtensorMap *map, float *storage, int pitch, int nj, int nkl, int by, int bz, int bx = 16) {
     cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)nj, (cuuint64_t)nkl};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * (cuuint64_t)nj * 4};
-    cuuint32_t box[3] = {16, (cuuint32_t)by, (cuuint32_t)bz};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, storage, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -706,8 +706,8 @@ void make_brick_maps(gfs_context *c) {
             make_field_map_dense(&c->maps[0].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::nY, gfs::BrickTile<0>::nZ);
             make_field_map_dense(&c->maps[0].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<0>::sY, gfs::BrickTile<0>::sZ);
         }
-        make_field_map(&c->maps_tri_skew.m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::nY, gfs::TriTile<true>::nZ);
-        make_field_map(&c->maps_tri_skew.m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::sY, gfs::TriTile<true>::sZ);
+        make_field_map_dense(&c->maps_tri_wide.m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::nY, gfs::TriTile<true>::nZ, gfs::TriTile<true>::kX);
+        make_field_map_dense(&c->maps_tri_wide.m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::TriTile<true>::sY, gfs::TriTile<true>::sZ, gfs::TriTile<true>::kX);
         make_field_map(&c->maps[1].m[a], c->field[GFS_FIELD_NEW][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::nY, gfs::BrickTile<1>::nZ);
         make_field_map(&c->maps[1].m[3 + a], c->field[GFS_FIELD_SAVED][a].p, g.pitch[a], nj[a], nk[a], gfs::BrickTile<1>::sY, gfs::BrickTile<1>::sZ);
     }

@@ -10,28 +10,31 @@
 //     possible when dt |v| exceeds the one-cell margin) is put on a list and done in full by k_g2p_slow afterwards --
 //     the hot loop carries no fallback branches and fits 4 CTAs per SM;
 //   * the out-of-grid bin is not this kernel's business either (k_g2p_brick handles it, launched on that bin alone);
-//   * bank-skewed tile (SKEW): box {x_lo 8, z, x_hi 2, y} through the 4-D view of the row-padded arrays, as the
-//     tricubic kernel uses -- the two candidate rows in y and in z of a half-cell staggered lookup land in four
-//     disjoint 8-bank windows.  The variable x-neighbour offset costs two instructions per component sample.
+//   * WIDE tile: a 20-word row pitch makes the staggered lookups bank-conflict free with plain address arithmetic (see
+//     TriTile); it costs a quarter more shared memory (3 CTAs per SM instead of 4).  The 4-D bank-skewed box of the
+//     tricubic kernel was tried here too and lost: its split-column addresses cost more issue slots than the conflicts.
 #pragma once
 #include "gfs_kernels.cuh"
 
 namespace gfs {
 
-template <bool SKEW> struct TriTile {
+// WIDE = false: box [z][y][x 16] (the tensor maps of k_g2p_brick<0>).  WIDE = true: box [z][y][x 20] -- four unused
+// columns per row, chosen for the banks: a half-cell staggered lookup has two candidate rows in y and two in z, and with
+// a 20-word row pitch and a 20*nY-word plane pitch (== 16 mod 32 for nY = 12, == 8 for nY = 10) the four (y, z) candidates
+// of the cells of a warp fall into disjoint bank windows ({0,20,16,4}+x and {0,20,8,28}+x, x < 4) -- in the 16-wide box
+// both shifts are multiples of 16 banks and 42 % of the kernel's shared-memory wavefronts were conflicts.
+template <bool WIDE> struct TriTile {
     static constexpr int kMargin = 1;
-    static constexpr int kOrgX = 4, kX = 16;                 // x: nodes [8b-4, 8b+11]
+    static constexpr int kOrgX = 4, kX = WIDE ? 20 : 16;     // x: nodes [8b-4, 8b+11] (+4 unused when WIDE)
     static constexpr int nOrg = 1 + kMargin, nY = 9 + 2 * kMargin + 1;           // NEW: y/z nodes [8b-2, 8b+9]  (12)
     static constexpr int sOrg = 1, sY = 10;                                       // SAVED: [8b-1, 8b+8]
-    static constexpr int nZ = SKEW ? (nY | 1) : nY, sZ = SKEW ? (sY | 1) : sY;    // odd plane counts for the skew
+    static constexpr int nZ = nY, sZ = sY;
     static constexpr int nBox = kX * nY * nZ, sBox = kX * sY * sZ;
     static constexpr int nCount = (nBox + 31) / 32 * 32, sCount = (sBox + 31) / 32 * 32;
     static constexpr uint32_t kTxBytes = 3 * (nBox + sBox) * sizeof(float);
     static constexpr size_t kSmemBytes = 3 * (nCount + sCount) * sizeof(float) + 128 + 16;
-    // word strides: dense [z][y][x16];  skew: word = (x&7) + 8 (z + NZ ((x>>3) + 2 y))
-    template <int NYY, int NZZ> struct Str {
-        static constexpr int sy = SKEW ? 16 * NZZ : 16, sz = SKEW ? 8 : 16 * NYY, sxh = SKEW ? 8 * NZZ - 8 : 0;
-    };
+    static constexpr int kCtas = WIDE ? 3 : 4;
+    template <int NYY> struct Str { static constexpr int sy = kX, sz = kX * NYY; };
 };
 
 struct AxL { int i; float t; };         // tile-local node index and fraction
@@ -61,12 +64,11 @@ __device__ __forceinline__ IdxL idx_tile(float ux, float uy, float uz, int biasx
 }
 
 // one component from a staged tile; x, y, z: tile-local indices (y, z relative to the tile's own y/z origin)
-template <bool SKEW, int SY, int SZ, int SXH>
+template <int SY, int SZ>
 __device__ __forceinline__ float tri_sample(const float *__restrict__ t, int x, float tx, int y, float ty, int z, float tz) {
-    const float *r0 = t + SY * y + SZ * z + (SKEW ? x + (x >> 3) * SXH : x);
-    const float *r1 = SKEW ? t + SY * y + SZ * z + ((x + 1) + ((x + 1) >> 3) * SXH) : r0 + 1;
-    const float p000 = r0[0], p100 = r1[0], p010 = r0[SY], p110 = r1[SY];
-    const float p001 = r0[SZ], p101 = r1[SZ], p011 = r0[SZ + SY], p111 = r1[SZ + SY];
+    const float *r = t + SY * y + SZ * z + x;
+    const float p000 = r[0], p100 = r[1], p010 = r[SY], p110 = r[SY + 1];
+    const float p001 = r[SZ], p101 = r[SZ + 1], p011 = r[SZ + SY], p111 = r[SZ + SY + 1];
     const float c00 = fmaf(tx, __fsub_rn(p100, p000), p000), c10 = fmaf(tx, __fsub_rn(p110, p010), p010);
     const float c01 = fmaf(tx, __fsub_rn(p101, p001), p001), c11 = fmaf(tx, __fsub_rn(p111, p011), p011);
     const float c0 = fmaf(ty, __fsub_rn(c10, c00), c00), c1 = fmaf(ty, __fsub_rn(c11, c01), c01);
@@ -75,8 +77,8 @@ __device__ __forceinline__ float tri_sample(const float *__restrict__ t, int x, 
 
 struct SlowList { int32_t *list; unsigned int *count; };      // sorted slots left to k_g2p_slow
 
-template <bool SKEW, bool MIGRATE>
-__global__ void __launch_bounds__(256, 4)
+template <bool WIDE, bool MIGRATE>
+__global__ void __launch_bounds__(256, TriTile<WIDE>::kCtas)
 k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
           const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
           int order, RkCoef rk, float ratio_pic, float ratio_flip,
@@ -87,9 +89,9 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
           unsigned long long *__restrict__ counters, uint32_t nkeys, uint32_t *__restrict__ keys_out,
           uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
           Migrate mg, CollList coll, SlowList slow) {
-    typedef TriTile<SKEW> T;
-    typedef typename T::template Str<T::nY, T::nZ> SN;
-    typedef typename T::template Str<T::sY, T::sZ> SS;
+    typedef TriTile<WIDE> T;
+    typedef typename T::template Str<T::nY> SN;
+    typedef typename T::template Str<T::sY> SS;
     extern __shared__ unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     uint64_t &bar = *reinterpret_cast<uint64_t *>(tiles + 3 * (T::nCount + T::sCount));
@@ -105,13 +107,8 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(T::kTxBytes) : "memory");
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            if (SKEW) {
-                tma_load_box(tnew + c * T::nCount, &maps.m[c], bz - g.k0 - T::nOrg, bi, by - T::nOrg, &bar);
-                tma_load_box(tsav + c * T::sCount, &maps.m[3 + c], bz - g.k0 - T::sOrg, bi, by - T::sOrg, &bar);
-            } else {
-                tma_load_3d(tnew + c * T::nCount, &maps.m[c], 8 * bi, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
-                tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], 8 * bi, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
-            }
+            tma_load_3d(tnew + c * T::nCount, &maps.m[c], 8 * bi, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
+            tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], 8 * bi, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
         }
     }
     // NEW tile origin: x from node 8b-4, y/z from 8b-nOrg
@@ -153,13 +150,13 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
         float k1x, k1y, k1z, sx, sy, sz;
         {
             const IdxL s = idx_tile(__fmul_rn(px, invdx), __fmul_rn(py, invdx), __fmul_rn(pz, invdx), biasx, biasy, biasz);
-            k1x = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew, s.ux.i, s.ux.t, s.sy.i, s.sy.t, s.sz.i, s.sz.t);
-            k1y = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew + T::nCount, s.sx.i, s.sx.t, s.uy.i, s.uy.t, s.sz.i, s.sz.t);
-            k1z = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew + 2 * T::nCount, s.sx.i, s.sx.t, s.sy.i, s.sy.t, s.uz.i, s.uz.t);
+            k1x = tri_sample<SN::sy, SN::sz>(tnew, s.ux.i, s.ux.t, s.sy.i, s.sy.t, s.sz.i, s.sz.t);
+            k1y = tri_sample<SN::sy, SN::sz>(tnew + T::nCount, s.sx.i, s.sx.t, s.uy.i, s.uy.t, s.sz.i, s.sz.t);
+            k1z = tri_sample<SN::sy, SN::sz>(tnew + 2 * T::nCount, s.sx.i, s.sx.t, s.sy.i, s.sy.t, s.uz.i, s.uz.t);
             constexpr int d = T::nOrg - T::sOrg;          // the SAVED tile starts d nodes later in y and z
-            sx = tri_sample<SKEW, SS::sy, SS::sz, SS::sxh>(tsav, s.ux.i, s.ux.t, s.sy.i - d, s.sy.t, s.sz.i - d, s.sz.t);
-            sy = tri_sample<SKEW, SS::sy, SS::sz, SS::sxh>(tsav + T::sCount, s.sx.i, s.sx.t, s.uy.i - d, s.uy.t, s.sz.i - d, s.sz.t);
-            sz = tri_sample<SKEW, SS::sy, SS::sz, SS::sxh>(tsav + 2 * T::sCount, s.sx.i, s.sx.t, s.sy.i - d, s.sy.t, s.uz.i - d, s.uz.t);
+            sx = tri_sample<SS::sy, SS::sz>(tsav, s.ux.i, s.ux.t, s.sy.i - d, s.sy.t, s.sz.i - d, s.sz.t);
+            sy = tri_sample<SS::sy, SS::sz>(tsav + T::sCount, s.sx.i, s.sx.t, s.uy.i - d, s.uy.t, s.sz.i - d, s.sz.t);
+            sz = tri_sample<SS::sy, SS::sz>(tsav + 2 * T::sCount, s.sx.i, s.sx.t, s.sy.i - d, s.sy.t, s.uz.i - d, s.uz.t);
         }
         float nx = k1x, ny = k1y, nz = k1z;
         validate3(nx, ny, nz);
@@ -181,13 +178,13 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
             } else {
                 const IdxL s = idx_tile(__fmul_rn(ex, invdx), __fmul_rn(ey, invdx), __fmul_rn(ez, invdx), biasx, biasy, biasz);
                 // taps c, c+1 of the six index variants must lie inside the staged box: 0 <= i <= n-2
-                const bool in = (unsigned)s.ux.i <= (unsigned)(T::kX - 2) && (unsigned)s.sx.i <= (unsigned)(T::kX - 2) &&
+                const bool in = (unsigned)s.ux.i <= 14u && (unsigned)s.sx.i <= 14u &&          // 16 loaded columns
                                 (unsigned)s.uy.i <= (unsigned)(T::nY - 2) && (unsigned)s.sy.i <= (unsigned)(T::nY - 2) &&
                                 (unsigned)s.uz.i <= (unsigned)(T::nY - 2) && (unsigned)s.sz.i <= (unsigned)(T::nY - 2);
                 if (!in) { leave = true; break; }
-                kx = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew, s.ux.i, s.ux.t, s.sy.i, s.sy.t, s.sz.i, s.sz.t);
-                ky = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew + T::nCount, s.sx.i, s.sx.t, s.uy.i, s.uy.t, s.sz.i, s.sz.t);
-                kz = tri_sample<SKEW, SN::sy, SN::sz, SN::sxh>(tnew + 2 * T::nCount, s.sx.i, s.sx.t, s.sy.i, s.sy.t, s.uz.i, s.uz.t);
+                kx = tri_sample<SN::sy, SN::sz>(tnew, s.ux.i, s.ux.t, s.sy.i, s.sy.t, s.sz.i, s.sz.t);
+                ky = tri_sample<SN::sy, SN::sz>(tnew + T::nCount, s.sx.i, s.sx.t, s.uy.i, s.uy.t, s.sz.i, s.sz.t);
+                kz = tri_sample<SN::sy, SN::sz>(tnew + 2 * T::nCount, s.sx.i, s.sx.t, s.sy.i, s.sy.t, s.uz.i, s.uz.t);
             }
             sx_ = __fadd_rn(sx_, __fmul_rn(kx, bb)); sy_ = __fadd_rn(sy_, __fmul_rn(ky, bb)); sz_ = __fadd_rn(sz_, __fmul_rn(kz, bb));
         }

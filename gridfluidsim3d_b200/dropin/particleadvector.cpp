@@ -62,6 +62,13 @@ std::string ParticleAdvector::getKernelInfo() {
 }
 
 void ParticleAdvector::printKernelInfo() { std::cout << getKernelInfo() << std::endl; }
+gfs_context *ParticleAdvector::context() {
+    if (!_isInitialized && !initialize()) {
+        _check(GFS_FAIL, "initialize");
+    }
+    return _ctx;
+}
+
 bool ParticleAdvector::isUsingGPU() { return _isInitialized; }
 bool ParticleAdvector::isUsingCPU() { return false; }
 void ParticleAdvector::disableOpenCL() { _isOpenCLEnabled = false; }

@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "vmath.h"
+#include <memory>
+
 #include "macvelocityfield.h"
 
 struct gfs_context;
@@ -57,6 +59,12 @@ public:
                              std::vector<vmath::vec3> &output);
     // method will overwrite particles with output data
     void tricubicInterpolate(std::vector<vmath::vec3> &particles, MACVelocityField *vfield);
+
+    // ---- not in the reference's class: the device-resident path (dropin/fluidsimulation_resident.cpp) ------------
+    // the CUDA context of this accelerator (initialised on demand) and a slot for the per-simulation state of the
+    // resident FluidSimulation stages, which cannot add members to FluidSimulation itself
+    gfs_context *context();
+    std::shared_ptr<void> residentState;
 
 private:
     ParticleAdvector(const ParticleAdvector &);              // the context is not shareable

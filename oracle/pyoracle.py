@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgfsref.so")
 DROPIN_SO = os.path.join(HERE, "_ref", "libgfsref_dropin.so")   # the reference simulator + the CUDA drop-in classes
+RESIDENT_SO = os.path.join(HERE, "_ref", "libgfsref_resident.so")   # ... + stages 1/5/11/12 of _stepFluid device resident
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -362,6 +363,43 @@ class RefSim:
         self.lib.ref_sim_enable_mesh_output.restype = C.c_char_p
         self.lib.ref_sim_enable_mesh_output.argtypes = [C.c_void_p]
         return self.lib.ref_sim_enable_mesh_output(self.h).decode()
+
+    def log_path(self):
+        """Path of the simulator's own log (its directory is created); call before update()."""
+        self.lib.ref_sim_log_path.restype = C.c_char_p
+        self.lib.ref_sim_log_path.argtypes = [C.c_void_p]
+        return self.lib.ref_sim_log_path(self.h).decode()
+
+    @staticmethod
+    def stage_times(path):
+        """{stage name: seconds summed over the logged substeps} from the reference's own StopWatch lines."""
+        out, steps = {}, 0
+        names = ("Update Fluid Cells", "Reconstruct Fluid Surface", "Update Level set", "Reconstruct Output Surface",
+                 "Advect Velocity Field", "Apply Body Forces", "Update Pressure Grid", "Apply Pressure",
+                 "Extrapolate Fluid Velocities", "Update Diffuse Material", "Update PIC/FLIP Velocities",
+                 "Advance Marker Particles", "Update time")
+        try:
+            with open(path) as f:
+                lines = f.readlines()
+        except OSError:
+            return out, 0
+        past_breakdown = False
+        for ln in lines:
+            if ln.startswith("---Percentage Breakdown---"):
+                past_breakdown = True
+            if ln.startswith("Frame:") or ln.startswith("Step time"):
+                past_breakdown = False
+            if past_breakdown and not ln.startswith("Update time"):
+                continue
+            for nm in names:
+                if ln.startswith(nm + ":"):
+                    try:
+                        out[nm] = out.get(nm, 0.0) + float(ln.split(":", 1)[1].strip().split()[0])
+                    except (ValueError, IndexError):
+                        pass
+                    if nm == "Update time":
+                        steps += 1
+        return out, steps
 
     def mesh_particles(self, use_accelerator, cap=4000000):
         """IsotropicParticleMesher::meshParticles on the current state -> (vertices (n,3), triangle count)."""
