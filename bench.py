@@ -465,17 +465,24 @@ def run_gfs(args):
     p2g_out = [t.numpy() for t in p2g_pinned]                                                         # e2e leg is pinned
     mat_pinned = torch.empty(G, dtype=torch.uint8, pin_memory=True)
     nu, nv, nw = [t.numel() for t in new_host]
-    h2d = n_local * 24 + 2 * 4 * (nu + nv + nw)
-    d2h = n_local * 24 + 4 * (nu + nv + nw) + G
+    if world == 1:
+        up_lo, up_n, dn_lo, dn_n = 0, dims[2], 0, dims[2]
+    else:           # a z-slab rank moves its owned layers + the G2P halo up, and what it owns down
+        up_lo, up_hi = max(0, owned[0] - halo), min(dims[2], owned[1] + halo)
+        up_n, dn_lo, dn_n = up_hi - up_lo, owned[0], owned[1] - owned[0]
+    per_layer = (dims[0] + 1) * dims[1] + dims[0] * (dims[1] + 1) + dims[0] * dims[1]
+    h2d = n_local * 24 + 2 * 4 * (per_layer * up_n + dims[0] * dims[1])
+    d2h = n_local * 24 + 4 * (per_layer * dn_n + dims[0] * dims[1]) + dims[0] * dims[1] * dn_n
+    new_np, saved_np = [t.numpy() for t in new_host], [t.numpy() for t in saved_host]
 
     def e2e_step():
         ctx.set_particles_aos(aos_host.numpy())                                  # H2D 24 B/particle
-        ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])           # H2D post-pressure field
-        ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])       # H2D saved field
+        ctx.set_field_layers(capi.FIELD_NEW, *new_np, up_lo, up_n)              # H2D post-pressure field (owned layers + halo)
+        ctx.set_field_layers(capi.FIELD_SAVED, *saved_np, up_lo, up_n)          # H2D saved field
         substep()
         ctx.get_particles_aos(aos_out.numpy().reshape(-1)[: ctx.num_particles * 6])   # D2H particles
-        ctx.get_field(capi.FIELD_P2G, out=p2g_out)                               # D2H P2G u,v,w
-        ctx.get_material(out=mat_pinned.numpy())                                  # D2H material
+        ctx.get_field_layers(capi.FIELD_P2G, p2g_out, dn_lo, dn_n)              # D2H P2G u,v,w (owned layers)
+        ctx.get_material_layers(mat_pinned.numpy(), dn_lo, dn_n)                 # D2H material
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
@@ -487,8 +494,8 @@ def run_gfs(args):
     e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
     e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d), "d2h_bytes_per_step": allsum(d2h),
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "gfs_set_particles + gfs_set_field x2 + substep + gfs_get_particles + gfs_get_field + gfs_get_material"
-                  + (" (per rank; whole fields are moved by every rank)" if world > 1 else "")}
+           "api": "gfs_set_particles + gfs_set_field_layers x2 + substep + gfs_get_particles + gfs_get_field_layers + gfs_get_material_layers"
+                  + (" (per rank: owned layers + halo up, owned layers down)" if world > 1 else " (all layers)")}
 
     # ---- the other interpolation, short --------------------------------------------------------------------
     other = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR

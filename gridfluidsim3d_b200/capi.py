@@ -24,13 +24,13 @@ SYMBOLS = [
     "gfs_sample", "gfs_advect", "gfs_add_point_values", "gfs_add_points",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
-    "gfs_set_field", "gfs_get_field", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
+    "gfs_set_field", "gfs_get_field", "gfs_set_field_layers", "gfs_get_field_layers", "gfs_get_material_layers", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
     "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
-    "gfs_comm_allmax_scale", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
+    "gfs_comm_allmax_scale", "gfs_comm_allmax_post", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_state_hash", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
@@ -93,6 +93,9 @@ def load_library():
     L.gfs_get_particle_order.argtypes = [V, _i32, _err]
     L.gfs_set_field.argtypes = [V, I, _f32, _f32, _f32, _err]
     L.gfs_get_field.argtypes = [V, I, _f32, _f32, _f32, _err]
+    L.gfs_set_field_layers.argtypes = [V, I, _f32, _f32, _f32, I, I, _err]
+    L.gfs_get_field_layers.argtypes = [V, I, _f32, _f32, _f32, I, I, _err]
+    L.gfs_get_material_layers.argtypes = [V, _u8, I, I, _err]
     L.gfs_sort.argtypes = [V, _err]
     L.gfs_sort_unstable.argtypes = [V, _err]
     L.gfs_set_option.argtypes = [V, I, I, _err]
@@ -125,6 +128,7 @@ def load_library():
     L.gfs_comm_world_connect.argtypes = [V, I, C.c_char_p, _err]
     L.gfs_comm_world_connect_local.argtypes = [V, I, V, _err]
     L.gfs_comm_allmax_scale.argtypes = [V, _err]
+    L.gfs_comm_allmax_post.argtypes = [V, _err]
     L.gfs_sort_index.argtypes = [V, _err]
     L.gfs_extrapolate.argtypes = [V, I, I, _err]
     L.gfs_extrapolate_field.argtypes = [V, _f32, _f32, _f32, I, I, I, _u8, I, _err]
@@ -337,6 +341,18 @@ class Context:
             nu, nv, nw = face_counts(self.dims)
             out = (np.empty(nu, np.float32), np.empty(nv, np.float32), np.empty(nw, np.float32))
         self._call(self.lib.gfs_get_field, slot, *out)
+        return out
+
+    def set_field_layers(self, slot, u, v, w, k_first, k_count):
+        """Upload only cell layers [k_first, k_first + k_count) of the caller's WHOLE arrays (z-slab ranks)."""
+        self._call(self.lib.gfs_set_field_layers, slot, _c(u), _c(v), _c(w), int(k_first), int(k_count))
+
+    def get_field_layers(self, slot, out, k_first, k_count):
+        self._call(self.lib.gfs_get_field_layers, slot, *out, int(k_first), int(k_count))
+        return out
+
+    def get_material_layers(self, out, k_first, k_count):
+        self._call(self.lib.gfs_get_material_layers, out, int(k_first), int(k_count))
         return out
 
     def sort(self):

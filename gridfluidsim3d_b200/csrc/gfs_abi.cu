@@ -180,6 +180,9 @@ struct gfs_context {
     long long comm_timeout_cycles = 8000000000ll;     // option 7: device-side wait limit (SM clocks; ~4 s)
     int64_t coll_cap_user = 0;                          // option 8: collision list capacity in particles (0 = n/16 + 4096)
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
+    uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
+    uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
+    bool allmax_posted = false;           // this rank's max |v| of the coming substep is already on its way (post after G2P)
     DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 3;                  // 0 = global atomics only; brick tiles in shared memory: 1 = round-1 kernel, 2 = round-2
                                           // kernel, 3 = round-2 kernel with the lane transposition (default)
@@ -293,17 +296,52 @@ int64_t read_dead_bin(gfs_context *c) {
     return (int64_t)*c->removal_host;
 }
 
+// brick layers around the owned cell layers, one brick layer (8 cells) of slack each side: where this rank's particles can
+// be between two migrations
+void set_key_range(gfs_context *c) {
+    const Grid &g = c->grid;
+    const bool whole = c->own_k0 <= g.k0 && c->own_k1 >= g.k1;
+    int bk_lo = 0, bk_hi = g.nbk;
+    if (!whole) {
+        bk_lo = (c->own_k0 - g.k0 - gfs::kBrick) / gfs::kBrick;
+        bk_hi = (c->own_k1 - g.k0 + gfs::kBrick - 1) / gfs::kBrick + 1;
+        if (bk_lo < 0) bk_lo = 0;
+        if (bk_hi > g.nbk) bk_hi = g.nbk;
+    }
+    const uint32_t per_layer = (uint32_t)g.nbi * (uint32_t)g.nbj;
+    c->brick_lo = (uint32_t)bk_lo * per_layer; c->brick_hi = (uint32_t)bk_hi * per_layer;
+    c->key_lo = c->brick_lo * gfs::kBrickCells; c->key_hi = c->brick_hi * gfs::kBrickCells;
+}
+
+gfs::KeyRange key_range(const gfs_context *c) { gfs::KeyRange kr; kr.lo = c->key_lo; kr.hi = c->key_hi; return kr; }
+bool full_range(const gfs_context *c) { return c->key_lo == 0 && c->key_hi == c->nkeys; }
+
+// zero the cell counters the next binning pass will tick: the key range of this rank plus the three tail bins
+void reset_counts(gfs_context *c) {
+    if (full_range(c)) {
+        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * ((size_t)c->nkeys + 3), c->stream));
+    } else {
+        GFS_CUDA(cudaMemsetAsync(c->counts.p + c->key_lo, 0, sizeof(uint32_t) * (size_t)(c->key_hi - c->key_lo), c->stream));
+        GFS_CUDA(cudaMemsetAsync(c->counts.p + c->nkeys, 0, sizeof(uint32_t) * 3, c->stream));
+    }
+}
+
 void scan_counts(gfs_context *c) {
     if (c->cell_cap > 0)
         LAUNCH(c, gfs::k_clamp_counts, ceil_div((long long)c->nkeys, 256), 256, c->nkeys, (uint32_t)c->cell_cap, c->counts.p);
-    const size_t nbins = (size_t)c->nkeys + 3;
+    // single domain: one scan over every cell and the tail bins; z-slab rank: only the keys of its own bricks (an eighth of
+    // the table at 8 GPUs), the tail bins fixed up by k_scan_tail
+    const bool full = full_range(c);
+    const size_t first = full ? 0 : c->key_lo, nbins = full ? (size_t)c->nkeys + 3 : (size_t)(c->key_hi - c->key_lo);
     size_t tmp_bytes = 0;
-    GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p + first, (uint32_t *)c->cell_start.p + first, (int)nbins, c->stream));
     c->cub_tmp.reserve(tmp_bytes);
     int prof_id = c->prof_begin("cub::DeviceScan::ExclusiveSum");
-    GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)nbins, c->stream));
+    if (nbins > 0)
+        GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p + first, (uint32_t *)c->cell_start.p + first, (int)nbins, c->stream));
     c->prof_end(prof_id);
     c->launches += 2;
+    if (!full) LAUNCH(c, gfs::k_scan_tail, 1, 1, c->counts.p, c->cell_start.p, c->key_lo, c->key_hi, c->nkeys);
 }
 
 // Dead slots (particles the fused G2P handed to a neighbour GPU) only make sense to kernels that walk the sorted
@@ -342,14 +380,14 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     }
     const int src = c->cur, dst = 1 - c->cur;
     const int B = 256;
-    const size_t nbins = (size_t)c->nkeys + 3;
     if (!c->keys_ready) {
-        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * nbins, c->stream));
+        reset_counts(c);
+        c->allmax_posted = false;                  // a fresh max |v| is computed here: nothing posted for it yet
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
         if (n > 0)
             LAUNCH(c, gfs::k_hist, ceil_div(n, B), B, c->grid, c->nkeys, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
                    c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, n, c->keys[0].p, c->rank.p, c->perm[0].p,
-                   c->counts.p, c->vmax_bits.p, c->remove_in_solid ? c->material.p : (const uint8_t *)nullptr, (uint32_t)c->cell_cap);
+                   c->counts.p, c->vmax_bits.p, c->remove_in_solid ? c->material.p : (const uint8_t *)nullptr, (uint32_t)c->cell_cap, key_range(c));
         if (removal_on(c) && n > 0) { c->dead = read_dead_bin(c); c->removed += c->dead; }
     }
     scan_counts(c);
@@ -426,9 +464,9 @@ void do_p2g_begin(gfs_context *c, int arith) {
                        c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p,
                        c->acc[0].p, c->acc[1].p, c->acc[2].p);
         } else {
-            const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
+            const int nbricks = (int)(c->brick_hi - c->brick_lo);          // the bricks around the owned layers (all, single domain)
             const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
-#define GFS_TILE_ARGS g, sp, c->cell_start.p, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, \
+#define GFS_TILE_ARGS g, sp, c->cell_start.p, c->brick_lo, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, \
                       c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p
             if (pow2 && c->p2g_variant == 3) {
                 const size_t smem3 = smem + 6 * gfs::kStageChunk * sizeof(float);
@@ -522,7 +560,8 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     // fast arithmetic: bin the advected positions for the next counting sort in the kernel's epilogue
     uint32_t *keys_out = nullptr, *rank_out = nullptr, *counts = nullptr;
     if (bin_next) {
-        GFS_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(uint32_t) * ((size_t)c->nkeys + 3), c->stream));
+        reset_counts(c);
+        c->allmax_posted = false;
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
         keys_out = c->keys[0].p; rank_out = c->rank.p; counts = c->counts.p;
     }
@@ -548,8 +587,9 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     if (migrate) mg = *migrate;
     else { mg.own_lo = (int)0x80000000; mg.own_hi = 0x7FFFFFFF; mg.out[0] = mg.out[1] = nullptr; mg.count = nullptr; mg.cap = 0; }
     if (brick) {
-        const int nbricks = (int)(c->nkeys / gfs::kBrickCells);
-        const int nb = nbricks + 1;          // + the overflow-bin CTA
+        const int nbricks_all = (int)(c->nkeys / gfs::kBrickCells);          // the out-of-grid bin's CTA index
+        const int nbricks = (int)(c->brick_hi - c->brick_lo);               // bricks around the owned layers (all, single domain)
+        const bool ranged = !full_range(c);
 #define GFS_BRICK_ARGS c->grid, c->maps[interp], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, c->cell_start.p, \
                (c->indexed ? c->index.p : nullptr), c->tag[src].p, c->tag[dst].p, order, rk, rp, rf, c->n,                                                                                                  \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
@@ -563,7 +603,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
             c->slow_count.reserve(1);
             slow.list = c->perm[0].p; slow.count = c->slow_count.p;
             GFS_CUDA(cudaMemsetAsync(c->slow_count.p, 0, sizeof(unsigned int), c->stream));
-#define GFS_TRI_ARGS c->grid, (skew ? c->maps_tri_wide : c->maps[0]), c->material.p, c->cell_start.p, (c->indexed ? c->index.p : nullptr), \
+#define GFS_TRI_ARGS c->grid, (skew ? c->maps_tri_wide : c->maps[0]), c->material.p, c->cell_start.p, c->brick_lo, (c->indexed ? c->index.p : nullptr), \
                c->tag[src].p, c->tag[dst].p, order, rk, rp, rf,                                                                         \
                c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,            \
                c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,            \
@@ -580,8 +620,8 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
             GFS_CUDA(cudaGetLastError());
 #undef GFS_TRI_ARGS
             int prof_id2_ = c->prof_begin("gfs::k_g2p_brick<0> (out-of-grid bin)");
-            if (migrate) gfs::k_g2p_brick<0, true><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks);
-            else gfs::k_g2p_brick<0, false><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks);
+            if (migrate) gfs::k_g2p_brick<0, true><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks_all);
+            else gfs::k_g2p_brick<0, false><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, (uint32_t)nbricks_all);
             c->prof_end(prof_id2_);
             GFS_CUDA(cudaGetLastError());
 #define GFS_SLOW_ARGS c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_SAVED), c->material.p, (c->indexed ? c->index.p : nullptr), \
@@ -594,17 +634,23 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
 #undef GFS_SLOW_ARGS
             c->launches += 2;
         } else {
+            // single domain: every brick + the out-of-grid bin's CTA in one launch; z-slab rank: its brick range, then that CTA alone
             int prof_id_ = c->prof_begin(interp == GFS_TRICUBIC ? "gfs::k_g2p_brick<1>" : "gfs::k_g2p_brick<0>");
-            if (interp == GFS_TRICUBIC) {
-                if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
-                else gfs::k_g2p_brick<1, false><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
-            } else {
-                if (migrate) gfs::k_g2p_brick<0, true><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
-                else gfs::k_g2p_brick<0, false><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, 0u);
+            for (int part = 0; part < (ranged ? 2 : 1); part++) {
+                const int nb = ranged ? (part == 0 ? nbricks : 1) : nbricks + 1;
+                const uint32_t b0 = ranged ? (part == 0 ? c->brick_lo : (uint32_t)nbricks_all) : 0u;
+                if (nb <= 0) continue;
+                if (interp == GFS_TRICUBIC) {
+                    if (migrate) gfs::k_g2p_brick<1, true><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, b0);
+                    else gfs::k_g2p_brick<1, false><<<nb, 256, gfs::BrickTile<1>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, b0);
+                } else {
+                    if (migrate) gfs::k_g2p_brick<0, true><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, b0);
+                    else gfs::k_g2p_brick<0, false><<<nb, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(GFS_BRICK_ARGS, b0);
+                }
+                c->launches++;
+                GFS_CUDA(cudaGetLastError());
             }
             c->prof_end(prof_id_);
-            c->launches++;
-            GFS_CUDA(cudaGetLastError());
         }
 #undef GFS_BRICK_ARGS
     }
@@ -614,7 +660,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
 #undef GFS_G2P_ARGS
     if (coll.list)
         LAUNCH(c, gfs::k_resolve_collisions, 64, 128, c->grid, c->material.p, coll, c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p,
-               c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->nkeys, keys_out, rank_out, counts, mg);
+               c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->nkeys, keys_out, rank_out, counts, mg, key_range(c));
     // tags travel with the slot: the per-particle kernels keep slot order (copy the tag array across buffers); the brick
     // kernel moves the tags itself (it may be reading through the lazy sort index)
     if (!brick)
@@ -1046,6 +1092,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->has_domain = true;
     c->have_maps = false;
     c->own_k0 = 0; c->own_k1 = K;
+    set_key_range(c);
     if (g.pow2) make_brick_maps(c);
     LAUNCH(c, gfs::k_border_solid, grid3(I, J, kl), 128, g, c->material.p);
     GFS_END()
@@ -1169,6 +1216,56 @@ void gfs_get_field(gfs_context *c, int slot, float *u, float *v, float *w, int *
     for (int a = 0; a < 3; a++)
         GFS_CUDA(cudaMemcpy2DAsync(h[a], (size_t)ni[a] * 4, c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, (size_t)ni[a] * 4,
                                    c->face_count[a] / (size_t)ni[a], cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+/* Layer-range forms of gfs_set_field / gfs_get_field / gfs_get_material for z-slab ranks: u, v, w (material) are the
+ * caller's WHOLE arrays in the reference's layout; only the cell layers [k_first, k_first + k_count) travel (the w array
+ * has one more face layer: it is moved too).  A rank uploads its owned layers plus the halo and downloads what it owns. */
+void gfs_set_field_layers(gfs_context *c, int slot, const float *u, const float *v, const float *w, int k_first, int k_count, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(k_first >= 0 && k_count >= 0 && k_first + k_count <= g.K, "layer range out of bounds");
+    const float *h[3] = {u, v, w};
+    const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J};
+    for (int a = 0; a < 3; a++) {
+        const size_t rows = (size_t)nj[a] * (size_t)(k_count + (a == 2 ? 1 : 0)), row0 = (size_t)nj[a] * (size_t)k_first;
+        if (rows == 0) continue;
+        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad + row0 * g.pitch[a], (size_t)g.pitch[a] * 4, h[a] + row0 * ni[a],
+                                   (size_t)ni[a] * 4, (size_t)ni[a] * 4, rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_field_layers(gfs_context *c, int slot, float *u, float *v, float *w, int k_first, int k_count, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(k_first >= 0 && k_count >= 0 && k_first + k_count <= g.K, "layer range out of bounds");
+    float *h[3] = {u, v, w};
+    const int ni[3] = {g.I + 1, g.I, g.I}, nj[3] = {g.J, g.J + 1, g.J};
+    for (int a = 0; a < 3; a++) {
+        const size_t rows = (size_t)nj[a] * (size_t)(k_count + (a == 2 ? 1 : 0)), row0 = (size_t)nj[a] * (size_t)k_first;
+        if (rows == 0) continue;
+        GFS_CUDA(cudaMemcpy2DAsync(h[a] + row0 * ni[a], (size_t)ni[a] * 4, c->field[slot][a].p + gfs::kRowPad + row0 * g.pitch[a],
+                                   (size_t)g.pitch[a] * 4, (size_t)ni[a] * 4, rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_END()
+}
+
+void gfs_get_material_layers(gfs_context *c, uint8_t *material, int k_first, int k_count, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    const Grid &g = c->grid;
+    GFS_REQUIRE(material && k_first >= 0 && k_count >= 0 && k_first + k_count <= g.K, "bad arguments");
+    const size_t plane = (size_t)g.I * g.J;
+    GFS_CUDA(cudaMemcpyAsync(material + plane * k_first, c->material.p + plane * k_first, plane * k_count, cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
@@ -1354,6 +1451,7 @@ void gfs_set_owned_layers(gfs_context *c, int k0, int k1, int *err) {
     require_domain(c);
     GFS_REQUIRE(k0 >= 0 && k1 > k0 && k1 <= c->grid.K, "bad layer range");
     c->own_k0 = k0; c->own_k1 = k1;
+    set_key_range(c);
     c->graph_epoch++;
     GFS_END()
 }
@@ -1703,7 +1801,7 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
             LAUNCH(c, gfs::k_append_bin, ceil_div((int64_t)n_in[s], 256), 256, c->grid, c->nkeys, (int64_t)n_in[s], c->n,
                    (const float *)comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles),
                    c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, c->soa[b][5].p, c->tag[b].p,
-                   c->keys[0].p, c->rank.p, c->counts.p);
+                   c->keys[0].p, c->rank.p, c->counts.p, key_range(c));
             c->n += n_in[s];
         }
     } else {
@@ -1761,6 +1859,9 @@ void gfs_comm_substep(gfs_context *c, double dt, double ratio, int order, int in
     }
     do_p2g_end(c);
     GFS_SUB(gfs_comm_g2p_advect(c, dt, ratio, order, interp, arith, has_down, has_up, &e2));
+    // this rank's max |v| for the NEXT substep is final now (the G2P epilogue took it over every particle it advected,
+    // leavers included; arrivals were counted by their sender): start the all-ranks maximum a whole sort ahead of its use
+    if (c->world_table && c->comm_world > 1 && c->keys_ready) GFS_SUB(gfs_comm_allmax_post(c, &e2));
     GFS_SUB(gfs_comm_migrate_finish(c, moved, &e2));
 #undef GFS_SUB
     GFS_END()
@@ -1822,7 +1923,27 @@ void gfs_comm_allmax_scale(gfs_context *c, int *err) {
     GFS_CUDA(cudaSetDevice(c->device));
     gfs::AllMaxPeers peers;
     for (int r = 0; r < 16; r++) peers.table[r] = c->world_peer[r];
-    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles);
+    // mode 0: the whole all-ranks maximum here; after gfs_comm_allmax_post only the wait is left
+    const int mode = c->allmax_posted ? 2 : 0;
+    if (!c->allmax_posted) ++c->seq_world;
+    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles, mode);
+    c->allmax_posted = false;
+    GFS_END()
+}
+
+/* First half of gfs_comm_allmax_scale, issued as soon as this rank's max |v| is final (right after its G2P epilogue and
+ * collision resolve): the value travels to every rank while they sort and scan; gfs_comm_allmax_scale then only waits. */
+void gfs_comm_allmax_post(gfs_context *c, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(c->world_table, "gfs_comm_world_alloc first");
+    for (int r = 0; r < c->comm_world; r++) GFS_REQUIRE(c->world_peer[r], "gfs_comm_world_connect every rank first");
+    GFS_REQUIRE(!c->allmax_posted, "gfs_comm_allmax_post twice without gfs_comm_allmax_scale");
+    GFS_CUDA(cudaSetDevice(c->device));
+    gfs::AllMaxPeers peers;
+    for (int r = 0; r < 16; r++) peers.table[r] = c->world_peer[r];
+    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles, 1);
+    c->allmax_posted = true;
     GFS_END()
 }
 

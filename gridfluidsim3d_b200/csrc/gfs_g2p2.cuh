@@ -80,7 +80,7 @@ struct SlowList { int32_t *list; unsigned int *count; };      // sorted slots le
 template <bool WIDE, bool MIGRATE>
 __global__ void __launch_bounds__(256, TriTile<WIDE>::kCtas)
 k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
-          const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
+          uint32_t brick0, const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
           int order, RkCoef rk, float ratio_pic, float ratio_flip,
           const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
           const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
@@ -95,7 +95,7 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
     extern __shared__ unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     uint64_t &bar = *reinterpret_cast<uint64_t *>(tiles + 3 * (T::nCount + T::sCount));
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x + brick0;
     const int start = cell_start[(size_t)b * kBrickCells], end = cell_start[(size_t)(b + 1) * kBrickCells];
     if (start >= end) return;
     const int bi = (int)(b % (uint32_t)g.nbi), bj = (int)((b / (uint32_t)g.nbi) % (uint32_t)g.nbj), bk = (int)(b / ((uint32_t)g.nbi * (uint32_t)g.nbj));

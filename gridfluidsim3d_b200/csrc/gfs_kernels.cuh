@@ -107,6 +107,14 @@ __device__ __forceinline__ uint32_t position_key(const Grid &g, uint32_t nkeys, 
     return nkeys;
 }
 
+// z-slab runs keep a cell table only for the bricks around the owned layers [key_lo, key_hi): a key outside that range
+// (a particle more than one hop away from its owner: never with CFL-limited steps) goes to the out-of-grid bin, where the
+// global-path CTA still advects and forwards it.
+struct KeyRange { uint32_t lo, hi; };
+__device__ __forceinline__ uint32_t clamp_key(uint32_t key, uint32_t nkeys, KeyRange kr) {
+    return (key < nkeys && (key < kr.lo || key >= kr.hi)) ? nkeys : key;
+}
+
 // Ticket of a particle in its cell; with a per-cell cap (FluidSimulation::_removeMarkerParticles,
 // fluidsimulation.cpp:3221-3243: at most _maxMarkerParticlesPerCell particles survive per cell, WHICH ones is decided
 // by the reference's rand() shuffle and here by the ticket order -- equally arbitrary) a particle whose ticket is past
@@ -131,11 +139,11 @@ __global__ void __launch_bounds__(256) k_hist(Grid g, uint32_t nkeys, const floa
                        const float *__restrict__ z, const float *__restrict__ vx, const float *__restrict__ vy,
                        const float *__restrict__ vz, int64_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ rank,
                        int32_t *__restrict__ perm, uint32_t *__restrict__ counts, unsigned int *__restrict__ vmax_bits,
-                       const uint8_t *__restrict__ solid, uint32_t cap) {
+                       const uint8_t *__restrict__ solid, uint32_t cap, KeyRange kr) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (r < n) {
-        uint32_t key = position_key(g, nkeys, x[r], y[r], z[r]);
+        uint32_t key = clamp_key(position_key(g, nkeys, x[r], y[r], z[r]), nkeys, kr);
         if (solid && key < nkeys) {
             const int i = cell_floor((double)x[r], g.invdx), j = cell_floor((double)y[r], g.invdx), k = cell_floor((double)z[r], g.invdx);
             if (solid[(size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)(k - g.k0))] == GFS_SOLID) key = nkeys + 1;
@@ -381,14 +389,14 @@ __device__ __forceinline__ void splat_pow2(const Grid &g, const SplatParams &sp,
 // then flushed to the global 64-bit accumulators with one integer atomic per touched value.  Because every
 // add is an integer add, the result is bit-identical to k_p2g_scatter's for any particle order.
 template <int ARITH>
-__global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start,
+__global__ void __launch_bounds__(256) k_p2g_tile(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start, uint32_t brick0,
                               const int32_t *__restrict__ index /* nullable: sorted slot -> storage slot */,
                               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
                               const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
                               unsigned long long *__restrict__ accu, unsigned long long *__restrict__ accv,
                               unsigned long long *__restrict__ accw) {
     extern __shared__ uint32_t tile[];                    // [3 comps][4 words][1000 nodes] = 48 000 B
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x + brick0;
     const int start = cell_start[(size_t)b * kBrickCells], end = cell_start[(size_t)(b + 1) * kBrickCells];
     if (start == end) return;
     // a cell with more than 63 particles could overflow the 32-bit words (511 contributions per node): such
@@ -1074,7 +1082,7 @@ __global__ void __launch_bounds__(128) k_resolve_collisions(Grid g, const uint8_
                                                             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz,
                                                             const float *__restrict__ ovx, const float *__restrict__ ovy, const float *__restrict__ ovz,
                                                             uint32_t nkeys, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out,
-                                                            uint32_t *__restrict__ counts, Migrate mg) {
+                                                            uint32_t *__restrict__ counts, Migrate mg, KeyRange kr) {
     const unsigned int n = min(*coll.count, coll.cap);
     for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const float4 e = coll.list[t];
@@ -1084,7 +1092,7 @@ __global__ void __launch_bounds__(128) k_resolve_collisions(Grid g, const uint8_
         resolve_collision(g, material, p0, p1, q);
         ox[r] = q[0]; oy[r] = q[1]; oz[r] = q[2];
         if (keys_out) {
-            uint32_t key = position_key(g, nkeys, q[0], q[1], q[2]);
+            uint32_t key = clamp_key(position_key(g, nkeys, q[0], q[1], q[2]), nkeys, kr);
             if (key < nkeys && (mg.out[0] || mg.out[1])) {
                 const int k = cell_floor((double)q[2], g.invdx);
                 const int side = k < mg.own_lo ? 0 : (k >= mg.own_hi ? 1 : -1);
@@ -1542,14 +1550,14 @@ __global__ void k_append_aos(int64_t n, int64_t at, const float *__restrict__ ao
 // G2P epilogue bins the residents
 __global__ void __launch_bounds__(256) k_append_bin(Grid g, uint32_t nkeys, int64_t n, int64_t at, const float *__restrict__ aos,
                              float *x, float *y, float *z, float *vx, float *vy, float *vz, int32_t *tag,
-                             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts) {
+                             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ rank_out, uint32_t *__restrict__ counts, KeyRange kr) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const float2 *p = reinterpret_cast<const float2 *>(aos + 6 * r);
     const float2 a = p[0], b = p[1], c = p[2];
     x[at + r] = a.x; y[at + r] = a.y; z[at + r] = b.x; vx[at + r] = b.y; vy[at + r] = c.x; vz[at + r] = c.y;
     tag[at + r] = -1;
-    const uint32_t key = position_key(g, nkeys, a.x, a.y, b.x);
+    const uint32_t key = clamp_key(position_key(g, nkeys, a.x, a.y, b.x), nkeys, kr);
     keys_out[at + r] = key;
     rank_out[at + r] = atomicAdd(counts + key, 1u);
 }
@@ -1559,17 +1567,22 @@ __global__ void __launch_bounds__(256) k_append_bin(Grid g, uint32_t nkeys, int6
 // buffered by the parity of seq.  value is compared as an unsigned integer (bit patterns of non-negative floats order
 // like the floats).  One CTA of >= world threads.
 struct AllMaxPeers { unsigned long long *table[16]; };
-__global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int seq, unsigned int *value, unsigned int *error, long long timeout) {
+// mode 0: post + wait; 1: post only (this rank's value is final -- right after its G2P -- long before anyone needs the
+// maximum); 2: wait only (just before the splat).  Splitting takes the all-ranks round trip off the critical path.
+__global__ void k_allmax(AllMaxPeers peers, int rank, int world, unsigned int seq, unsigned int *value, unsigned int *error, long long timeout, int mode) {
     __shared__ unsigned int s_max;
     const int t = threadIdx.x;
     if (t == 0) s_max = 0u;
     __syncthreads();
     const unsigned int mine = *value;
     const size_t base = (size_t)(seq & 1u) * 16;
-    if (t < world) {
+    if (t < world && mode != 2) {
         volatile unsigned long long *slot = peers.table[t] + base + rank;
         *slot = ((unsigned long long)seq << 32) | mine;
         __threadfence_system();
+    }
+    if (mode == 1) return;
+    if (t < world) {
         const volatile unsigned long long *in = peers.table[rank] + base + t;
         const long long t0 = clock64();
         unsigned long long v;
@@ -1621,6 +1634,16 @@ __global__ void __launch_bounds__(256) k_hash_particles(int64_t n, const uint32_
         h += mix64(a ^ (((unsigned long long)vz[r] << 32) | vy[r]));
     }
     hash_commit(h, out);
+}
+
+// after the exclusive scan of the key range [lo, hi): the end marker of its last brick and the three tail bins
+// (out-of-grid, dead, end) -- what a scan over the whole table would have left there
+__global__ void k_scan_tail(const uint32_t *__restrict__ counts, int32_t *__restrict__ cell_start, uint32_t lo, uint32_t hi, uint32_t nkeys) {
+    const int32_t total = hi > lo ? cell_start[hi - 1] + (int32_t)counts[hi - 1] : 0;
+    if (hi < nkeys) cell_start[hi] = total;
+    cell_start[nkeys] = total;
+    cell_start[nkeys + 1] = total + (int32_t)counts[nkeys];
+    cell_start[nkeys + 2] = total + (int32_t)counts[nkeys] + (int32_t)counts[nkeys + 1];
 }
 
 __global__ void k_border_solid(Grid g, uint8_t *__restrict__ material) {

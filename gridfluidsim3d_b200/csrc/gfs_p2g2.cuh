@@ -83,12 +83,12 @@ constexpr int kStageChunk = 1024;
 
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(TRANSPOSE ? 512 : 256, TRANSPOSE ? 2 : 4)
-k_p2g_tile2(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ index,
+k_p2g_tile2(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start, uint32_t brick0, const int32_t *__restrict__ index,
             const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
             const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
             unsigned long long *__restrict__ accu, unsigned long long *__restrict__ accv, unsigned long long *__restrict__ accw) {
     extern __shared__ uint32_t tile[];                    // [3 comps][4 words][1000 nodes] (+ [6][1024] staging floats)
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x + brick0;
     const int start = cell_start[(size_t)b * kBrickCells], end = cell_start[(size_t)(b + 1) * kBrickCells];
     if (start == end) return;
     int dense = 0;

@@ -171,6 +171,12 @@ void gfs_get_particle_order(gfs_context *ctx, int32_t *order, int *err);
 void gfs_set_field(gfs_context *ctx, int slot, const float *u, const float *v, const float *w, int *err);
 void gfs_get_field(gfs_context *ctx, int slot, float *u, float *v, float *w, int *err);
 
+/* the same for the cell layers [k_first, k_first + k_count) only (u, v, w, material: the caller's WHOLE arrays; the w array's
+ * extra face layer k_first + k_count travels too): what a z-slab rank moves -- owned layers + halo up, owned layers down */
+void gfs_set_field_layers(gfs_context *ctx, int slot, const float *u, const float *v, const float *w, int k_first, int k_count, int *err);
+void gfs_get_field_layers(gfs_context *ctx, int slot, float *u, float *v, float *w, int k_first, int k_count, int *err);
+void gfs_get_material_layers(gfs_context *ctx, uint8_t *material, int k_first, int k_count, int *err);
+
 /* K0: bin particles by cell (brick-major key) and build the cell table.  gfs_sort is stable (radix sort: particles
  * of one cell keep their relative order, which the exact-arithmetic P2G relies on); gfs_sort_unstable is the
  * counting sort the fast substep uses (the order inside a cell is unspecified; nothing in fast mode depends on it). */
@@ -291,6 +297,10 @@ void gfs_comm_world_export(gfs_context *ctx, void *handle64, int *err);
 void gfs_comm_world_connect(gfs_context *ctx, int rank, const void *handle64, int *err);
 void gfs_comm_world_connect_local(gfs_context *ctx, int rank, gfs_context *other, int *err);
 void gfs_comm_allmax_scale(gfs_context *ctx, int *err);
+/* The two halves apart: gfs_comm_allmax_post sends this rank's max |v| to every rank as soon as it is final (after the
+ * G2P of the previous substep: its epilogue takes the maximum over every particle it advected), gfs_comm_allmax_scale
+ * then only waits for the others' values -- a whole sort later, off the critical path.  gfs_comm_substep does this. */
+void gfs_comm_allmax_post(gfs_context *ctx, int *err);
 
 /* Raw device pointers of resident buffers for zero-copy interop (halo exchange by the multi-GPU driver).
  * which: 0..2 NEW u,v,w; 3..5 SAVED u,v,w; 6..8 P2G u,v,w; 9 material; 10..15 particle x,y,z,vx,vy,vz;
