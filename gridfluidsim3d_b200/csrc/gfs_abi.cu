@@ -182,6 +182,8 @@ struct gfs_context {
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
+    int allmax_early = 1;                 // option 9: post the max right after G2P (1, default) or exchange it where it is needed (0)
+    bool allmax_redo = false;             // the particle set was replaced after the post: consume it, then exchange afresh
     bool allmax_posted = false;           // this rank's max |v| of the coming substep is already on its way (post after G2P)
     DevBuf<unsigned int> split_counters;  // kept, down, up
     int p2g_variant = 3;                  // 0 = global atomics only; brick tiles in shared memory: 1 = round-1 kernel, 2 = round-2
@@ -382,7 +384,9 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     const int B = 256;
     if (!c->keys_ready) {
         reset_counts(c);
-        c->allmax_posted = false;                  // a fresh max |v| is computed here: nothing posted for it yet
+        // (a max |v| already posted to the other ranks stays valid: this pass re-derives the LOCAL maximum of the same
+        // global particle set -- e.g. after gfs_get_particles compacted dead slots on this rank only -- and whether a post is
+        // outstanding must never depend on rank-local state, or the ranks' sequence numbers part ways)
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
         if (n > 0)
             LAUNCH(c, gfs::k_hist, ceil_div(n, B), B, c->grid, c->nkeys, c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p,
@@ -561,7 +565,6 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     uint32_t *keys_out = nullptr, *rank_out = nullptr, *counts = nullptr;
     if (bin_next) {
         reset_counts(c);
-        c->allmax_posted = false;
         GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
         keys_out = c->keys[0].p; rank_out = c->rank.p; counts = c->counts.p;
     }
@@ -1140,6 +1143,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
     c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false; c->storage_sorted = false;
+    if (c->allmax_posted) c->allmax_redo = true;
     c->graph_epoch++;
     if (n > 0) {
         // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
@@ -1344,6 +1348,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 9) { GFS_REQUIRE(value == 0 || value == 1, "early all-ranks max must be 0 or 1"); c->allmax_early = value; }
     else if (option == 8) { GFS_REQUIRE(value >= 0, "collision list capacity must be >= 0"); c->coll_cap_user = value; c->coll_list.release(); }
     else throw GfsError("gfs_set_option: unknown option");
     c->graph_epoch++;
@@ -1616,7 +1621,7 @@ void gfs_comm_alloc(gfs_context *c, int64_t layer_bytes, int64_t particle_cap, i
     if (!c->comm_host) GFS_CUDA(cudaHostAlloc((void **)&c->comm_host, 64, cudaHostAllocMapped));
     c->comm_error.reserve(1);
     GFS_CUDA(cudaMemset(c->comm_error.p, 0, sizeof(unsigned int)));
-    c->split_counters.reserve(4);
+    c->split_counters.reserve(8);
     GFS_END()
 }
 
@@ -1807,12 +1812,14 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
     } else {
         if (c->n > 0) c->cur = 1 - c->cur;
         c->n = h[0]; c->sorted = false; c->keys_ready = false; c->indexed = false;
+        const bool redo0 = c->allmax_redo;          // appending migrated particles is not a "new particle set" (their max |v| travelled with the sender's)
         for (int s = 0; s < 2; s++) {
             if (n_in[s] == 0) continue;
             int e2 = GFS_SUCCESS;
             gfs_append_particles_device(c, comm_arrivals(c, c->comm[s].block, c->comm[s].seq_particles), n_in[s], &e2);
             if (e2 != GFS_SUCCESS) throw GfsError(g_error);
         }
+        c->allmax_redo = redo0;
     }
     if (moved) { moved[0] = (int64_t)h[1] + h[2]; moved[1] = (int64_t)n_in[0] + n_in[1]; }
     GFS_END()
@@ -1861,7 +1868,13 @@ void gfs_comm_substep(gfs_context *c, double dt, double ratio, int order, int in
     GFS_SUB(gfs_comm_g2p_advect(c, dt, ratio, order, interp, arith, has_down, has_up, &e2));
     // this rank's max |v| for the NEXT substep is final now (the G2P epilogue took it over every particle it advected,
     // leavers included; arrivals were counted by their sender): start the all-ranks maximum a whole sort ahead of its use
-    if (c->world_table && c->comm_world > 1 && c->keys_ready) GFS_SUB(gfs_comm_allmax_post(c, &e2));
+    // Whether to post is decided by CONFIGURATION only (the same on every rank): a rank whose G2P did not go through the
+    // binning brick kernel this step (it held no particles) posts 0 -- its arrivals were counted by their senders.
+    const bool config_fused = arith != GFS_EXACT && c->grid.pow2 && c->have_maps && c->g2p_variant >= 1 && c->p2g_variant >= 1 && c->lazy_sort;
+    if (c->world_table && c->comm_world > 1 && c->allmax_early && config_fused) {
+        if (!c->keys_ready) GFS_CUDA(cudaMemsetAsync(c->vmax_bits.p, 0, sizeof(unsigned int), c->stream));
+        GFS_SUB(gfs_comm_allmax_post(c, &e2));
+    }
     GFS_SUB(gfs_comm_migrate_finish(c, moved, &e2));
 #undef GFS_SUB
     GFS_END()
@@ -1923,11 +1936,17 @@ void gfs_comm_allmax_scale(gfs_context *c, int *err) {
     GFS_CUDA(cudaSetDevice(c->device));
     gfs::AllMaxPeers peers;
     for (int r = 0; r < 16; r++) peers.table[r] = c->world_peer[r];
-    // mode 0: the whole all-ranks maximum here; after gfs_comm_allmax_post only the wait is left
-    const int mode = c->allmax_posted ? 2 : 0;
-    if (!c->allmax_posted) ++c->seq_world;
-    LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles, mode);
-    c->allmax_posted = false;
+    // mode 0: the whole all-ranks maximum here; after gfs_comm_allmax_post only the wait is left.  A particle upload between
+    // the post and here (a collective act: every rank of a sharded run replaces its particles or none does) consumes the
+    // outstanding round and exchanges afresh.
+    if (c->allmax_posted) {
+        unsigned int *dst = c->vmax_bits.p;
+        if (c->allmax_redo) { c->split_counters.reserve(8); dst = c->split_counters.p + 4; }        // discard into a scratch word
+        LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, c->seq_world, dst, c->comm_error.p, c->comm_timeout_cycles, 2);
+    }
+    if (!c->allmax_posted || c->allmax_redo)
+        LAUNCH(c, gfs::k_allmax, 1, 32, peers, c->comm_rank, c->comm_world, ++c->seq_world, c->vmax_bits.p, c->comm_error.p, c->comm_timeout_cycles, 0);
+    c->allmax_posted = false; c->allmax_redo = false;
     GFS_END()
 }
 
@@ -1956,7 +1975,7 @@ void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device
     *n_down = *n_up = 0;
     drop_dead(c);
     if (c->n == 0) return;
-    c->split_counters.reserve(4);
+    c->split_counters.reserve(8);
     launch_split(c, k_lo, k_hi, down_device, up_device, cap, c->split_counters.p);
     unsigned int h[4];
     GFS_CUDA(cudaMemcpyAsync(h, c->split_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -2067,6 +2086,7 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
     c->n = n;
     c->sorted = false;
     c->keys_ready = false;
+    if (c->allmax_posted) c->allmax_redo = true;
     GFS_END()
 }
 

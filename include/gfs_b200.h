@@ -213,7 +213,9 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * single-domain entry points (gfs_sort*, gfs_substep, gfs_g2p_advect; the sharded gfs_comm_* entry points refuse to run
  * with them on); gfs_stats_t.removed_particles counts.  option 7: limit, in seconds (default 4), of the device-side
  * waits of the peer exchange; a wait that exceeds it fails gfs_comm_migrate_finish / gfs_comm_substep.  option 8:
- * capacity of the collision list in particles (default 0 = n/16 + 4096); see gfs_stats_t.collision_overflow. */
+ * capacity of the collision list in particles (default 0 = n/16 + 4096); see gfs_stats_t.collision_overflow.  option 9:
+ * 1 = gfs_comm_substep posts this rank's max |v| right after its G2P (default), 0 = the all-ranks maximum is exchanged
+ * where it is needed, between the sort and the splat. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid

@@ -34,6 +34,8 @@ def check(rank, world, local, dev, name=None):
         c.domain_init(s["dims"], s["dx"]); c.set_material(s["material"]); c.set_sources([])
         c.set_particles(s["pos"][mine], s["vel"][mine])
         c.set_field(capi.FIELD_NEW, *s["new"]); c.set_field(capi.FIELD_SAVED, *s["saved"])
+        if os.environ.get("PEER_CHECK_ALLMAX_EARLY"):
+            c.set_option(9, int(os.environ["PEER_CHECK_ALLMAX_EARLY"]))
         for interp in (capi.TRILINEAR, capi.TRICUBIC):
             drv = slabs.SlabDriver(slabs.CudaSlabBackend(c, s["dims"], (k0, k1), interp, shared_stream=True), rank, world,
                                    halo=capi.slab_halo_cells(interp, 0.5 * s["dx"], s["dx"]))
@@ -44,6 +46,8 @@ def check(rank, world, local, dev, name=None):
                 tr = slabs.DistTransport() if kind == "nccl" else slabs.PeerTransport(drv, particle_cap=len(s["pos"]), layer_bytes=big)
             out = []
             for step in range(3):
+                if os.environ.get("PEER_CHECK_VERBOSE"):
+                    print("rank %d %s interp %d step %d" % (rank, kind, interp, step), file=sys.stderr, flush=True)
                 slabs.substep(drv, tr, 1.5 * s["dt"], pressure_solve_between=(step == 1))
                 torch.cuda.synchronize()
                 p, v = c.get_particles()
