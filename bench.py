@@ -331,53 +331,93 @@ def run_gfs(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    t_gen = time.time()
-    sc = make_scene_device(args.workload, dev, seed=12345, k_range=owned if world > 1 else None)
-    torch.cuda.synchronize()
-    n_local = sc["aos"].shape[0]
-    N = allsum(n_local)
-    if rank == 0:
-        log("scene %s: %d particles (%d on rank 0), %d cells, generated in %.1fs" % (args.workload, N, n_local, G, time.time() - t_gen))
-
+    halo = capi.slab_halo_cells(interp, 0.5 * dx, dx)
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: events and kernels share it
     torch.cuda.set_stream(stream)
-    ctx = capi.Context(local, stream=stream.cuda_stream)
-    if rank == 0:
-        log(ctx.device_info())
-    ctx.domain_init(dims, dx)
-    ctx.set_material(sc["material"])
-    # pinned host copies: the e2e leg's inputs, and the source of the resident upload
-    aos_host = torch.empty(sc["aos"].shape, dtype=torch.float32, pin_memory=True)
-    aos_host.copy_(sc["aos"])
-    new_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["new"]]
-    saved_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["saved"]]
-    torch.cuda.synchronize()
-    ctx.set_particles_aos(aos_host.numpy())
-    ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])
-    ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])
-    dt = sc["dt"]
-    host_small = scene_to_host(sc, max_particles=args.cpu_sample * 32) if (world == 1 and not args.no_cpu_baseline) else None
-    del sc["aos"]
-    torch.cuda.empty_cache()
 
-    halo = capi.slab_halo_cells(interp, 0.5 * dx, dx)
+    def build(owned, final):
+        """Scene (this rank's layers), context, resident upload and -- for N > 1 -- the slab driver and its transport."""
+        t_gen = time.time()
+        sc = make_scene_device(args.workload, dev, seed=12345, k_range=owned if world > 1 else None)
+        torch.cuda.synchronize()
+        n_local = sc["aos"].shape[0]
+        N = allsum(n_local)
+        if rank == 0:
+            log("scene %s: %d particles (%d on rank 0), %d cells, generated in %.1fs" % (args.workload, N, n_local, G, time.time() - t_gen))
+        ctx = capi.Context(local, stream=stream.cuda_stream)
+        if rank == 0 and final:
+            log(ctx.device_info())
+        ctx.domain_init(dims, dx)
+        ctx.set_material(sc["material"])
+        # pinned host copies: the e2e leg's inputs, and the source of the resident upload
+        aos_host = torch.empty(sc["aos"].shape, dtype=torch.float32, pin_memory=True)
+        aos_host.copy_(sc["aos"])
+        new_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["new"]]
+        saved_host = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True).copy_(t) for t in sc["saved"]]
+        torch.cuda.synchronize()
+        ctx.set_particles_aos(aos_host.numpy())
+        ctx.set_field(capi.FIELD_NEW, *[t.numpy() for t in new_host])
+        ctx.set_field(capi.FIELD_SAVED, *[t.numpy() for t in saved_host])
+        host_small = scene_to_host(sc, max_particles=args.cpu_sample * 32) if (final and world == 1 and not args.no_cpu_baseline) else None
+        dt = sc["dt"]
+        del sc
+        torch.cuda.empty_cache()
+        drv = transport = make_driver = None
+        if world > 1:
+            def make_driver(ip):
+                return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8), shared_stream=True), rank, world,
+                                        halo=capi.slab_halo_cells(ip, 0.5 * dx, dx))
+            drv = make_driver(interp)
+            if args.transport == "peer":      # neighbours write into each other's HBM over NVLink (gfs_comm_*), no NCCL in the data path
+                other_ip = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR
+                transport = slabs.PeerTransport(drv, particle_cap=max(4096, n_local // 8),
+                                                layer_bytes=slabs.PeerTransport.layer_bytes(make_driver(other_ip)))
+            else:
+                transport = slabs.DistTransport()
+        return dict(ctx=ctx, n_local=n_local, N=N, aos_host=aos_host, new_host=new_host, saved_host=saved_host, dt=dt,
+                    host_small=host_small, drv=drv, transport=transport, make_driver=make_driver)
+
+    balance = None
+    if world > 1 and args.cuts == "weighted" and not args.no_balance:
+        # One calibration pass: particle-weighted cuts equalise the particle COUNT, but the cost per particle is not the same
+        # in every slab (partially filled bricks at the free surface, one exchange partner instead of two at the ends), and a
+        # rank that finishes early only spins on its neighbours' flags.  Measure every rank's busy time (its kernels minus the
+        # flag waits) over a few substeps, turn it into a cost per particle of its layers, and cut again.
+        B = build(owned, final=False)
+        for _ in range(3):
+            slabs.substep(B["drv"], B["transport"], B["dt"])
+        B["ctx"].profile_enable(True); B["ctx"].profile_read(reset=True)
+        for _ in range(4):
+            slabs.substep(B["drv"], B["transport"], B["dt"])
+        prof = B["ctx"].profile_read(reset=True)
+        B["ctx"].profile_enable(False)
+        waits = ("k_gather_counts", "k_copy_batch_wait", "k_allmax")
+        busy = sum(ms for k, (ms, cnt) in prof.items() if not any(w in k for w in waits)) / 4.0
+        wait = sum(ms for k, (ms, cnt) in prof.items() if any(w in k for w in waits)) / 4.0
+        rows = [None] * world
+        dist.all_gather_object(rows, (busy, wait, B["n_local"]))
+        cost = [b_ / max(1, n_) for (b_, w_, n_) in rows]
+        weights = np.asarray(layer_counts, np.float64).copy()
+        for r, (k0, k1) in enumerate(ranges):
+            weights[k0:k1] *= cost[r] / (sum(cost) / world)
+        old_ranges = ranges
+        ranges = slabs.slab_ranges_weighted(weights, world, min_layers=max(4, capi.slab_halo_cells(capi.TRICUBIC, 0.5 * dx, dx)))
+        owned = ranges[rank]
+        balance = {"calibration_cuts": [list(r) for r in old_ranges], "busy_ms": [round(r_[0], 4) for r_ in rows],
+                   "wait_ms": [round(r_[1], 4) for r_ in rows], "particles": [r_[2] for r_ in rows]}
+        dist.barrier()
+        B["ctx"].close()
+        del B
+        torch.cuda.empty_cache()
+        dist.barrier()
+
+    B = build(owned, final=True)
+    ctx, n_local, N, aos_host, new_host, saved_host, dt = B["ctx"], B["n_local"], B["N"], B["aos_host"], B["new_host"], B["saved_host"], B["dt"]
+    host_small, drv, transport, make_driver = B["host_small"], B["drv"], B["transport"], B["make_driver"]
     if world > 1:
-        def make_driver(ip):
-            return slabs.SlabDriver(slabs.CudaSlabBackend(ctx, dims, owned, ip, migrate_cap=max(4096, n_local // 8), shared_stream=True), rank, world,
-                                    halo=capi.slab_halo_cells(ip, 0.5 * dx, dx))
-        drv = make_driver(interp)
-        if args.transport == "peer":      # neighbours write into each other's HBM over NVLink (gfs_comm_*), no NCCL in the data path
-            other_ip = capi.TRICUBIC if interp == capi.TRILINEAR else capi.TRILINEAR
-            transport = slabs.PeerTransport(drv, particle_cap=max(4096, n_local // 8),
-                                            layer_bytes=slabs.PeerTransport.layer_bytes(make_driver(other_ip)))
-        else:
-            transport = slabs.DistTransport()
-
         def substep():
             slabs.substep(drv, transport, dt)
     else:
-        transport = None
-
         def substep():
             ctx.substep(dt, order=4, interp=interp, arith=capi.FAST)
 
@@ -607,6 +647,7 @@ def run_gfs(args):
         sub["dropin"] = dropin_submetric()
     line["submetrics"] = sub
     if world > 1:
+        line["multi_gpu_balance"] = balance
         line["multi_gpu"] = {"transport": "peer memory (CUDA IPC, NVLink) written by gfs kernels" if args.transport == "peer"
                              else "torch.distributed batch_isend_irecv (NCCL)", "comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
                              "particles_mean": n_now / world, "particles_after": n_now}
@@ -710,6 +751,7 @@ def main():
                     help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N>1: keep the particle-count-weighted cuts (no timing calibration pass)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the FluidSimulation::update drop-in sub-metric (64^3, CPU vs CUDA classes)")
     ap.add_argument("--no-peer-check", action="store_true", help="N>1: skip the peer-memory vs NCCL transport cross-check after the timed runs")
     args = ap.parse_args()
