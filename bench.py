@@ -643,6 +643,12 @@ def run_gfs(args):
         sub["advect_only"] = {"particles": n_adv, "kernel_ms": k_ms, "value": n_adv / (k_ms * 1e-3) if k_ms > 0 else None, "unit": "particles/s",
                               "algorithmic_bytes": b, "hbm_frac": b / (k_ms * 1e-3) / 1e9 / hbm_gbs if k_ms > 0 else None,
                               "through_host_value": n_adv / wall, "api": "gfs_advect (host pointers, unsorted random positions, global loads)"}
+    if world == 1 and not args.no_sweep:
+        ctx.close()                       # the sweep's 1 B-particle point needs the memory
+        ctx = None
+        torch.cuda.empty_cache()
+        free_b, _total = torch.cuda.mem_get_info(dev)
+        sub["advect_sweep"] = advect_sweep(local, dev, stream, hbm_gbs, [1 << 20, 1 << 22, 1 << 24, 1 << 26, 1 << 28, 1000000000], free_b - (6 << 30))
     if world == 1 and not args.no_cpu_baseline and not args.no_dropin:
         sub["dropin"] = dropin_submetric()
     line["submetrics"] = sub
@@ -651,7 +657,8 @@ def run_gfs(args):
         line["multi_gpu"] = {"transport": "peer memory (CUDA IPC, NVLink) written by gfs kernels" if args.transport == "peer"
                              else "torch.distributed batch_isend_irecv (NCCL)", "comm_bytes_per_step_rank0": comm_bytes, "particles_max_over_ranks": int(n_max),
                              "particles_mean": n_now / world, "particles_after": n_now}
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1 and not args.no_peer_check:
         # the CUDA-IPC peer transport against the torch.distributed (NCCL) one on a small sharded scene, across these very
         # processes: owned P2G layers, material and particle rows bit for bit after every substep (tests/peer_check.py)
@@ -667,6 +674,80 @@ def run_gfs(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def advect_sweep(local, dev, stream, hbm_gbs, sizes, budget_bytes):
+    """BASELINE configs[4]: RK4-only advection of N uniformly random particles through the 256^3 vortex field on the sorted
+    brick path (gfs_advect_substep: index sort + trilinear brick kernel, positions only).  Algorithmic bytes 24 N + 12 G
+    (SURVEY 8d).  Particles are generated straight into the context's device arrays."""
+    import torch
+    from gridfluidsim3d_b200 import capi, synth
+    dims, dx, _ = synth.CONFIGS["splash256"]
+    G = dims[0] * dims[1] * dims[2]
+    ext = (dims[0] * dx, dims[1] * dx, dims[2] * dx)
+    ctx = capi.Context(local, stream=stream.cuda_stream)
+    ctx.domain_init(dims, dx)
+    ctx.set_material(synth.border_material(dims))
+    for comp_slot in (capi.FIELD_NEW,):
+        fields = []
+        for comp, (ni, nj, nk) in enumerate(synth.face_dims(dims)):
+            i = torch.arange(ni, device=dev, dtype=torch.float32)[None, None, :]
+            j = torch.arange(nj, device=dev, dtype=torch.float32)[None, :, None]
+            k = torch.arange(nk, device=dev, dtype=torch.float32)[:, None, None]
+            x = (i + (0.0 if comp == 0 else 0.5)) * dx
+            y = (j + (0.0 if comp == 1 else 0.5)) * dx
+            z = (k + (0.0 if comp == 2 else 0.5)) * dx
+            fields.append(synth.vortex_t(x, y, z, ext)[comp].expand(nk, nj, ni).contiguous().reshape(-1).cpu().numpy())
+        ctx.set_field(comp_slot, *fields)
+    dt = synth.cfl_dt(dx)
+
+    class _Arr:
+        pass
+
+    def dev_f32(ptr, n):
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(a, device=dev)
+    rows = []
+    for n in sizes:
+        if n * 96 > budget_bytes:            # 80 B of resident arrays per particle + slack
+            rows.append({"particles": n, "skipped": "needs %.0f GB" % (n * 96 / 1e9)})
+            continue
+        try:
+            ctx.resize_particles(n)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(12345 + int(np.log2(n)))
+            lo, span = 1.5 * dx, (min(dims) - 3) * dx
+            chunk = 1 << 26
+            for a in range(6):
+                t = dev_f32(ctx.device_ptr(10 + a), n)
+                for c0 in range(0, n, chunk):
+                    c1 = min(n, c0 + chunk)
+                    if a < 3:
+                        t[c0:c1] = lo + span * torch.rand(c1 - c0, generator=gen, device=dev, dtype=torch.float32)
+                    else:
+                        t[c0:c1] = 0.0
+            torch.cuda.synchronize()
+            for _ in range(2):
+                ctx.advect_substep(dt, order=4)
+            ctx.sync()
+            steps = 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                ctx.advect_substep(dt, order=4)
+            e1.record(stream)
+            ctx.sync()
+            ms = e0.elapsed_time(e1) / steps
+            b = 24 * n + 12 * G
+            rows.append({"particles": n, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "particles/s", "algorithmic_bytes": b,
+                         "hbm_frac": b / (ms * 1e-3) / 1e9 / hbm_gbs, "stats_particles": int(ctx.num_particles)})
+        except Exception as e:
+            rows.append({"particles": n, "error": repr(e)[:200]})
+            break
+    ctx.close()
+    return {"field": "256^3 analytic vortex, CFL 0.5", "operator": "gfs_advect_substep (index sort + k_g2p_tri<advect only>, RK4, trilinear)",
+            "bytes": "24 N + 12 G", "points": rows}
 
 
 def dropin_submetric(n=64, frames=1):
@@ -751,6 +832,7 @@ def main():
                     help="N>1 neighbour exchange: peer = CUDA-IPC peer memory written by our kernels; nccl = torch.distributed P2P batches")
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the advection-only sweep 1 M .. 1 B particles (BASELINE configs[4])")
     ap.add_argument("--no-balance", action="store_true", help="N>1: keep the particle-count-weighted cuts (no timing calibration pass)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the FluidSimulation::update drop-in sub-metric (64^3, CPU vs CUDA classes)")
     ap.add_argument("--no-peer-check", action="store_true", help="N>1: skip the peer-memory vs NCCL transport cross-check after the timed runs")

@@ -24,7 +24,7 @@ SYMBOLS = [
     "gfs_sample", "gfs_advect", "gfs_add_point_values", "gfs_add_points",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
     "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
-    "gfs_set_field", "gfs_get_field", "gfs_set_field_layers", "gfs_get_field_layers", "gfs_get_material_layers", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep",
+    "gfs_set_field", "gfs_get_field", "gfs_set_field_layers", "gfs_get_field_layers", "gfs_get_material_layers", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep", "gfs_advect_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
     "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
     "gfs_comm_alloc", "gfs_comm_export", "gfs_comm_connect", "gfs_comm_connect_local", "gfs_comm_push_layers",
@@ -102,6 +102,7 @@ def load_library():
     L.gfs_p2g.argtypes = [V, I, _err]
     L.gfs_g2p_advect.argtypes = [V, D, D, I, I, I, _err]
     L.gfs_substep.argtypes = [V, D, D, I, I, I, _err]
+    L.gfs_advect_substep.argtypes = [V, D, I, _err]
     L.gfs_set_owned_layers.argtypes = [V, I, I, _err]
     L.gfs_p2g_begin.argtypes = [V, I, _err]
     L.gfs_p2g_end.argtypes = [V, _err]
@@ -276,6 +277,10 @@ class Context:
         self._call(self.lib.gfs_add_points, pos, len(pos), radius, _c(offset), dx, *ndims, field, int(accumulate),
                    int(threshold is not None), float(threshold or 0.0), arith)
         return field
+
+    def advect_substep(self, dt, order=4):
+        """Index sort + RK advection of the resident positions through field NEW (trilinear brick kernel, positions only)."""
+        self._call(self.lib.gfs_advect_substep, float(dt), int(order))
 
     def state_hash(self):
         """-> [material, p2g_u, p2g_v, p2g_w, particles] order/distribution-independent 64-bit hashes (ints)."""
@@ -497,6 +502,9 @@ class Context:
         moved = (C.c_int64 * 2)()
         self._call(self.lib.gfs_comm_migrate_finish, moved)
         return moved[0], moved[1]
+
+    def resize_particles(self, n):
+        self._call(self.lib.gfs_resize_particles, int(n))
 
     def device_ptr(self, which):
         return self._call(self.lib.gfs_device_ptr, which)

@@ -182,6 +182,7 @@ struct gfs_context {
     int own_k0 = 0, own_k1 = 0;           // cell layers this context owns (z-slab sharding); grid kernels run on them + 1 halo
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
+    bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
     int allmax_early = 1;                 // option 9: post the max right after G2P (1, default) or exchange it where it is needed (0)
     bool allmax_redo = false;             // the particle set was replaced after the post: consume it, then exchange afresh
     bool allmax_posted = false;           // this rank's max |v| of the coming substep is already on its way (post after G2P)
@@ -443,6 +444,7 @@ void work_layers(gfs_context *c, int *lo, int *hi) {
 void do_p2g_begin(gfs_context *c, int arith) {
     require_domain(c);
     GFS_REQUIRE(c->sorted, "gfs_p2g needs gfs_sort first");
+    GFS_REQUIRE(c->velocities_valid, "the particle velocities are undefined after gfs_advect_substep: upload the particles again");
     const Grid &g = c->grid;
     const int b = c->cur;
     gfs::SplatParams sp = make_splat(g.dx, c->vmax_bits.p);
@@ -554,6 +556,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     require_domain(c);
     GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
     GFS_REQUIRE(interp == GFS_TRILINEAR || interp == GFS_TRICUBIC, "bad interpolation mode");
+    GFS_REQUIRE(c->velocities_valid, "the particle velocities are undefined after gfs_advect_substep: upload the particles again");
     if (c->dead > 0 && !(g2p_uses_bricks(c, arith) && c->indexed)) drop_dead(c);
     GFS_REQUIRE(!migrate || (g2p_uses_bricks(c, arith) && bin_next), "internal: fused migration needs the brick kernel");
     if (c->n == 0) return;
@@ -1143,6 +1146,7 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
     c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false; c->storage_sorted = false;
+    c->velocities_valid = true;
     if (c->allmax_posted) c->allmax_redo = true;
     c->graph_epoch++;
     if (n > 0) {
@@ -1432,6 +1436,67 @@ void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp,
     g.launches = c->launches - launches0;
     for (int i = 0; i < 3; i++) g.scratch[i] = scratch[i];
     GFS_CUDA(cudaGraphLaunch(g.exec, c->stream));          // the capture recorded the step, this performs it
+    GFS_END()
+}
+
+/* Advection only on the resident particles (SURVEY 8d sub-metric "C5": ParticleAdvector::advectParticlesRK1..4,
+ * src/particleadvector.cpp:209-399, on the device-resident, cell-sorted set): index sort + RK `order` through field slot
+ * NEW with the trilinear brick kernel (TMA-staged tiles, positions only: 12 B read + 12 B written per particle), binned for
+ * the next call by the kernel's epilogue.  No solid test (that is FluidSimulation's, :3198-3208), no velocity update: the
+ * velocity arrays are left undefined.  dx must be a power of two. */
+void gfs_advect_substep(gfs_context *c, double dt, int order, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(order >= 1 && order <= 4, "RK order must be 1..4");
+    GFS_REQUIRE(c->grid.pow2 && c->have_maps, "gfs_advect_substep needs a power-of-two dx (brick kernels)");
+    GFS_CUDA(cudaSetDevice(c->device));
+    do_sort(c, false, /*lazy=*/c->lazy_sort != 0);
+    if (c->n == 0) return;
+    const int src = c->cur, dst = 1 - c->cur;
+    gfs::RkCoef rk = make_rk(dt);
+    reset_counts(c);
+    gfs::CollList coll; coll.list = nullptr; coll.count = nullptr; coll.cap = 0; coll.cell_cap = 0;
+    gfs::Migrate mg; mg.own_lo = (int)0x80000000; mg.own_hi = 0x7FFFFFFF; mg.out[0] = mg.out[1] = nullptr; mg.count = nullptr; mg.cap = 0;
+    gfs::SlowList slow;
+    c->slow_count.reserve(1);
+    slow.list = c->perm[0].p; slow.count = c->slow_count.p;
+    GFS_CUDA(cudaMemsetAsync(c->slow_count.p, 0, sizeof(unsigned int), c->stream));
+    const int nbricks = (int)(c->brick_hi - c->brick_lo), nbricks_all = (int)(c->nkeys / gfs::kBrickCells);
+    const int32_t *idx = c->indexed ? c->index.p : nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GFS_CUDA(cudaFuncSetAttribute(gfs::k_g2p_tri<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfs::TriTile<false>::kSmemBytes));
+        attr_set = true;
+    }
+    int prof_id = c->prof_begin("gfs::k_g2p_tri<0> (advect only)");
+    gfs::k_g2p_tri<false, false, true><<<nbricks, 256, gfs::TriTile<false>::kSmemBytes, c->stream>>>(
+        c->grid, c->maps[0], (const uint8_t *)nullptr, c->cell_start.p, c->brick_lo, idx, c->tag[src].p, c->tag[dst].p, order, rk, 0.0f, 0.0f,
+        c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+        c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+        c->counters.p, c->nkeys, c->keys[0].p, c->rank.p, c->counts.p, c->vmax_bits.p, mg, coll, slow);
+    c->prof_end(prof_id);
+    GFS_CUDA(cudaGetLastError());
+    // the out-of-grid bin (global loads; its velocity output is as undefined as everyone's) and the stage-leavers
+    gfs::k_g2p_brick<0, false><<<1, 256, gfs::BrickTile<0>::kSmemBytes, c->stream>>>(
+        c->grid, c->maps[0], field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_NEW), (const uint8_t *)nullptr, c->cell_start.p, idx,
+        c->tag[src].p, c->tag[dst].p, order, rk, 0.0f, 0.0f, c->n,
+        c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+        c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+        c->counters.p, c->nkeys, c->keys[0].p, c->rank.p, c->counts.p, c->vmax_bits.p, mg, coll, (uint32_t)nbricks_all);
+    GFS_CUDA(cudaGetLastError());
+    LAUNCH(c, (gfs::k_g2p_slow<false, true>), 296, 128, c->grid, field_ptrs(c, GFS_FIELD_NEW), field_ptrs(c, GFS_FIELD_NEW), (const uint8_t *)nullptr, idx,
+           c->tag[src].p, c->tag[dst].p, GFS_TRILINEAR, order, rk, 0.0f, 0.0f,
+           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
+           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p,
+           c->counters.p, c->nkeys, c->keys[0].p, c->rank.p, c->counts.p, c->vmax_bits.p, mg, coll, slow);
+    c->launches += 2;
+    if (c->indexed) { c->n -= c->dead; c->dead = 0; }
+    c->indexed = false;
+    c->cur = dst;
+    c->sorted = false;
+    c->keys_ready = true;
+    c->velocities_valid = false;
+    c->graph_epoch++;
     GFS_END()
 }
 

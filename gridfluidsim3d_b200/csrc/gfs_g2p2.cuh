@@ -77,7 +77,9 @@ __device__ __forceinline__ float tri_sample(const float *__restrict__ t, int x, 
 
 struct SlowList { int32_t *list; unsigned int *count; };      // sorted slots left to k_g2p_slow
 
-template <bool WIDE, bool MIGRATE>
+// ADVECT = true: positions only -- RK1..4 through the NEW field (ParticleAdvector::advectParticlesRK*, the advection-only
+// sub-metric): no SAVED tiles, no PIC/FLIP, the velocity arrays are neither read nor written.
+template <bool WIDE, bool MIGRATE, bool ADVECT = false>
 __global__ void __launch_bounds__(256, TriTile<WIDE>::kCtas)
 k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restrict__ material, const int32_t *__restrict__ cell_start,
           uint32_t brick0, const int32_t *__restrict__ index, const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out,
@@ -104,11 +106,12 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(T::kTxBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)),
+                     "r"(ADVECT ? (uint32_t)(3 * T::nBox * sizeof(float)) : T::kTxBytes) : "memory");
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             tma_load_3d(tnew + c * T::nCount, &maps.m[c], 8 * bi, by - T::nOrg, bz - g.k0 - T::nOrg, &bar);
-            tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], 8 * bi, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
+            if (!ADVECT) tma_load_3d(tsav + c * T::sCount, &maps.m[3 + c], 8 * bi, by - T::sOrg, bz - g.k0 - T::sOrg, &bar);
         }
     }
     // NEW tile origin: x from node 8b-4, y/z from 8b-nOrg
@@ -119,7 +122,8 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
     int ntag = 0;
     if (r < end) {
         const int s_ = index ? index[r] : r;
-        nx_ = x[s_]; ny_ = y[s_]; nz_ = z[s_]; nvx = vx[s_]; nvy = vy[s_]; nvz = vz[s_]; ntag = tag_in[s_];
+        nx_ = x[s_]; ny_ = y[s_]; nz_ = z[s_]; ntag = tag_in[s_];
+        if (!ADVECT) { nvx = vx[s_]; nvy = vy[s_]; nvz = vz[s_]; }
     }
     __syncthreads();
     {
@@ -142,21 +146,24 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
             const int rn = r + blockDim.x;
             if (rn < end) {
                 const int s_ = index ? index[rn] : rn;
-                nx_ = x[s_]; ny_ = y[s_]; nz_ = z[s_]; nvx = vx[s_]; nvy = vy[s_]; nvz = vz[s_]; ntag = tag_in[s_];
+                nx_ = x[s_]; ny_ = y[s_]; nz_ = z[s_]; ntag = tag_in[s_];
+                if (!ADVECT) { nvx = vx[s_]; nvy = vy[s_]; nvz = vz[s_]; }
             }
         }
         if (pend_r >= 0) { rank_out[pend_r] = pend_rank; pend_r = -1; }
         // ---- p0: NEW and SAVED share one index/fraction set (p0 lies in this brick: every tap is staged)
-        float k1x, k1y, k1z, sx, sy, sz;
+        float k1x, k1y, k1z, sx = 0.0f, sy = 0.0f, sz = 0.0f;
         {
             const IdxL s = idx_tile(__fmul_rn(px, invdx), __fmul_rn(py, invdx), __fmul_rn(pz, invdx), biasx, biasy, biasz);
             k1x = tri_sample<SN::sy, SN::sz>(tnew, s.ux.i, s.ux.t, s.sy.i, s.sy.t, s.sz.i, s.sz.t);
             k1y = tri_sample<SN::sy, SN::sz>(tnew + T::nCount, s.sx.i, s.sx.t, s.uy.i, s.uy.t, s.sz.i, s.sz.t);
             k1z = tri_sample<SN::sy, SN::sz>(tnew + 2 * T::nCount, s.sx.i, s.sx.t, s.sy.i, s.sy.t, s.uz.i, s.uz.t);
             constexpr int d = T::nOrg - T::sOrg;          // the SAVED tile starts d nodes later in y and z
+            if (!ADVECT) {
             sx = tri_sample<SS::sy, SS::sz>(tsav, s.ux.i, s.ux.t, s.sy.i - d, s.sy.t, s.sz.i - d, s.sz.t);
             sy = tri_sample<SS::sy, SS::sz>(tsav + T::sCount, s.sx.i, s.sx.t, s.uy.i - d, s.uy.t, s.sz.i - d, s.sz.t);
             sz = tri_sample<SS::sy, SS::sz>(tsav + 2 * T::sCount, s.sx.i, s.sx.t, s.sy.i - d, s.sy.t, s.uz.i - d, s.uz.t);
+            }
         }
         float nx = k1x, ny = k1y, nz = k1z;
         validate3(nx, ny, nz);
@@ -223,10 +230,10 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
             }
         }
         ox[r] = qx; oy[r] = qy; oz[r] = qz;
-        ovx[r] = wx; ovy[r] = wy; ovz[r] = wz;
+        if (!ADVECT) { ovx[r] = wx; ovy[r] = wy; ovz[r] = wz; }
         tag_out[r] = tag;
         if (keys_out) {
-            const float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
+            const float mm = ADVECT ? 0.0f : fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (mm < 3.0e38f) m = fmaxf(m, mm);
             if (!deferred) {
                 uint32_t key = nkeys;
@@ -251,12 +258,12 @@ k_g2p_tri(Grid g, const __grid_constant__ BrickMaps maps, const uint8_t *__restr
         }
     }
     if (pend_r >= 0) rank_out[pend_r] = pend_rank;
-    if (keys_out) block_vmax(m, vmax_bits);
+    if (keys_out && !ADVECT) block_vmax(m, vmax_bits);
 }
 
 // The particles k_g2p_tri left on its list (an RK stage position outside the staged block): the whole per-particle
 // update through global memory, same arithmetic (evaluate_pow2 / rk_advance<2>), written to the particle's sorted slot.
-template <bool MIGRATE>
+template <bool MIGRATE, bool ADVECT = false>
 __global__ void __launch_bounds__(128)
 k_g2p_slow(Grid g, FieldPtrs fnew, FieldPtrs fsaved, const uint8_t *__restrict__ material, const int32_t *__restrict__ index,
            const int32_t *__restrict__ tag_in, int32_t *__restrict__ tag_out, int interp, int order, RkCoef rk, float ratio_pic, float ratio_flip,
@@ -304,10 +311,10 @@ k_g2p_slow(Grid g, FieldPtrs fnew, FieldPtrs fsaved, const uint8_t *__restrict__
             }
         }
         ox[r] = qx; oy[r] = qy; oz[r] = qz;
-        ovx[r] = wx; ovy[r] = wy; ovz[r] = wz;
+        if (!ADVECT) { ovx[r] = wx; ovy[r] = wy; ovz[r] = wz; }
         tag_out[r] = tag_in[s_];
         if (keys_out) {
-            const float mm = fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
+            const float mm = ADVECT ? 0.0f : fmaxf(fabsf(wx), fmaxf(fabsf(wy), fabsf(wz)));
             if (mm < 3.0e38f) m = fmaxf(m, mm);
             if (!deferred) {
                 uint32_t key = position_key(g, nkeys, qx, qy, qz);
@@ -328,7 +335,7 @@ k_g2p_slow(Grid g, FieldPtrs fnew, FieldPtrs fsaved, const uint8_t *__restrict__
             }
         }
     }
-    if (keys_out) block_vmax(m, vmax_bits);
+    if (keys_out && !ADVECT) block_vmax(m, vmax_bits);
 }
 
 }  // namespace gfs

@@ -229,6 +229,13 @@ void gfs_g2p_advect(gfs_context *ctx, double dt, double ratio_picflip, int order
  * binned by the previous call's G2P epilogue; the steady-state launch sequence is replayed from a CUDA graph, option 4). */
 void gfs_substep(gfs_context *ctx, double dt, double ratio_picflip, int order, int interp, int arith, int *err);
 
+/* Advection only, device resident (ParticleAdvector::advectParticlesRK1..4, src/particleadvector.cpp:209-399, on the
+ * resident cell-sorted particles): index sort + RK `rk_order` through field slot NEW with the trilinear brick kernel,
+ * positions only (12 B read + 12 B written per particle; binned for the next call in the kernel's epilogue).  No solid
+ * test, no velocity update: the velocity arrays are undefined afterwards (gfs_p2g / gfs_g2p_advect refuse to run until
+ * the particles are uploaded again).  Power-of-two dx only.  This is BASELINE configs[4]'s advection sweep operator. */
+void gfs_advect_substep(gfs_context *ctx, double dt, int rk_order, int *err);
+
 /* ---- z-slab sharding across GPUs (one context per GPU; the exchange itself is the caller's: NCCL) ----------
  * Every rank allocates the whole grid but OWNS the cell layers [k0,k1): its particles are those whose cell lies in
  * them, and its grid kernels only touch the owned layers plus one halo layer.  A sharded P2G is

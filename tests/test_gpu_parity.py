@@ -908,3 +908,35 @@ def test_particles_in_solid_cells_are_removed(oracle):
             for got, ref in zip(c.get_field(capi.FIELD_P2G), want):
                 assert np.array_equal(bits(got), bits(ref))
         c.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: advection only, device resident (gfs_advect_substep)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order_rk", [1, 2, 3, 4])
+@pytest.mark.parametrize("cfl", [0.5, 2.6])
+def test_advect_substep_equals_host_pointer_advect(ctx, oracle, order_rk, cfl):
+    """The resident advection-only operator (index sort + trilinear brick kernel, positions only) == gfs_advect on the same
+    positions, bit for bit (same fp32 arithmetic through global loads), over several chained calls, also when stage
+    positions leave the staged block (cfl 2.6: k_g2p_slow) and for particles outside the grid; and == the oracle's
+    ParticleAdvector loop within the fast-arithmetic tolerance."""
+    s = scene("slab24")
+    new = rough_fields(s["dims"], 41, 0.5)
+    extra = probes(s["dims"], s["dx"], 400, 43)
+    pos = np.concatenate([s["pos"], extra]).astype(np.float32)
+    dt = cfl * s["dx"]
+    ctx.domain_init(s["dims"], s["dx"]); ctx.set_material(s["material"]); ctx.set_sources([])
+    ctx.set_particles(pos, np.zeros_like(pos))
+    ctx.set_field(capi.FIELD_NEW, *new)
+    want = pos
+    for step in range(3):
+        ref = oracle.advect(want, *new, s["dims"], s["dx"], dt, order_rk, capi.TRILINEAR)
+        want = ctx.advect(want, *new, s["dims"], s["dx"], dt, order=order_rk, interp=capi.TRILINEAR, arith=capi.FAST)
+        assert_close(want, ref, "host-pointer advect vs oracle")
+        ctx.advect_substep(dt, order=order_rk)
+        o = ctx.get_particle_order()
+        p, _ = ctx.get_particles()
+        assert sorted(o.tolist()) == list(range(len(pos)))
+        assert np.array_equal(bits(p), bits(want[o])), "step %d" % step
+    with pytest.raises(capi.GfsError):          # velocities are undefined now: the transfer stages refuse to run
+        ctx.sort_unstable(); ctx.p2g(capi.FAST)
