@@ -31,7 +31,10 @@ SYMBOLS = [
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
     "gfs_comm_allmax_scale", "gfs_comm_allmax_post", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
-    "gfs_device_ptr", "gfs_resize_particles", "gfs_state_hash", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
+    "gfs_device_ptr", "gfs_resize_particles", "gfs_reserve", "gfs_state_hash",
+    "gfs_mg_get_error_message", "gfs_mg_create", "gfs_mg_destroy", "gfs_mg_num_devices", "gfs_mg_context", "gfs_mg_get_slab", "gfs_mg_set_option",
+    "gfs_mg_set_material", "gfs_mg_set_sources", "gfs_mg_set_field", "gfs_mg_get_field", "gfs_mg_get_material", "gfs_mg_scatter_particles",
+    "gfs_mg_num_particles", "gfs_mg_gather_particles", "gfs_mg_substep", "gfs_mg_state_hash", "gfs_mg_sync", "gfs_slab_range", "gfs_slab_owner", "gfs_slab_halo_cells",
 ]
 
 
@@ -140,6 +143,7 @@ def load_library():
     L.gfs_device_ptr.argtypes = [V, I, _err]
     L.gfs_device_ptr.restype = V
     L.gfs_resize_particles.argtypes = [V, L64, _err]
+    L.gfs_reserve.argtypes = [V, L64, _err]
     L.gfs_slab_range.argtypes = [I, I, I, C.POINTER(I), C.POINTER(I), _err]
     L.gfs_slab_owner.argtypes = [I, I, I, _err]
     L.gfs_slab_owner.restype = I

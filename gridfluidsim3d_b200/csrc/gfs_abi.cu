@@ -183,6 +183,7 @@ struct gfs_context {
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
     bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
+    int split_wait = 0;                   // option 10: device-side waits in a single-thread kernel of their own (slabs sharing a GPU)
     int allmax_early = 1;                 // option 9: post the max right after G2P (1, default) or exchange it where it is needed (0)
     bool allmax_redo = false;             // the particle set was replaced after the post: consume it, then exchange afresh
     bool allmax_posted = false;           // this rank's max |v| of the coming substep is already on its way (post after G2P)
@@ -1352,6 +1353,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 10) { GFS_REQUIRE(value == 0 || value == 1, "split wait must be 0 or 1"); c->split_wait = value; }
     else if (option == 9) { GFS_REQUIRE(value == 0 || value == 1, "early all-ranks max must be 0 or 1"); c->allmax_early = value; }
     else if (option == 8) { GFS_REQUIRE(value >= 0, "collision list capacity must be >= 0"); c->coll_cap_user = value; c->coll_list.release(); }
     else throw GfsError("gfs_set_option: unknown option");
@@ -1756,8 +1758,13 @@ void gfs_comm_pull_layers(gfs_context *c, int side, int n, const int *what, cons
     long long largest;
     fill_batch(c, cb, 1, n, what, k_first, k_count, offsets, add, comm_layers(c, c->comm[side].block, seq), &largest);
     GFS_REQUIRE(cb.n > 0, "nothing to unpack");
-    LAUNCH(c, gfs::k_copy_batch_wait, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb,
-           (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p, c->comm_timeout_cycles);
+    if (c->split_wait) {
+        LAUNCH(c, gfs::k_wait_flag, 1, 1, (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p, c->comm_timeout_cycles);
+        LAUNCH(c, gfs::k_copy_batch, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb);
+    } else {
+        LAUNCH(c, gfs::k_copy_batch_wait, dim3((unsigned)batch_blocks(largest), (unsigned)cb.n), 256, cb,
+               (const volatile unsigned int *)c->comm[side].block, seq, c->comm_error.p, c->comm_timeout_cycles);
+    }
     GFS_END()
 }
 
@@ -1956,6 +1963,7 @@ void gfs_comm_world_alloc(gfs_context *c, int rank, int world, int *err) {
     if (!c->world_table) GFS_CUDA(cudaMalloc((void **)&c->world_table, 2 * 16 * sizeof(unsigned long long)));
     GFS_CUDA(cudaMemset(c->world_table, 0, 2 * 16 * sizeof(unsigned long long)));
     c->comm_rank = rank; c->comm_world = world; c->seq_world = 0;
+    c->allmax_posted = false; c->allmax_redo = false;
     for (int r = 0; r < 16; r++) c->world_peer[r] = nullptr;
     c->world_peer[rank] = c->world_table;
     c->comm_error.reserve(1);
@@ -2139,6 +2147,55 @@ void gfs_state_hash(gfs_context *c, uint64_t *out5, int *err) {
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     d.release();
     for (int i = 0; i < 5; i++) out5[i] = (uint64_t)h[i];
+    GFS_END()
+}
+
+/* Allocate, now, everything a substep would otherwise size lazily: particle arrays for `particle_capacity` slots (current
+ * contents kept) and the scratch of the sort / G2P / exchange.  cudaMalloc / cudaFree synchronise the device, which a
+ * sharded step cannot afford between its device-side waits when several slabs share one GPU -- and is wasted time anywhere. */
+void gfs_reserve(gfs_context *c, int64_t particle_capacity, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(particle_capacity >= 0 && particle_capacity < 0x7FFFFFFFll, "bad capacity");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const int64_t cap = particle_capacity > c->n ? particle_capacity : c->n;
+    if ((size_t)cap > c->soa[0][0].cap) {
+        const int64_t n0 = c->n;
+        // ensure_capacity grows to n + n/8 + 1024 of its argument: ask for what is wanted, net of that slack
+        ensure_capacity(c, cap);
+        c->n = n0;
+    }
+    size_t tmp_bytes = 0;
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)((size_t)c->nkeys + 3), c->stream));
+    c->cub_tmp.reserve(tmp_bytes);
+    if (c->resolve_collisions) {
+        const size_t want = c->coll_cap_user > 0 ? (size_t)c->coll_cap_user : (size_t)(cap / 16 + 4096) + (size_t)cap / 64;
+        if (want > c->coll_list.cap) c->coll_list.reserve(want);
+        c->coll_count.reserve(1);
+    }
+    c->slow_count.reserve(1);
+    c->split_counters.reserve(8);
+    if (!c->removal_host) GFS_CUDA(cudaHostAlloc((void **)&c->removal_host, 64, cudaHostAllocDefault));
+    // CUDA loads kernels lazily, at their first launch, and a load can synchronise the device like an allocation does:
+    // touch every kernel a (sharded) substep launches, and run the scan once for cub's
+    {
+        cudaFuncAttributes fa;
+#define GFS_TOUCH(k) GFS_CUDA(cudaFuncGetAttributes(&fa, k))
+        GFS_TOUCH(gfs::k_hist); GFS_TOUCH(gfs::k_build_index); GFS_TOUCH(gfs::k_scatter_sorted); GFS_TOUCH(gfs::k_scan_tail);
+        GFS_TOUCH(gfs::k_clamp_counts); GFS_TOUCH(gfs::k_classify); GFS_TOUCH(gfs::k_p2g_finalize); GFS_TOUCH(gfs::k_assemble);
+        GFS_TOUCH(gfs::k_p2g_tile<0>); GFS_TOUCH(gfs::k_p2g_tile<2>); GFS_TOUCH(gfs::k_p2g_tile2<false>); GFS_TOUCH(gfs::k_p2g_tile2<true>);
+        GFS_TOUCH(gfs::k_p2g_scatter<0>); GFS_TOUCH(gfs::k_p2g_scatter<2>);
+        GFS_TOUCH((gfs::k_g2p_tri<false, false>)); GFS_TOUCH((gfs::k_g2p_tri<false, true>)); GFS_TOUCH((gfs::k_g2p_tri<true, false>)); GFS_TOUCH((gfs::k_g2p_tri<true, true>));
+        GFS_TOUCH((gfs::k_g2p_brick<0, false>)); GFS_TOUCH((gfs::k_g2p_brick<0, true>)); GFS_TOUCH((gfs::k_g2p_brick<1, false>)); GFS_TOUCH((gfs::k_g2p_brick<1, true>));
+        GFS_TOUCH(gfs::k_g2p_slow<false>); GFS_TOUCH(gfs::k_g2p_slow<true>); GFS_TOUCH(gfs::k_g2p_advect<0>); GFS_TOUCH(gfs::k_g2p_advect<2>);
+        GFS_TOUCH(gfs::k_resolve_collisions); GFS_TOUCH(gfs::k_copy_batch); GFS_TOUCH(gfs::k_copy_batch_wait); GFS_TOUCH(gfs::k_wait_flag);
+        GFS_TOUCH(gfs::k_signal); GFS_TOUCH(gfs::k_gather_counts); GFS_TOUCH(gfs::k_allmax); GFS_TOUCH(gfs::k_append_bin);
+        GFS_TOUCH(gfs::k_append_aos); GFS_TOUCH(gfs::k_split_by_layer); GFS_TOUCH(gfs::k_add_u64);
+#undef GFS_TOUCH
+        GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)((size_t)c->nkeys + 3), c->stream));
+        c->sorted = false;                         // (the cell table is scratch until the next sort)
+    }
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
 

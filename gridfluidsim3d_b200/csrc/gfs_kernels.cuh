@@ -1469,6 +1469,12 @@ __global__ void __launch_bounds__(256) k_copy_batch_wait(CopyBatch cb, const vol
     }
 }
 
+// the wait of k_copy_batch_wait alone, in ONE thread: for groups whose slabs share a GPU (tests), where thousands of
+// spinning CTAs of one context would keep the other context's push kernel off the SMs for ever
+__global__ void k_wait_flag(const volatile unsigned int *flag, unsigned int seq, unsigned int *error, long long timeout) {
+    wait_flag(flag, seq, error, timeout);
+}
+
 // wait for both neighbours' particle flags, then publish {my kept/down/up counts, arrivals from down, arrivals from up}
 // to pinned host memory: the one word set the host reads per substep
 __global__ void k_gather_counts(const volatile unsigned int *flag_down, const volatile unsigned int *flag_up, unsigned int seq,

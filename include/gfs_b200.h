@@ -215,7 +215,9 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * waits of the peer exchange; a wait that exceeds it fails gfs_comm_migrate_finish / gfs_comm_substep.  option 8:
  * capacity of the collision list in particles (default 0 = n/16 + 4096); see gfs_stats_t.collision_overflow.  option 9:
  * 1 = gfs_comm_substep posts this rank's max |v| right after its G2P (default), 0 = the all-ranks maximum is exchanged
- * where it is needed, between the sort and the splat. */
+ * where it is needed, between the sort and the splat.  option 10: 1 = the device-side wait for a neighbour's layers runs
+ * in a single-thread kernel of its own instead of inside the unpack kernel (needed when several slabs share one GPU, where
+ * the spinning CTAs of one context would starve the other's push; gfs_mg_create sets it), 0 = fused (default). */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
@@ -321,8 +323,43 @@ void *gfs_device_ptr(gfs_context *ctx, int which, int *err);
  * 2^64 of per-element hashes keyed by GLOBAL element index (particles: by their six words), so the per-rank hashes of a
  * z-slab run add up to the single-GPU run's.  Synchronises; compacts dead slots like gfs_get_particles. */
 void gfs_state_hash(gfs_context *ctx, uint64_t *out5, int *err);
+/* Allocate now what a substep would size lazily (particle arrays for particle_capacity slots, sort / G2P / exchange
+ * scratch): no cudaMalloc / cudaFree -- device-wide synchronisations -- inside the steps that follow. */
+void gfs_reserve(gfs_context *ctx, int64_t particle_capacity, int *err);
 /* Resize the resident particle set to n (contents of [0,min(old,n)) kept) -- used by slab migration. */
 void gfs_resize_particles(gfs_context *ctx, int64_t n, int *err);
+
+/* ---- native multi-GPU group (gfs_mg_create / scatter / substep / gather) --------------------------------
+ * One process, one context and one host thread per GPU, z-slab sharding with particle-weighted cuts, neighbour exchange
+ * through peer memory (cudaDeviceEnablePeerAccess; the kernels of one GPU write layers, migrating particles and flags
+ * straight into its neighbour's HBM).  No NCCL, no IPC handles, no interpreter: what a C++11 host of the reference calls
+ * in place of the single-GPU entry points.  The sharded result is bit-identical to the single-GPU one (integer partial
+ * sums; gfs_mg_state_hash equals gfs_state_hash of the unsharded run).  `devices` may be NULL (GPUs 0..ndev-1) and may
+ * name a GPU more than once (several slabs on one GPU: tests).  halo_layers: cell layers of the NEW / SAVED fields a
+ * slab needs from each neighbour = gfs_slab_halo_cells(interp, max displacement per substep, dx).  Errors of these
+ * entry points are read with gfs_mg_get_error_message(). */
+typedef struct gfs_mg gfs_mg;
+const char *gfs_mg_get_error_message(void);
+gfs_mg *gfs_mg_create(int ndev, const int *devices, int isize, int jsize, int ksize, double dx, int halo_layers, int *err);
+void gfs_mg_destroy(gfs_mg *mg, int *err);
+int gfs_mg_num_devices(gfs_mg *mg);
+gfs_context *gfs_mg_context(gfs_mg *mg, int rank);            /* the per-GPU context (stats, options, profiling) */
+void gfs_mg_get_slab(gfs_mg *mg, int rank, int *k0, int *k1, int *err);
+void gfs_mg_set_option(gfs_mg *mg, int option, int value, int *err);
+void gfs_mg_set_material(gfs_mg *mg, const uint8_t *material, int *err);
+void gfs_mg_set_sources(gfs_mg *mg, const gfs_source_t *sources, int nsources, int *err);
+/* u, v, w: whole arrays in the reference's layout; every GPU takes (delivers) its own layers (+ halo on the way in) */
+void gfs_mg_set_field(gfs_mg *mg, int slot, const float *u, const float *v, const float *w, int *err);
+void gfs_mg_get_field(gfs_mg *mg, int slot, float *u, float *v, float *w, int *err);
+void gfs_mg_get_material(gfs_mg *mg, uint8_t *material, int *err);
+/* distribute the particles over the slabs (cuts balance the particle count) and build the exchange plans */
+void gfs_mg_scatter_particles(gfs_mg *mg, const gfs_marker_particle_t *particles, int64_t n, int *err);
+int64_t gfs_mg_num_particles(gfs_mg *mg, int *err);
+void gfs_mg_gather_particles(gfs_mg *mg, gfs_marker_particle_t *particles, int *err);
+/* gfs_substep on every GPU with the slab exchange (gfs_comm_substep per rank, one host thread each) */
+void gfs_mg_substep(gfs_mg *mg, double dt, double ratio_picflip, int rk_order, int interp, int arith, int64_t *moved2, int *err);
+void gfs_mg_state_hash(gfs_mg *mg, uint64_t *out5, int *err);
+void gfs_mg_sync(gfs_mg *mg, int *err);
 
 /* ---- z-slab helpers for the multi-GPU driver (host-only arithmetic, usable without a GPU) ----- */
 

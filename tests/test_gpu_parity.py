@@ -940,3 +940,22 @@ def test_advect_substep_equals_host_pointer_advect(ctx, oracle, order_rk, cfl):
         assert np.array_equal(bits(p), bits(want[o])), "step %d" % step
     with pytest.raises(capi.GfsError):          # velocities are undefined now: the transfer stages refuse to run
         ctx.sort_unstable(); ctx.p2g(capi.FAST)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the native multi-GPU group (gfs_mg_*), driven by a C++11 host without Python
+# ---------------------------------------------------------------------------------------------------
+def test_native_multi_gpu_group_cpp():
+    """tests/cpp/mg_test.cpp (built by __graft_entry__.build()): a C++ program shards the path over 2 and 3 slabs through
+    gfs_mg_create / scatter_particles / substep / state_hash / get_field and must reproduce the single-GPU state hashes
+    and arrays after every substep.  On a one-GPU box the slabs share the GPU; with more GPUs they are spread."""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "mg_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/mg_test is not built")
+    ngpu = torch.cuda.device_count()
+    for nslabs in (2, 3):
+        devs = [str(r % ngpu) for r in range(nslabs)]
+        r = subprocess.run([exe, str(nslabs)] + devs, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "MG_TEST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
