@@ -183,6 +183,8 @@ struct gfs_context {
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
     bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
+    int fused_grid = 1;                   // option 11: 1 = k_finalize_assemble (no node grid / mask in HBM), 0 = k_p2g_finalize + k_assemble
+    bool acc_dirty = false;               // the accumulators still hold the previous splat (fused grid pass): memset before the next
     int split_wait = 0;                   // option 10: device-side waits in a single-thread kernel of their own (slabs sharing a GPU)
     int allmax_early = 1;                 // option 9: post the max right after G2P (1, default) or exchange it where it is needed (0)
     bool allmax_redo = false;             // the particle set was replaced after the post: consume it, then exchange afresh
@@ -458,6 +460,21 @@ void do_p2g_begin(gfs_context *c, int arith) {
     c->p2g_arith = arith;
     GFS_REQUIRE(!(arith == GFS_EXACT && c->indexed), "internal: exact P2G needs physically sorted particles");
     if (arith == GFS_EXACT) return;               // the exact gather does everything in do_p2g_end
+    if (c->acc_dirty) {
+        // the fused grid pass leaves the accumulators as they are (its threads read their neighbours'): clear the node
+        // layers this rank splats into or receives partial sums for
+        const int kl_ = g.k1 - g.k0;
+        const int dims_[3][2] = {{g.I + 1, g.J}, {g.I, g.J + 1}, {g.I, g.J}};
+        for (int comp = 0; comp < 3; comp++) {
+            const int layers = kl_ + (comp == 2 ? 1 : 0);
+            int l0 = lo - 1, l1 = hi + 1 + (comp == 2 ? 1 : 0);
+            if (l0 < 0) l0 = 0;
+            if (l1 > layers) l1 = layers;
+            const size_t plane = (size_t)dims_[comp][0] * dims_[comp][1] * 2;
+            GFS_CUDA(cudaMemsetAsync(c->acc[comp].p + plane * (size_t)l0, 0, plane * (size_t)(l1 - l0) * sizeof(unsigned long long), c->stream));
+        }
+        c->acc_dirty = false;
+    }
     if (c->n > 0) {
         const bool pow2 = g.pow2 != 0;
         const int32_t *idx = c->indexed ? c->index.p : nullptr;
@@ -523,6 +540,16 @@ void do_p2g_end(gfs_context *c) {
     // node layers [lo, hi) for u,v and [lo, hi] for w.  Finalize covers them all (it also re-zeroes the accumulators);
     // assemble only the owned layers' faces -- its 26-neighbourhood reads one finalized layer beyond them.
     long long plane[3] = {(long long)dims[0][0] * dims[0][1], (long long)dims[1][0] * dims[1][1], (long long)dims[2][0] * dims[2][1]};
+    if (c->p2g_arith != GFS_EXACT && c->fused_grid) {
+        gfs::FusedArgs fu;
+        const int a_lo = whole ? 0 : c->own_k0, a_hi = whole ? g.K : c->own_k1;
+        for (int comp = 0; comp < 3; comp++) { fu.acc[comp] = c->acc[comp].p; fu.out[comp] = c->field[GFS_FIELD_P2G][comp].p + gfs::kRowPad; }
+        fu.k_lo = a_lo; fu.k_hi = a_hi; fu.k_hi_w = a_hi + (a_hi == g.K ? 1 : 0);
+        LAUNCH(c, gfs::k_finalize_assemble, dim3((unsigned)ceil_div((long long)(g.I + 1) * (g.J + 1), 256), (unsigned)(fu.k_hi_w - a_lo)), 256,
+               g, sp, c->sources, c->material.p, fu);
+        c->acc_dirty = true;
+        return;
+    }
     if (c->p2g_arith != GFS_EXACT) {
         gfs::FinalizeArgs fa;
         long long total = 0;
@@ -1353,6 +1380,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 11) { GFS_REQUIRE(value == 0 || value == 1, "fused grid pass must be 0 or 1"); c->fused_grid = value; }
     else if (option == 10) { GFS_REQUIRE(value == 0 || value == 1, "split wait must be 0 or 1"); c->split_wait = value; }
     else if (option == 9) { GFS_REQUIRE(value == 0 || value == 1, "early all-ranks max must be 0 or 1"); c->allmax_early = value; }
     else if (option == 8) { GFS_REQUIRE(value >= 0, "collision list capacity must be >= 0"); c->coll_cap_user = value; c->coll_list.release(); }
@@ -2183,6 +2211,7 @@ void gfs_reserve(gfs_context *c, int64_t particle_capacity, int *err) {
 #define GFS_TOUCH(k) GFS_CUDA(cudaFuncGetAttributes(&fa, k))
         GFS_TOUCH(gfs::k_hist); GFS_TOUCH(gfs::k_build_index); GFS_TOUCH(gfs::k_scatter_sorted); GFS_TOUCH(gfs::k_scan_tail);
         GFS_TOUCH(gfs::k_clamp_counts); GFS_TOUCH(gfs::k_classify); GFS_TOUCH(gfs::k_p2g_finalize); GFS_TOUCH(gfs::k_assemble);
+        GFS_TOUCH(gfs::k_finalize_assemble);
         GFS_TOUCH(gfs::k_p2g_tile<0>); GFS_TOUCH(gfs::k_p2g_tile<2>); GFS_TOUCH(gfs::k_p2g_tile2<false>); GFS_TOUCH(gfs::k_p2g_tile2<true>);
         GFS_TOUCH(gfs::k_p2g_scatter<0>); GFS_TOUCH(gfs::k_p2g_scatter<2>);
         GFS_TOUCH((gfs::k_g2p_tri<false, false>)); GFS_TOUCH((gfs::k_g2p_tri<false, true>)); GFS_TOUCH((gfs::k_g2p_tri<true, false>)); GFS_TOUCH((gfs::k_g2p_tri<true, true>));

@@ -669,6 +669,85 @@ __global__ void __launch_bounds__(256) k_assemble(Grid g, const uint8_t *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1b+c fused (fast arithmetic): normalisation (ScalarField::applyWeightField), isValueSet, inflow override and face
+// assembly in ONE pass over the nodes, straight from the fixed-point accumulators -- the node grid "ugrid" and its
+// isValueSet mask (val / setmask of k_p2g_finalize + k_assemble) are never materialised.  A face that borders fluid but
+// was not set needs the 26 neighbours' values: they are re-derived from the neighbours' accumulators on the spot (rare:
+// free-surface faces only).  Same arithmetic, same bits as the two-kernel form.  The accumulators are NOT cleared here
+// (neighbouring threads still read them): the next P2G starts with a memset of its layers.
+// ------------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const unsigned long long *acc[3];
+    float *out[3];
+    int k_lo, k_hi, k_hi_w;
+};
+
+template <int COMP>
+__device__ __forceinline__ float node_value(const Grid &g, const SplatParams &sp, const Sources &src, const unsigned long long *__restrict__ acc,
+                                            int i, int j, int kl, double inv_ns, bool &isset) {
+    const int ni = g.I + (COMP == 0), nj = g.J + (COMP == 1);
+    const size_t node = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)kl);
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(acc) + node);
+    const float wf = (float)((double)(long long)v.y * (1.0 / kWeightScaleD));
+    const float nf = (float)((double)(long long)v.x * inv_ns);
+    float value = nf;
+    if (wf > 0.0f) value = nf / wf;
+    isset = (double)wf > 1e-9;
+    if (isset && src.n > 0) {
+        const int k = kl + g.k0;
+        const float fx = (float)(COMP == 0 ? __dmul_rn((double)(float)i, g.dx) : __dmul_rn(__dadd_rn((double)(float)i, 0.5), g.dx));
+        const float fy = (float)(COMP == 1 ? __dmul_rn((double)(float)j, g.dx) : __dmul_rn(__dadd_rn((double)(float)j, 0.5), g.dx));
+        const float fz = (float)(COMP == 2 ? __dmul_rn((double)(float)k, g.dx) : __dmul_rn(__dadd_rn((double)(float)k, 0.5), g.dx));
+        for (int q = 0; q < src.n; q++)
+            if (source_contains(src.s[q], fx, fy, fz)) value = src.s[q].velocity[COMP];
+    }
+    return value;
+}
+
+template <int COMP>
+__device__ __forceinline__ void fused_face(const Grid &g, const SplatParams &sp, const Sources &src, const FusedArgs &fa, double inv_ns,
+                                           int i, int j, int kl, bool borders) {
+    const int ni = g.I + (COMP == 0), nj = g.J + (COMP == 1), nkl = g.k1 - g.k0 + (COMP == 2);
+    float r = 0.0f;
+    if (borders) {
+        bool isset;
+        const float own = node_value<COMP>(g, sp, src, fa.acc[COMP], i, j, kl, inv_ns, isset);
+        if (isset) {
+            r = own;
+        } else {
+            double avg = 0.0, cnt = 0.0;
+            for (int nk = kl - 1; nk <= kl + 1; nk++)
+                for (int nj_ = j - 1; nj_ <= j + 1; nj_++)
+                    for (int ni_ = i - 1; ni_ <= i + 1; ni_++) {
+                        if (ni_ == i && nj_ == j && nk == kl) continue;
+                        if (ni_ < 0 || nj_ < 0 || nk < 0 || ni_ >= ni || nj_ >= nj || nk >= nkl) continue;
+                        bool nset;
+                        const float v = node_value<COMP>(g, sp, src, fa.acc[COMP], ni_, nj_, nk, inv_ns, nset);
+                        const bool ok = COMP == 0 ? (fabs((double)v) > 0.0) : nset;
+                        if (ok) { avg = __dadd_rn(avg, (double)v); cnt += 1.0; }
+                    }
+            if (cnt > 0.0) r = (float)__ddiv_rn(avg, cnt);
+        }
+    }
+    fa.out[COMP][(size_t)i + (size_t)g.pitch[COMP] * ((size_t)j + (size_t)nj * (size_t)kl)] = r;
+}
+
+__global__ void __launch_bounds__(256) k_finalize_assemble(Grid g, SplatParams sp, Sources src, const uint8_t *__restrict__ material, FusedArgs fa) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)g.I + 1u;
+    if (t >= w * ((uint32_t)g.J + 1u)) return;
+    const int i = (int)(t % w), j = (int)(t / w);
+    const int k = fa.k_lo + (int)blockIdx.y, kl = k - g.k0;
+    const double inv_ns = inv_num_scale_d(num_exponent(sp));
+    const bool f = cell_is_fluid(g, material, i, j, k), fi = cell_is_fluid(g, material, i - 1, j, k);
+    const bool fj = cell_is_fluid(g, material, i, j - 1, k), fk = cell_is_fluid(g, material, i, j, k - 1);
+    const bool uv = k < fa.k_hi;
+    if (uv && j < g.J) fused_face<0>(g, sp, src, fa, inv_ns, i, j, kl, f | fi);
+    if (uv && i < g.I) fused_face<1>(g, sp, src, fa, inv_ns, i, j, kl, f | fj);
+    if (k < fa.k_hi_w && i < g.I && j < g.J) fused_face<2>(g, sp, src, fa, inv_ns, i, j, kl, f | fk);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: MACVelocityField::extrapolateVelocityField (macvelocityfield.cpp:577-798) on a resident field.
 // The reference's sweeps are sequential and in place; every one of them is order independent (a layer pass only turns
 // -1 cells into L and only reads "== L-1"; a face pass writes faces that do not border layer L-1 and reads faces that
