@@ -23,7 +23,7 @@ SYMBOLS = [
     "gfs_profile_enable", "gfs_profile_read",
     "gfs_sample", "gfs_advect", "gfs_add_point_values", "gfs_add_points",
     "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
-    "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
+    "gfs_emit_from_sources", "gfs_remove_in_sources", "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_set_field_layers", "gfs_get_field_layers", "gfs_get_material_layers", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep", "gfs_advect_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
     "gfs_copy_layers_batch", "gfs_extract_particles", "gfs_extract_particles_async", "gfs_extract_commit", "gfs_append_particles_device",
@@ -89,6 +89,8 @@ def load_library():
     L.gfs_set_material.argtypes = [V, _u8, _err]
     L.gfs_get_material.argtypes = [V, _u8, _err]
     L.gfs_set_sources.argtypes = [V, V, I, _err]
+    L.gfs_emit_from_sources.argtypes = [V, D, C.c_uint64, C.POINTER(L64), _err]
+    L.gfs_remove_in_sources.argtypes = [V, V, I, C.POINTER(L64), _err]
     L.gfs_set_particles.argtypes = [V, _f32, L64, _err]
     L.gfs_num_particles.argtypes = [V, _err]
     L.gfs_num_particles.restype = L64
@@ -313,6 +315,28 @@ class Context:
             s.a, s.b, s.c = d.get("a", 0.0), d.get("b", 0.0), d.get("c", 0.0)
             s.velocity[:] = d["velocity"]
         self._call(self.lib.gfs_set_sources, C.cast(arr, C.c_void_p), len(sources))
+
+    @staticmethod
+    def _source_array(sources):
+        arr = (Source * max(1, len(sources)))()
+        for s, d in zip(arr, sources):
+            s.kind = d["kind"]
+            s.p[:] = d["p"]
+            s.a, s.b, s.c = d.get("a", 0.0), d.get("b", 0.0), d.get("c", 0.0)
+            s.velocity[:] = d.get("velocity", (0.0, 0.0, 0.0))
+        return arr
+
+    def emit_from_sources(self, jitter, seed=1):
+        """FluidSimulation::_updateFluidSources for the active inflow sources of set_sources -> particles added."""
+        n = C.c_int64(0)
+        self._call(self.lib.gfs_emit_from_sources, float(jitter), int(seed), C.byref(n))
+        return int(n.value)
+
+    def remove_in_sources(self, sources):
+        """The outflow half: particles in the fluid cells the given sources overlap are removed -> how many."""
+        n = C.c_int64(0)
+        self._call(self.lib.gfs_remove_in_sources, C.cast(self._source_array(sources), C.c_void_p), len(sources), C.byref(n))
+        return int(n.value)
 
     def set_particles(self, pos, vel):
         """pos, vel: (N,3) float32 -> MarkerParticle_t AoS (24 B) -> device SoA."""

@@ -19,6 +19,7 @@
 #include "gfs_kernels.cuh"
 #include "gfs_p2g2.cuh"
 #include "gfs_g2p2.cuh"
+#include "gfs_sources.cuh"
 
 namespace {
 
@@ -197,6 +198,8 @@ struct gfs_context {
                                           // kernel on the 16-wide tile (default), 3 = on the 20-wide tile; tricubic: k_g2p_brick<1>
     gfs::BrickMaps maps[2];               // [interp]: NEW u,v,w + SAVED u,v,w tensor maps
     gfs::BrickMaps maps_tri_wide;         // dense boxes 20 columns wide (k_g2p_tri<true>: bank-conflict free row pitch)
+    DevBuf<unsigned int> src_occ, src_count;   // sources: sub-cell occupancy bitmap, emission / survivor counter
+    DevBuf<uint8_t> src_removal;          // outflow: cells whose particles go
     DevBuf<unsigned int> slow_count;      // k_g2p_tri's list of particles left to k_g2p_slow (the list itself lives in perm[0])
     bool have_maps = false;
     size_t field_floats[3] = {0, 0, 0};   // padded element counts of the resident u,v,w arrays
@@ -2175,6 +2178,155 @@ void gfs_state_hash(gfs_context *c, uint64_t *out5, int *err) {
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     d.release();
     for (int i = 0; i < 5; i++) out5[i] = (uint64_t)h[i];
+    GFS_END()
+}
+
+namespace {
+// the geometry FluidSimulation derives from a source before it touches a particle, with the reference's arithmetic:
+// FluidSource::_getOverlappingCells bounds, getAABB, Grid3d::fitAABBtoGrid, Grid3d::getGridIndexBounds(AABB), GridIndexToPosition
+gfs::Emitter make_emitter(const gfs_source_t &src, const Grid &g) {
+    gfs::Emitter e;
+    e.src = src;
+    const double dx = g.dx, inv = 1.0 / dx;
+    const int size[3] = {g.I, g.J, g.K};
+    auto idx = [&](float p) { return (int)std::floor((double)p * inv); };                       // positionToGridIndex, grid3d.h:58-63
+    auto gpos = [&](int i) { return (float)((double)(float)i * dx); };                          // GridIndexToPosition, grid3d.h:83-85
+    float bp[3];
+    double bw[3];
+    if (src.kind == 0) {
+        const double r = src.a;
+        for (int a = 0; a < 3; a++) {                                                           // getGridIndexBounds(p, r, dx, ...), grid3d.h:350-371
+            const int c = idx(src.p[a]);
+            const float trans = src.p[a] - gpos(c);
+            const int lo = c - (int)std::fmax(0.0, std::ceil((r - (double)trans) * inv));
+            const int hi = c + (int)std::fmax(0.0, std::ceil((r - dx + (double)trans) * inv));
+            e.smin[a] = (int)std::fmax((double)lo, 0.0);
+            e.smax[a] = (int)std::fmin((double)hi, (double)(size[a] - 1));
+            bp[a] = src.p[a] - (float)r;                                                        // SphericalFluidSource::getAABB
+            bw[a] = 2.0 * r;
+        }
+    } else {
+        const double ext[3] = {src.a, src.b, src.c};
+        for (int a = 0; a < 3; a++) {                                                           // getGridIndexBounds(AABB), grid3d.h:426-439
+            bp[a] = src.p[a]; bw[a] = ext[a];
+            e.smin[a] = (int)std::fmax((double)idx(bp[a]), 0.0);
+            e.smax[a] = (int)std::fmin((double)idx(bp[a] + (float)bw[a]), (double)(size[a] - 1));
+        }
+    }
+    // fitAABBtoGrid (grid3d.h:485-501)
+    float pmin[3], pmax[3];
+    int gmin[3], gmax[3];
+    for (int a = 0; a < 3; a++) { pmin[a] = bp[a]; pmax[a] = bp[a] + (float)bw[a]; gmin[a] = idx(pmin[a]); gmax[a] = idx(pmax[a]); }
+    auto inrange = [&](const int *q) { return q[0] >= 0 && q[1] >= 0 && q[2] >= 0 && q[0] < size[0] && q[1] < size[1] && q[2] < size[2]; };
+    if (!inrange(gmin)) for (int a = 0; a < 3; a++) pmin[a] = 0.0f;
+    if (!inrange(gmax)) for (int a = 0; a < 3; a++) pmax[a] = (gpos(gmax[a]) + (float)dx) - 10e-9f;
+    for (int a = 0; a < 3; a++) {                                                               // AABB(p1, p2), aabb.cpp:33-45
+        const double lo = std::fmin((double)pmin[a], (double)pmax[a]), hi = std::fmax((double)pmin[a], (double)pmax[a]);
+        e.bpos[a] = (float)lo; e.bext[a] = hi - lo;
+        e.bmin[a] = (int)std::fmax((double)idx(e.bpos[a]), 0.0);
+        e.bmax[a] = (int)std::fmin((double)idx(e.bpos[a] + (float)e.bext[a]), (double)(size[a] - 1));
+        e.offset[a] = gpos(e.bmin[a]);
+    }
+    return e;
+}
+}  // namespace
+
+/* FluidSimulation::_updateFluidSources for the ACTIVE INFLOW sources last given to gfs_set_sources
+ * (src/fluidsimulation.cpp:1823-1879): air cells a source overlaps are seeded with 8 particles, and every empty half-dx
+ * sub-cell of its fluid-or-air cells (occupancy taken from the particles inside its grid-fitted bounding box) gets one
+ * particle; all with the source's velocity.  jitter = 0.25 * jitter factor * dx (src/fluidsimulation.cpp:1219-1221); the
+ * reference draws it from rand(), here it is a hash of (seed, cell, sub-cell): the set of emitting sub-cells is the
+ * reference's, positions agree to the jitter.  Uses the resident material grid (the previous classification) like the
+ * reference; single domain.  *emitted = particles added. */
+void gfs_emit_from_sources(gfs_context *c, double jitter, uint64_t seed, int64_t *emitted, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(jitter >= 0, "bad jitter");
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == c->grid.K, "gfs_emit_from_sources is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (emitted) *emitted = 0;
+    if (c->sources.n == 0) return;
+    drop_dead(c);
+    const Grid &g = c->grid;
+    std::vector<gfs::Emitter> em;
+    int64_t bound = 0;
+    size_t occ_words = 1;
+    for (int s = 0; s < c->sources.n; s++) {
+        gfs::Emitter e = make_emitter(c->sources.s[s], g);
+        const int64_t w = e.bmax[0] - e.bmin[0] + 1, h = e.bmax[1] - e.bmin[1] + 1, d = e.bmax[2] - e.bmin[2] + 1;
+        if (w <= 0 || h <= 0 || d <= 0) continue;
+        bound += 16 * w * h * d;
+        occ_words = std::max(occ_words, (size_t)((8 * w * h * d + 31) / 32));
+        em.push_back(e);
+    }
+    if (em.empty()) return;
+    GFS_REQUIRE(c->n + bound < 0x7FFFFFFFll, "particle count must fit int32");
+    const int64_t n0 = c->n;
+    ensure_capacity(c, n0 + bound);
+    c->src_occ.reserve(occ_words);
+    c->src_count.reserve(1);
+    GFS_CUDA(cudaMemsetAsync(c->src_count.p, 0, sizeof(unsigned int), c->stream));
+    const int b = c->cur;
+    gfs::EmitOut o;
+    o.x = c->soa[b][0].p; o.y = c->soa[b][1].p; o.z = c->soa[b][2].p; o.vx = c->soa[b][3].p; o.vy = c->soa[b][4].p; o.vz = c->soa[b][5].p;
+    o.tag = c->tag[b].p; o.count = c->src_count.p; o.at = n0; o.cap = bound;
+    for (size_t s = 0; s < em.size(); s++) {
+        const gfs::Emitter &e = em[s];
+        const long long cells = (long long)(e.bmax[0] - e.bmin[0] + 1) * (e.bmax[1] - e.bmin[1] + 1) * (e.bmax[2] - e.bmin[2] + 1);
+        GFS_CUDA(cudaMemsetAsync(c->src_occ.p, 0, occ_words * sizeof(unsigned int), c->stream));
+        if (n0 > 0)
+            LAUNCH(c, gfs::k_source_mark, ceil_div(n0, 256), 256, g, e, (int64_t)0, n0, (const unsigned int *)nullptr, o.x, o.y, o.z, c->src_occ.p);
+        if (s > 0)          // what the earlier sources of this call emitted counts too
+            LAUNCH(c, gfs::k_source_mark, ceil_div(bound, 256), 256, g, e, n0, bound, (const unsigned int *)c->src_count.p, o.x, o.y, o.z, c->src_occ.p);
+        LAUNCH(c, gfs::k_source_emit, ceil_div(cells, 128), 128, g, e, c->material.p, c->src_occ.p, o, (unsigned long long)seed + 0x9E3779B97F4A7C15ull * (s + 1), jitter);
+    }
+    unsigned int count = 0;
+    GFS_CUDA(cudaMemcpyAsync(&count, c->src_count.p, sizeof(count), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    GFS_REQUIRE((int64_t)count <= bound, "internal: emission bound exceeded");
+    c->n = n0 + count;
+    if (count > 0) {
+        c->sorted = false; c->keys_ready = false; c->indexed = false;
+        if (c->allmax_posted) c->allmax_redo = true;
+    }
+    c->graph_epoch++;
+    if (emitted) *emitted = count;
+    GFS_END()
+}
+
+/* The outflow half of _updateFluidSources (:1853-1877): the particles in the FLUID cells (resident material grid) that the
+ * given outflow sources overlap are removed (_removeMarkerParticlesFromCells, :1717-1730).  *removed = particles gone. */
+void gfs_remove_in_sources(gfs_context *c, const gfs_source_t *outflow, int nsources, int64_t *removed, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(nsources >= 0 && (nsources == 0 || outflow), "bad arguments");
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == c->grid.K, "gfs_remove_in_sources is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    if (removed) *removed = 0;
+    if (nsources == 0 || c->n - c->dead == 0) return;
+    drop_dead(c);
+    const Grid &g = c->grid;
+    c->src_removal.reserve(c->cell_count);
+    c->src_count.reserve(1);
+    GFS_CUDA(cudaMemsetAsync(c->src_removal.p, 0, c->cell_count, c->stream));
+    GFS_CUDA(cudaMemsetAsync(c->src_count.p, 0, sizeof(unsigned int), c->stream));
+    for (int s = 0; s < nsources; s++) {
+        const gfs::Emitter e = make_emitter(outflow[s], g);
+        const long long cells = (long long)(e.smax[0] - e.smin[0] + 1) * (e.smax[1] - e.smin[1] + 1) * (e.smax[2] - e.smin[2] + 1);
+        if (cells > 0) LAUNCH(c, gfs::k_outflow_cells, ceil_div(cells, 128), 128, g, e, c->material.p, c->src_removal.p);
+    }
+    const int src = c->cur, dst = 1 - c->cur;
+    LAUNCH(c, gfs::k_remove_in_cells, ceil_div(c->n, 256), 256, g, c->n, c->src_removal.p,
+           c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p, c->tag[src].p,
+           c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->tag[dst].p, c->src_count.p);
+    unsigned int kept = 0;
+    GFS_CUDA(cudaMemcpyAsync(&kept, c->src_count.p, sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    if (removed) *removed = c->n - (int64_t)kept;
+    c->removed += c->n - (int64_t)kept;
+    c->n = kept; c->cur = dst;
+    c->sorted = false; c->keys_ready = false; c->indexed = false;
+    c->graph_epoch++;
     GFS_END()
 }
 

@@ -161,6 +161,16 @@ void gfs_set_material(gfs_context *ctx, const uint8_t *material, int *err);
 void gfs_get_material(gfs_context *ctx, uint8_t *material, int *err);
 /* inflow sources used by P2G (copied) */
 void gfs_set_sources(gfs_context *ctx, const gfs_source_t *sources, int nsources, int *err);
+/* FluidSimulation::_updateFluidSources on the resident particles (src/fluidsimulation.cpp:1771-1879).
+ * gfs_emit_from_sources: every ACTIVE INFLOW source given to gfs_set_sources seeds the air cells it overlaps with 8 particles
+ * (_addNewFluidCells, :1749-1759) and puts one particle into every empty half-dx sub-cell of its fluid-or-air cells
+ * (_getNewFluidParticles, :1771-1821), all with the source's velocity.  jitter = 0.25 * jitter factor * dx (:1219-1221).
+ * The reference draws the jitter from rand(); here it is a hash of (seed, cell, sub-cell): the set of emitting sub-cells is
+ * the reference's, positions agree to within the jitter.  gfs_remove_in_sources: the particles in the FLUID cells that the
+ * given outflow sources overlap are removed (:1853-1877, _removeMarkerParticlesFromCells :1717-1730).  Both read the
+ * resident material grid as the previous classification left it, like the reference; single domain. */
+void gfs_emit_from_sources(gfs_context *ctx, double jitter, uint64_t seed, int64_t *emitted, int *err);
+void gfs_remove_in_sources(gfs_context *ctx, const gfs_source_t *outflow_sources, int nsources, int64_t *removed, int *err);
 /* AoS MarkerParticle_t[n] <-> device SoA */
 void gfs_set_particles(gfs_context *ctx, const gfs_marker_particle_t *particles, int64_t n, int *err);
 int64_t gfs_num_particles(gfs_context *ctx, int *err);

@@ -354,6 +354,16 @@ class RefSim:
     def add_inflow_source(self, kind, p, a, b, c, velocity):
         self.lib.ref_sim_add_inflow_source(self.h, kind, *p, a, b, c, *velocity)
 
+    def add_outflow_source(self, kind, p, a, b=0.0, c=0.0):
+        fn = self.lib.ref_sim_add_outflow_source
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double]
+        fn(self.h, kind, *p, a, b, c)
+
+    def update_fluid_sources(self):
+        """FluidSimulation::_updateFluidSources on the current state (inflow emission, outflow removal)."""
+        self.lib.ref_sim_update_fluid_sources.argtypes = [C.c_void_p]
+        self.lib.ref_sim_update_fluid_sources(self.h)
+
     def initialize(self):
         self.lib.ref_sim_initialize(self.h)
         self._init = True

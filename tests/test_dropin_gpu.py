@@ -186,3 +186,71 @@ def test_resident_fluidsimulation_step_parity(resident_lib, n, frames, fast):
     assert (m0 != m1).mean() < 1e-3
     for a, b in zip(f0, f1):
         assert np.abs(a - b).max() < 1e-3 * max(1.0, np.abs(a).max()) and np.median(np.abs(a - b)) < 1e-5
+
+
+def test_sources_emission_and_outflow_match_reference(libs):
+    """gfs_emit_from_sources / gfs_remove_in_sources against FluidSimulation::_updateFluidSources of the unmodified reference
+    (src/fluidsimulation.cpp:1771-1879) on the same particles and material grid: a spherical and a cuboid inflow source
+    (one partly over fluid, one over air) and a cuboid outflow source.  The reference jitters new particles with rand();
+    the set of emitting half-dx sub-cells, the velocities and the surviving old particles must be identical, positions
+    agree to within the jitter."""
+    from gridfluidsim3d_b200 import capi
+    ref, _ = libs
+    n, dx = 32, 0.25
+    ctypes.CDLL(None).srand(3)
+    sim = ref.sim((n, n, n), dx)
+    sim.add_fluid_cuboid((0.25, 0.25, 0.25), 7.5, 2.6, 7.5)
+    sim.add_body_force((0.0, -25.0, 0.0))
+    inflow = [dict(kind=0, p=(2.1, 2.9, 2.3), a=0.93, velocity=(1.5, -0.5, 0.25)),
+              dict(kind=1, p=(4.6, 4.1, 5.2), a=1.3, b=0.8, c=1.1, velocity=(-0.75, 0.0, 0.5))]
+    outflow = [dict(kind=1, p=(5.5, 0.3, 0.4), a=1.7, b=1.2, c=2.3)]
+    sim.initialize()
+    sim.update(1.0 / 30.0)                       # particles off their seeding lattice, material = last classification
+    for s_ in inflow:                            # (added now, so that this very call of _updateFluidSources is their first)
+        sim.add_inflow_source(s_["kind"], s_["p"], s_["a"], s_.get("b", 0.0), s_.get("c", 0.0), s_["velocity"])
+    for s_ in outflow:
+        sim.add_outflow_source(s_["kind"], s_["p"], s_["a"], s_.get("b", 0.0), s_.get("c", 0.0))
+    p0, v0 = sim.get_particles()
+    mat = sim.get_material()
+    sim.update_fluid_sources()
+    p1, v1 = sim.get_particles()
+    sim.close()
+
+    c = capi.Context(0)
+    c.domain_init((n, n, n), dx); c.set_material(mat); c.set_sources(inflow)
+    c.set_particles(p0, v0)
+    jitter = 0.25 * 0.1 * dx
+    emitted = c.emit_from_sources(jitter, seed=7)
+    removed = c.remove_in_sources(outflow)
+    pg, vg = c.get_particles()
+    c.close()
+    assert emitted > 500 and removed > 500
+    assert len(pg) == len(p1) == len(p0) + emitted - removed
+
+    def rows(p, v):
+        a = np.ascontiguousarray(np.concatenate([p, v], 1))
+        return np.sort(a.view([("f%d" % i, "f4") for i in range(6)]).reshape(-1), order=["f%d" % i for i in range(6)])
+    old = rows(p0, v0)
+    is_old_ref = np.isin(rows(p1, v1), old)
+    is_old_gpu = np.isin(rows(pg, vg), old)
+    assert is_old_ref.sum() == is_old_gpu.sum() == len(p0) - removed
+    # survivors of the old set: identical
+    assert np.array_equal(rows(p1, v1)[is_old_ref], rows(pg, vg)[is_old_gpu])
+
+    # the new particles: same (half-dx sub-cell, velocity) multiset, positions within the jitter of each other
+    def new_of(p, v):
+        a = np.ascontiguousarray(np.concatenate([p, v], 1)).view([("f%d" % i, "f4") for i in range(6)]).reshape(-1)
+        keep = ~np.isin(a, old)
+        return p[keep], v[keep]
+    (pn_ref, vn_ref), (pn_gpu, vn_gpu) = new_of(p1, v1), new_of(pg, vg)
+    assert len(pn_ref) == len(pn_gpu) > 500
+
+    def keyed(p, v):
+        sub = np.floor(p.astype(np.float64) / (0.5 * dx)).astype(np.int64)
+        key = sub[:, 0] + 4 * n * (sub[:, 1] + 4 * n * sub[:, 2])
+        o = np.lexsort((v[:, 2], v[:, 1], v[:, 0], key))
+        return key[o], p[o], v[o]
+    (k_ref, pr, vr), (k_gpu, pq, vq) = keyed(pn_ref, vn_ref), keyed(pn_gpu, vn_gpu)
+    assert np.array_equal(k_ref, k_gpu)
+    assert np.array_equal(vr.view(np.uint32), vq.view(np.uint32))
+    assert np.abs(pr - pq).max() <= 2.0 * jitter * (1 + 1e-5)
