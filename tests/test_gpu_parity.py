@@ -267,6 +267,29 @@ def test_p2g_variants_bit_identical(ctx, name):
     assert all(np.count_nonzero(a) > 1000 for a in out[0])
 
 
+@pytest.mark.parametrize("name,solids", [("small32", False), ("slab24", True), ("odd20", False)])
+def test_fused_grid_pass_bit_identical(ctx, name, solids):
+    """k_finalize_assemble (option 11 = 1, default: normalise + isValueSet + sources + neighbour fill straight from the
+    accumulators) == k_p2g_finalize + k_assemble (option 11 = 0), bit for bit, also on a second P2G of the same context
+    (the fused pass leaves the clearing of the accumulators to the next splat)."""
+    s = scene(name, solids)
+    out = []
+    for fused in (0, 1):
+        load_domain(ctx, s, SOURCES)
+        ctx.set_option(11, fused)
+        ctx.sort_unstable()
+        ctx.p2g(capi.FAST)
+        first = ctx.get_field(capi.FIELD_P2G)
+        ctx.p2g(capi.FAST)
+        out.append((first, ctx.get_field(capi.FIELD_P2G)))
+    ctx.set_option(11, 1)
+    for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+        assert np.array_equal(bits(a), bits(b))
+    for a, b in zip(out[1][0], out[1][1]):
+        assert np.array_equal(bits(a), bits(b))
+    assert all(np.count_nonzero(a) > 500 for a in out[1][0])
+
+
 def test_p2g_dense_cells(ctx, oracle):
     """More than 63 particles in one cell: the tile kernel must take its 64-bit path for that brick and still
     agree with the oracle (the reference caps at 100 per cell, src/fluidsimulation.cpp:3221-3243, so this is
