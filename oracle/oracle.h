@@ -100,6 +100,16 @@ void orc_g2p_advect_resolve(const float *pos, const float *vel, long n,
 /* MACVelocityField::extrapolateVelocityField (src/macvelocityfield.cpp:577-798), in place on u, v, w */
 void orc_extrapolate(float *u, float *v, float *w, int I, int J, int K, const unsigned char *material, int nlayers);
 
+/* Stages 6-8 (oracle_pressure.c): constant body forces, MICCG(0) pressure solve, pressure update.
+ * src/fluidsimulation.cpp:2765-2805, 2870-2889, 2895-3061; src/pressuresolver.cpp:116-505 */
+void orc_body_force(float *u, float *v, float *w, int I, int J, int K, const unsigned char *material,
+                    const float force[3], double dt);
+double orc_pressure_solve(const float *u, const float *v, const float *w, int I, int J, int K, double dx,
+                          const unsigned char *material, double dt, double density, double tolerance, int max_iterations,
+                          float *pressure, int *info);
+void orc_apply_pressure(float *u, float *v, float *w, int I, int J, int K, double dx, const unsigned char *material,
+                        const float *pressure, double dt, double density);
+
 #ifdef __cplusplus
 }
 #endif

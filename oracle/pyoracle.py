@@ -119,6 +119,35 @@ class Oracle:
         self.lib.orc_extrapolate(u, v, w, *dims, np.ascontiguousarray(material, np.uint8).reshape(-1), int(nlayers))
         return u, v, w
 
+    # -- stages 6-8 (oracle_pressure.c)
+    def body_force(self, u, v, w, dims, material, force, dt):
+        """FluidSimulation::_applyConstantBodyForces on copies of u, v, w."""
+        u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
+        f = np.asarray(force, np.float32)
+        self.lib.orc_body_force.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int, _u8, _f32, C.c_double]
+        self.lib.orc_body_force(u, v, w, *dims, np.ascontiguousarray(material, np.uint8).reshape(-1), f, float(dt))
+        return u, v, w
+
+    def pressure_solve(self, u, v, w, dims, dx, material, dt, density=20.0, tolerance=1e-6, max_iterations=200):
+        """PressureSolver::solve + the narrowing of FluidSimulation::_updatePressureGrid: (float pressure per cell,
+        CG iterations (-1: right-hand side below tolerance), hit the iteration limit, last residual max-norm)."""
+        out = np.zeros(int(np.prod(dims)), np.float32)
+        info = np.zeros(2, np.int32)
+        self.lib.orc_pressure_solve.restype = C.c_double
+        self.lib.orc_pressure_solve.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double, _u8, C.c_double,
+                                                C.c_double, C.c_double, C.c_int, _f32, _i32]
+        err = self.lib.orc_pressure_solve(_c(u), _c(v), _c(w), *dims, dx, np.ascontiguousarray(material, np.uint8).reshape(-1),
+                                          float(dt), float(density), float(tolerance), int(max_iterations), out, info)
+        return out, int(info[0]), bool(info[1]), float(err)
+
+    def apply_pressure(self, u, v, w, dims, dx, material, pressure, dt, density=20.0):
+        """FluidSimulation::_applyPressureToVelocityField on copies of u, v, w."""
+        u, v, w = [np.array(a, np.float32, copy=True).reshape(-1) for a in (u, v, w)]
+        self.lib.orc_apply_pressure.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_double, _u8, _f32, C.c_double, C.c_double]
+        self.lib.orc_apply_pressure(u, v, w, *dims, dx, np.ascontiguousarray(material, np.uint8).reshape(-1),
+                                    np.ascontiguousarray(pressure, np.float32).reshape(-1), float(dt), float(density))
+        return u, v, w
+
     def sample(self, pos, u, v, w, dims, dx, mode, validate=True):
         pos = _c(pos)
         out = np.empty_like(pos)
@@ -463,6 +492,31 @@ class RefSim:
 
     def advance_particles(self, dt):
         self.lib.ref_sim_advance_particles(self.h, dt)
+
+    def apply_body_forces(self, dt):
+        self.lib.ref_sim_apply_body_forces.argtypes = [C.c_void_p, C.c_double]
+        self.lib.ref_sim_apply_body_forces(self.h, dt)
+
+    def update_pressure_grid(self, dt):
+        """FluidSimulation::_updatePressureGrid on the simulator's current _MACVelocity / material / fluid cell list."""
+        out = np.zeros(int(np.prod(self.dims)), np.float32)
+        self.lib.ref_sim_update_pressure_grid.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        self.lib.ref_sim_update_pressure_grid(self.h, dt, out.ctypes.data)
+        return out
+
+    def apply_pressure(self, dt, pressure):
+        p = np.ascontiguousarray(pressure, np.float32)
+        self.lib.ref_sim_apply_pressure.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        self.lib.ref_sim_apply_pressure(self.h, dt, p.ctypes.data)
+
+    def extrapolate_velocities(self):
+        self.lib.ref_sim_extrapolate_velocities.argtypes = [C.c_void_p]
+        self.lib.ref_sim_extrapolate_velocities(self.h)
+
+    def density(self):
+        self.lib.ref_sim_density.restype = C.c_double
+        self.lib.ref_sim_density.argtypes = [C.c_void_p]
+        return self.lib.ref_sim_density(self.h)
 
     def save_state(self, path):
         self.lib.ref_sim_save_state.argtypes = [C.c_void_p, C.c_char_p]

@@ -156,6 +156,44 @@ def test_picflip_and_rk4_bit_exact(oracle, reference, name):
     assert np.array_equal(pos.view(np.uint32), pos_ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("name,solids,dt", [("tiny16", False, 1.0 / 60), ("slab24", True, 1.0 / 30), ("slab24", False, 1.0 / 300)])
+def test_body_force_pressure_solve_and_update_bit_exact(oracle, reference, name, solids, dt):
+    """Stages 6, 7, 8 of _stepFluid (constant body forces, PressureSolver::solve behind _updatePressureGrid,
+    _applyPressureToVelocityField) vs oracle_pressure.c on the reference's own stage-5 field: every float bit for bit --
+    the restatement keeps the MICCG(0) operation order, so the CG trajectory and iteration count are the reference's."""
+    s = _scene(name, solids)
+    force = (0.3, -9.8, 0.05)
+    sim = _ref_sim(reference, s)
+    sim.add_body_force(force)
+    sim.update_fluid_cells()
+    sim.advect_velocity_field()
+    mat = sim.get_material()
+    f5 = sim.get_fields()
+    sim.apply_body_forces(dt)
+    f6 = sim.get_fields()
+    p_ref = sim.update_pressure_grid(dt)
+    sim.apply_pressure(dt, p_ref)
+    f8 = sim.get_fields()
+    density = sim.density()
+    sim.close()
+
+    g6 = oracle.body_force(*f5, s["dims"], mat, force, dt)
+    for a, b in zip(g6, f6):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    p, iters, limit, err = oracle.pressure_solve(*g6, s["dims"], s["dx"], mat, dt, density)
+    assert iters > 3 and not limit and err < 1e-6
+    assert np.count_nonzero(p) > 0.9 * (mat == synth.FLUID).sum()
+    assert np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
+    g8 = oracle.apply_pressure(*g6, s["dims"], s["dx"], mat, p, dt, density)
+    for a, b in zip(g8, f8):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # the projected field is divergence free in the fluid cells to the solver's tolerance
+    I, J, K = s["dims"]
+    u = g8[0].reshape(K, J, I + 1); v = g8[1].reshape(K, J + 1, I); w = g8[2].reshape(K + 1, J, I)
+    div = (u[:, :, 1:] - u[:, :, :-1] + v[:, 1:, :] - v[:, :-1, :] + w[1:] - w[:-1]) / s["dx"]
+    assert np.abs(div[mat.reshape(K, J, I) == synth.FLUID]).max() < 1e-3
+
+
 @pytest.mark.parametrize("nlayers", [0, 1, 3, 7])
 def test_extrapolate_bit_exact(oracle, reference, nlayers):
     """SURVEY 8(f) rank 1: MACVelocityField::extrapolateVelocityField, with interior solids, a fluid blob against the
