@@ -31,6 +31,7 @@ SYMBOLS = [
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
     "gfs_comm_allmax_scale", "gfs_comm_allmax_post", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
+    "gfs_apply_body_force", "gfs_pressure_solve", "gfs_apply_pressure", "gfs_get_pressure",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_reserve", "gfs_state_hash",
     "gfs_mg_get_error_message", "gfs_mg_create", "gfs_mg_destroy", "gfs_mg_num_devices", "gfs_mg_context", "gfs_mg_get_slab", "gfs_mg_set_option",
     "gfs_mg_set_material", "gfs_mg_set_sources", "gfs_mg_set_field", "gfs_mg_get_field", "gfs_mg_get_material", "gfs_mg_scatter_particles",
@@ -139,6 +140,10 @@ def load_library():
     L.gfs_extrapolate.argtypes = [V, I, I, _err]
     L.gfs_extrapolate_field.argtypes = [V, _f32, _f32, _f32, I, I, I, _u8, I, _err]
     L.gfs_copy_field.argtypes = [V, I, I, _err]
+    L.gfs_apply_body_force.argtypes = [V, I, C.c_float, C.c_float, C.c_float, C.c_double, _err]
+    L.gfs_pressure_solve.argtypes = [V, I, C.c_double, C.c_double, C.c_double, I, C.POINTER(I), C.POINTER(C.c_double), _err]
+    L.gfs_apply_pressure.argtypes = [V, I, I, C.c_double, C.c_double, _err]
+    L.gfs_get_pressure.argtypes = [V, _f32, _err]
     PI, PL = C.POINTER(I), C.POINTER(L64)
     L.gfs_comm_set_plan.argtypes = [V, I, I, PI, PI, PI, PL, I, PI, PI, PI, PL, PI, _err]
     L.gfs_comm_substep.argtypes = [V, C.c_double, C.c_double, I, I, I, I, I, PL, _err]
@@ -405,6 +410,26 @@ class Context:
 
     def copy_field(self, dst_slot, src_slot):
         self._call(self.lib.gfs_copy_field, int(dst_slot), int(src_slot))
+
+    # -- stages 6-8 on the resident grid (FluidSimulation::_applyConstantBodyForces, PressureSolver::solve,
+    #    _applyPressureToVelocityField; reference defaults: density 20, tolerance 1e-6, 200 iterations)
+    def apply_body_force(self, slot, force, dt):
+        self._call(self.lib.gfs_apply_body_force, int(slot), float(force[0]), float(force[1]), float(force[2]), float(dt))
+
+    def pressure_solve(self, slot, dt, density=20.0, tolerance=1e-6, max_iterations=200):
+        """-> (iterations, last residual max-norm); iterations as the reference counts them (-1: nothing to solve)."""
+        it, res = C.c_int(0), C.c_double(0.0)
+        self._call(self.lib.gfs_pressure_solve, int(slot), float(dt), float(density), float(tolerance), int(max_iterations),
+                   C.byref(it), C.byref(res))
+        return it.value, res.value
+
+    def apply_pressure(self, src_slot, dst_slot, dt, density=20.0):
+        self._call(self.lib.gfs_apply_pressure, int(src_slot), int(dst_slot), float(dt), float(density))
+
+    def get_pressure(self):
+        out = np.empty(int(np.prod(self.dims)), np.float32)
+        self._call(self.lib.gfs_get_pressure, out)
+        return out
 
     def sort_index(self):
         self._call(self.lib.gfs_sort_index)

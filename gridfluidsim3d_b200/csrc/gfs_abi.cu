@@ -20,6 +20,7 @@
 #include "gfs_p2g2.cuh"
 #include "gfs_g2p2.cuh"
 #include "gfs_sources.cuh"
+#include "gfs_pressure.cuh"
 
 namespace {
 
@@ -134,6 +135,21 @@ struct gfs_context {
     DevBuf<int32_t> n_valid;              // 1 word
     DevBuf<unsigned int> vmax_bits;       // 1 word
     DevBuf<int8_t> ext_layer;             // gfs_extrapolate: layer index per cell
+    // ---- pressure solve (gfs_pressure.cuh): dense vectors over the cells, wavefront tiles, reduction partials
+    struct Pressure {
+        DevBuf<double> vec[6];            // r, z, s, p, q, precon
+        DevBuf<double> scal;              // partial[3 * kPressBlocks], sigma[2], resid[1]
+        DevBuf<uint8_t> flags;
+        DevBuf<int> state, order;
+        DevBuf<unsigned long long> ticket;
+        DevBuf<unsigned int> tile_done;
+        DevBuf<float> pressure;
+        int dims[3] = {0, 0, 0};          // grid the tile order was built for
+        unsigned int epoch = 0;
+        bool valid = false;               // `pressure` holds the result of a solve on the current domain
+        int *host_state = nullptr;        // pinned {done, iterations, spare} + resid behind it
+        double *host_resid = nullptr;
+    } press;
     DevBuf<float4> coll_list;             // particles advected into a solid cell: {slot, p1}, resolved by k_resolve_collisions
     DevBuf<unsigned int> coll_count;
     // ---- CUDA graphs of the fused single-domain substep: one per buffer parity, replayed while nothing it baked in changes
@@ -861,6 +877,11 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int a = 0; a < 3; a++) { c->val[a].release(); c->setmask[a].release(); c->acc[a].release(); c->h_field[a].release(); }
     c->material.release(); c->cell_start.release(); c->counts.release(); c->rank.release(); c->index.release();
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
+    for (int a = 0; a < 6; a++) c->press.vec[a].release();
+    c->press.scal.release(); c->press.flags.release(); c->press.state.release(); c->press.order.release();
+    c->press.ticket.release(); c->press.tile_done.release(); c->press.pressure.release();
+    if (c->press.host_state) cudaFreeHost(c->press.host_state);
+    if (c->press.host_resid) cudaFreeHost(c->press.host_resid);
     c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release(); c->h_mat.release(); c->h_layer.release();
     for (int sd = 0; sd < 2; sd++) {
         if (c->comm[sd].peer && c->comm[sd].peer_ipc) cudaIpcCloseMemHandle(c->comm[sd].peer);
@@ -1127,6 +1148,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     // a new domain invalidates every key, index and cell table of the old one
     c->keys_ready = false; c->indexed = false; c->storage_sorted = false; c->sorted = false;
     c->has_domain = true;
+    c->press.valid = false;
     c->have_maps = false;
     c->own_k0 = 0; c->own_k1 = K;
     set_key_range(c);
@@ -1342,6 +1364,166 @@ void gfs_copy_field(gfs_context *c, int dst_slot, int src_slot, int *err) {
         for (int a = 0; a < 3; a++)
             GFS_CUDA(cudaMemcpyAsync(c->field[dst_slot][a].p, c->field[src_slot][a].p, c->field_floats[a] * sizeof(float),
                                      cudaMemcpyDeviceToDevice, c->stream));
+    GFS_END()
+}
+
+/* ---- stages 6-8 on the resident grid (kernels and the parity argument: gfs_pressure.cuh) -------- */
+
+/* FluidSimulation::_applyConstantBodyForces (src/fluidsimulation.cpp:2765-2805): every face of `slot` bordering a fluid
+ * cell gets (float)(force * dt) added; a component whose force is exactly zero is skipped, as the reference does. */
+void gfs_apply_body_force(gfs_context *c, int slot, float fx, float fy, float fz, double dt, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3, "bad field slot");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_apply_body_force is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const float force[3] = {fx, fy, fz};
+    gfs::Float3 add;
+    int mask = 0;
+    for (int a = 0; a < 3; a++) {
+        add.v[a] = (float)(force[a] * dt);                     /* bodyForce.x * dt: float * double, narrowed by addU */
+        if (std::fabs(force[a]) > 0.0) mask |= 1 << a;
+    }
+    if (mask) {
+        gfs::FieldRW f;
+        for (int a = 0; a < 3; a++) f.c[a] = c->field[slot][a].p + gfs::kRowPad;
+        const unsigned nodes = (unsigned)ceil_div((long long)(g.I + 1) * (g.J + 1), 256);
+        LAUNCH(c, gfs::k_body_force, dim3(nodes, (unsigned)g.K + 1), 256, g, c->material.p, f, add, mask);
+        c->graph_epoch++;
+    }
+    GFS_END()
+}
+
+namespace {
+gfs::PressSys pressure_system(gfs_context *c, double dt, double density, double tolerance) {
+    const Grid &g = c->grid;
+    gfs_context::Pressure &P = c->press;
+    const size_t cells = (size_t)g.I * g.J * g.K;
+    for (int a = 0; a < 6; a++) P.vec[a].reserve(cells);
+    P.scal.reserve(3 * gfs::kPressBlocks + 4);
+    P.flags.reserve(cells); P.state.reserve(4); P.ticket.reserve(4); P.pressure.reserve(cells);
+    if (!P.host_state) GFS_CUDA(cudaMallocHost((void **)&P.host_state, 4 * sizeof(int)));
+    if (!P.host_resid) GFS_CUDA(cudaMallocHost((void **)&P.host_resid, sizeof(double)));
+    gfs::PressSys S;
+    S.I = g.I; S.J = g.J; S.K = g.K;
+    S.ntx = ceil_div(g.I, gfs::kTileX); S.nty = ceil_div(g.J, gfs::kTileY); S.ntz = ceil_div(g.K, gfs::kTileZ);
+    S.ntiles = S.ntx * S.nty * S.ntz;
+    if (P.dims[0] != g.I || P.dims[1] != g.J || P.dims[2] != g.K) {
+        /* tiles in wavefront order: a tile's three predecessors always come earlier */
+        std::vector<int> order((size_t)S.ntiles), start((size_t)(S.ntx + S.nty + S.ntz) + 1, 0);
+        auto stage = [&](int t) { return t % S.ntx + (t / S.ntx) % S.nty + t / (S.ntx * S.nty); };
+        for (int t = 0; t < S.ntiles; t++) start[(size_t)stage(t) + 1]++;
+        for (size_t q = 1; q < start.size(); q++) start[q] += start[q - 1];
+        for (int t = 0; t < S.ntiles; t++) order[(size_t)start[(size_t)stage(t)]++] = t;
+        P.order.reserve((size_t)S.ntiles); P.tile_done.reserve((size_t)S.ntiles);
+        GFS_CUDA(cudaMemcpyAsync(P.order.p, order.data(), (size_t)S.ntiles * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        GFS_CUDA(cudaStreamSynchronize(c->stream));                       /* `order` is a local */
+        GFS_CUDA(cudaMemsetAsync(P.tile_done.p, 0, (size_t)S.ntiles * sizeof(unsigned int), c->stream));
+        P.epoch = 0;
+        P.dims[0] = g.I; P.dims[1] = g.J; P.dims[2] = g.K;
+    }
+    S.material = c->material.p; S.flags = P.flags.p;
+    S.r = P.vec[0].p; S.z = P.vec[1].p; S.s = P.vec[2].p; S.p = P.vec[3].p; S.q = P.vec[4].p; S.precon = P.vec[5].p;
+    S.partial = P.scal.p; S.sigma = P.scal.p + 3 * gfs::kPressBlocks; S.resid = P.scal.p + 3 * gfs::kPressBlocks + 2;
+    S.state = P.state.p; S.ticket = P.ticket.p; S.tile_done = P.tile_done.p; S.order = P.order.p; S.pressure = P.pressure.p;
+    S.cells = (long long)cells;
+    S.scale = dt / (density * g.dx * g.dx);
+    S.tol = tolerance;
+    return S;
+}
+}  // namespace
+
+/* PressureSolver::solve (src/pressuresolver.cpp:116-139, 452-505) on the velocity field in `slot` and the resident material
+ * grid, narrowed to the float grid of FluidSimulation::_updatePressureGrid (src/fluidsimulation.cpp:2870-2889).
+ * tolerance / max_iterations: the reference's 1e-6 / 200 (src/pressuresolver.h:159-160), density its 20.0
+ * (src/fluidsimulation.h:1154).  *iterations = the reference's iterationNumber when it returns (-1: the right-hand side
+ * was already below the tolerance, pressure = 0; max_iterations: limit reached, the estimate so far is kept, as the
+ * reference does).  *residual = the last max-norm of the residual.  The pressure stays on the device for
+ * gfs_apply_pressure / gfs_get_pressure. */
+void gfs_pressure_solve(gfs_context *c, int slot, double dt, double density, double tolerance, int max_iterations,
+                        int *iterations, double *residual, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3, "bad field slot");
+    GFS_REQUIRE(dt > 0 && density > 0 && tolerance > 0 && max_iterations >= 0, "bad solver parameters");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_pressure_solve is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    gfs_context::Pressure &P = c->press;
+    gfs::PressSys S = pressure_system(c, dt, density, tolerance);
+    const size_t cells = (size_t)S.cells;
+    for (int a = 1; a < 6; a++) GFS_CUDA(cudaMemsetAsync(P.vec[a].p, 0, cells * sizeof(double), c->stream));
+    GFS_CUDA(cudaMemsetAsync(P.state.p, 0, 4 * sizeof(int), c->stream));
+    GFS_CUDA(cudaMemsetAsync(P.ticket.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    int sms = 148;
+    GFS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int sweep_blocks = 2 * sms;
+    const int B = gfs::kPressBlocks, T = gfs::kPressThreads;
+
+    LAUNCH(c, gfs::k_press_setup, B, T, g, field_ptrs(c, slot), S, g.dx);
+    LAUNCH(c, gfs::k_press_check, 1, T, S, -1);
+    LAUNCH(c, gfs::k_press_sweep<0>, sweep_blocks, T, S, ++P.epoch);
+    LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
+    LAUNCH(c, gfs::k_press_sweep<2>, sweep_blocks, T, S, ++P.epoch);
+    LAUNCH(c, gfs::k_press_dot_zr, B, T, S);
+    LAUNCH(c, gfs::k_press_search, B, T, S, 0, 1);
+    int it = 0;
+    bool done = false;
+    auto poll = [&]() {
+        GFS_CUDA(cudaMemcpyAsync(P.host_state, P.state.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GFS_CUDA(cudaMemcpyAsync(P.host_resid, S.resid, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GFS_CUDA(cudaStreamSynchronize(c->stream));
+        done = P.host_state[0] != 0;
+    };
+    while (it < max_iterations && !done) {
+        LAUNCH(c, gfs::k_press_apply_matrix, B, T, S);
+        LAUNCH(c, gfs::k_press_update, B, T, S, it);
+        LAUNCH(c, gfs::k_press_check, 1, T, S, it);
+        LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
+        LAUNCH(c, gfs::k_press_sweep<2>, sweep_blocks, T, S, ++P.epoch);
+        LAUNCH(c, gfs::k_press_dot_zr, B, T, S);
+        LAUNCH(c, gfs::k_press_search, B, T, S, it, 0);
+        it++;
+        if (it % 8 == 0) poll();
+    }
+    LAUNCH(c, gfs::k_press_finish, B, T, S);
+    poll();
+    P.valid = true;
+    if (iterations) *iterations = done ? P.host_state[1] : max_iterations;
+    if (residual) *residual = *P.host_resid;
+    GFS_END()
+}
+
+/* FluidSimulation::_applyPressureToVelocityField (src/fluidsimulation.cpp:2895-3061) with the pressure of the last
+ * gfs_pressure_solve: dst_slot := projected src_slot (the two may be the same slot). */
+void gfs_apply_pressure(gfs_context *c, int src_slot, int dst_slot, double dt, double density, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(src_slot >= 0 && src_slot < 3 && dst_slot >= 0 && dst_slot < 3, "bad field slot");
+    GFS_REQUIRE(dt > 0 && density > 0, "bad parameters");
+    GFS_REQUIRE(c->press.valid, "gfs_pressure_solve has not been called on this domain");
+    const Grid &g = c->grid;
+    GFS_CUDA(cudaSetDevice(c->device));
+    gfs::FieldRW dst;
+    for (int a = 0; a < 3; a++) dst.c[a] = c->field[dst_slot][a].p + gfs::kRowPad;
+    const unsigned nodes = (unsigned)ceil_div((long long)(g.I + 1) * (g.J + 1), 256);
+    LAUNCH(c, gfs::k_apply_pressure, dim3(nodes, (unsigned)g.K + 1), 256, g, c->material.p, field_ptrs(c, src_slot), dst,
+           c->press.pressure.p, dt / (density * g.dx));
+    c->graph_epoch++;
+    GFS_END()
+}
+
+/* the float pressure grid of the last solve, one value per cell (i fastest), 0 outside fluid cells */
+void gfs_get_pressure(gfs_context *c, float *pressure, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(pressure, "null output");
+    GFS_REQUIRE(c->press.valid, "gfs_pressure_solve has not been called on this domain");
+    GFS_CUDA(cudaSetDevice(c->device));
+    GFS_CUDA(cudaMemcpyAsync(pressure, c->press.pressure.p, (size_t)c->grid.I * c->grid.J * c->grid.K * sizeof(float),
+                             cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
 

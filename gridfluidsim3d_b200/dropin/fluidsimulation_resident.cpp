@@ -1,27 +1,41 @@
-/* fluidsimulation_resident.cpp -- the four particle<->grid stages of FluidSimulation::_stepFluid
- * (/root/reference/src/fluidsimulation.cpp:3262-3390) on the device-resident path of libgfs_b200:
+/* fluidsimulation_resident.cpp -- the particle<->grid stages AND the grid stages between them of
+ * FluidSimulation::_stepFluid (/root/reference/src/fluidsimulation.cpp:3262-3390) on the device-resident path of
+ * libgfs_b200:
  *
  *    stage  1  _updateFluidCells                  :1990-2040   -> gfs_set_particles (only when the host set changed),
  *                                                                 gfs_sort_index + gfs_p2g (classification + splat)
- *    stage  5  _advectVelocityField               :2597-2740   -> gfs_get_field(P2G) into _MACVelocity
- *    stage 11  _updateMarkerParticleVelocities    :3104-3138   -> gfs_set_field(NEW, SAVED)
+ *    stage  5  _advectVelocityField               :2597-2740   -> nothing left to do: the splat of stage 1 is the P2G slot
+ *              _extrapolateFluidVelocities(saved) :3067-3070   -> gfs_copy_field(SAVED <- P2G) + gfs_extrapolate(SAVED)
+ *    stage  6  _applyBodyForcesToVelocityField    :2846-2849   -> gfs_apply_body_force(P2G) (constant forces; variable
+ *                                                                 force fields are host callbacks: the field makes one
+ *                                                                 round trip through the reference's own loop)
+ *    stage  7  _updatePressureGrid                :2870-2889   -> gfs_pressure_solve(P2G): the reference's MICCG(0)
+ *    stage  8  _applyPressureToVelocityField      :3015-3061   -> gfs_apply_pressure(P2G -> NEW)
+ *    stage  9  _extrapolateFluidVelocities(MAC)   :3067-3070   -> gfs_extrapolate(NEW); NEW is then copied down into
+ *                                                                 _MACVelocity for the host stages that read it
+ *                                                                 (diffuse particles, getVelocityField())
+ *    stage 11  _updateMarkerParticleVelocities    :3104-3138   -> nothing to ship: NEW and SAVED are on the device
  *    stage 12  _advanceMarkerParticles            :3245-3256   -> gfs_g2p_advect (PIC/FLIP + RK4 + collision resolve),
  *                                                                 gfs_get_particles, then the reference's own
  *                                                                 _removeMarkerParticles
  *
  * These are DEFINITIONS OF THE REFERENCE'S OWN PRIVATE MEMBER FUNCTIONS: the unmodified fluidsimulation.cpp is compiled
- * as it lies, its four definitions are made weak in the object file (objcopy --weaken-symbol, oracle/Makefile target
- * `resident`) and the strong ones below win at link time; every call site inside the reference (all PLT calls) lands
- * here.  Everything else of the simulator -- surface reconstruction, level set, body forces, pressure solve,
- * extrapolation, diffuse particles, output -- is the reference's code, unchanged, on the host.
+ * as it lies, the definitions listed in oracle/Makefile (RESIDENT_WEAK) are made weak in the object file (objcopy
+ * --weaken-symbol) and the strong ones below win at link time; every call site inside the reference (all PLT calls)
+ * lands here.  Everything else of the simulator -- surface reconstruction, level set, diffuse particles, sources,
+ * output -- is the reference's code, unchanged, on the host.
  *
  * Data kept in HBM across substeps: the marker particles (uploaded once; re-uploaded only when the host vector changed
- * size or a source / cell queue edited it), the material grid, the three field slots.  Per substep over PCIe: the
- * material grid and the P2G field down, the post-pressure and the saved field up, the advanced particles down (the
+ * size or a source / cell queue edited it), the material grid, the three field slots, the pressure system.  Per substep
+ * over PCIe: the material grid both ways (1 B per cell), the final velocity field down, the advanced particles down (the
  * host stages between -- meshing, per-cell cap -- read the host vector).
+ *
+ * The Array3d<float> pressure grid the reference passes from stage 7 to stage 8 stays zero on the host: both stages are
+ * here and the pressure lives on the device (gfs_get_pressure reads it).
  *
  * C++11, no CUDA types: only the C-ABI of include/gfs_b200.h.
  */
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -163,24 +177,78 @@ void FluidSimulation::_updateFluidCells() {
 }
 
 /* Stage 5: _advectVelocityFieldU/V/W each clear their component and refill it (:2597-2730); the three refilled arrays
- * are the P2G slot the splat of stage 1 left on the device. */
+ * are the P2G slot the splat of stage 1 left on the device.  The host _MACVelocity is refreshed after stage 9. */
 void FluidSimulation::_advectVelocityField() {
+}
+
+/* Stages 5 (saved field) and 9 (solved field): MACVelocityField::extrapolateVelocityField(_materialGrid,
+ * ceil(CFL + 2)) (:3067-3070) -- bit-identical on the device (gfs_extrapolate). */
+void FluidSimulation::_extrapolateFluidVelocities(MACVelocityField &MACGrid) {
+    const int numLayers = (int)ceil(_CFLConditionNumber + 2);
     gfs_context *ctx = _particleAdvector.context();
     int err;
-    gfs_get_field(ctx, GFS_FIELD_P2G, _MACVelocity.getRawArrayU(), _MACVelocity.getRawArrayV(), _MACVelocity.getRawArrayW(), &err);
-    check(err, "gfs_get_field");
+    if (&MACGrid == &_savedVelocityField) {               /* "_savedVelocityField = _MACVelocity" (:3306) on the device */
+        gfs_copy_field(ctx, GFS_FIELD_SAVED, GFS_FIELD_P2G, &err);
+        check(err, "gfs_copy_field");
+        gfs_extrapolate(ctx, GFS_FIELD_SAVED, numLayers, &err);
+        check(err, "gfs_extrapolate(saved)");
+    } else if (&MACGrid == &_MACVelocity) {
+        gfs_extrapolate(ctx, GFS_FIELD_NEW, numLayers, &err);
+        check(err, "gfs_extrapolate(new)");
+        gfs_get_field(ctx, GFS_FIELD_NEW, _MACVelocity.getRawArrayU(), _MACVelocity.getRawArrayV(), _MACVelocity.getRawArrayW(), &err);
+        check(err, "gfs_get_field");
+    } else {
+        MACGrid.extrapolateVelocityField(_materialGrid, numLayers);
+    }
+}
+
+/* Stage 6 (:2846-2849).  Constant forces on the device; variable force fields are user callbacks on the host, so with
+ * any registered the field makes one round trip through the reference's own two loops. */
+void FluidSimulation::_applyBodyForcesToVelocityField(double dt) {
+    gfs_context *ctx = _particleAdvector.context();
+    int err;
+    if (!_variableBodyForces.empty()) {
+        gfs_get_field(ctx, GFS_FIELD_P2G, _MACVelocity.getRawArrayU(), _MACVelocity.getRawArrayV(), _MACVelocity.getRawArrayW(), &err);
+        check(err, "gfs_get_field");
+        _applyConstantBodyForces(dt);
+        _applyVariableBodyForces(dt);
+        gfs_set_field(ctx, GFS_FIELD_P2G, _MACVelocity.getRawArrayU(), _MACVelocity.getRawArrayV(), _MACVelocity.getRawArrayW(), &err);
+        check(err, "gfs_set_field");
+        return;
+    }
+    vmath::vec3 bf = _getConstantBodyForce();
+    gfs_apply_body_force(ctx, GFS_FIELD_P2G, bf.x, bf.y, bf.z, dt, &err);
+    check(err, "gfs_apply_body_force");
+}
+
+/* Stage 7 (:2870-2889): PressureSolver::solve with the reference's own parameters (PressureSolver's tolerance and
+ * iteration limit are private constants, src/pressuresolver.h:159-160). */
+void FluidSimulation::_updatePressureGrid(Array3d<float> &pressureGrid, double dt) {
+    (void)pressureGrid;
+    gfs_context *ctx = _particleAdvector.context();
+    int err, iterations = 0;
+    double residual = 0.0;
+    gfs_pressure_solve(ctx, GFS_FIELD_P2G, dt, _density, 1e-6, 200, &iterations, &residual, &err);
+    check(err, "gfs_pressure_solve");
+    if (iterations >= 200) {
+        _logfile.log("Iterations limit reached.\t Estimated error : ", residual, 1);      /* :502-503 */
+    } else if (iterations >= 0) {
+        _logfile.log("CG Iterations: ", iterations, 1);                                    /* :479 */
+    }
+}
+
+/* Stage 8 (:3015-3061) */
+void FluidSimulation::_applyPressureToVelocityField(Array3d<float> &pressureGrid, double dt) {
+    (void)pressureGrid;
+    gfs_context *ctx = _particleAdvector.context();
+    int err;
+    gfs_apply_pressure(ctx, GFS_FIELD_P2G, GFS_FIELD_NEW, dt, _density, &err);
+    check(err, "gfs_apply_pressure");
 }
 
 /* Stage 11 needs both fields and no dt; stage 12 has the dt.  The fused G2P kernel does both stages in one pass over the
- * particles, so stage 11 only ships the two fields (the caller clears _savedVelocityField right after, :3350). */
+ * particles and both fields are already in their slots (the caller clears _savedVelocityField right after, :3350). */
 void FluidSimulation::_updateMarkerParticleVelocities() {
-    gfs_context *ctx = _particleAdvector.context();
-    int err;
-    gfs_set_field(ctx, GFS_FIELD_NEW, _MACVelocity.getRawArrayU(), _MACVelocity.getRawArrayV(), _MACVelocity.getRawArrayW(), &err);
-    check(err, "gfs_set_field(new)");
-    gfs_set_field(ctx, GFS_FIELD_SAVED, _savedVelocityField.getRawArrayU(), _savedVelocityField.getRawArrayV(),
-                  _savedVelocityField.getRawArrayW(), &err);
-    check(err, "gfs_set_field(saved)");
 }
 
 /* Stages 11 + 12 on the device: PIC/FLIP update (:3118-3128), RK4 (src/particleadvector.cpp:1045-1054), solid test and

@@ -199,6 +199,28 @@ void gfs_sort_unstable(gfs_context *ctx, int *err);
  * it with num_layers = ceil(CFL + 2) on the saved field after P2G and on the solved field before G2P
  * (src/fluidsimulation.cpp:3067-3070, 3306-3307, 3334).  gfs_copy_field: dst slot := src slot (":3306"). */
 void gfs_extrapolate(gfs_context *ctx, int slot, int num_layers, int *err);
+
+/* Stages 6-8 of FluidSimulation::_stepFluid on the resident grid, single domain.
+ *
+ * gfs_apply_body_force = FluidSimulation::_applyConstantBodyForces (src/fluidsimulation.cpp:2765-2805): adds
+ *     (float)(force * dt) to every face of `slot` that borders a fluid cell; zero components are skipped.
+ * gfs_pressure_solve  = PressureSolver::solve behind FluidSimulation::_updatePressureGrid (src/pressuresolver.cpp:116-505,
+ *     src/fluidsimulation.cpp:2870-2889): the reference's MICCG(0) -- same right-hand side, same modified incomplete
+ *     Cholesky factor, same substitutions and updates, operation for operation in double; the sequential sweeps run as
+ *     tile wavefronts, which respects every data dependency and therefore gives the same bits.  Only the summation order
+ *     of the dot products differs (last-place effects on alpha / beta).  The reference's parameters are density 20.0
+ *     (src/fluidsimulation.h:1154), tolerance 1e-6 and 200 iterations (src/pressuresolver.h:159-160).  *iterations
+ *     receives the reference's iterationNumber at return (-1: right-hand side below the tolerance, pressure 0;
+ *     max_iterations: limit reached, estimate kept), *residual the last max |residual|; both may be NULL.
+ * gfs_apply_pressure  = FluidSimulation::_applyPressureToVelocityField (src/fluidsimulation.cpp:2895-3061) with the
+ *     float pressure grid of the last solve: dst_slot := src_slot projected (faces bordering fluid: 0 next to a solid,
+ *     U - dt/(density dx) (p1 - p0) otherwise; all other faces copied).  src_slot == dst_slot is allowed.
+ * gfs_get_pressure    : that float grid, isize*jsize*ksize values, i fastest (0 outside fluid cells). */
+void gfs_apply_body_force(gfs_context *ctx, int slot, float fx, float fy, float fz, double dt, int *err);
+void gfs_pressure_solve(gfs_context *ctx, int slot, double dt, double density, double tolerance, int max_iterations,
+                        int *iterations, double *residual, int *err);
+void gfs_apply_pressure(gfs_context *ctx, int src_slot, int dst_slot, double dt, double density, int *err);
+void gfs_get_pressure(gfs_context *ctx, float *pressure, int *err);
 void gfs_copy_field(gfs_context *ctx, int dst_slot, int src_slot, int *err);
 /* gfs_sort_index: the counting sort without moving the particles -- only the sorted index is materialised and the
  * P2G / G2P kernels fetch through it (G2P stores its results in sorted order).  What gfs_substep does internally;
