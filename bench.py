@@ -515,18 +515,26 @@ def run_gfs(args):
     d2h = n_local * 24 + 4 * (per_layer * dn_n + dims[0] * dims[1]) + dims[0] * dims[1] * dn_n
     new_np, saved_np = [t.numpy() for t in new_host], [t.numpy() for t in saved_host]
 
+    e2e_parts = {}
+
+    def timed(name, fn, *a):
+        t = time.perf_counter()
+        fn(*a)                                  # every one of these C-ABI calls returns after its own stream synchronisation
+        e2e_parts[name] = e2e_parts.get(name, 0.0) + time.perf_counter() - t
+
     def e2e_step():
-        ctx.set_particles_aos(aos_host.numpy())                                  # H2D 24 B/particle
-        ctx.set_field_layers(capi.FIELD_NEW, *new_np, up_lo, up_n)              # H2D post-pressure field (owned layers + halo)
-        ctx.set_field_layers(capi.FIELD_SAVED, *saved_np, up_lo, up_n)          # H2D saved field
-        substep()
-        ctx.get_particles_aos(aos_out.numpy().reshape(-1)[: ctx.num_particles * 6])   # D2H particles
-        ctx.get_field_layers(capi.FIELD_P2G, p2g_out, dn_lo, dn_n)              # D2H P2G u,v,w (owned layers)
-        ctx.get_material_layers(mat_pinned.numpy(), dn_lo, dn_n)                 # D2H material
+        timed("set_particles", ctx.set_particles_aos, aos_host.numpy())                                  # H2D 24 B/particle
+        timed("set_fields", ctx.set_field_layers, capi.FIELD_NEW, *new_np, up_lo, up_n)                  # H2D post-pressure field (owned layers + halo)
+        timed("set_fields", ctx.set_field_layers, capi.FIELD_SAVED, *saved_np, up_lo, up_n)              # H2D saved field
+        timed("substep", substep)
+        timed("get_particles", ctx.get_particles_aos, aos_out.numpy().reshape(-1)[: ctx.num_particles * 6])   # D2H particles
+        timed("get_fields", ctx.get_field_layers, capi.FIELD_P2G, p2g_out, dn_lo, dn_n)                  # D2H P2G u,v,w (owned layers)
+        timed("get_material", ctx.get_material_layers, mat_pinned.numpy(), dn_lo, dn_n)                  # D2H material
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
     barrier()
+    e2e_parts.clear()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -534,6 +542,7 @@ def run_gfs(args):
     e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
     e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d), "d2h_bytes_per_step": allsum(d2h),
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "breakdown_ms_rank0": {k: round(v / e2e_steps * 1e3, 3) for k, v in e2e_parts.items()},
            "api": "gfs_set_particles + gfs_set_field_layers x2 + substep + gfs_get_particles + gfs_get_field_layers + gfs_get_material_layers"
                   + (" (per rank: owned layers + halo up, owned layers down)" if world > 1 else " (all layers)")}
 
@@ -643,6 +652,37 @@ def run_gfs(args):
         sub["advect_only"] = {"particles": n_adv, "kernel_ms": k_ms, "value": n_adv / (k_ms * 1e-3) if k_ms > 0 else None, "unit": "particles/s",
                               "algorithmic_bytes": b, "hbm_frac": b / (k_ms * 1e-3) / 1e9 / hbm_gbs if k_ms > 0 else None,
                               "through_host_value": n_adv / wall, "api": "gfs_advect (host pointers, unsorted random positions, global loads)"}
+    if world == 1 and not args.no_pressure:
+        # stages 6-8 on the field the last substep's P2G left on the device (this workload's grid and
+        # fluid cells): constant gravity, the reference's MICCG(0) with its own tolerance / iteration limit, the update.
+        try:
+            ctx.profile_enable(True)
+            ctx.profile_read(reset=True)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.apply_body_force(capi.FIELD_P2G, (0.0, -9.8, 0.0), dt)
+            with torch.cuda.stream(stream):
+                ev0.record(stream)
+            iters, resid = ctx.pressure_solve(capi.FIELD_P2G, dt)
+            with torch.cuda.stream(stream):
+                ev1.record(stream)
+            ctx.apply_pressure(capi.FIELD_P2G, capi.FIELD_NEW, dt)
+            torch.cuda.synchronize(dev)
+            pk = ctx.profile_read(reset=True)
+            ctx.profile_enable(False)
+            fluid = int(st["fluid_cells"])
+            solve_ms = ev0.elapsed_time(ev1)
+            n_it = max(1, iters)
+            kms = {k.replace("gfs::", ""): {"ms_per_launch": v[0] / max(1, v[1]), "launches": int(v[1])} for k, v in pk.items() if "press" in k or "body_force" in k}
+            am = [v for k, v in kms.items() if "apply_matrix" in k]
+            sub["pressure_solve"] = {
+                "cells": G, "fluid_cells": fluid, "iterations": iters, "residual_max": resid, "tolerance": 1e-6, "max_iterations": 200,
+                "solve_ms": solve_ms, "ms_per_iteration": solve_ms / n_it, "kernels": kms,
+                "apply_matrix": {"algorithmic_bytes": 17 * G, "hbm_frac": (17 * G / (am[0]["ms_per_launch"] * 1e-3) / 1e9 / hbm_gbs) if am and am[0]["ms_per_launch"] > 0 else None,
+                                 "note": "dense 7-point SpMV over all cells: search vector read (8 B) + flags (1 B) + result written (8 B) per cell"},
+                "note": "PressureSolver::solve restated operation for operation (fp64, MIC(0) sweeps as tile wavefronts); "
+                        "the reference's CPU time for the same stage is in submetrics.dropin.*.stage_seconds['Update Pressure Grid'] at 64^3"}
+        except Exception as e:
+            sub["pressure_solve"] = {"unavailable": repr(e)[:200]}
     if world == 1 and not args.no_sweep:
         ctx.close()                       # the sweep's 1 B-particle point needs the memory
         ctx = None
@@ -755,8 +795,9 @@ def dropin_submetric(n=64, frames=1):
     BASELINE configs[0]) three ways: its own CPU accelerator classes, the CUDA drop-in classes (host-pointer C-ABI calls
     per stage), and the device-resident stages of dropin/fluidsimulation_resident.cpp.  The libraries are the reference
     sources compiled where they lie (oracle/Makefile: ref, dropin, resident); particle-substeps/s counts every substep
-    the simulator's own log reports.  The pressure solve, meshing and everything else stay reference CPU code in all
-    three, so this is the speed-up a user of the reference sees today, not the kernel speed-up."""
+    the simulator's own log reports.  Meshing, level set and output stay reference CPU code in all three (the resident
+    build also runs body forces, the pressure solve, the pressure update and both extrapolations on the device), so this is
+    the speed-up a user of the reference sees, not the kernel speed-up."""
     import ctypes
     from oracle import pyoracle
     from oracle.pyoracle import RefSim
@@ -790,14 +831,17 @@ def dropin_submetric(n=64, frames=1):
             npart = sim.n
             sim.close()
             hot = sum(stages.get(k, 0.0) for k in ("Update Fluid Cells", "Advect Velocity Field", "Update PIC/FLIP Velocities", "Advance Marker Particles"))
+            grid = sum(stages.get(k, 0.0) for k in ("Apply Body Forces", "Update Pressure Grid", "Apply Pressure", "Extrapolate Fluid Velocities"))
             out[name] = {"value": npart * max(1, substeps) / wall, "seconds": wall, "substeps": substeps, "particles": npart,
                          "hot_path_stage_seconds": hot, "hot_path_value": npart * max(1, substeps) / hot if hot > 0 else None,
+                         "grid_stage_seconds": grid,
                          "stage_seconds": {k: round(v, 4) for k, v in stages.items()}}
         except Exception as e:
             out[name] = {"unavailable": repr(e)[:200]}
     try:
         out["speedup_whole_update"] = out["cuda_resident"]["value"] / out["cpu_classes"]["value"]
         out["speedup_hot_path_stages"] = out["cuda_resident"]["hot_path_value"] / out["cpu_classes"]["hot_path_value"]
+        out["speedup_grid_stages_6_to_9"] = out["cpu_classes"]["grid_stage_seconds"] / max(1e-9, out["cuda_resident"]["grid_stage_seconds"])
     except (KeyError, TypeError, ZeroDivisionError):
         pass
     return out
@@ -834,6 +878,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the advection-only sweep 1 M .. 1 B particles (BASELINE configs[4])")
     ap.add_argument("--no-balance", action="store_true", help="N>1: keep the particle-count-weighted cuts (no timing calibration pass)")
+    ap.add_argument("--no-pressure", action="store_true", help="skip the pressure-solve sub-metric (stages 6-8 on the workload's grid)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the FluidSimulation::update drop-in sub-metric (64^3, CPU vs CUDA classes)")
     ap.add_argument("--no-peer-check", action="store_true", help="N>1: skip the peer-memory vs NCCL transport cross-check after the timed runs")
     args = ap.parse_args()
