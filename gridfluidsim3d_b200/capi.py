@@ -31,7 +31,7 @@ SYMBOLS = [
     "gfs_comm_pull_layers", "gfs_comm_migrate_begin", "gfs_comm_migrate_finish", "gfs_comm_g2p_advect",
     "gfs_comm_world_alloc", "gfs_comm_world_export", "gfs_comm_world_connect", "gfs_comm_world_connect_local",
     "gfs_comm_allmax_scale", "gfs_comm_allmax_post", "gfs_sort_index", "gfs_comm_set_plan", "gfs_comm_substep", "gfs_extrapolate", "gfs_copy_field", "gfs_extrapolate_field",
-    "gfs_apply_body_force", "gfs_pressure_solve", "gfs_apply_pressure", "gfs_get_pressure",
+    "gfs_apply_body_force", "gfs_pressure_solve", "gfs_apply_pressure", "gfs_get_pressure", "gfs_pressure_solve_field",
     "gfs_device_ptr", "gfs_resize_particles", "gfs_reserve", "gfs_state_hash",
     "gfs_mg_get_error_message", "gfs_mg_create", "gfs_mg_destroy", "gfs_mg_num_devices", "gfs_mg_context", "gfs_mg_get_slab", "gfs_mg_set_option",
     "gfs_mg_set_material", "gfs_mg_set_sources", "gfs_mg_set_field", "gfs_mg_get_field", "gfs_mg_get_material", "gfs_mg_scatter_particles",
@@ -144,6 +144,8 @@ def load_library():
     L.gfs_pressure_solve.argtypes = [V, I, C.c_double, C.c_double, C.c_double, I, C.POINTER(I), C.POINTER(C.c_double), _err]
     L.gfs_apply_pressure.argtypes = [V, I, I, C.c_double, C.c_double, _err]
     L.gfs_get_pressure.argtypes = [V, _f32, _err]
+    L.gfs_pressure_solve_field.argtypes = [V, _f32, _f32, _f32, I, I, I, C.c_double, _u8, C.c_double, C.c_double, C.c_double, I,
+                                           np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.POINTER(I), C.POINTER(C.c_double), _err]
     PI, PL = C.POINTER(I), C.POINTER(L64)
     L.gfs_comm_set_plan.argtypes = [V, I, I, PI, PI, PI, PL, I, PI, PI, PI, PL, PI, _err]
     L.gfs_comm_substep.argtypes = [V, C.c_double, C.c_double, I, I, I, I, I, PL, _err]
@@ -430,6 +432,15 @@ class Context:
         out = np.empty(int(np.prod(self.dims)), np.float32)
         self._call(self.lib.gfs_get_pressure, out)
         return out
+
+    def pressure_solve_field(self, u, v, w, dims, dx, material, dt, density=20.0, tolerance=1e-6, max_iterations=200):
+        """Host-pointer operator (the body of PressureSolver::solve): -> (double pressure per cell, iterations, residual)."""
+        out = np.zeros(int(np.prod(dims)), np.float64)
+        it, res = C.c_int(0), C.c_double(0.0)
+        self._call(self.lib.gfs_pressure_solve_field, _c(u), _c(v), _c(w), *dims, float(dx),
+                   np.ascontiguousarray(material, np.uint8).reshape(-1), float(dt), float(density), float(tolerance),
+                   int(max_iterations), out, C.byref(it), C.byref(res))
+        return out, it.value, res.value
 
     def sort_index(self):
         self._call(self.lib.gfs_sort_index)

@@ -1396,8 +1396,7 @@ void gfs_apply_body_force(gfs_context *c, int slot, float fx, float fy, float fz
 }
 
 namespace {
-gfs::PressSys pressure_system(gfs_context *c, double dt, double density, double tolerance) {
-    const Grid &g = c->grid;
+gfs::PressSys pressure_system(gfs_context *c, const Grid &g, const uint8_t *material, double dt, double density, double tolerance) {
     gfs_context::Pressure &P = c->press;
     const size_t cells = (size_t)g.I * g.J * g.K;
     for (int a = 0; a < 6; a++) P.vec[a].reserve(cells);
@@ -1423,7 +1422,7 @@ gfs::PressSys pressure_system(gfs_context *c, double dt, double density, double 
         P.epoch = 0;
         P.dims[0] = g.I; P.dims[1] = g.J; P.dims[2] = g.K;
     }
-    S.material = c->material.p; S.flags = P.flags.p;
+    S.material = material; S.flags = P.flags.p;
     S.r = P.vec[0].p; S.z = P.vec[1].p; S.s = P.vec[2].p; S.p = P.vec[3].p; S.q = P.vec[4].p; S.precon = P.vec[5].p;
     S.partial = P.scal.p; S.sigma = P.scal.p + 3 * gfs::kPressBlocks; S.resid = P.scal.p + 3 * gfs::kPressBlocks + 2;
     S.state = P.state.p; S.ticket = P.ticket.p; S.tile_done = P.tile_done.p; S.order = P.order.p; S.pressure = P.pressure.p;
@@ -1432,26 +1431,12 @@ gfs::PressSys pressure_system(gfs_context *c, double dt, double density, double 
     S.tol = tolerance;
     return S;
 }
-}  // namespace
 
-/* PressureSolver::solve (src/pressuresolver.cpp:116-139, 452-505) on the velocity field in `slot` and the resident material
- * grid, narrowed to the float grid of FluidSimulation::_updatePressureGrid (src/fluidsimulation.cpp:2870-2889).
- * tolerance / max_iterations: the reference's 1e-6 / 200 (src/pressuresolver.h:159-160), density its 20.0
- * (src/fluidsimulation.h:1154).  *iterations = the reference's iterationNumber when it returns (-1: the right-hand side
- * was already below the tolerance, pressure = 0; max_iterations: limit reached, the estimate so far is kept, as the
- * reference does).  *residual = the last max-norm of the residual.  The pressure stays on the device for
- * gfs_apply_pressure / gfs_get_pressure. */
-void gfs_pressure_solve(gfs_context *c, int slot, double dt, double density, double tolerance, int max_iterations,
-                        int *iterations, double *residual, int *err) {
-    GFS_BEGIN
-    require_domain(c);
-    GFS_REQUIRE(slot >= 0 && slot < 3, "bad field slot");
-    GFS_REQUIRE(dt > 0 && density > 0 && tolerance > 0 && max_iterations >= 0, "bad solver parameters");
-    const Grid &g = c->grid;
-    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_pressure_solve is single-domain only");
-    GFS_CUDA(cudaSetDevice(c->device));
+/* the solve itself, on any field / material the caller has on the device (g gives the rows' pitch) */
+gfs::PressSys pressure_solve_device(gfs_context *c, const Grid &g, gfs::FieldPtrs f, const uint8_t *material, double dt, double density,
+                                    double tolerance, int max_iterations, int *iterations, double *residual) {
     gfs_context::Pressure &P = c->press;
-    gfs::PressSys S = pressure_system(c, dt, density, tolerance);
+    gfs::PressSys S = pressure_system(c, g, material, dt, density, tolerance);
     const size_t cells = (size_t)S.cells;
     for (int a = 1; a < 6; a++) GFS_CUDA(cudaMemsetAsync(P.vec[a].p, 0, cells * sizeof(double), c->stream));
     GFS_CUDA(cudaMemsetAsync(P.state.p, 0, 4 * sizeof(int), c->stream));
@@ -1461,7 +1446,7 @@ void gfs_pressure_solve(gfs_context *c, int slot, double dt, double density, dou
     const int sweep_blocks = 2 * sms;
     const int B = gfs::kPressBlocks, T = gfs::kPressThreads;
 
-    LAUNCH(c, gfs::k_press_setup, B, T, g, field_ptrs(c, slot), S, g.dx);
+    LAUNCH(c, gfs::k_press_setup, B, T, g, f, S, g.dx);
     LAUNCH(c, gfs::k_press_check, 1, T, S, -1);
     LAUNCH(c, gfs::k_press_sweep<0>, sweep_blocks, T, S, ++P.epoch);
     LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
@@ -1489,9 +1474,55 @@ void gfs_pressure_solve(gfs_context *c, int slot, double dt, double density, dou
     }
     LAUNCH(c, gfs::k_press_finish, B, T, S);
     poll();
-    P.valid = true;
     if (iterations) *iterations = done ? P.host_state[1] : max_iterations;
     if (residual) *residual = *P.host_resid;
+    return S;
+}
+}  // namespace
+
+/* PressureSolver::solve (src/pressuresolver.cpp:116-139, 452-505) on the velocity field in `slot` and the resident material
+ * grid, narrowed to the float grid of FluidSimulation::_updatePressureGrid (src/fluidsimulation.cpp:2870-2889).
+ * tolerance / max_iterations: the reference's 1e-6 / 200 (src/pressuresolver.h:159-160), density its 20.0
+ * (src/fluidsimulation.h:1154).  *iterations = the reference's iterationNumber when it returns (-1: the right-hand side
+ * was already below the tolerance, pressure = 0; max_iterations: limit reached, the estimate so far is kept, as the
+ * reference does).  *residual = the last max-norm of the residual.  The pressure stays on the device for
+ * gfs_apply_pressure / gfs_get_pressure. */
+void gfs_pressure_solve(gfs_context *c, int slot, double dt, double density, double tolerance, int max_iterations,
+                        int *iterations, double *residual, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(slot >= 0 && slot < 3, "bad field slot");
+    GFS_REQUIRE(dt > 0 && density > 0 && tolerance > 0 && max_iterations >= 0, "bad solver parameters");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_pressure_solve is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    c->press.valid = false;
+    pressure_solve_device(c, g, field_ptrs(c, slot), c->material.p, dt, density, tolerance, max_iterations, iterations, residual);
+    c->press.valid = true;
+    GFS_END()
+}
+
+/* The same solve on caller-owned host arrays: the body of PressureSolver::solve for a simulator that keeps its grids on
+ * the host (dropin/pressuresolver.cpp).  u, v, w: the reference's raw Array3d<float> storage; material: one byte per
+ * cell; pressure: isize*jsize*ksize DOUBLES, i fastest, the solver's own precision (0 outside fluid cells) -- the caller
+ * picks the fluid cells' entries in its own order. */
+void gfs_pressure_solve_field(gfs_context *c, const float *u, const float *v, const float *w, int I, int J, int K, double dx,
+                              const uint8_t *material, double dt, double density, double tolerance, int max_iterations,
+                              double *pressure, int *iterations, double *residual, int *err) {
+    GFS_BEGIN
+    GFS_REQUIRE(c && u && v && w && material && pressure, "bad arguments");
+    GFS_REQUIRE(I > 0 && J > 0 && K > 0 && dx > 0, "bad grid");
+    GFS_REQUIRE(dt > 0 && density > 0 && tolerance > 0 && max_iterations >= 0, "bad solver parameters");
+    GFS_CUDA(cudaSetDevice(c->device));
+    Grid g = make_grid(I, J, K, dx, 0, K);                  // unpadded rows
+    gfs::FieldPtrs fp = upload_field(c, u, v, w, I, J, K);
+    const size_t cells = (size_t)I * J * K;
+    c->h_mat.reserve(cells);
+    GFS_CUDA(cudaMemcpyAsync(c->h_mat.p, material, cells, cudaMemcpyHostToDevice, c->stream));
+    c->press.valid = false;                                 // the resident float grid no longer belongs to the resident domain
+    gfs::PressSys S = pressure_solve_device(c, g, fp, c->h_mat.p, dt, density, tolerance, max_iterations, iterations, residual);
+    GFS_CUDA(cudaMemcpyAsync(pressure, S.p, cells * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
 

@@ -221,6 +221,13 @@ void gfs_pressure_solve(gfs_context *ctx, int slot, double dt, double density, d
                         int *iterations, double *residual, int *err);
 void gfs_apply_pressure(gfs_context *ctx, int src_slot, int dst_slot, double dt, double density, int *err);
 void gfs_get_pressure(gfs_context *ctx, float *pressure, int *err);
+/* gfs_pressure_solve_field: the same solve on caller-owned host arrays -- the one-call body of PressureSolver::solve
+ * (src/pressuresolver.cpp:116-139) for a simulator that keeps its grids on the host (dropin/pressuresolver.cpp).
+ * u, v, w = MACVelocityField::getRawArrayU/V/W(), material = one byte per cell; pressure receives isize*jsize*ksize
+ * DOUBLES (the solver's precision; i fastest; 0 outside fluid cells). */
+void gfs_pressure_solve_field(gfs_context *ctx, const float *u, const float *v, const float *w, int isize, int jsize, int ksize,
+                              double dx, const uint8_t *material, double dt, double density, double tolerance,
+                              int max_iterations, double *pressure, int *iterations, double *residual, int *err);
 void gfs_copy_field(gfs_context *ctx, int dst_slot, int src_slot, int *err);
 /* gfs_sort_index: the counting sort without moving the particles -- only the sorted index is materialised and the
  * P2G / G2P kernels fetch through it (G2P stores its results in sorted order).  What gfs_substep does internally;
