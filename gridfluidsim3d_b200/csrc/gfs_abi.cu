@@ -200,6 +200,7 @@ struct gfs_context {
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
     bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
+    int press_variant = 1;                // option 12: substitution sweeps of the pressure solve, 1 = staged in shared memory, 0 = from global memory
     int fused_grid = 1;                   // option 11: 1 = k_finalize_assemble (no node grid / mask in HBM), 0 = k_p2g_finalize + k_assemble
     bool acc_dirty = false;               // the accumulators still hold the previous splat (fused grid pass): memset before the next
     int split_wait = 0;                   // option 10: device-side waits in a single-thread kernel of their own (slabs sharing a GPU)
@@ -222,6 +223,8 @@ struct gfs_context {
 
     // ---- scratch for host-pointer operators
     DevBuf<float> h_pos, h_out, h_val, h_fld, h_wgt, h_field[3];
+    DevBuf<float> aos_stage;              // the AoS records of the last gfs_set_particles, kept for the first sort (k_gather_sorted_aos)
+    bool aos_valid = false;               // aos_stage still equals the SoA storage, slot for slot (nothing moved or edited since the upload)
     DevBuf<uint8_t> h_mat;
     DevBuf<int8_t> h_layer;
     DevBuf<unsigned long long> h_acc;
@@ -388,6 +391,7 @@ void drop_dead(gfs_context *c) {
     c->keys_ready = false;
     c->storage_sorted = true;
     c->sorted = true;           // physically sorted now, and cell_start describes it
+    c->aos_valid = false;
 }
 
 void do_sort(gfs_context *c, bool stable, bool lazy = false) {
@@ -396,7 +400,7 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     // particle read of the P2G and G2P kernels into a random 4-byte gather (measured 13 ms instead of 3.3 ms per kernel at
     // 96 M particles).  The first sort after an upload therefore moves the data; later ones only re-index it.
     if (lazy && !c->storage_sorted) lazy = false;
-    if (c->dead > 0 && !(lazy && !stable && c->keys_ready)) { drop_dead(c); c->sorted = false; }
+    if (c->dead > 0 && !(lazy && !stable && c->keys_ready)) { drop_dead(c); c->sorted = false; c->aos_valid = false; }
     const int64_t n = c->n;
     if (c->resolve_collisions) {
         const size_t want = c->coll_cap_user > 0 ? (size_t)c->coll_cap_user : (size_t)(n / 16 + 4096);
@@ -439,6 +443,11 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
                    c->tag[dst].p);
         } else if (lazy) {
             LAUNCH(c, gfs::k_build_index, ceil_div(n, 4 * B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p, c->index.p);
+        } else if (c->aos_valid && src == 0) {
+            // first sort after an upload: gather the sorted SoA arrays from the uploaded AoS records
+            LAUNCH(c, gfs::k_build_index, ceil_div(n, 4 * B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p, c->index.p);
+            LAUNCH(c, gfs::k_gather_sorted_aos, ceil_div(n, B), B, n, c->index.p, reinterpret_cast<const float2 *>(c->aos_stage.p),
+                   c->soa[dst][0].p, c->soa[dst][1].p, c->soa[dst][2].p, c->soa[dst][3].p, c->soa[dst][4].p, c->soa[dst][5].p, c->tag[dst].p);
         } else {
             LAUNCH(c, gfs::k_scatter_sorted, ceil_div(n, B), B, n, c->keys[0].p, c->rank.p, c->cell_start.p,
                    c->soa[src][0].p, c->soa[src][1].p, c->soa[src][2].p, c->soa[src][3].p, c->soa[src][4].p, c->soa[src][5].p,
@@ -454,6 +463,7 @@ void do_sort(gfs_context *c, bool stable, bool lazy = false) {
     c->indexed = lazy && !stable && n > 0;
     c->keys_ready = false;
     c->sorted = true;
+    if (!(lazy && !stable)) c->aos_valid = false;          // the storage order changed
 }
 
 // layer range [lo,hi) of cells the grid kernels process: the owned slab plus one halo layer each side
@@ -725,7 +735,7 @@ void do_g2p(gfs_context *c, double dt, double ratio, int order, int interp, int 
     }
     c->indexed = false;
     c->cur = dst;
-    c->sorted = false;          // positions moved: the cell table no longer describes them
+    c->sorted = false; c->aos_valid = false;          // positions moved: the cell table no longer describes them
     c->keys_ready = bin_next;
 }
 
@@ -895,7 +905,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     if (c->world_table) cudaFree(c->world_table);
     for (int gi = 0; gi < 2; gi++) if (c->graphs[gi].exec) cudaGraphExecDestroy(c->graphs[gi].exec);
     c->cub_tmp.release(); c->n_valid.release(); c->vmax_bits.release(); c->counters.release();
-    c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
+    c->aos_stage.release(); c->h_pos.release(); c->h_out.release(); c->h_val.release(); c->h_fld.release(); c->h_wgt.release(); c->h_acc.release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     GFS_END()
@@ -1146,7 +1156,7 @@ void gfs_domain_init(gfs_context *c, int I, int J, int K, double dx, int *err) {
     c->cell_start.reserve((size_t)c->nkeys + 3);
     c->counts.reserve((size_t)c->nkeys + 3);
     // a new domain invalidates every key, index and cell table of the old one
-    c->keys_ready = false; c->indexed = false; c->storage_sorted = false; c->sorted = false;
+    c->keys_ready = false; c->indexed = false; c->storage_sorted = false; c->sorted = false; c->aos_valid = false;
     c->has_domain = true;
     c->press.valid = false;
     c->have_maps = false;
@@ -1198,17 +1208,17 @@ void gfs_set_particles(gfs_context *c, const gfs_marker_particle_t *particles, i
     GFS_REQUIRE(n < 0x7FFFFFFFll, "particle count must fit int32");
     GFS_CUDA(cudaSetDevice(c->device));
     c->reserve_particles(n > 0 ? n : 1);
-    c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->keys_ready = false; c->indexed = false; c->storage_sorted = false;
+    c->n = n; c->dead = 0; c->cur = 0; c->sorted = false; c->aos_valid = false; c->keys_ready = false; c->indexed = false; c->storage_sorted = false;
     c->velocities_valid = true;
     if (c->allmax_posted) c->allmax_redo = true;
     c->graph_epoch++;
     if (n > 0) {
-        // stage the AoS through the (not yet used) second SoA buffer set: 6 floats per particle fit exactly
-        c->h_pos.reserve((size_t)n * 6);
-        GFS_CUDA(cudaMemcpyAsync(c->h_pos.p, particles, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
-        LAUNCH(c, gfs::k_aos_to_soa, ceil_div(n, 256), 256, n, c->h_pos.p, c->soa[0][0].p, c->soa[0][1].p, c->soa[0][2].p,
+        c->aos_stage.reserve((size_t)n * 6);
+        GFS_CUDA(cudaMemcpyAsync(c->aos_stage.p, particles, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, gfs::k_aos_to_soa, ceil_div(n, 256), 256, n, c->aos_stage.p, c->soa[0][0].p, c->soa[0][1].p, c->soa[0][2].p,
                c->soa[0][3].p, c->soa[0][4].p, c->soa[0][5].p, c->tag[0].p);
     }
+    c->aos_valid = n > 0;
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
@@ -1261,9 +1271,14 @@ void gfs_set_field(gfs_context *c, int slot, const float *u, const float *v, con
     GFS_REQUIRE(slot >= 0 && slot < 3 && u && v && w, "bad arguments");
     const float *h[3] = {u, v, w};
     const int ni[3] = {c->grid.I + 1, c->grid.I, c->grid.I};
-    for (int a = 0; a < 3; a++)        // reference rows (ni floats) -> resident rows (pitch floats)
-        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, h[a], (size_t)ni[a] * 4, (size_t)ni[a] * 4,
-                                   c->face_count[a] / (size_t)ni[a], cudaMemcpyHostToDevice, c->stream));
+    // reference rows (ni floats) -> resident rows (pitch floats): one contiguous copy over PCIe into scratch, then a
+    // strided copy on the device (a strided host-to-device copy ran at 18 GB/s against 55 GB/s for the contiguous one)
+    for (int a = 0; a < 3; a++) {
+        c->h_field[a].reserve(c->face_count[a]);
+        GFS_CUDA(cudaMemcpyAsync(c->h_field[a].p, h[a], c->face_count[a] * 4, cudaMemcpyHostToDevice, c->stream));
+        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad, (size_t)c->grid.pitch[a] * 4, c->h_field[a].p, (size_t)ni[a] * 4, (size_t)ni[a] * 4,
+                                   c->face_count[a] / (size_t)ni[a], cudaMemcpyDeviceToDevice, c->stream));
+    }
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
 }
@@ -1295,8 +1310,10 @@ void gfs_set_field_layers(gfs_context *c, int slot, const float *u, const float 
     for (int a = 0; a < 3; a++) {
         const size_t rows = (size_t)nj[a] * (size_t)(k_count + (a == 2 ? 1 : 0)), row0 = (size_t)nj[a] * (size_t)k_first;
         if (rows == 0) continue;
-        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad + row0 * g.pitch[a], (size_t)g.pitch[a] * 4, h[a] + row0 * ni[a],
-                                   (size_t)ni[a] * 4, (size_t)ni[a] * 4, rows, cudaMemcpyHostToDevice, c->stream));
+        c->h_field[a].reserve(c->face_count[a]);              // contiguous over PCIe, strided on the device (see gfs_set_field)
+        GFS_CUDA(cudaMemcpyAsync(c->h_field[a].p, h[a] + row0 * ni[a], rows * ni[a] * 4, cudaMemcpyHostToDevice, c->stream));
+        GFS_CUDA(cudaMemcpy2DAsync(c->field[slot][a].p + gfs::kRowPad + row0 * g.pitch[a], (size_t)g.pitch[a] * 4, c->h_field[a].p,
+                                   (size_t)ni[a] * 4, (size_t)ni[a] * 4, rows, cudaMemcpyDeviceToDevice, c->stream));
     }
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
@@ -1448,9 +1465,18 @@ gfs::PressSys pressure_solve_device(gfs_context *c, const Grid &g, gfs::FieldPtr
 
     LAUNCH(c, gfs::k_press_setup, B, T, g, f, S, g.dx);
     LAUNCH(c, gfs::k_press_check, 1, T, S, -1);
+    const int subst_blocks = 5 * sms, subst_threads = gfs::kSubstWarps * 32;
+    auto substitutions = [&]() {                              /* _applyPreconditioner: z = M^-1 r */
+        if (c->press_variant == 0) {
+            LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
+            LAUNCH(c, gfs::k_press_sweep<2>, sweep_blocks, T, S, ++P.epoch);
+        } else {
+            LAUNCH(c, gfs::k_press_subst<false>, subst_blocks, subst_threads, S, ++P.epoch);
+            LAUNCH(c, gfs::k_press_subst<true>, subst_blocks, subst_threads, S, ++P.epoch);
+        }
+    };
     LAUNCH(c, gfs::k_press_sweep<0>, sweep_blocks, T, S, ++P.epoch);
-    LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
-    LAUNCH(c, gfs::k_press_sweep<2>, sweep_blocks, T, S, ++P.epoch);
+    substitutions();
     LAUNCH(c, gfs::k_press_dot_zr, B, T, S);
     LAUNCH(c, gfs::k_press_search, B, T, S, 0, 1);
     int it = 0;
@@ -1465,8 +1491,7 @@ gfs::PressSys pressure_solve_device(gfs_context *c, const Grid &g, gfs::FieldPtr
         LAUNCH(c, gfs::k_press_apply_matrix, B, T, S);
         LAUNCH(c, gfs::k_press_update, B, T, S, it);
         LAUNCH(c, gfs::k_press_check, 1, T, S, it);
-        LAUNCH(c, gfs::k_press_sweep<1>, sweep_blocks, T, S, ++P.epoch);
-        LAUNCH(c, gfs::k_press_sweep<2>, sweep_blocks, T, S, ++P.epoch);
+        substitutions();
         LAUNCH(c, gfs::k_press_dot_zr, B, T, S);
         LAUNCH(c, gfs::k_press_search, B, T, S, it, 0);
         it++;
@@ -1596,6 +1621,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 12) { GFS_REQUIRE(value == 0 || value == 1, "pressure sweep variant must be 0 or 1"); c->press_variant = value; }
     else if (option == 11) { GFS_REQUIRE(value == 0 || value == 1, "fused grid pass must be 0 or 1"); c->fused_grid = value; }
     else if (option == 10) { GFS_REQUIRE(value == 0 || value == 1, "split wait must be 0 or 1"); c->split_wait = value; }
     else if (option == 9) { GFS_REQUIRE(value == 0 || value == 1, "early all-ranks max must be 0 or 1"); c->allmax_early = value; }
@@ -1656,7 +1682,7 @@ void gfs_substep(gfs_context *c, double dt, double ratio, int order, int interp,
         GFS_CUDA(cudaGraphLaunch(g.exec, c->stream));
         c->p2g_arith = arith;
         c->cur = 1 - c->cur;
-        c->sorted = false; c->indexed = false; c->keys_ready = true;
+        c->sorted = false; c->aos_valid = false; c->indexed = false; c->keys_ready = true;
         c->launches += g.launches;
         c->graph_replays++;
         return;
@@ -1739,7 +1765,7 @@ void gfs_advect_substep(gfs_context *c, double dt, int order, int *err) {
     if (c->indexed) { c->n -= c->dead; c->dead = 0; }
     c->indexed = false;
     c->cur = dst;
-    c->sorted = false;
+    c->sorted = false; c->aos_valid = false;
     c->keys_ready = true;
     c->velocities_valid = false;
     c->graph_epoch++;
@@ -2127,7 +2153,7 @@ void gfs_comm_migrate_finish(gfs_context *c, int64_t *moved, int *err) {
         }
     } else {
         if (c->n > 0) c->cur = 1 - c->cur;
-        c->n = h[0]; c->sorted = false; c->keys_ready = false; c->indexed = false;
+        c->n = h[0]; c->sorted = false; c->aos_valid = false; c->keys_ready = false; c->indexed = false;
         const bool redo0 = c->allmax_redo;          // appending migrated particles is not a "new particle set" (their max |v| travelled with the sender's)
         for (int s = 0; s < 2; s++) {
             if (n_in[s] == 0) continue;
@@ -2298,7 +2324,7 @@ void gfs_extract_particles(gfs_context *c, int k_lo, int k_hi, void *down_device
     GFS_CUDA(cudaMemcpyAsync(h, c->split_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_REQUIRE((int64_t)h[1] <= cap && (int64_t)h[2] <= cap, "migration buffer too small");
-    c->n = h[0]; c->cur = 1 - c->cur; c->sorted = false; c->keys_ready = false;
+    c->n = h[0]; c->cur = 1 - c->cur; c->sorted = false; c->aos_valid = false; c->keys_ready = false;
     *n_down = h[1]; *n_up = h[2];
     GFS_END()
 }
@@ -2323,7 +2349,7 @@ void gfs_extract_commit(gfs_context *c, int64_t n_kept, int *err) {
     require_domain(c);
     GFS_REQUIRE(n_kept >= 0 && n_kept <= c->n, "bad kept count");
     if (c->n > 0) c->cur = 1 - c->cur;
-    c->n = n_kept; c->sorted = false; c->keys_ready = false;
+    c->n = n_kept; c->sorted = false; c->aos_valid = false; c->keys_ready = false;
     GFS_END()
 }
 
@@ -2499,7 +2525,7 @@ void gfs_emit_from_sources(gfs_context *c, double jitter, uint64_t seed, int64_t
     GFS_REQUIRE((int64_t)count <= bound, "internal: emission bound exceeded");
     c->n = n0 + count;
     if (count > 0) {
-        c->sorted = false; c->keys_ready = false; c->indexed = false;
+        c->sorted = false; c->aos_valid = false; c->keys_ready = false; c->indexed = false;
         if (c->allmax_posted) c->allmax_redo = true;
     }
     c->graph_epoch++;
@@ -2538,7 +2564,7 @@ void gfs_remove_in_sources(gfs_context *c, const gfs_source_t *outflow, int nsou
     if (removed) *removed = c->n - (int64_t)kept;
     c->removed += c->n - (int64_t)kept;
     c->n = kept; c->cur = dst;
-    c->sorted = false; c->keys_ready = false; c->indexed = false;
+    c->sorted = false; c->aos_valid = false; c->keys_ready = false; c->indexed = false;
     c->graph_epoch++;
     GFS_END()
 }
@@ -2587,7 +2613,7 @@ void gfs_reserve(gfs_context *c, int64_t particle_capacity, int *err) {
         GFS_TOUCH(gfs::k_append_aos); GFS_TOUCH(gfs::k_split_by_layer); GFS_TOUCH(gfs::k_add_u64);
 #undef GFS_TOUCH
         GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)((size_t)c->nkeys + 3), c->stream));
-        c->sorted = false;                         // (the cell table is scratch until the next sort)
+        c->sorted = false; c->aos_valid = false;                         // (the cell table is scratch until the next sort)
     }
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
@@ -2600,7 +2626,7 @@ void gfs_resize_particles(gfs_context *c, int64_t n, int *err) {
     drop_dead(c);
     ensure_capacity(c, n);
     c->n = n;
-    c->sorted = false;
+    c->sorted = false; c->aos_valid = false;
     c->keys_ready = false;
     if (c->allmax_posted) c->allmax_redo = true;
     GFS_END()

@@ -174,6 +174,22 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(int64_t n, const uint32_
     dtag[d] = stag[r];
 }
 
+// K0c, first sort after an upload: the uploaded AoS records (24 contiguous bytes each) are still on the device, so the
+// sorted SoA arrays are GATHERED from them through the index -- one or two 32-byte sectors read per particle, fully
+// coalesced writes -- instead of scattering seven 4-byte streams to random slots (k_scatter_sorted: a 32-byte sector
+// touched per 4 bytes written; 25 ms against 1 ms at 96 M shuffled particles).  tag = upload index = the source slot.
+__global__ void __launch_bounds__(256) k_gather_sorted_aos(int64_t n, const int32_t *__restrict__ index, const float2 *__restrict__ aos,
+                                 float *__restrict__ dx_, float *__restrict__ dy, float *__restrict__ dz,
+                                 float *__restrict__ dvx, float *__restrict__ dvy, float *__restrict__ dvz, int32_t *__restrict__ dtag) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const int32_t r = index[d];
+    const float2 *p = aos + 3 * (int64_t)r;
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    dx_[d] = a.x; dy[d] = a.y; dz[d] = b.x; dvx[d] = b.y; dvy[d] = c.x; dvz[d] = c.y;
+    dtag[d] = r;
+}
+
 // K0c (lazy variant used inside the fused substep): only the permutation is materialised, index[sorted slot] = current
 // slot; P2G and G2P then fetch their particles through it, and G2P -- which rewrites every particle anyway -- stores
 // its results at the sorted slot.  Saves moving 56 bytes per particle once per substep.

@@ -275,6 +275,145 @@ __global__ void __launch_bounds__(kPressThreads) k_press_sweep(PressSys S, unsig
     }
 }
 
+// The two substitutions of every CG iteration, same schedule and same arithmetic as k_press_sweep<1> / <2>, built for
+// latency: the first version read r / precon from global memory inside the 26 dependent steps of a tile (1.8-2.2 ms per
+// sweep at 256^3, ncu).  Here everything a tile needs that does NOT depend on its predecessors -- its own rows of the
+// input vector and of the MIC(0) diagonal, the diagonal's halo rows, the fluid masks -- is staged into shared memory
+// with coalesced loads BEFORE the warp waits for its predecessor tiles, so the wait hides the loads and the step loop
+// touches only shared memory, shuffles and the one store per cell.
+constexpr int kSubstWarps = 3;                      // 96-thread CTAs: 37.5 KB of static shared memory each, 5 per SM
+constexpr int kRowPitch = 19;                       // doubles.  Lane (lj, lk) reads word 19 (lj + 8 lk) + step - lj - lk: the bank pair
+                                                    // (2 lj + 7 lk + step) mod 16 is hit by exactly two lanes -- the minimum for 64-bit reads
+
+struct SubstSmem {
+    double in[32][kRowPitch];                       // r (forward) or q (backward), my 32 rows
+    double pc[32][kRowPitch];                       // precon, my 32 rows
+    double hp[kTileZ + kTileY][kTileX];             // forward only: precon of the predecessor tiles' boundary rows
+    double hd[kTileZ + kTileY][kTileX];             // the produced vector on the predecessor tiles' boundary rows
+};
+
+template <bool REV>
+__global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst(PressSys S, unsigned int epoch) {
+    __shared__ SubstSmem sm_all[kSubstWarps];
+    if (S.state[0]) return;
+    SubstSmem &sm = sm_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, lj = lane & 7, lk = lane >> 3;
+    const int a = REV ? kTileY - 1 - lj : lj, b = REV ? kTileZ - 1 - lk : lk;
+    const double *__restrict__ in = REV ? S.q : S.r;
+    double *dyn = REV ? S.z : S.q;
+    const double negscale = -S.scale;
+    const size_t sy = (size_t)S.I, sz = (size_t)S.I * (size_t)S.J;
+    const int d = REV ? 1 : -1;
+    const int ly = REV ? lane + 1 : lane - 1, lz = REV ? lane + 8 : lane - 8;       // the lanes holding my y / z predecessor rows
+    constexpr int MODE = REV ? 2 : 1;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(S.ticket + MODE, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned long long)S.ntiles) break;
+        const int tile = S.order[REV ? S.ntiles - 1 - (int)t : (int)t];
+        const int tx = tile % S.ntx, ty = (tile / S.ntx) % S.nty, tz = tile / (S.ntx * S.nty);
+        const int i0 = tx * kTileX, j0 = ty * kTileY, k0 = tz * kTileZ;
+        const int j = j0 + lj, k = k0 + lk;
+        const bool row_in = j < S.J && k < S.K;
+        const size_t row = (size_t)j * sy + (size_t)k * sz;
+
+        // ---- static part, before the wait: fluid masks, my rows of the input vector and of the diagonal, the diagonal's halo
+        unsigned fl = 0;
+        if (row_in)
+            for (int ii = 0; ii < kTileX; ii++)
+                if (i0 + ii < S.I && (S.flags[row + i0 + ii] & kPfFluid)) fl |= 1u << ii;
+        const bool any = __any_sync(0xffffffffu, fl != 0);
+        const int ix = REV ? i0 + kTileX : i0 - 1;
+        double pc_x = 0.0;
+        if (any) {
+            const int half = lane >> 4, ii = lane & 15;                                // two rows per pass, 16 lanes (128 B) each
+            for (int rr = 0; rr < 32; rr += 2) {
+                const int r2 = rr + half, rj = j0 + (r2 & 7), rk = k0 + (r2 >> 3);
+                double vi = 0.0, vp = 0.0;
+                if (rj < S.J && rk < S.K && i0 + ii < S.I) {
+                    const size_t c = (size_t)(i0 + ii) + (size_t)rj * sy + (size_t)rk * sz;
+                    vi = in[c]; vp = S.precon[c];
+                }
+                sm.in[r2][ii] = vi; sm.pc[r2][ii] = vp;
+            }
+            if (!REV) {
+                for (int h = lane; h < (kTileZ + kTileY) * kTileX; h += 32) {
+                    const int hr = h / kTileX, hi = h % kTileX;
+                    int hj, hk;
+                    if (hr < kTileZ) { hj = j0 - 1; hk = k0 + hr; } else { hj = j0 + (hr - kTileZ); hk = k0 - 1; }
+                    double v = 0.0;
+                    if (hj >= 0 && hk >= 0 && hj < S.J && hk < S.K && i0 + hi < S.I) v = S.precon[(size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz];
+                    sm.hp[hr][hi] = v;
+                }
+                if (row_in && ix >= 0) pc_x = S.precon[row + ix];
+            }
+
+            // ---- predecessor tiles, then the part that depends on them
+            if (lane < 3) {
+                const int px = tx + (lane == 0 ? d : 0), py = ty + (lane == 1 ? d : 0), pz = tz + (lane == 2 ? d : 0);
+                if (px >= 0 && py >= 0 && pz >= 0 && px < S.ntx && py < S.nty && pz < S.ntz) {
+                    const volatile unsigned int *flag = S.tile_done + (px + S.ntx * (py + S.nty * pz));
+                    while (*flag != epoch) { }
+                }
+            }
+            __syncwarp();
+            __threadfence();
+            for (int h = lane; h < (kTileZ + kTileY) * kTileX; h += 32) {
+                const int hr = h / kTileX, hi = h % kTileX;
+                int hj, hk;
+                if (hr < kTileZ) { hj = j0 + (REV ? kTileY : -1); hk = k0 + hr; } else { hj = j0 + (hr - kTileZ); hk = k0 + (REV ? kTileZ : -1); }
+                double v = 0.0;
+                if (hj >= 0 && hk >= 0 && hj < S.J && hk < S.K && i0 + hi < S.I) v = __ldcg(dyn + (size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz);
+                sm.hd[hr][hi] = v;
+            }
+            double xh = 0.0;
+            if (row_in && ix >= 0 && ix < S.I) xh = __ldcg(dyn + row + ix);
+            __syncwarp();
+
+            double mine = 0.0;
+#pragma unroll 2
+            for (int step = 0; step < kTileX + kTileY + kTileZ - 2; step++) {
+                const int li = step - a - b;
+                const bool active = (unsigned)li < (unsigned)kTileX;
+                const int ii = (REV ? kTileX - 1 - li : li) & (kTileX - 1);
+                double from_y = REV ? __shfl_down_sync(0xffffffffu, mine, 1) : __shfl_up_sync(0xffffffffu, mine, 1);
+                double from_z = REV ? __shfl_down_sync(0xffffffffu, mine, 8) : __shfl_up_sync(0xffffffffu, mine, 8);
+                double val = 0.0;
+                if (active && ((fl >> ii) & 1u)) {
+                    if (a == 0) from_y = sm.hd[lk][ii];
+                    if (b == 0) from_z = sm.hd[kTileZ + lj][ii];
+                    const double from_x = li == 0 ? xh : mine;
+                    const double pc = sm.pc[lane][ii];
+                    double tt = sm.in[lane][ii];
+                    if (!REV) {
+                        const double py = a == 0 ? sm.hp[lk][ii] : sm.pc[ly][ii];
+                        const double pz = b == 0 ? sm.hp[kTileZ + lj][ii] : sm.pc[lz][ii];
+                        tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, pc_x), from_x));
+                        tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, py), from_y));
+                        tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, pz), from_z));
+                    } else {
+                        const double np = __dmul_rn(negscale, pc);
+                        tt = __dsub_rn(tt, __dmul_rn(np, from_x));
+                        tt = __dsub_rn(tt, __dmul_rn(np, from_y));
+                        tt = __dsub_rn(tt, __dmul_rn(np, from_z));
+                    }
+                    val = __dmul_rn(tt, pc);
+                    dyn[row + i0 + ii] = val;
+                    pc_x = pc;
+                } else if (active) {
+                    pc_x = 0.0;                                          // not fluid: precon 0
+                }
+                mine = val;
+            }
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) *(volatile unsigned int *)(S.tile_done + tile) = epoch;
+    }
+}
+
 // _applyMatrix (:392-433): z = A s, and the partial sums of dot(z, s)
 __global__ void __launch_bounds__(kPressThreads) k_press_apply_matrix(PressSys S) {
     __shared__ double sh[kPressThreads / 32];

@@ -115,6 +115,37 @@ def test_pressure_solve_repeats_bit_for_bit_and_handles_limits(ctx, oracle):
     assert it4 == -1 and r4 == 0.0 and not ctx.get_pressure().any()
 
 
+@pytest.mark.parametrize("name,solids", [("slab24", True), ("odd20", False), ("hello64", False)])
+def test_pressure_sweep_variants_bit_identical(ctx, name, solids):
+    """option 12: the shared-memory staged substitution kernels == the global-memory ones, every double of the result."""
+    s = make_case(name, solids)
+    dt = 1.0 / 30
+    stage5(ctx, s)
+    ctx.apply_body_force(capi.FIELD_P2G, (0.1, -9.8, 0.2), dt)
+    out = []
+    for variant in (0, 1):
+        ctx.set_option(12, variant)
+        it, res = ctx.pressure_solve(capi.FIELD_P2G, dt)
+        out.append((it, res, ctx.get_pressure()))
+    ctx.set_option(12, 1)
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.array_equal(bits(out[0][2]), bits(out[1][2]))
+    assert out[0][0] > 3
+
+
+def test_pressure_solve_field_host_pointer_operator(ctx, oracle):
+    """gfs_pressure_solve_field (the body of the drop-in PressureSolver::solve): double pressures per cell from host arrays."""
+    s = make_case("slab24", True)
+    dt = 1.0 / 30
+    mat, f5 = stage5(ctx, s)
+    g6 = oracle.body_force(*f5, s["dims"], mat, (0.0, -9.8, 0.0), dt)
+    p_ref, it_ref, limit, err_ref = oracle.pressure_solve(*g6, s["dims"], s["dx"], mat, dt)
+    p, it, res = ctx.pressure_solve_field(*g6, s["dims"], s["dx"], mat, dt)
+    assert it == it_ref and not limit
+    assert np.array_equal(bits(p.astype(np.float32)), bits(p_ref)) or np.abs(p.astype(np.float32) - p_ref).max() <= 2e-6 * np.abs(p_ref).max()
+    assert not p[mat != synth.FLUID].any()
+
+
 def test_pressure_requires_domain_and_solve(ctx):
     with pytest.raises(capi.GfsError):
         ctx.pressure_solve(capi.FIELD_P2G, 1.0 / 30)
