@@ -28,6 +28,7 @@ namespace gfs {
 constexpr int kPressBlocks = 592;                 // grid of the flat kernels = partial sums per reduction (4 x 148)
 constexpr int kPressThreads = 256;
 constexpr int kTileX = 16, kTileY = 8, kTileZ = 4;
+constexpr long long kPressSentinel = (long long)0xFFF8C0DEC0DEC0DEull;    // "not produced yet" (k_press_subst_df): a NaN pattern no computation yields
 
 // flags byte per cell: bits 0-2 diag (non-solid neighbours), 3 plusi, 4 plusj, 5 plusk (MatrixCell, pressuresolver.h), 6 fluid
 constexpr uint8_t kPfPlusI = 8, kPfPlusJ = 16, kPfPlusK = 32, kPfFluid = 64;
@@ -88,7 +89,7 @@ __device__ __forceinline__ double reduce_partials_max(const double *part, double
 }
 
 // _calculateNegativeDivergenceVector (:164-211) + _calculateMatrixCoefficients (:213-250); r = b
-__global__ void __launch_bounds__(kPressThreads) k_press_setup(Grid g, FieldPtrs f, PressSys S, double dx) {
+__global__ void __launch_bounds__(kPressThreads) k_press_setup(Grid g, FieldPtrs f, PressSys S, double dx, int sentinel) {
     __shared__ double sh[kPressThreads / 32];
     const double scale = (double)(1.0f / (float)dx);
     const float fscale = (float)scale;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kPressThreads) k_press_setup(Grid g, FieldPtrs
         }
         S.flags[c] = fl;
         S.r[c] = b;
+        if (sentinel && fl) { S.q[c] = __longlong_as_double(kPressSentinel); S.z[c] = __longlong_as_double(kPressSentinel); }
     }
     mx = block_max(mx, sh);
     if (threadIdx.x == 0) S.partial[blockIdx.x] = mx;
@@ -414,6 +416,140 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst(PressSys S, un
     }
 }
 
+// Third form of the substitutions: no tile flags and no fences at all -- the DATA carries the synchronisation.  Before a
+// sweep every fluid cell of the vector it produces holds a sentinel (a NaN bit pattern no computation yields; written by
+// k_press_update / k_press_setup, which pass over those cells anyway), every cell is written exactly once by an aligned
+// 8-byte store, and a tile simply polls the fluid cells of its halo through L2 until none of them is the sentinel.  One
+// L2 round trip per tile-to-tile hand-over instead of flag + fence + halo load, and a tile starts the moment its own
+// halo is there, not when the last of three whole predecessor tiles has been flagged.
+
+template <bool REV>
+__global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S) {
+    __shared__ SubstSmem sm_all[kSubstWarps];
+    __shared__ uint8_t hf_all[kSubstWarps][(kTileZ + kTileY) * kTileX];
+    if (S.state[0]) return;
+    SubstSmem &sm = sm_all[threadIdx.x >> 5];
+    uint8_t *hf = hf_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, lj = lane & 7, lk = lane >> 3;
+    const int a = REV ? kTileY - 1 - lj : lj, b = REV ? kTileZ - 1 - lk : lk;
+    const double *__restrict__ in = REV ? S.q : S.r;
+    double *dyn = REV ? S.z : S.q;
+    const double negscale = -S.scale;
+    const size_t sy = (size_t)S.I, sz = (size_t)S.I * (size_t)S.J;
+    const int ly = REV ? lane + 1 : lane - 1, lz = REV ? lane + 8 : lane - 8;
+    constexpr int MODE = REV ? 2 : 1;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(S.ticket + MODE, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned long long)S.ntiles) break;
+        const int tile = S.order[REV ? S.ntiles - 1 - (int)t : (int)t];
+        const int tx = tile % S.ntx, ty = (tile / S.ntx) % S.nty, tz = tile / (S.ntx * S.nty);
+        const int i0 = tx * kTileX, j0 = ty * kTileY, k0 = tz * kTileZ;
+        const int j = j0 + lj, k = k0 + lk;
+        const bool row_in = j < S.J && k < S.K;
+        const size_t row = (size_t)j * sy + (size_t)k * sz;
+
+        unsigned fl = 0;
+        if (row_in)
+            for (int ii = 0; ii < kTileX; ii++)
+                if (i0 + ii < S.I && (S.flags[row + i0 + ii] & kPfFluid)) fl |= 1u << ii;
+        if (!__any_sync(0xffffffffu, fl != 0)) continue;                          // nothing to produce, nobody waits for it
+
+        // ---- static part: my rows of the input vector and of the diagonal, the halo's diagonal and fluid flags
+        const int ix = REV ? i0 + kTileX : i0 - 1;
+        const bool x_in = row_in && ix >= 0 && ix < S.I;
+        double pc_x = 0.0;
+        bool x_fluid = false;
+        {
+            const int half = lane >> 4, ii = lane & 15;
+            for (int rr = 0; rr < 32; rr += 2) {
+                const int r2 = rr + half, rj = j0 + (r2 & 7), rk = k0 + (r2 >> 3);
+                double vi = 0.0, vp = 0.0;
+                if (rj < S.J && rk < S.K && i0 + ii < S.I) {
+                    const size_t c = (size_t)(i0 + ii) + (size_t)rj * sy + (size_t)rk * sz;
+                    vi = in[c]; vp = S.precon[c];
+                }
+                sm.in[r2][ii] = vi; sm.pc[r2][ii] = vp;
+            }
+            for (int h = lane; h < (kTileZ + kTileY) * kTileX; h += 32) {
+                const int hr = h / kTileX, hi = h % kTileX;
+                int hj, hk;
+                if (hr < kTileZ) { hj = j0 + (REV ? kTileY : -1); hk = k0 + hr; } else { hj = j0 + (hr - kTileZ); hk = k0 + (REV ? kTileZ : -1); }
+                double v = 0.0;
+                uint8_t f = 0;
+                if (hj >= 0 && hk >= 0 && hj < S.J && hk < S.K && i0 + hi < S.I) {
+                    const size_t c = (size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz;
+                    f = S.flags[c] & kPfFluid;
+                    if (!REV) v = S.precon[c];
+                }
+                sm.hp[hr][hi] = v; hf[h] = f;
+                sm.hd[hr][hi] = 0.0;
+            }
+            if (x_in) { x_fluid = S.flags[row + ix] & kPfFluid; if (!REV) pc_x = S.precon[row + ix]; }
+        }
+        __syncwarp();
+
+        // ---- the halo of the produced vector: poll the fluid cells until their values have arrived
+        double xh = 0.0;
+        for (;;) {
+            bool ok = true;
+            for (int h = lane; h < (kTileZ + kTileY) * kTileX; h += 32) {
+                if (!hf[h]) continue;
+                const int hr = h / kTileX, hi = h % kTileX;
+                int hj, hk;
+                if (hr < kTileZ) { hj = j0 + (REV ? kTileY : -1); hk = k0 + hr; } else { hj = j0 + (hr - kTileZ); hk = k0 + (REV ? kTileZ : -1); }
+                const double v = __ldcg(dyn + (size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz);
+                if (__double_as_longlong(v) == kPressSentinel) ok = false; else sm.hd[hr][hi] = v;
+            }
+            if (x_fluid) {
+                xh = __ldcg(dyn + row + ix);
+                if (__double_as_longlong(xh) == kPressSentinel) ok = false;
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+        }
+        __syncwarp();
+
+        double mine = 0.0;
+#pragma unroll 2
+        for (int step = 0; step < kTileX + kTileY + kTileZ - 2; step++) {
+            const int li = step - a - b;
+            const bool active = (unsigned)li < (unsigned)kTileX;
+            const int ii = (REV ? kTileX - 1 - li : li) & (kTileX - 1);
+            double from_y = REV ? __shfl_down_sync(0xffffffffu, mine, 1) : __shfl_up_sync(0xffffffffu, mine, 1);
+            double from_z = REV ? __shfl_down_sync(0xffffffffu, mine, 8) : __shfl_up_sync(0xffffffffu, mine, 8);
+            double val = 0.0;
+            if (active && ((fl >> ii) & 1u)) {
+                if (a == 0) from_y = sm.hd[lk][ii];
+                if (b == 0) from_z = sm.hd[kTileZ + lj][ii];
+                const double from_x = li == 0 ? xh : mine;
+                const double pc = sm.pc[lane][ii];
+                double tt = sm.in[lane][ii];
+                if (!REV) {
+                    const double py = a == 0 ? sm.hp[lk][ii] : sm.pc[ly][ii];
+                    const double pz = b == 0 ? sm.hp[kTileZ + lj][ii] : sm.pc[lz][ii];
+                    tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, pc_x), from_x));
+                    tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, py), from_y));
+                    tt = __dsub_rn(tt, __dmul_rn(__dmul_rn(negscale, pz), from_z));
+                } else {
+                    const double np = __dmul_rn(negscale, pc);
+                    tt = __dsub_rn(tt, __dmul_rn(np, from_x));
+                    tt = __dsub_rn(tt, __dmul_rn(np, from_y));
+                    tt = __dsub_rn(tt, __dmul_rn(np, from_z));
+                }
+                val = __dmul_rn(tt, pc);
+                __stcg(dyn + row + i0 + ii, val);
+                pc_x = pc;
+            } else if (active) {
+                pc_x = 0.0;
+            }
+            mine = val;
+        }
+        __syncwarp();
+    }
+}
+
 // _applyMatrix (:392-433): z = A s, and the partial sums of dot(z, s)
 __global__ void __launch_bounds__(kPressThreads) k_press_apply_matrix(PressSys S) {
     __shared__ double sh[kPressThreads / 32];
@@ -443,7 +579,7 @@ __global__ void __launch_bounds__(kPressThreads) k_press_apply_matrix(PressSys S
 }
 
 // alpha = sigma / dot(z, s); pressure += search alpha; residual += auxillary (-alpha) (:473-476); partial max |r|
-__global__ void __launch_bounds__(kPressThreads) k_press_update(PressSys S, int it) {
+__global__ void __launch_bounds__(kPressThreads) k_press_update(PressSys S, int it, int sentinel) {
     __shared__ double sh[kPressThreads / 32];
     if (S.state[0]) return;
     const double dot = reduce_partials_sum(S.partial + kPressBlocks, sh);
@@ -455,6 +591,7 @@ __global__ void __launch_bounds__(kPressThreads) k_press_update(PressSys S, int 
         const double r = __dadd_rn(S.r[c], __dmul_rn(S.z[c], nalpha));
         S.r[c] = r;
         mx = fmax(mx, fabs(r));
+        if (sentinel) { S.q[c] = __longlong_as_double(kPressSentinel); S.z[c] = __longlong_as_double(kPressSentinel); }   // arm the data-flow sweeps
     }
     __syncthreads();
     mx = block_max(mx, sh);

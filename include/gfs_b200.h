@@ -259,8 +259,9 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * the spinning CTAs of one context would starve the other's push; gfs_mg_create sets it), 0 = fused (default).  option 11:
  * 1 = normalisation, isValueSet, inflow override and face assembly in one pass straight from the accumulators (default),
  * 0 = the two-kernel form with the node grid and its mask in HBM; identical results.  option 12: substitution sweeps of
- * gfs_pressure_solve, 1 = each tile's inputs staged in shared memory before it waits for its predecessors (default),
- * 0 = read from global memory inside the dependent steps; identical results. */
+ * gfs_pressure_solve: 0 = inputs read from global memory inside the dependent steps, tiles synchronised by completion
+ * flags; 1 = each tile's inputs staged in shared memory before it waits; 2 = staged, and synchronised by the data itself
+ * (cells hold a sentinel until produced; no flags, no fences) (default).  Identical results. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
