@@ -498,6 +498,22 @@ def run_gfs(args):
             import re
             m = re.search(r"(\w+)\s*<\s*(\d+)", top)          # "gfs::k_g2p_brick<0>" -> "k_g2p_brick<0>", as profiles/summarize.py keys it
             roofline["traffic"] = json.load(f).get(args.workload, {}).get("%s<%s>" % (m.group(1), m.group(2)) if m else top.split("::")[-1])
+    # The HBM fraction above is the contract's number; what the kernel is actually bound by comes from its ncu capture
+    # (profiles/bounds.json, written by profiles/summarize.py): both hot kernels of this path sit on the shared-memory pipe.
+    bounds_file = os.path.join(ROOT, "profiles", "bounds.json")
+    if os.path.exists(bounds_file):
+        import re
+        with open(bounds_file) as f:
+            allb = json.load(f).get(args.workload, {})
+
+        def bkey(name):
+            m = re.search(r"(\w+)\s*<\s*(\d+)", name)
+            return "%s<%s>" % (m.group(1), m.group(2)) if m else name.split("::")[-1]
+        roofline["ncu_pipe_utilisation"] = {k: allb[bkey(k)] for k, _ in ranked[:3] if bkey(k) in allb} or None
+        if bkey(top) in allb and allb[bkey(top)].get("lsu_wavefronts_pct_of_peak"):
+            roofline["limiting_pipe"] = {"pipe": "shared-memory LSU wavefronts (1 per clock per SM)",
+                                         "frac": allb[bkey(top)]["lsu_wavefronts_pct_of_peak"] / 100.0,
+                                         "source": allb[bkey(top)]["source"]}
 
     # ---- e2e: the same substep through host buffers ------------------------------------------------------
     aos_out = torch.empty((int(n_max) + 1024, 6), dtype=torch.float32, pin_memory=True)

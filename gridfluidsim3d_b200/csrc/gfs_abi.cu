@@ -200,7 +200,7 @@ struct gfs_context {
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
     bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
-    int press_variant = 2;                // option 12: substitution sweeps of the pressure solve: 0 = global memory + tile flags, 1 = staged in shared memory + tile flags, 2 = staged + data-flow (sentinel) synchronisation
+    int press_variant = 3;                // option 12 (3 = 2 with per-value waiting inside the steps): substitution sweeps of the pressure solve: 0 = global memory + tile flags, 1 = staged in shared memory + tile flags, 2 = staged + data-flow (sentinel) synchronisation
     int fused_grid = 1;                   // option 11: 1 = k_finalize_assemble (no node grid / mask in HBM), 0 = k_p2g_finalize + k_assemble
     bool acc_dirty = false;               // the accumulators still hold the previous splat (fused grid pass): memset before the next
     int split_wait = 0;                   // option 10: device-side waits in a single-thread kernel of their own (slabs sharing a GPU)
@@ -1463,7 +1463,7 @@ gfs::PressSys pressure_solve_device(gfs_context *c, const Grid &g, gfs::FieldPtr
     const int sweep_blocks = 2 * sms;
     const int B = gfs::kPressBlocks, T = gfs::kPressThreads;
 
-    const int sentinel = c->press_variant == 2 ? 1 : 0;
+    const int sentinel = c->press_variant >= 2 ? 1 : 0;
     LAUNCH(c, gfs::k_press_setup, B, T, g, f, S, g.dx, sentinel);
     LAUNCH(c, gfs::k_press_check, 1, T, S, -1);
     const int subst_blocks = 5 * sms, subst_threads = gfs::kSubstWarps * 32;
@@ -1474,9 +1474,12 @@ gfs::PressSys pressure_solve_device(gfs_context *c, const Grid &g, gfs::FieldPtr
         } else if (c->press_variant == 1) {
             LAUNCH(c, gfs::k_press_subst<false>, subst_blocks, subst_threads, S, ++P.epoch);
             LAUNCH(c, gfs::k_press_subst<true>, subst_blocks, subst_threads, S, ++P.epoch);
+        } else if (c->press_variant == 2) {
+            LAUNCH(c, (gfs::k_press_subst_df<false, false>), subst_blocks, subst_threads, S);
+            LAUNCH(c, (gfs::k_press_subst_df<true, false>), subst_blocks, subst_threads, S);
         } else {
-            LAUNCH(c, gfs::k_press_subst_df<false>, subst_blocks, subst_threads, S);
-            LAUNCH(c, gfs::k_press_subst_df<true>, subst_blocks, subst_threads, S);
+            LAUNCH(c, (gfs::k_press_subst_df<false, true>), subst_blocks, subst_threads, S);
+            LAUNCH(c, (gfs::k_press_subst_df<true, true>), subst_blocks, subst_threads, S);
         }
     };
     LAUNCH(c, gfs::k_press_sweep<0>, sweep_blocks, T, S, ++P.epoch);
@@ -1625,7 +1628,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
-    else if (option == 12) { GFS_REQUIRE(value >= 0 && value <= 2, "pressure sweep variant must be 0, 1 or 2"); c->press_variant = value; }
+    else if (option == 12) { GFS_REQUIRE(value >= 0 && value <= 3, "pressure sweep variant must be 0..3"); c->press_variant = value; }
     else if (option == 11) { GFS_REQUIRE(value == 0 || value == 1, "fused grid pass must be 0 or 1"); c->fused_grid = value; }
     else if (option == 10) { GFS_REQUIRE(value == 0 || value == 1, "split wait must be 0 or 1"); c->split_wait = value; }
     else if (option == 9) { GFS_REQUIRE(value == 0 || value == 1, "early all-ranks max must be 0 or 1"); c->allmax_early = value; }

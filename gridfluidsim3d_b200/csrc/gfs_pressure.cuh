@@ -56,6 +56,13 @@ __device__ __forceinline__ int press_mat(const PressSys &S, int i, int j, int k)
     return S.material[(size_t)i + (size_t)S.I * ((size_t)j + (size_t)S.J * (size_t)k)];
 }
 
+// a load the compiler may neither hoist out of a polling loop nor serve from L1
+__device__ __forceinline__ double ld_poll(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // deterministic block reductions (fixed tree): every block that reduces the same input gets the same bits
 __device__ __forceinline__ double block_sum(double v, double *sh) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -423,7 +430,13 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst(PressSys S, un
 // L2 round trip per tile-to-tile hand-over instead of flag + fence + halo load, and a tile starts the moment its own
 // halo is there, not when the last of three whole predecessor tiles has been flagged.
 
-template <bool REV>
+//
+// FINE = true goes one step further: nothing is waited for up front.  The halo is read once (whatever is there), and a
+// boundary lane that meets a sentinel when it actually needs the value spins on that one address.  A tile then runs a
+// few steps behind its predecessors instead of after them -- the sweep approaches the hyperplane schedule (I + J + K
+// dependent steps) instead of (tiles along the diagonal) x (steps per tile).  Every step is a chain of five dependent
+// fp64 operations plus a shuffle (~290 clocks measured), so the length of that chain of steps is the whole cost.
+template <bool REV, bool FINE>
 __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S) {
     __shared__ SubstSmem sm_all[kSubstWarps];
     __shared__ uint8_t hf_all[kSubstWarps][(kTileZ + kTileY) * kTileX];
@@ -491,8 +504,10 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
         }
         __syncwarp();
 
-        // ---- the halo of the produced vector: poll the fluid cells until their values have arrived
+        // ---- the halo of the produced vector: poll the fluid cells until their values have arrived (FINE: one look only)
         double xh = 0.0;
+        const double *halo_y = dyn + (size_t)i0 + (size_t)(j0 + (REV ? kTileY : -1)) * sy + (size_t)k * sz;      // my row in the y neighbour
+        const double *halo_z = dyn + (size_t)i0 + (size_t)j * sy + (size_t)(k0 + (REV ? kTileZ : -1)) * sz;      // ... in the z neighbour
         for (;;) {
             bool ok = true;
             for (int h = lane; h < (kTileZ + kTileY) * kTileX; h += 32) {
@@ -500,14 +515,15 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
                 const int hr = h / kTileX, hi = h % kTileX;
                 int hj, hk;
                 if (hr < kTileZ) { hj = j0 + (REV ? kTileY : -1); hk = k0 + hr; } else { hj = j0 + (hr - kTileZ); hk = k0 + (REV ? kTileZ : -1); }
-                const double v = __ldcg(dyn + (size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz);
-                if (__double_as_longlong(v) == kPressSentinel) ok = false; else sm.hd[hr][hi] = v;
+                const double v = ld_poll(dyn + (size_t)(i0 + hi) + (size_t)hj * sy + (size_t)hk * sz);
+                if (FINE) sm.hd[hr][hi] = v;
+                else if (__double_as_longlong(v) == kPressSentinel) ok = false; else sm.hd[hr][hi] = v;
             }
             if (x_fluid) {
-                xh = __ldcg(dyn + row + ix);
-                if (__double_as_longlong(xh) == kPressSentinel) ok = false;
+                xh = ld_poll(dyn + row + ix);
+                if (!FINE && __double_as_longlong(xh) == kPressSentinel) ok = false;
             }
-            if (__all_sync(0xffffffffu, ok)) break;
+            if (FINE || __all_sync(0xffffffffu, ok)) break;
         }
         __syncwarp();
 
@@ -521,9 +537,19 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
             double from_z = REV ? __shfl_down_sync(0xffffffffu, mine, 8) : __shfl_up_sync(0xffffffffu, mine, 8);
             double val = 0.0;
             if (active && ((fl >> ii) & 1u)) {
-                if (a == 0) from_y = sm.hd[lk][ii];
-                if (b == 0) from_z = sm.hd[kTileZ + lj][ii];
-                const double from_x = li == 0 ? xh : mine;
+                if (a == 0) {
+                    from_y = sm.hd[lk][ii];
+                    if (FINE) while (__double_as_longlong(from_y) == kPressSentinel) from_y = ld_poll(halo_y + ii);
+                }
+                if (b == 0) {
+                    from_z = sm.hd[kTileZ + lj][ii];
+                    if (FINE) while (__double_as_longlong(from_z) == kPressSentinel) from_z = ld_poll(halo_z + ii);
+                }
+                double from_x = mine;
+                if (li == 0) {
+                    from_x = xh;
+                    if (FINE) while (__double_as_longlong(from_x) == kPressSentinel) from_x = ld_poll(dyn + row + ix);
+                }
                 const double pc = sm.pc[lane][ii];
                 double tt = sm.in[lane][ii];
                 if (!REV) {

@@ -261,7 +261,8 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * 0 = the two-kernel form with the node grid and its mask in HBM; identical results.  option 12: substitution sweeps of
  * gfs_pressure_solve: 0 = inputs read from global memory inside the dependent steps, tiles synchronised by completion
  * flags; 1 = each tile's inputs staged in shared memory before it waits; 2 = staged, and synchronised by the data itself
- * (cells hold a sentinel until produced; no flags, no fences) (default).  Identical results. */
+ * (cells hold a sentinel until produced; no flags, no fences), a tile waiting for its whole halo first; 3 = as 2, but a
+ * lane waits for a halo value only at the step that needs it (default).  Identical results. */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid

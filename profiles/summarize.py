@@ -75,8 +75,10 @@ def launches(tag):
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.1f | %.1f | %.1f %% |\n" % (name[:90], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / tot))
         # the kernels of ONE trilinear substep, by mean launch time: the shares to compare with bench.py's "kernels" block
-        step = ["k_p2g_tile<2>", "k_g2p_brick<0, 0>", "k_build_index", "k_assemble", "k_p2g_finalize", "k_classify",
-                "DeviceScanKernel", "k_resolve_collisions"]
+        step = ["k_p2g_tile2<1>", "k_g2p_tri<0, 0, 0>", "k_finalize_assemble", "k_p2g_tile<2>", "k_g2p_brick<0, 0>", "k_build_index", "k_assemble",
+                "k_p2g_finalize", "k_classify", "DeviceScanKernel", "k_resolve_collisions", "k_g2p_slow"]
+        if any("k_p2g_tile2<1>" in n for n in per):       # round 2 default path: the round-1 kernels run only in variant sweeps
+            step = [k for k in step if k not in ("k_p2g_tile<2>", "k_g2p_brick<0, 0>", "k_assemble", "k_p2g_finalize")]
         rows = []
         for key in step:
             hit = [(n, v) for n, v in per.items() if key in n and "at_cuda_detail" not in n.split("DeviceScanKernel")[0][:0]]
@@ -133,6 +135,20 @@ def kernel_report(tag, kernel, workload, traffic):
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     traffic.setdefault(workload, {})[kernel_key(name)] = \
         num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    # which pipe the kernel actually sits on (bench.py attaches this to its roofline object next to the HBM fraction)
+    bpath = os.path.join(OUT, "bounds.json")
+    bounds = json.load(open(bpath)) if os.path.exists(bpath) else {}
+
+    def pct(k):
+        return round(float(m[k][0].replace(",", "")), 2) if k in m else None
+    bounds.setdefault(workload, {})[kernel_key(name)] = {
+        "tag": tag,
+        "lsu_wavefronts_pct_of_peak": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "dram_throughput_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "shared_atomic_wavefronts": pct("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum"),
+        "source": "profiles/%s_%s.md (ncu --set full)" % (tag, kernel)}
+    json.dump(bounds, open(bpath, "w"), indent=1, sort_keys=True)
     print("wrote", kernel, tag)
 
 

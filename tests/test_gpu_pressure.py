@@ -118,17 +118,17 @@ def test_pressure_solve_repeats_bit_for_bit_and_handles_limits(ctx, oracle):
 @pytest.mark.parametrize("name,solids", [("slab24", True), ("odd20", False), ("hello64", False)])
 def test_pressure_sweep_variants_bit_identical(ctx, name, solids):
     """option 12: substitution kernels reading global memory / staged in shared memory behind tile flags / staged with
-    data-flow (sentinel) synchronisation -- every float of the result identical, same iteration count and residual."""
+    data-flow (sentinel) synchronisation, waiting per tile or per value -- every float of the result identical, same iteration count and residual."""
     s = make_case(name, solids)
     dt = 1.0 / 30
     stage5(ctx, s)
     ctx.apply_body_force(capi.FIELD_P2G, (0.1, -9.8, 0.2), dt)
     out = []
-    for variant in (0, 1, 2, 2):
+    for variant in (0, 1, 2, 3, 3):
         ctx.set_option(12, variant)
         it, res = ctx.pressure_solve(capi.FIELD_P2G, dt)
         out.append((it, res, ctx.get_pressure()))
-    ctx.set_option(12, 2)
+    ctx.set_option(12, 3)
     for other in out[1:]:
         assert out[0][0] == other[0] and out[0][1] == other[1]
         assert np.array_equal(bits(out[0][2]), bits(other[2]))
