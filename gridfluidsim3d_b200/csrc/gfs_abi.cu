@@ -200,7 +200,7 @@ struct gfs_context {
     uint32_t key_lo = 0, key_hi = 0;      // keys of the bricks around the owned layers (+- 8 layers): the cell table, the scan, the
     uint32_t brick_lo = 0, brick_hi = 0;  // count resets and the brick kernels cover only them (everything, single domain)
     bool velocities_valid = true;         // false after gfs_advect_substep (positions only): P2G / G2P need a fresh upload
-    int press_variant = 3;                // option 12 (3 = 2 with per-value waiting inside the steps): substitution sweeps of the pressure solve: 0 = global memory + tile flags, 1 = staged in shared memory + tile flags, 2 = staged + data-flow (sentinel) synchronisation
+    int press_variant = 2;                // option 12 (3 = 2 with per-value waiting inside the steps; measured slower): substitution sweeps of the pressure solve: 0 = global memory + tile flags, 1 = staged in shared memory + tile flags, 2 = staged + data-flow (sentinel) synchronisation
     int fused_grid = 1;                   // option 11: 1 = k_finalize_assemble (no node grid / mask in HBM), 0 = k_p2g_finalize + k_assemble
     bool acc_dirty = false;               // the accumulators still hold the previous splat (fused grid pass): memset before the next
     int split_wait = 0;                   // option 10: device-side waits in a single-thread kernel of their own (slabs sharing a GPU)
@@ -2383,6 +2383,7 @@ void *gfs_device_ptr(gfs_context *c, int which, int *err) {
     if (which == 9) return c->material.p;
     if (which >= 10 && which < 16) return c->soa[c->cur][which - 10].p;
     if (which == 16) return c->vmax_bits.p;
+    if (which >= 40 && which < 46) return c->press.vec[which - 40].p;       // pressure system: r, z, s, p, q, precon (doubles per cell)
     throw GfsError("gfs_device_ptr: unknown buffer id");
     GFS_END(nullptr)
 }

@@ -56,11 +56,16 @@ __device__ __forceinline__ int press_mat(const PressSys &S, int i, int j, int k)
     return S.material[(size_t)i + (size_t)S.I * ((size_t)j + (size_t)S.J * (size_t)k)];
 }
 
-// a load the compiler may neither hoist out of a polling loop nor serve from L1
+// The data-flow sweeps communicate through plain global memory: the producer's store and the consumer's polling load are
+// STRONG (relaxed, gpu scope) operations.  A weak load -- even ld.global.cg inside asm volatile -- lets ptxas assume
+// nobody else writes the location and turn "while (v == sentinel) v = load(p)" into a single load (it did).
 __device__ __forceinline__ double ld_poll(const double *p) {
     double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_publish(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
 // deterministic block reductions (fixed tree): every block that reduces the same input gets the same bits
@@ -436,6 +441,9 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst(PressSys S, un
 // few steps behind its predecessors instead of after them -- the sweep approaches the hyperplane schedule (I + J + K
 // dependent steps) instead of (tiles along the diagonal) x (steps per tile).  Every step is a chain of five dependent
 // fp64 operations plus a shuffle (~290 clocks measured), so the length of that chain of steps is the whole cost.
+// MEASURED SLOWER (256^3: 1.8 ms per sweep against 0.68 ms): once a tile has caught up with its predecessor, every
+// boundary step waits for a store to travel through L2 (~1 us), and that latency now sits on each of the 26 steps
+// instead of once per tile.  Kept as option 12 = 3 for the record and for the bit-identity test.
 template <bool REV, bool FINE>
 __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S) {
     __shared__ SubstSmem sm_all[kSubstWarps];
@@ -565,7 +573,7 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
                     tt = __dsub_rn(tt, __dmul_rn(np, from_z));
                 }
                 val = __dmul_rn(tt, pc);
-                __stcg(dyn + row + i0 + ii, val);
+                st_publish(dyn + row + i0 + ii, val);
                 pc_x = pc;
             } else if (active) {
                 pc_x = 0.0;
