@@ -67,7 +67,45 @@ def golden_state(ref):
     sim.close()
 
 
+def golden_pressure(ref):
+    """Stages 6-8 (body forces, MICCG(0) pressure solve, pressure update) of the unmodified reference on its own stage-5
+    field of the stage scene (interior solids, fluid against walls): inputs and outputs of every stage."""
+    dims, dx = (12, 10, 14), 0.25
+    I, J, K = dims
+    material = synth.border_material(dims)
+    m3 = material.reshape(K, J, I)
+    m3[2:5, 1:4, 3:6] = synth.SOLID
+    mask = synth.fluid_cells("dam", dims, material)
+    p = synth.make_particles(mask, dx, seed=778)
+    vel = (synth.particle_velocities(p, dims, dx) + 0.05 * np.random.default_rng(204).standard_normal(p.shape)).astype(np.float32)
+    kk, jj, ii = np.nonzero(m3 == synth.SOLID)
+    force, dt = (0.3, -9.8, 0.05), 1.0 / 30
+    sim = ref.sim(dims, dx)
+    sim.add_solid_cells(np.stack([ii, jj, kk], 1).astype(np.int32))
+    sim.add_body_force(force)
+    sim.initialize()
+    sim.set_particles(p, vel)
+    sim.update_fluid_cells()
+    sim.advect_velocity_field()
+    mat = sim.get_material()
+    f5 = sim.get_fields()
+    sim.apply_body_forces(dt)
+    f6 = sim.get_fields()
+    pr = sim.update_pressure_grid(dt)
+    sim.apply_pressure(dt, pr)
+    f8 = sim.get_fields()
+    density = sim.density()
+    sim.close()
+    np.savez_compressed(os.path.join(OUT, "pressure.npz"), dims=np.array(dims, np.int32), dx=np.float64(dx), material=mat,
+                        force=np.array(force, np.float32), dt=np.float64(dt), density=np.float64(density),
+                        u5=f5[0], v5=f5[1], w5=f5[2], u6=f6[0], v6=f6[1], w6=f6[2], pressure=pr, u8=f8[0], v8=f8[1], w8=f8[2])
+    print("pressure.npz", os.path.getsize(os.path.join(OUT, "pressure.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pressure":          # only this fixture (the others stay byte for byte)
+        golden_pressure(Reference())
+        return
     ref = Reference()
     os.makedirs(OUT, exist_ok=True)
     if "--only-extrapolate" in sys.argv:             # added after the other fixtures were committed

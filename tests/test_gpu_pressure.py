@@ -148,6 +148,28 @@ def test_pressure_solve_field_host_pointer_operator(ctx, oracle):
     assert not p[mat != synth.FLUID].any()
 
 
+def test_pressure_stages_golden_fixture_through_cuda(ctx):
+    """The committed outputs of the unmodified reference (tests/golden/pressure.npz) straight against the CUDA path, no
+    oracle in between: body forces and the pressure update bit-exact, the float pressure grid to 2e-6 of its maximum."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pressure.npz"))
+    dims, dx, dt, density = tuple(int(x) for x in g["dims"]), float(g["dx"]), float(g["dt"]), float(g["density"])
+    ctx.domain_init(dims, dx)
+    ctx.set_material(g["material"])
+    ctx.set_field(capi.FIELD_P2G, g["u5"], g["v5"], g["w5"])
+    ctx.apply_body_force(capi.FIELD_P2G, g["force"], dt)
+    for a, nm in zip(ctx.get_field(capi.FIELD_P2G), ("u6", "v6", "w6")):
+        assert np.array_equal(bits(a), bits(g[nm]))
+    iters, resid = ctx.pressure_solve(capi.FIELD_P2G, dt, density)
+    p = ctx.get_pressure()
+    assert iters > 3 and resid < 1e-6
+    assert np.abs(p - g["pressure"]).max() <= 2e-6 * np.abs(g["pressure"]).max()
+    assert (bits(p) == bits(g["pressure"])).mean() > 0.98
+    ctx.apply_pressure(capi.FIELD_P2G, capi.FIELD_NEW, dt, density)
+    for a, nm in zip(ctx.get_field(capi.FIELD_NEW), ("u8", "v8", "w8")):
+        assert np.abs(a - g[nm]).max() <= 2e-6 * max(1.0, np.abs(g[nm]).max())
+
+
 def test_pressure_requires_domain_and_solve(ctx):
     with pytest.raises(capi.GfsError):
         ctx.pressure_solve(capi.FIELD_P2G, 1.0 / 30)

@@ -54,6 +54,41 @@ def test_dambreak128_full_parity(oracle):
         assert (ca != cb).any(1).mean() < 1e-4
 
 
+def test_dambreak128_pressure_solve_parity(oracle):
+    """Stages 6-8 at BASELINE.json configs[1] (128^3 dam break, ~0.9 M fluid cells): the device MICCG(0) must take the
+    oracle's iteration count (or hit the reference's 200-iteration limit with it) and produce its float pressure grid."""
+    s = synth.make_scene("dambreak128")
+    dt = 1.0 / 30
+    c = capi.Context(0)
+    c.domain_init(s["dims"], s["dx"]); c.set_material(s["material"]); c.set_sources([])
+    c.set_particles(s["pos"], s["vel"])
+    c.sort_index(); c.p2g(capi.FAST)
+    mat = c.get_material()
+    f5 = c.get_field(capi.FIELD_P2G)
+    force = (0.0, -9.8, 0.0)
+    c.apply_body_force(capi.FIELD_P2G, force, dt)
+    f6 = c.get_field(capi.FIELD_P2G)
+    g6 = oracle.body_force(*f5, s["dims"], mat, force, dt)
+    for a, b in zip(f6, g6):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    iters, resid = c.pressure_solve(capi.FIELD_P2G, dt)
+    p = c.get_pressure()
+    c.apply_pressure(capi.FIELD_P2G, capi.FIELD_NEW, dt)
+    f8 = c.get_field(capi.FIELD_NEW)
+    c.close()
+    p_ref, it_ref, limit, err_ref = oracle.pressure_solve(*g6, s["dims"], s["dx"], mat, dt)
+    print("dambreak128 pressure: %d iterations (oracle %d, limit %s), residual %.3e (oracle %.3e), %d fluid cells"
+          % (iters, it_ref, limit, resid, err_ref, int((mat == synth.FLUID).sum())))
+    assert iters == it_ref
+    assert abs(resid - err_ref) <= 1e-3 * err_ref + 1e-12
+    scale = np.abs(p_ref).max()
+    assert np.abs(p - p_ref).max() <= 2e-6 * scale
+    assert (p.view(np.uint32) == p_ref.view(np.uint32)).mean() > 0.98
+    g8 = oracle.apply_pressure(*g6, s["dims"], s["dx"], mat, p, dt)
+    for a, b in zip(f8, g8):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 # sub-boxes (lower corner, in cells) per workload: at the free surface, deep inside, and in a domain corner (border solids,
 # boundary faces); river: also one straddling x = 256..288 where 32-bit linear indices pass 2^24 per plane
 BOXES = {

@@ -119,3 +119,22 @@ def test_extrapolate_golden(oracle):
         out = oracle.extrapolate(g["u"], g["v"], g["w"], dims, g["material"], nl)
         for got, name in zip(out, "uvw"):
             assert np.array_equal(bits(got), bits(g["%s_%d" % (name, nl)]))
+
+
+def test_pressure_stages_golden(oracle):
+    """Stages 6-8 of the unmodified reference (tests/golden/pressure.npz, written by `oracle/make_golden.py pressure`):
+    the oracle reproduces the force-added field, the MICCG(0) float pressure grid and the projected field bit for bit."""
+    g = load("pressure.npz")
+    dims, dx, dt, density = tuple(int(x) for x in g["dims"]), float(g["dx"]), float(g["dt"]), float(g["density"])
+    mat = g["material"]
+    f6 = oracle.body_force(g["u5"], g["v5"], g["w5"], dims, mat, g["force"], dt)
+    for a, nm in zip(f6, ("u6", "v6", "w6")):
+        assert np.array_equal(bits(a), bits(g[nm]))
+    p, iters, limit, err = oracle.pressure_solve(*f6, dims, dx, mat, dt, density)
+    assert iters > 3 and not limit and err < 1e-6
+    assert np.array_equal(bits(p), bits(g["pressure"]))
+    f8 = oracle.apply_pressure(*f6, dims, dx, mat, p, dt, density)
+    for a, nm in zip(f8, ("u8", "v8", "w8")):
+        assert np.array_equal(bits(a), bits(g[nm]))
+    assert np.count_nonzero(g["pressure"]) > 100
+
