@@ -521,14 +521,7 @@ void do_p2g_begin(gfs_context *c, int arith) {
             const size_t smem = 12 * gfs::kTileNodes * sizeof(uint32_t);
 #define GFS_TILE_ARGS g, sp, c->cell_start.p, c->brick_lo, idx, c->soa[b][0].p, c->soa[b][1].p, c->soa[b][2].p, c->soa[b][3].p, c->soa[b][4].p, \
                       c->soa[b][5].p, c->acc[0].p, c->acc[1].p, c->acc[2].p
-            if (pow2 && c->p2g_variant == 4) {
-                static bool attr4 = false;
-                const size_t smem4 = smem + 6 * gfs::kStageChunk * sizeof(float);
-                if (!attr4) { GFS_CUDA(cudaFuncSetAttribute((gfs::k_p2g_tile2<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); attr4 = true; }
-                int prof_id_ = c->prof_begin("gfs::k_p2g_tile2<1,oct>");
-                gfs::k_p2g_tile2<true, true><<<nbricks, 512, smem4, c->stream>>>(GFS_TILE_ARGS);
-                c->prof_end(prof_id_);
-            } else if (pow2 && c->p2g_variant == 3) {
+            if (pow2 && c->p2g_variant == 3) {
                 const size_t smem3 = smem + 6 * gfs::kStageChunk * sizeof(float);
                 static bool attr_set = false;
                 if (!attr_set) {
@@ -1627,7 +1620,7 @@ void gfs_sort_index(gfs_context *c, int *err) {
 void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     GFS_BEGIN
     GFS_REQUIRE(c, "null context");
-    if (option == 0) { GFS_REQUIRE(value >= 0 && value <= 4, "p2g variant must be 0..4"); c->p2g_variant = value; }
+    if (option == 0) { GFS_REQUIRE(value >= 0 && value <= 3, "p2g variant must be 0..3"); c->p2g_variant = value; }
     else if (option == 1) { GFS_REQUIRE(value >= 0 && value <= 3, "g2p variant must be 0..3"); c->g2p_variant = value; }
     else if (option == 2) { GFS_REQUIRE(value == 0 || value == 1, "lazy sort must be 0 or 1"); c->lazy_sort = value; }
     else if (option == 3) { GFS_REQUIRE(value == 0 || value == 1, "collision resolve must be 0 or 1"); c->resolve_collisions = value; }

@@ -81,11 +81,7 @@ __device__ __forceinline__ int stage_slot(int p) { return p ^ ((((p >> 5) & 1) <
 
 constexpr int kStageChunk = 1024;
 
-// OCT (with TRANSPOSE): while a chunk is staged, every aligned group of 8 consecutive particles (about one cell) is put
-// in order of the half-cell octant the particle sits in.  The lanes of a warp read the SAME within-group position of 32
-// different groups; a staggered component's base node is the cell's plus a shift that depends only on the octant, so lanes
-// of equal octant keep the conflict-free bank pattern of their cells where lanes of random octants collide.
-template <bool TRANSPOSE, bool OCT = false>
+template <bool TRANSPOSE>
 __global__ void __launch_bounds__(TRANSPOSE ? 512 : 256, TRANSPOSE ? 2 : 4)
 k_p2g_tile2(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start, uint32_t brick0, const int32_t *__restrict__ index,
             const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
@@ -151,20 +147,7 @@ k_p2g_tile2(Grid g, SplatParams sp, const int32_t *__restrict__ cell_start, uint
             const int cn = min(kStageChunk, end - c0);
 #pragma unroll
             for (int k = 0; k < kPer; k++) {
-                int p = threadIdx.x + 512 * k;
-                if (OCT) {
-                    // rank of my particle inside its group of 8 by (octant, position): eight ballots, no shared memory
-                    const float ux = __fmul_rn(rx[k], invdx), uy = __fmul_rn(ry[k], invdx), uz = __fmul_rn(rz[k], invdx);
-                    const int oct = p < cn ? ((ux - floorf(ux) >= 0.5f) | ((uy - floorf(uy) >= 0.5f) << 1) | ((uz - floorf(uz) >= 0.5f) << 2)) : 8;
-                    const unsigned seg = 0xFFu << (lane & 24), lt = (1u << lane) - 1u;
-                    int rank = 0;
-#pragma unroll
-                    for (int o = 0; o < 8; o++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, oct == o) & seg;
-                        rank += oct > o ? __popc(m) : (oct == o ? __popc(m & lt) : 0);
-                    }
-                    if (oct < 8) p = (p & ~7) + rank;
-                }
+                const int p = threadIdx.x + 512 * k;
                 if (p < cn) {
                     const int s = stage_slot(p);
                     stage[s] = rx[k]; stage[kStageChunk + s] = ry[k]; stage[2 * kStageChunk + s] = rz[k];
