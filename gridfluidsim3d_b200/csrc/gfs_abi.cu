@@ -144,6 +144,8 @@ struct gfs_context {
         DevBuf<unsigned long long> ticket;
         DevBuf<unsigned int> tile_done;
         DevBuf<float> pressure;
+        DevBuf<long long> trace;          // option 13: per-tile timestamps of the last substitution sweeps (debugging)
+        int trace_on = 0;
         int dims[3] = {0, 0, 0};          // grid the tile order was built for
         unsigned int epoch = 0;
         bool valid = false;               // `pressure` holds the result of a solve on the current domain
@@ -889,7 +891,7 @@ void gfs_destroy(gfs_context *c, int *err) {
     for (int b = 0; b < 2; b++) { for (int a = 0; a < 6; a++) c->soa[b][a].release(); c->tag[b].release(); c->keys[b].release(); c->perm[b].release(); }
     for (int a = 0; a < 6; a++) c->press.vec[a].release();
     c->press.scal.release(); c->press.flags.release(); c->press.state.release(); c->press.order.release();
-    c->press.ticket.release(); c->press.tile_done.release(); c->press.pressure.release();
+    c->press.ticket.release(); c->press.tile_done.release(); c->press.pressure.release(); c->press.trace.release();
     if (c->press.host_state) cudaFreeHost(c->press.host_state);
     if (c->press.host_resid) cudaFreeHost(c->press.host_resid);
     c->split_counters.release(); c->comm_error.release(); c->ext_layer.release(); c->coll_list.release(); c->coll_count.release(); c->h_mat.release(); c->h_layer.release();
@@ -1446,6 +1448,8 @@ gfs::PressSys pressure_system(gfs_context *c, const Grid &g, const uint8_t *mate
     S.cells = (long long)cells;
     S.scale = dt / (density * g.dx * g.dx);
     S.tol = tolerance;
+    S.trace = nullptr;
+    if (P.trace_on) { P.trace.reserve((size_t)S.ntiles * 8); GFS_CUDA(cudaMemsetAsync(P.trace.p, 0, (size_t)S.ntiles * 8 * sizeof(long long), c->stream)); S.trace = P.trace.p; }
     return S;
 }
 
@@ -1628,6 +1632,7 @@ void gfs_set_option(gfs_context *c, int option, int value, int *err) {
     else if (option == 5) { GFS_REQUIRE(value >= 0 && value < (1 << 20), "cell cap must be >= 0"); c->cell_cap = value; }
     else if (option == 6) { GFS_REQUIRE(value == 0 || value == 1, "solid-cell removal must be 0 or 1"); c->remove_in_solid = value; }
     else if (option == 7) { GFS_REQUIRE(value >= 1 && value <= 3600, "peer-exchange wait limit must be 1..3600 seconds"); c->comm_timeout_cycles = 2000000000ll * value; }
+    else if (option == 13) { GFS_REQUIRE(value == 0 || value == 1, "pressure trace must be 0 or 1"); c->press.trace_on = value; }
     else if (option == 12) { GFS_REQUIRE(value >= 0 && value <= 3, "pressure sweep variant must be 0..3"); c->press_variant = value; }
     else if (option == 11) { GFS_REQUIRE(value == 0 || value == 1, "fused grid pass must be 0 or 1"); c->fused_grid = value; }
     else if (option == 10) { GFS_REQUIRE(value == 0 || value == 1, "split wait must be 0 or 1"); c->split_wait = value; }
@@ -2383,7 +2388,8 @@ void *gfs_device_ptr(gfs_context *c, int which, int *err) {
     if (which == 9) return c->material.p;
     if (which >= 10 && which < 16) return c->soa[c->cur][which - 10].p;
     if (which == 16) return c->vmax_bits.p;
-    if (which >= 40 && which < 46) return c->press.vec[which - 40].p;       // pressure system: r, z, s, p, q, precon (doubles per cell)
+    if (which >= 40 && which < 46) return c->press.vec[which - 40].p;
+    if (which == 46) return c->press.trace.p;       // pressure system: r, z, s, p, q, precon (doubles per cell)
     throw GfsError("gfs_device_ptr: unknown buffer id");
     GFS_END(nullptr)
 }

@@ -49,6 +49,7 @@ struct PressSys {
     long long cells;
     double scale;                             // dt / (density dx^2)
     double tol;
+    long long *trace;                         // debugging (option 13): per tile {ticket, static done, halo there, steps done} in ns, or null
 };
 
 __device__ __forceinline__ int press_mat(const PressSys &S, int i, int j, int k) {
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= (unsigned long long)S.ntiles) break;
         const int tile = S.order[REV ? S.ntiles - 1 - (int)t : (int)t];
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (S.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         const int tx = tile % S.ntx, ty = (tile / S.ntx) % S.nty, tz = tile / (S.ntx * S.nty);
         const int i0 = tx * kTileX, j0 = ty * kTileY, k0 = tz * kTileZ;
         const int j = j0 + lj, k = k0 + lk;
@@ -511,6 +514,7 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
             if (x_in) { x_fluid = S.flags[row + ix] & kPfFluid; if (!REV) pc_x = S.precon[row + ix]; }
         }
         __syncwarp();
+        if (S.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
 
         // ---- the halo of the produced vector: poll the fluid cells until their values have arrived (FINE: one look only)
         double xh = 0.0;
@@ -534,6 +538,7 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
             if (FINE || __all_sync(0xffffffffu, ok)) break;
         }
         __syncwarp();
+        if (S.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
 
         double mine = 0.0;
 #pragma unroll 2
@@ -581,6 +586,12 @@ __global__ void __launch_bounds__(kSubstWarps * 32) k_press_subst_df(PressSys S)
             mine = val;
         }
         __syncwarp();
+        if (S.trace && lane == 0) {
+            long long t3;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3));
+            long long *tr = S.trace + 4 * ((size_t)tile + (REV ? (size_t)S.ntiles : 0));
+            tr[0] = t0; tr[1] = t1; tr[2] = t2; tr[3] = t3;
+        }
     }
 }
 

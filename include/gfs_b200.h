@@ -263,7 +263,8 @@ void gfs_sort_index(gfs_context *ctx, int *err);
  * flags; 1 = each tile's inputs staged in shared memory before it waits; 2 = staged, and synchronised by the data itself
  * (cells hold a sentinel until produced; no flags, no fences), a tile waiting for its whole halo first (default); 3 = as
  * 2, but a lane waits for a halo value only at the step that needs it (measured slower: an L2 round trip lands on every
- * boundary step of the dependent chain).  Identical results. */
+ * boundary step of the dependent chain).  Identical results.  option 13: 1 = record per-tile timestamps of the last
+ * substitution sweeps (gfs_device_ptr 46; profiles/press_trace.py reads them), 0 = off (default). */
 void gfs_set_option(gfs_context *ctx, int option, int value, int *err);
 /* K1: stage 1 + stage 5 of _stepFluid on the resident particles: material classification
  * (src/fluidsimulation.cpp:1998-2017), u/v/w splat + normalisation + inflow override + bordering-fluid
@@ -364,7 +365,7 @@ void gfs_comm_allmax_post(gfs_context *ctx, int *err);
  * 16 the word holding max |v| of the resident particles (float bits; the P2G fixed-point scale derives from it --
  * sharded runs must replace it by the maximum over all ranks between the sort and gfs_p2g_begin); 40..45 the dense
  * double vectors of the last pressure solve: residual, auxillary, search, pressure, forward-solve temporary, MIC(0)
- * diagonal (verification hook of tests/test_gpu_pressure.py). */
+ * diagonal (verification hook of tests/test_gpu_pressure.py); 46 the per-tile timestamps of option 13. */
 void *gfs_device_ptr(gfs_context *ctx, int which, int *err);
 /* Verification hook: order- and distribution-independent 64-bit hashes of the resident state.  out5[0] = material of the
  * owned cell layers, out5[1..3] = P2G u, v, w faces of the owned layers, out5[4] = the particle set.  Each is a sum mod
