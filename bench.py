@@ -174,7 +174,7 @@ class CpuHotpath:
     cost (measured once with zero particles) is charged pro rata n_sample/N, so the figure estimates the
     throughput of the full workload spread over `cores` threads."""
 
-    def __init__(self, scene_host, interp, per_thread):
+    def __init__(self, scene_host, interp, per_thread, force_cores=None):
         from oracle import pyoracle
         self.s, self.interp = scene_host, interp
         dims = scene_host["dims"]
@@ -182,6 +182,8 @@ class CpuHotpath:
         ncpu, avail_kb = host_threads()
         per_sim_kb = max(1, cells * 90 // 1024)          # ~90 B/cell per private simulator (measured at 128^3)
         self.cores = int(max(1, min(ncpu, 32, avail_kb // 2 // per_sim_kb)))
+        if force_cores:
+            self.cores = int(force_cores)
         self.kind, self.ref = "port", None
         try:
             self.ref = pyoracle.Reference(build=os.path.isdir("/root/reference/src"))
@@ -189,7 +191,7 @@ class CpuHotpath:
         except (FileNotFoundError, OSError) as e:
             log("reference library unavailable (%s): timing the oracle port instead" % e)
             self.orc = pyoracle.Oracle()
-            self.cores = int(min(ncpu, self.orc.lib.orc_max_threads()))
+            self.cores = int(force_cores) if force_cores else int(min(ncpu, self.orc.lib.orc_max_threads()))
         N = len(scene_host["pos"])
         self.n = int(min(N, per_thread * self.cores))
         self.N = N
@@ -643,6 +645,13 @@ def run_gfs(args):
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_desc(),
                             "seconds": spent}
             cpu.close()
+            if cpu.kind == "reference":
+                # the reference is single-threaded -- its faithful number is one core's
+                one = CpuHotpath(host_small, interp, min(args.cpu_sample, 20000), force_cores=1)
+                one.N = N
+                v1, spent1 = one.step()
+                cpu_baseline["one_core"] = {"value": v1, "cores": 1, "sample": one.sample_desc(), "seconds": spent1}
+                one.close()
         except Exception as e:          # the baseline leg must never take the GPU numbers down with it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
 
