@@ -376,6 +376,11 @@ class RefSim:
     def add_body_force(self, f):
         self.lib.ref_sim_add_body_force(self.h, *f)
 
+    def add_swirl_force(self):
+        """a variable body force field (host callback) about the vertical axis through (4, *, 4)"""
+        self.lib.ref_sim_add_swirl_force.argtypes = [C.c_void_p]
+        self.lib.ref_sim_add_swirl_force(self.h)
+
     def add_solid_cells(self, ijk):
         ijk = _c(ijk, np.int32)
         self.lib.ref_sim_add_solid_cells(self.h, ijk, len(ijk))

@@ -136,9 +136,10 @@ def test_whole_simulator_stock_settings_with_surface_mesher(libs):
 
 @pytest.mark.parametrize("n,frames,fast", [(32, 3, True), (32, 2, False), (64, 1, True)])
 def test_resident_fluidsimulation_step_parity(resident_lib, n, frames, fast):
-    """The UNMODIFIED reference simulator with stages 1, 5, 11, 12 of _stepFluid (src/fluidsimulation.cpp:3262-3390) on the
-    device-resident path (dropin/fluidsimulation_resident.cpp: gfs_set_particles once, gfs_p2g, gfs_g2p_advect) against
-    the same simulator on its CPU paths: N frames of FluidSimulation::update() at 32^3 and at BASELINE configs[0]'s 64^3.
+    """The UNMODIFIED reference simulator with stages 1, 5-9, 11, 12 of _stepFluid (src/fluidsimulation.cpp:3262-3390) on the
+    device-resident path (dropin/fluidsimulation_resident.cpp: gfs_set_particles once, gfs_p2g, gfs_extrapolate,
+    gfs_apply_body_force, gfs_pressure_solve, gfs_apply_pressure, gfs_g2p_advect) against the same simulator on its CPU
+    paths: N frames of FluidSimulation::update() at 32^3 and at BASELINE configs[0]'s 64^3.
     Particles are compared as sorted sets (the resident path keeps its own particle order; the reference shuffles its
     own every substep anyway), grids element by element.  The reference's own stage timers are printed side by side."""
     from oracle.pyoracle import RefSim
@@ -186,6 +187,47 @@ def test_resident_fluidsimulation_step_parity(resident_lib, n, frames, fast):
     assert (m0 != m1).mean() < 1e-3
     for a, b in zip(f0, f1):
         assert np.abs(a - b).max() < 1e-3 * max(1.0, np.abs(a).max()) and np.median(np.abs(a - b)) < 1e-5
+
+
+def test_resident_simulation_with_solids_inflow_and_variable_force(resident_lib):
+    """The resident build on a scene that takes its less travelled paths: interior solid cells (solid corrections of the
+    pressure right-hand side, collision resolve), an inflow source (the host edits the particle vector every substep, so
+    the device set is re-uploaded) and a variable body-force field (a host callback: stage 6 makes its round trip through
+    the reference's own loops).  Both builds call rand() at the same places, so the emitted particles coincide."""
+    ref, res = resident_lib
+    libc = ctypes.CDLL(None)
+    n, dx = 32, 0.25
+    kk, jj, ii = np.meshgrid(np.arange(2, 6), np.arange(1, 5), np.arange(12, 18), indexing="ij")
+    solid = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], 1).astype(np.int32)
+    out = []
+    for lib in (ref, res):
+        libc.srand(5)
+        sim = lib.sim((n, n, n), dx)
+        sim.add_solid_cells(solid)
+        sim.add_fluid_cuboid((0.25, 0.25, 0.25), 7.5, 2.0, 7.5)
+        sim.add_body_force((0.0, -25.0, 0.0))
+        sim.add_swirl_force()
+        sim.add_inflow_source(0, (4.0, 5.5, 4.0), 0.8, 0.0, 0.0, (0.5, -2.0, 0.25))
+        if lib is res:
+            sim.set_accel(True, True)
+        sim.initialize()
+        for _ in range(2):
+            sim.update(1.0 / 30.0)
+        p, v = sim.get_particles()
+        out.append((p, v, sim.get_material(), sim.get_fields()))
+        sim.close()
+    (p0, v0, m0, f0), (p1, v1, m1, f1) = out
+    assert len(p0) == len(p1) > 40000
+    from scipy.spatial import cKDTree
+    dist, idx = cKDTree(p1).query(p0)
+    tol_p = 1e-4 * dx
+    assert np.median(dist) < tol_p and (dist < 50 * tol_p).mean() > 0.999 and dist.max() < dx
+    dv = np.abs(v0 - v1[idx]).max(1)
+    assert np.median(dv) < 1e-4 * max(1.0, np.abs(v0).max()) and (dv < 1e-2 * max(1.0, np.abs(v0).max())).mean() > 0.999
+    assert (m0 != m1).mean() < 1e-3
+    for a, b in zip(f0, f1):
+        assert np.abs(a - b).max() < 1e-2 * max(1.0, np.abs(a).max()) and np.median(np.abs(a - b)) < 1e-5
+    assert np.abs(f0[0]).max() > 0.5 and np.abs(f0[2]).max() > 0.5          # the swirl did something
 
 
 def test_sources_emission_and_outflow_match_reference(libs):
