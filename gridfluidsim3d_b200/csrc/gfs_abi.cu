@@ -2624,10 +2624,10 @@ void gfs_reserve(gfs_context *c, int64_t particle_capacity, int *err) {
         GFS_TOUCH(gfs::k_g2p_slow<false>); GFS_TOUCH(gfs::k_g2p_slow<true>); GFS_TOUCH(gfs::k_g2p_advect<0>); GFS_TOUCH(gfs::k_g2p_advect<2>);
         GFS_TOUCH(gfs::k_resolve_collisions); GFS_TOUCH(gfs::k_copy_batch); GFS_TOUCH(gfs::k_copy_batch_wait); GFS_TOUCH(gfs::k_wait_flag);
         GFS_TOUCH(gfs::k_signal); GFS_TOUCH(gfs::k_gather_counts); GFS_TOUCH(gfs::k_allmax); GFS_TOUCH(gfs::k_append_bin);
-        GFS_TOUCH(gfs::k_append_aos); GFS_TOUCH(gfs::k_split_by_layer); GFS_TOUCH(gfs::k_add_u64);
+        GFS_TOUCH(gfs::k_append_aos); GFS_TOUCH(gfs::k_split_by_layer); GFS_TOUCH(gfs::k_add_u64); GFS_TOUCH(gfs::k_gather_sorted_aos);
 #undef GFS_TOUCH
         GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->counts.p, (uint32_t *)c->cell_start.p, (int)((size_t)c->nkeys + 3), c->stream));
-        c->sorted = false; c->aos_valid = false;                         // (the cell table is scratch until the next sort)
+        c->sorted = false;                         // (the cell table is scratch until the next sort; the particles are untouched)
     }
     GFS_CUDA(cudaStreamSynchronize(c->stream));
     GFS_END()
