@@ -380,7 +380,7 @@ def run_gfs(args):
                     host_small=host_small, drv=drv, transport=transport, make_driver=make_driver)
 
     balance = None
-    if world > 1 and args.cuts == "weighted" and not args.no_balance:
+    for cal_pass in range(args.balance_passes if (world > 1 and args.cuts == "weighted" and not args.no_balance) else 0):
         # One calibration pass: particle-weighted cuts equalise the particle COUNT, but the cost per particle is not the same
         # in every slab (partially filled bricks at the free surface, one exchange partner instead of two at the ends), and a
         # rank that finishes early only spins on its neighbours' flags.  Measure every rank's busy time (its kernels minus the
@@ -399,14 +399,15 @@ def run_gfs(args):
         rows = [None] * world
         dist.all_gather_object(rows, (busy, wait, B["n_local"]))
         cost = [b_ / max(1, n_) for (b_, w_, n_) in rows]
-        weights = np.asarray(layer_counts, np.float64).copy()
+        weights = np.asarray(layer_counts, np.float64).copy()      # particles per layer x measured cost per particle of the slab it is in
         for r, (k0, k1) in enumerate(ranges):
             weights[k0:k1] *= cost[r] / (sum(cost) / world)
         old_ranges = ranges
         ranges = slabs.slab_ranges_weighted(weights, world, min_layers=max(4, capi.slab_halo_cells(capi.TRICUBIC, 0.5 * dx, dx)))
         owned = ranges[rank]
-        balance = {"calibration_cuts": [list(r) for r in old_ranges], "busy_ms": [round(r_[0], 4) for r_ in rows],
-                   "wait_ms": [round(r_[1], 4) for r_ in rows], "particles": [r_[2] for r_ in rows]}
+        balance = {"pass": cal_pass, "calibration_cuts": [list(r) for r in old_ranges], "busy_ms": [round(r_[0], 4) for r_ in rows],
+                   "wait_ms": [round(r_[1], 4) for r_ in rows], "particles": [r_[2] for r_ in rows],
+                   "earlier_passes": ([balance] if balance else [])}
         dist.barrier()
         B["ctx"].close()
         del B
@@ -928,6 +929,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=40000, help="CPU-baseline particles per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the advection-only sweep 1 M .. 1 B particles (BASELINE configs[4])")
+    ap.add_argument("--balance-passes", type=int, default=1, help="N>1: timing-calibration passes for the slab cuts")
     ap.add_argument("--no-balance", action="store_true", help="N>1: keep the particle-count-weighted cuts (no timing calibration pass)")
     ap.add_argument("--no-pressure", action="store_true", help="skip the pressure-solve sub-metric (stages 6-8 on the workload's grid)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the FluidSimulation::update drop-in sub-metric (64^3, CPU vs CUDA classes)")
