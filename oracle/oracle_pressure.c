@@ -128,78 +128,68 @@ static void matrix_coefficients(sys_t *s) {
     }
 }
 
-/* _calculatePreconditionerVector (modified incomplete Cholesky, level 0)  src/pressuresolver.cpp:252-310 */
+/* the three "minus" neighbours of an unknown, in the order -i, -j, -k: unknown number (-1: not a fluid cell), the MIC(0)
+ * diagonal there, and the scaled plusi / plusj / plusk entries of that neighbour's matrix row (0.0 where it does not exist,
+ * as the reference's ternaries give) */
+typedef struct { int at[3]; double precon[3]; double plus[3][3]; /* [which plus: i, j, k][neighbour] */ } lower_t;
+
+static void lower_neighbours(const sys_t *s, int idx, const double *precon, lower_t *L) {
+    const int i = s->cell[3 * idx], j = s->cell[3 * idx + 1], k = s->cell[3 * idx + 2];
+    const char *flag[3] = {s->pi, s->pj, s->pk};
+    const double negscale = -s->scale;
+    L->at[0] = key_at(s, i - 1, j, k); L->at[1] = key_at(s, i, j - 1, k); L->at[2] = key_at(s, i, j, k - 1);
+    for (int d = 0; d < 3; d++) {
+        const int n = L->at[d];
+        L->precon[d] = n != -1 ? precon[n] : 0.0;
+        for (int a = 0; a < 3; a++) L->plus[a][d] = n != -1 ? (double)flag[a][n] * negscale : 0.0;
+    }
+}
+
+/* _calculatePreconditionerVector (modified incomplete Cholesky, level 0)  src/pressuresolver.cpp:252-310
+ *     e = diag - sum_d (plus_d[d] precon[d])^2 - tau * sum_d plus_d[d] (sum of the other two plus entries of d) precon[d]^2,
+ *     each sum left to right over d = i, j, k; the safety rule e < sigma diag -> e = diag; precon = 1 / sqrt(e) */
 static void preconditioner(const sys_t *s, double *precon) {
-    const double scale = s->scale, negscale = -scale;
     const double tau = 0.97, sigma = 0.25;
     for (int idx = 0; idx < s->n; idx++) {
-        const int i = s->cell[3 * idx], j = s->cell[3 * idx + 1], k = s->cell[3 * idx + 2];
-        const int im1 = key_at(s, i - 1, j, k), jm1 = key_at(s, i, j - 1, k), km1 = key_at(s, i, j, k - 1);
-        const double diag = (double)s->diag[idx] * scale;
-
-        const double plusi_im1 = im1 != -1 ? (double)s->pi[im1] * negscale : 0.0;
-        const double plusi_jm1 = jm1 != -1 ? (double)s->pi[jm1] * negscale : 0.0;
-        const double plusi_km1 = km1 != -1 ? (double)s->pi[km1] * negscale : 0.0;
-        const double plusj_im1 = im1 != -1 ? (double)s->pj[im1] * negscale : 0.0;
-        const double plusj_jm1 = jm1 != -1 ? (double)s->pj[jm1] * negscale : 0.0;
-        const double plusj_km1 = km1 != -1 ? (double)s->pj[km1] * negscale : 0.0;
-        const double plusk_im1 = im1 != -1 ? (double)s->pk[im1] * negscale : 0.0;
-        const double plusk_jm1 = jm1 != -1 ? (double)s->pk[jm1] * negscale : 0.0;
-        const double plusk_km1 = km1 != -1 ? (double)s->pk[km1] * negscale : 0.0;
-
-        const double precon_im1 = im1 != -1 ? precon[im1] : 0.0;
-        const double precon_jm1 = jm1 != -1 ? precon[jm1] : 0.0;
-        const double precon_km1 = km1 != -1 ? precon[km1] : 0.0;
-
-        const double v1 = plusi_im1 * precon_im1;
-        const double v2 = plusj_jm1 * precon_jm1;
-        const double v3 = plusk_km1 * precon_km1;
-        const double v4 = precon_im1 * precon_im1;
-        const double v5 = precon_jm1 * precon_jm1;
-        const double v6 = precon_km1 * precon_km1;
-
-        double e = diag - v1 * v1 - v2 * v2 - v3 * v3 -
-                   tau * (plusi_im1 * (plusj_im1 + plusk_im1) * v4 +
-                          plusj_jm1 * (plusi_jm1 + plusk_jm1) * v5 +
-                          plusk_km1 * (plusi_km1 + plusj_km1) * v6);
+        lower_t L;
+        lower_neighbours(s, idx, precon, &L);
+        const double diag = (double)s->diag[idx] * s->scale;
+        double v[3], sq[3];
+        for (int d = 0; d < 3; d++) { v[d] = L.plus[d][d] * L.precon[d]; sq[d] = L.precon[d] * L.precon[d]; }
+        const double cross = L.plus[0][0] * (L.plus[1][0] + L.plus[2][0]) * sq[0] +
+                             L.plus[1][1] * (L.plus[0][1] + L.plus[2][1]) * sq[1] +
+                             L.plus[2][2] * (L.plus[0][2] + L.plus[1][2]) * sq[2];
+        double e = diag - v[0] * v[0] - v[1] * v[1] - v[2] * v[2] - tau * cross;
         if (e < sigma * diag) e = diag;
         if (fabs(e) > 10e-9) precon[idx] = 1.0 / sqrt(e);
     }
 }
 
-/* _applyPreconditioner: forward and backward substitution                 src/pressuresolver.cpp:312-390 */
+/* _applyPreconditioner: forward substitution over ascending unknowns (q), then backward substitution over descending
+ * unknowns (vect)                                                          src/pressuresolver.cpp:312-390 */
 static void apply_preconditioner(const sys_t *s, const double *precon, const double *residual, double *q, double *vect) {
     const double negscale = -s->scale;
     for (int idx = 0; idx < s->n; idx++) {
-        const int i = s->cell[3 * idx], j = s->cell[3 * idx + 1], k = s->cell[3 * idx + 2];
-        const int im1 = key_at(s, i - 1, j, k), jm1 = key_at(s, i, j - 1, k), km1 = key_at(s, i, j, k - 1);
-        double plusi_im1 = 0.0, precon_im1 = 0.0, q_im1 = 0.0;
-        if (im1 != -1) { plusi_im1 = (double)s->pi[im1] * negscale; precon_im1 = precon[im1]; q_im1 = q[im1]; }
-        double plusj_jm1 = 0.0, precon_jm1 = 0.0, q_jm1 = 0.0;
-        if (jm1 != -1) { plusj_jm1 = (double)s->pj[jm1] * negscale; precon_jm1 = precon[jm1]; q_jm1 = q[jm1]; }
-        double plusk_km1 = 0.0, precon_km1 = 0.0, q_km1 = 0.0;
-        if (km1 != -1) { plusk_km1 = (double)s->pk[km1] * negscale; precon_km1 = precon[km1]; q_km1 = q[km1]; }
-        double t = residual[idx] - plusi_im1 * precon_im1 * q_im1 -
-                                   plusj_jm1 * precon_jm1 * q_jm1 -
-                                   plusk_km1 * precon_km1 * q_km1;
-        t = t * precon[idx];
-        q[idx] = t;
+        lower_t L;
+        lower_neighbours(s, idx, precon, &L);
+        double qn[3];
+        for (int d = 0; d < 3; d++) qn[d] = L.at[d] != -1 ? q[L.at[d]] : 0.0;
+        const double t = residual[idx] - L.plus[0][0] * L.precon[0] * qn[0] -
+                                         L.plus[1][1] * L.precon[1] * qn[1] -
+                                         L.plus[2][2] * L.precon[2] * qn[2];
+        q[idx] = t * precon[idx];
     }
     for (int idx = s->n - 1; idx >= 0; idx--) {
         const int i = s->cell[3 * idx], j = s->cell[3 * idx + 1], k = s->cell[3 * idx + 2];
-        const int ip1 = key_at(s, i + 1, j, k), jp1 = key_at(s, i, j + 1, k), kp1 = key_at(s, i, j, k + 1);
-        const double vect_ip1 = ip1 != -1 ? vect[ip1] : 0.0;
-        const double vect_jp1 = jp1 != -1 ? vect[jp1] : 0.0;
-        const double vect_kp1 = kp1 != -1 ? vect[kp1] : 0.0;
-        const double plusi = (double)s->pi[idx] * negscale;
-        const double plusj = (double)s->pj[idx] * negscale;
-        const double plusk = (double)s->pk[idx] * negscale;
-        const double preconval = precon[idx];
-        double t = q[idx] - plusi * preconval * vect_ip1 -
-                            plusj * preconval * vect_jp1 -
-                            plusk * preconval * vect_kp1;
-        t = t * preconval;
-        vect[idx] = t;
+        const int up[3] = {key_at(s, i + 1, j, k), key_at(s, i, j + 1, k), key_at(s, i, j, k + 1)};
+        const char own[3] = {s->pi[idx], s->pj[idx], s->pk[idx]};
+        const double pc = precon[idx];
+        double t = q[idx];
+        for (int d = 0; d < 3; d++) {
+            const double ahead = up[d] != -1 ? vect[up[d]] : 0.0;
+            t = t - (double)own[d] * negscale * pc * ahead;        /* ((plus negscale) precon) vect, subtracted in the order i, j, k */
+        }
+        vect[idx] = t * pc;
     }
 }
 
