@@ -22,7 +22,7 @@ SYMBOLS = [
     "gfs_get_error_message", "gfs_create", "gfs_destroy", "gfs_device_info", "gfs_sync", "gfs_get_stats",
     "gfs_profile_enable", "gfs_profile_read",
     "gfs_sample", "gfs_advect", "gfs_add_point_values", "gfs_add_points",
-    "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_set_sources",
+    "gfs_domain_init", "gfs_set_material", "gfs_get_material", "gfs_get_fluid_cells", "gfs_set_sources",
     "gfs_emit_from_sources", "gfs_remove_in_sources", "gfs_set_particles", "gfs_num_particles", "gfs_get_particles", "gfs_get_particle_order",
     "gfs_set_field", "gfs_get_field", "gfs_set_field_layers", "gfs_get_field_layers", "gfs_get_material_layers", "gfs_sort", "gfs_sort_unstable", "gfs_set_option", "gfs_p2g", "gfs_g2p_advect", "gfs_substep", "gfs_advect_substep",
     "gfs_set_owned_layers", "gfs_p2g_begin", "gfs_p2g_end", "gfs_layer_bytes", "gfs_pack_layers", "gfs_unpack_layers",
@@ -140,6 +140,7 @@ def load_library():
     L.gfs_extrapolate.argtypes = [V, I, I, _err]
     L.gfs_extrapolate_field.argtypes = [V, _f32, _f32, _f32, I, I, I, _u8, I, _err]
     L.gfs_copy_field.argtypes = [V, I, I, _err]
+    L.gfs_get_fluid_cells.argtypes = [V, C.c_void_p, L64, C.POINTER(L64), _err]
     L.gfs_apply_body_force.argtypes = [V, I, C.c_float, C.c_float, C.c_float, C.c_double, _err]
     L.gfs_pressure_solve.argtypes = [V, I, C.c_double, C.c_double, C.c_double, I, C.POINTER(I), C.POINTER(C.c_double), _err]
     L.gfs_apply_pressure.argtypes = [V, I, I, C.c_double, C.c_double, _err]
@@ -409,6 +410,15 @@ class Context:
 
     def extrapolate(self, slot, num_layers):
         self._call(self.lib.gfs_extrapolate, int(slot), int(num_layers))
+
+    def get_fluid_cells(self):
+        """FluidSimulation::_fluidCellIndices: (n, 3) int32 array of (i, j, k), in the reference's k, j, i scan order."""
+        cnt = C.c_int64(0)
+        self._call(self.lib.gfs_get_fluid_cells, None, 0, C.byref(cnt))
+        out = np.empty((cnt.value, 3), np.int32)
+        if cnt.value:
+            self._call(self.lib.gfs_get_fluid_cells, out.ctypes.data, cnt.value, C.byref(cnt))
+        return out
 
     def copy_field(self, dst_slot, src_slot):
         self._call(self.lib.gfs_copy_field, int(dst_slot), int(src_slot))

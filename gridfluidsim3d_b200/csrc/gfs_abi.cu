@@ -1184,6 +1184,42 @@ void gfs_set_material(gfs_context *c, const uint8_t *material, int *err) {
     GFS_END()
 }
 
+/* FluidSimulation::_fluidCellIndices (src/fluidsimulation.cpp:2019-2039): the fluid cells of the resident material grid in
+ * the reference's k, j, i scan order, compacted on the device.  cells receives at most `capacity` triples; *count the number
+ * of fluid cells (call with capacity 0 to size the buffer).  Single domain. */
+void gfs_get_fluid_cells(gfs_context *c, gfs_grid_index_t *cells, int64_t capacity, int64_t *count, int *err) {
+    GFS_BEGIN
+    require_domain(c);
+    GFS_REQUIRE(count && capacity >= 0 && (capacity == 0 || cells), "bad arguments");
+    const Grid &g = c->grid;
+    GFS_REQUIRE(c->own_k0 == 0 && c->own_k1 == g.K, "gfs_get_fluid_cells is single-domain only");
+    GFS_CUDA(cudaSetDevice(c->device));
+    const long long n = (long long)c->cell_count;
+    DevBuf<uint32_t> flags, offs;
+    flags.reserve((size_t)n + 1); offs.reserve((size_t)n + 1);
+    GFS_CUDA(cudaMemsetAsync(flags.p + n, 0, sizeof(uint32_t), c->stream));
+    LAUNCH(c, gfs::k_fluid_flags, ceil_div(n, 256), 256, c->material.p, n, flags.p);
+    size_t tmp = 0;
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, flags.p, offs.p, (int)(n + 1), c->stream));
+    c->cub_tmp.reserve(tmp);
+    GFS_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, flags.p, offs.p, (int)(n + 1), c->stream));
+    uint32_t total = 0;
+    GFS_CUDA(cudaMemcpyAsync(&total, offs.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    GFS_CUDA(cudaStreamSynchronize(c->stream));
+    *count = (int64_t)total;
+    const int64_t m = std::min<int64_t>(capacity, (int64_t)total);
+    if (m > 0) {
+        DevBuf<int> out;
+        out.reserve((size_t)m * 3);
+        LAUNCH(c, gfs::k_fluid_cells, ceil_div(n, 256), 256, c->material.p, offs.p, n, g.I, g.J, (long long)m, out.p);
+        GFS_CUDA(cudaMemcpyAsync(cells, out.p, (size_t)m * 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GFS_CUDA(cudaStreamSynchronize(c->stream));
+        out.release();
+    }
+    flags.release(); offs.release();
+    GFS_END()
+}
+
 void gfs_get_material(gfs_context *c, uint8_t *material, int *err) {
     GFS_BEGIN
     require_domain(c);

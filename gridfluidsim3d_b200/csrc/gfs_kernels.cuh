@@ -174,6 +174,21 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(int64_t n, const uint32_
     dtag[d] = stag[r];
 }
 
+// _fluidCellIndices (fluidsimulation.cpp:2019-2039): the fluid cells in k, j, i scan order.  flag pass for the scan, then
+// the compaction writes (i, j, k) triples at the scanned offsets -- ascending linear index = the reference's order.
+__global__ void __launch_bounds__(256) k_fluid_flags(const uint8_t *__restrict__ material, long long cells, uint32_t *__restrict__ flags) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cells) flags[c] = material[c] == GFS_FLUID ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_fluid_cells(const uint8_t *__restrict__ material, const uint32_t *__restrict__ offset, long long cells,
+                                                     int I, int J, long long capacity, int *__restrict__ ijk) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells || material[c] != GFS_FLUID) return;
+    const long long o = offset[c];
+    if (o >= capacity) return;
+    ijk[3 * o] = (int)(c % I); ijk[3 * o + 1] = (int)((c / I) % J); ijk[3 * o + 2] = (int)(c / ((long long)I * J));
+}
+
 // K0c, first sort after an upload: the uploaded AoS records (24 contiguous bytes each) are still on the device, so the
 // sorted SoA arrays are GATHERED from them through the index -- one or two 32-byte sectors read per particle, fully
 // coalesced writes -- instead of scattering seven 4-byte streams to random slots (k_scatter_sorted: a 32-byte sector

@@ -53,6 +53,7 @@ struct ResidentState {
     size_t count;                     // particles on the device
     std::vector<unsigned char> material;
     std::vector<gfs_marker_particle_t> staging;
+    std::vector<gfs_grid_index_t> fluidCells;
     ResidentState() : domain(false), deviceValid(false), count(0) {}
 };
 
@@ -160,8 +161,6 @@ void FluidSimulation::_updateFluidCells() {
 
     gfs_get_material(ctx, &rs->material[0], &err);
     check(err, "gfs_get_material");
-    _fluidCellIndices.clear();
-    _fluidCellIndices.reserve((size_t)st.fluid_cells);
     c = 0;
     for (int k = 0; k < _ksize; k++)
         for (int j = 0; j < _jsize; j++)
@@ -170,10 +169,18 @@ void FluidSimulation::_updateFluidCells() {
                 if (m != _materialGrid(i, j, k)) {
                     _materialGrid.set(i, j, k, m);
                 }
-                if (m == Material::fluid) {
-                    _fluidCellIndices.push_back(i, j, k);
-                }
             }
+    /* the fluid-cell list in the reference's k, j, i order (:2019-2039), compacted on the device */
+    int64_t nfluid = 0;
+    rs->fluidCells.resize((size_t)st.fluid_cells + 1);
+    gfs_get_fluid_cells(ctx, &rs->fluidCells[0], (int64_t)rs->fluidCells.size(), &nfluid, &err);
+    check(err, "gfs_get_fluid_cells");
+    FLUIDSIM_ASSERT(nfluid == st.fluid_cells);
+    _fluidCellIndices.clear();
+    _fluidCellIndices.reserve((size_t)nfluid);
+    for (int64_t f = 0; f < nfluid; f++) {
+        _fluidCellIndices.push_back(rs->fluidCells[(size_t)f].i, rs->fluidCells[(size_t)f].j, rs->fluidCells[(size_t)f].k);
+    }
 }
 
 /* Stage 5: _advectVelocityFieldU/V/W each clear their component and refill it (:2597-2730); the three refilled arrays

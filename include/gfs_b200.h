@@ -159,6 +159,10 @@ void gfs_add_points(gfs_context *ctx, const float *pos, int64_t n, double radius
 void gfs_domain_init(gfs_context *ctx, int isize, int jsize, int ksize, double dx, int *err);
 void gfs_set_material(gfs_context *ctx, const uint8_t *material, int *err);
 void gfs_get_material(gfs_context *ctx, uint8_t *material, int *err);
+/* FluidSimulation::_fluidCellIndices (src/fluidsimulation.cpp:2019-2039): the fluid cells of the resident material grid in
+ * the reference's k, j, i scan order, compacted on the device (flags -> exclusive scan -> triples).  At most `capacity`
+ * cells are written; *count receives the number of fluid cells (capacity 0 sizes the buffer).  Single domain. */
+void gfs_get_fluid_cells(gfs_context *ctx, gfs_grid_index_t *cells, int64_t capacity, int64_t *count, int *err);
 /* inflow sources used by P2G (copied) */
 void gfs_set_sources(gfs_context *ctx, const gfs_source_t *sources, int nsources, int *err);
 /* FluidSimulation::_updateFluidSources on the resident particles (src/fluidsimulation.cpp:1771-1879).

@@ -290,6 +290,22 @@ def test_fused_grid_pass_bit_identical(ctx, name, solids):
     assert all(np.count_nonzero(a) > 500 for a in out[1][0])
 
 
+@pytest.mark.parametrize("name,solids", [("tiny16", False), ("slab24", True), ("odd20", False)])
+def test_fluid_cell_list_in_reference_order(ctx, name, solids):
+    """gfs_get_fluid_cells = FluidSimulation::_fluidCellIndices (src/fluidsimulation.cpp:2019-2039): the fluid cells of the
+    classified material grid in k, j, i scan order (ascending linear index), compacted on the device."""
+    s = scene(name, solids)
+    load_domain(ctx, s)
+    ctx.sort_unstable(); ctx.p2g(capi.FAST)
+    mat = ctx.get_material()
+    I, J, K = s["dims"]
+    lin = np.nonzero(mat == synth.FLUID)[0]
+    ref = np.stack([lin % I, (lin // I) % J, lin // (I * J)], 1).astype(np.int32)
+    cells = ctx.get_fluid_cells()
+    assert len(cells) == ctx.stats()["fluid_cells"] == len(ref) > 100
+    assert np.array_equal(cells, ref)
+
+
 def test_p2g_dense_cells(ctx, oracle):
     """More than 63 particles in one cell: the tile kernel must take its 64-bit path for that brick and still
     agree with the oracle (the reference caps at 100 per cell, src/fluidsimulation.cpp:3221-3243, so this is
